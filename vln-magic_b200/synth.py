@@ -1,0 +1,221 @@
+"""Synthetic MAGIC pretraining batches (SURVEY.md 8(d) "Synthetic inputs").
+
+Host-side only.  Produces per-sample dicts in the format of the reference task datasets
+(`MlmDataset.__getitem__` pretrain_src/data/tasks.py:67-108, `SapDataset.__getitem__` :352-390) and
+collates them into the batch schema of `mlm_collate` (:110-166) / `sap_collate` (:392-451):
+padded tensors + python lists of viewpoint-id strings.  The graph bookkeeping restates
+`get_gmap_inputs` / `get_vp_pos_fts` (pretrain_src/data/dataset.py:513-586).
+
+No dependency on the reference or the oracle: this is what bench.py and the GPU tests feed the model
+on the GPU box (where /root/reference does not exist).  tests/test_synth_collate.py checks the collate
+against the reference's own collate functions whenever /root/reference is present.
+"""
+import math
+import random
+
+import numpy as np
+import torch
+
+VOCAB_RANGE = (1996, 29611)  # tasks.py:59
+MASK_ID = 50264
+N_VIEWS = 36
+IMG_DIM = 768
+
+
+def random_word(tokens, vocab_range, mask, rng):
+    """BERT 15% masking, 80/10/10 (restates tasks.py:11-52 with an explicit `random.Random`)."""
+    out_tok, out_lab = [], []
+    for tok in tokens:
+        p = rng.random()
+        if p < 0.15:
+            p /= 0.15
+            if p < 0.8:
+                out_tok.append(mask)
+            elif p < 0.9:
+                out_tok.append(rng.choice(list(range(*vocab_range))))
+            else:
+                out_tok.append(tok)
+            out_lab.append(tok)
+        else:
+            out_tok.append(tok)
+            out_lab.append(-1)
+    if all(o == -1 for o in out_lab):
+        out_lab[0] = tokens[0]
+        out_tok[0] = mask
+    return out_tok, out_lab
+
+
+def _angle_fts(h, e):
+    return np.stack([np.sin(h), np.cos(h), np.sin(e), np.cos(e)], 1).astype(np.float32)
+
+
+def _make_graph(b, T, G_max, force_full, rs):
+    """Path + per-step candidate lists.  Returns (path, cands[t] list of vp-id strings)."""
+    path = [f"s{b}_p{t}" for t in range(T)]
+    fixed = [(1 if t < T - 1 else 0) + (1 if t > 0 else 0) for t in range(T)]
+    K = [int(rs.randint(max(2, fixed[t]), 7)) for t in range(T)]  # K in {2..6} candidates per step
+    cap = sum(6 - fixed[t] for t in range(T))
+    pool_cap = max(0, G_max - 1 - T)
+    F = min(pool_cap, cap) if force_full else int(rs.randint(0, min(pool_cap, cap) + 1))
+    while sum(K[t] - fixed[t] for t in range(T)) < F:
+        t = int(rs.randint(0, T))
+        if K[t] < 6:
+            K[t] += 1
+    slots = [(t, i) for t in range(T) for i in range(K[t] - fixed[t])]
+    new_slots = set(rs.choice(len(slots), size=F, replace=False).tolist()) if F > 0 else set()
+    pool = [f"s{b}_f{i}" for i in range(F)]
+    used, si, cands = 0, 0, []
+    for t in range(T):
+        c = []
+        if t < T - 1:
+            c.append(path[t + 1])
+        if t > 0:
+            c.append(path[t - 1])
+        for _ in range(K[t] - fixed[t]):
+            if si in new_slots:
+                c.append(pool[used])
+                used += 1
+            else:  # re-observe a frontier node already seen from an earlier step (or drop the slot)
+                choices = [p for p in pool[:used] if p not in c]
+                if choices:
+                    c.append(choices[int(rs.randint(0, len(choices)))])
+            si += 1
+        perm = rs.permutation(len(c))
+        cands.append([c[i] for i in perm])
+    return path, cands
+
+
+def _gmap(path, cands):
+    """dataset.py:513-549 restated: node order [None] + visited (first visit) + frontier (first seen)."""
+    visited, unvisited = {}, {}
+    for t, vp in enumerate(path):
+        visited[vp] = t + 1
+        if vp in unvisited:
+            del unvisited[vp]
+        for nv in cands[t]:
+            if nv not in visited:
+                unvisited[nv] = 0
+    vpids = [None] + list(visited.keys()) + list(unvisited.keys())
+    step_ids = [0] + list(visited.values()) + list(unvisited.values())
+    vmask = [0] + [1] * len(visited) + [0] * len(unvisited)
+    return vpids, step_ids, vmask
+
+
+def make_samples(task, B, L=80, T_max=5, G_max=20, seed=1234, with_labels=None):
+    rs = np.random.RandomState(seed)
+    rng = random.Random(seed)
+    samples = []
+    lens = rs.randint(L // 2, L + 1, size=B)
+    lens[int(rs.randint(0, B))] = L
+    Ts = rs.randint(2, T_max + 1, size=B) if T_max >= 2 else np.ones(B, dtype=np.int64)
+    full_idx = int(rs.randint(0, B))
+    Ts[full_idx] = T_max
+    for b in range(B):
+        n = int(lens[b])
+        toks = [0] + rs.randint(3, 50000, size=n - 2).tolist() + [2]
+        T = int(Ts[b])
+        path, cands = _make_graph(b, T, G_max, b == full_idx, rs)
+        out = {}
+        if task == "mlm":
+            ids, labs = random_word(toks, VOCAB_RANGE, MASK_ID, rng)
+            out["txt_ids"] = torch.LongTensor(ids)
+            out["txt_labels"] = torch.LongTensor(labs)
+        else:
+            out["txt_ids"] = torch.LongTensor(toks)
+        out["traj_view_img_fts"] = [torch.from_numpy(rs.randn(N_VIEWS, IMG_DIM).astype(np.float32)) for _ in range(T)]
+        loc, nav = [], []
+        for t in range(T):
+            ang = _angle_fts(rs.uniform(-math.pi, math.pi, N_VIEWS), rs.uniform(-math.pi / 6, math.pi / 6, N_VIEWS))
+            loc.append(torch.from_numpy(np.concatenate([ang, np.ones((N_VIEWS, 3), np.float32)], 1)))
+            nav.append(torch.LongTensor([1] * len(cands[t]) + [0] * (N_VIEWS - len(cands[t]))))
+        out["traj_loc_fts"] = loc
+        out["traj_nav_types"] = nav
+        out["traj_cand_vpids"] = cands
+        out["traj_vpids"] = path
+        vpids, step_ids, vmask = _gmap(path, cands)
+        G = len(vpids)
+        out["gmap_vpids"] = vpids
+        out["gmap_step_ids"] = torch.LongTensor(step_ids)
+        out["gmap_visited_masks"] = torch.BoolTensor(vmask)
+        pos = np.concatenate([_angle_fts(rs.uniform(-math.pi, math.pi, G), rs.uniform(-0.5, 0.5, G)),
+                              rs.uniform(0, 1, (G, 3)).astype(np.float32)], 1)
+        pos[0] = [0, 1, 0, 1, 0, 0, 0]  # [stop] row, dataset.py:556-558
+        out["gmap_pos_fts"] = torch.from_numpy(pos.astype(np.float32))
+        d = rs.uniform(0, 30, (G, G)).astype(np.float32)
+        d = np.triu(d, 1)
+        d = d + d.T
+        d[0, :] = 0
+        d[:, 0] = 0
+        out["gmap_pair_dists"] = torch.from_numpy(d)
+        K = len(cands[-1])
+        vp = np.zeros((N_VIEWS + 1, 14), np.float32)
+        start = np.concatenate([_angle_fts(rs.uniform(-math.pi, math.pi, 1), rs.uniform(-0.5, 0.5, 1)),
+                                rs.uniform(0, 1, (1, 3)).astype(np.float32)], 1)
+        vp[:, :7] = start
+        vp[1:K + 1, 7:] = np.concatenate([_angle_fts(rs.uniform(-math.pi, math.pi, K), rs.uniform(-0.5, 0.5, K)),
+                                          rs.uniform(0, 1, (K, 3)).astype(np.float32)], 1)
+        out["vp_pos_fts"] = torch.from_numpy(vp)
+        out["vp_angles"] = rs.uniform(-math.pi, math.pi, (N_VIEWS, 2)).astype(np.float32)
+        if task in ("sap", "cfp") if with_labels is None else with_labels:
+            visited = set(path)
+            opts = [(0, 0)] + [(vpids.index(c), j + 1) for j, c in enumerate(cands[-1]) if c not in visited]
+            g, l = opts[int(rs.randint(0, len(opts)))]
+            out["global_act_labels"] = g
+            out["local_act_labels"] = l
+        samples.append(out)
+    return samples
+
+
+def pad_tensors(tensors):
+    """common.py:9-24 semantics."""
+    m = max(t.size(0) for t in tensors)
+    out = torch.zeros(len(tensors), m, *tensors[0].shape[1:], dtype=tensors[0].dtype)
+    for i, t in enumerate(tensors):
+        out[i, :t.size(0)] = t
+    return out
+
+
+def _pad_1d(seqs, value):
+    m = max(len(s) for s in seqs)
+    out = torch.full((len(seqs), m), value, dtype=seqs[0].dtype)
+    for i, s in enumerate(seqs):
+        out[i, :len(s)] = s
+    return out
+
+
+def collate(samples):
+    """Same output schema as the reference mlm_collate / sap_collate (tasks.py:110-166, :392-451)."""
+    batch = {k: [x[k] for x in samples] for k in samples[0].keys()}
+    batch["txt_lens"] = torch.LongTensor([len(x) for x in batch["txt_ids"]])
+    batch["txt_ids"] = _pad_1d(batch["txt_ids"], 0)
+    if "txt_labels" in batch:
+        batch["txt_labels"] = _pad_1d(batch["txt_labels"], -1)
+    batch["traj_step_lens"] = [len(x) for x in batch["traj_view_img_fts"]]
+    batch["traj_vp_view_lens"] = torch.LongTensor(sum([[len(y) for y in x] for x in batch["traj_view_img_fts"]], []))
+    batch["traj_view_img_fts"] = pad_tensors(sum(batch["traj_view_img_fts"], []))
+    batch["traj_loc_fts"] = pad_tensors(sum(batch["traj_loc_fts"], []))
+    batch["traj_nav_types"] = _pad_1d(sum(batch["traj_nav_types"], []), 0)
+    batch["traj_reverie_loc_fts"] = None
+    batch["gmap_lens"] = torch.LongTensor([len(x) for x in batch["gmap_step_ids"]])
+    batch["gmap_step_ids"] = _pad_1d(batch["gmap_step_ids"], 0)
+    batch["gmap_visited_masks"] = _pad_1d(batch["gmap_visited_masks"], False)
+    batch["gmap_pos_fts"] = pad_tensors(batch["gmap_pos_fts"])
+    G = int(batch["gmap_lens"].max())
+    d = torch.zeros(len(samples), G, G)
+    for i, x in enumerate(batch["gmap_pair_dists"]):
+        d[i, :x.shape[0], :x.shape[1]] = x
+    batch["gmap_pair_dists"] = d
+    batch["vp_lens"] = torch.LongTensor([len(x) for x in batch["vp_pos_fts"]])
+    batch["vp_pos_fts"] = pad_tensors(batch["vp_pos_fts"])
+    if "global_act_labels" in batch:
+        batch["local_act_labels"] = torch.LongTensor(batch["local_act_labels"])
+        batch["global_act_labels"] = torch.LongTensor(batch["global_act_labels"])
+    return batch
+
+
+def make_batch(task, B, L=80, T_max=5, G_max=20, seed=1234):
+    return collate(make_samples(task, B, L, T_max, G_max, seed))
+
+
+def batch_to(batch, device, non_blocking=False):
+    return {k: (v.to(device, non_blocking=non_blocking) if torch.is_tensor(v) else v) for k, v in batch.items()}
