@@ -1,0 +1,187 @@
+/* libmagic_b200 -- C ABI of the B200-native MAGIC pretraining / distillation hot path.
+ *
+ * The reference (CrystalSixone/VLN-MAGIC) is pure PyTorch on this path and ships no FFI; its model file
+ * is absent (readme.md:75).  The entry points below are the operators its missing
+ * `model/pretrain_goat.py::GlocalTextPathCMTPreTraining.forward(batch, task, compute_loss)`
+ * (call sites pretrain_src/train_r2r_magic.py:448,483,510-512,545-546) decomposes into, plus the KD
+ * primitives of pretrain_src/optim/kd_loss.py and the optimizer of pretrain_src/optim/adamw.py.
+ * Each declaration cites the reference interface it replaces.  INTEGRATION.md shows the ctypes binding.
+ *
+ * Conventions: raw DEVICE pointers, explicit sizes, an explicit cudaStream_t, no internal
+ * synchronisation, `int` status return (0 = ok) with the message in magic_last_error().
+ * dtype: MAGIC_F32 = 0, MAGIC_BF16 = 1 (storage type of activations; all math is fp32).
+ * Dropout: p = 0 disables; `seed_ptr` is a DEVICE pointer to a 64-bit seed (CUDA-graph friendly),
+ * `salt` distinguishes call sites; backward regenerates the forward mask from (seed, salt, index).
+ */
+#ifndef MAGIC_B200_H_
+#define MAGIC_B200_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#ifndef __DRIVER_TYPES_H__
+typedef struct CUstream_st* cudaStream_t;
+#endif
+
+#define MAGIC_F32 0
+#define MAGIC_BF16 1
+#define MAGIC_ACT_NONE 0
+#define MAGIC_ACT_GELU 1
+#define MAGIC_ACT_RELU 2
+#define MAGIC_MAKD_MAX_SEGS 32
+
+const char* magic_last_error(void);
+int magic_version(void);
+/* 1 if the tcgen05/TMA GEMM path is compiled in and usable for (M,N,K) bf16 operands */
+int magic_gemm_tc_supported(int M, int N, int K);
+
+/* ---- dense contractions: nn.Linear forward / dgrad / wgrad of every encoder layer ------------------
+ * C[m,n] = epi(alpha * sum_k A(m,k) B(k,n) + bias[n]) + residual[m,n] + beta*C[m,n]
+ * A(m,k) = A[m*sam + k*sak], B(k,n) = B[k*sbk + n*sbn].  act/pre_out/dact_pre/dropout: see gemm_epi.cuh.
+ * Replaces torch F.linear + F.gelu + dropout + residual in BertLayer / BertCrossLayer /
+ * TransformerEncoderLayer (names pinned at train_r2r_magic.py:189-208).
+ * bf16 operands with 16-byte aligned, unit-stride layouts run on tcgen05 tensor cores (TMA-fed, TMEM
+ * accumulators); everything else runs the fp32 FFMA kernel. */
+int magic_gemm(const void* A, int a_dt, long sam, long sak, const void* B, int b_dt, long sbk, long sbn, void* C,
+               int c_dt, long ldc, int M, int N, int K, const float* bias, int act, void* pre_out,
+               const void* dact_pre, int dact_dt, long dact_ld, const void* residual, long res_ld, float alpha,
+               float beta, float drop_p, unsigned salt, const unsigned long long* seed_ptr, int allow_tc,
+               cudaStream_t st);
+
+/* ---- fused attention with graph-distance bias (GlobalMapEncoder: sprel_linear(gmap_pair_dists)) ----
+ * q/k/v: rows are tokens, head hd occupies columns [hd*64, hd*64+64) of a row; *_ld = row stride.
+ * out [B*Lq, H*64]; lse [B,H,Lq]; pbar (optional) = head-mean probabilities at
+ * pbar[b*pbar_bs + i*pbar_rs + j] (the KD attention map of agent.py:579,628,654,671). */
+int magic_attn_fwd(const void* q, const void* k, const void* v, long q_ld, long k_ld, long v_ld, void* out,
+                   float* lse, float* pbar, long pbar_bs, long pbar_rs, int B, int H, int Lq, int Lk,
+                   const int* key_lens, const float* dists, const float* sprel_w, const float* sprel_b, float scale,
+                   int dtype, float drop_p, unsigned salt, const unsigned long long* seed_ptr, cudaStream_t st);
+int magic_attn_bwd(const void* q, const void* k, const void* v, long q_ld, long k_ld, long v_ld, const void* dout,
+                   const float* lse, const float* dpbar, long pbar_bs, long pbar_rs, float* delta, void* dq,
+                   void* dk, void* dv, long dq_ld, long dk_ld, long dv_ld, float* dsprel, int B, int H, int Lq,
+                   int Lk, const int* key_lens, const float* dists, const float* sprel_w, const float* sprel_b,
+                   float scale, int dtype, float drop_p, unsigned salt, const unsigned long long* seed_ptr,
+                   cudaStream_t st);
+
+/* ---- LayerNorm (+residual, +dropout): BertSelfOutput / BertOutput / norm1,norm2 / head LNs ---------
+ * y = drop_out(LN(drop_in(x) + res) * gamma + beta); stats[r] = (mean, rstd). Parameter grads ACCUMULATE. */
+int magic_ln_fwd(const void* x, const void* res, const float* gamma, const float* beta, void* y, float* stats,
+                 int M, int h, float eps, int dtype, float p_in, unsigned salt_in, float p_out, unsigned salt_out,
+                 const unsigned long long* seed_ptr, cudaStream_t st);
+int magic_ln_bwd(const void* dy, const void* x, const void* res, const float* gamma, const float* stats, void* dx,
+                 void* dres, float* dgamma, float* dbeta, int M, int h, int dtype, float p_in, unsigned salt_in,
+                 float p_out, unsigned salt_out, const unsigned long long* seed_ptr, cudaStream_t st);
+
+/* ---- text embeddings (bert.embeddings.*: word + position + token_type -> LayerNorm -> dropout) ----- */
+int magic_embed_ln_fwd(const long long* ids, const float* word, const float* pos, const float* type0,
+                       const float* gamma, const float* beta, void* y, float* stats, int M, int L, int h, float eps,
+                       int dtype, float p_out, unsigned salt_out, const unsigned long long* seed_ptr,
+                       cudaStream_t st);
+int magic_embed_ln_bwd(const void* dy, const long long* ids, const float* word, const float* pos,
+                       const float* type0, const float* gamma, const float* stats, float* dword, float* dpos,
+                       float* dtype0, float* dgamma, float* dbeta, int M, int L, int h, int dtype, float p_out,
+                       unsigned salt_out, const unsigned long long* seed_ptr, cudaStream_t st);
+
+/* ---- positional fusion: y = xin + emb[idx] + cst + LN(W f + b)  (K <= 16) --------------------------
+ * loc_linear+loc_layer_norm+nav_type_embedding (img_embeddings), gmap_pos_embeddings+gmap_step_embeddings,
+ * vp_pos_embeddings.  backward: d(xin) == dy (not written); parameter grads ACCUMULATE. */
+int magic_posfuse_fwd(const void* xin, const long long* idx, const float* emb, const float* cst, const float* f,
+                      const float* W, const float* b, const float* gamma, const float* beta, void* y, float* stats,
+                      int M, int h, int K, float eps, int dtype, cudaStream_t st);
+int magic_posfuse_bwd(const void* dy, const long long* idx, const float* f, const float* W, const float* b,
+                      const float* gamma, const float* stats, float* demb, float* dcst, float* dW, float* db,
+                      float* dgamma, float* dbeta, int M, int h, int K, int dtype, cudaStream_t st);
+
+/* ---- row gather (idx < 0 -> zero row) / its adjoint scatter (unique idx; dsrc zero-filled first) ----
+ * MLM masked-token gather (train_r2r_magic.py:450-452 order) and the [stop] + last-step view assembly
+ * of the local branch (data/dataset.py:581-584). */
+int magic_gather_rows(const void* src, const long long* idx, void* out, int R, int h, int dtype, cudaStream_t st);
+int magic_scatter_rows(const void* dout, const long long* idx, void* dsrc, int R, int n_src_rows, int h, int dtype,
+                       cudaStream_t st);
+
+/* ---- adaptive panorama pooling (adaptive_pano_fusion, r2r_magic_model_config.json:57) -------------- */
+int magic_pano_fuse_fwd(const void* x, const float* w, const float* bias, const long long* lens, void* fused,
+                        float* probs, int R, int V, int h, int dtype, cudaStream_t st);
+int magic_pano_fuse_bwd(const void* dfused, const void* x, const float* w, const long long* lens, const float* probs,
+                        void* dx, float* dw, float* dbias, int R, int V, int h, int dtype, cudaStream_t st);
+
+/* ---- N = 1 heads (ClsPrediction.net.3) and bias gradients ----------------------------------------- */
+int magic_rowdot_fwd(const void* x, const float* w, const float* bias, float* y, int M, int h, int dtype,
+                     cudaStream_t st);
+int magic_rowdot_bwd(const float* dy, const void* x, const float* w, void* dx, float* dw, float* dbias, int M, int h,
+                     int dtype, cudaStream_t st);
+int magic_colsum(const void* x, float* out, int M, int N, long ld, int dtype, cudaStream_t st); /* out += */
+int magic_cast(const void* in, int in_dt, void* out, int out_dt, long long n, cudaStream_t st);
+/* glue: out = a + b (+ c); strided 2-D copy; segment sums (per-sample means of masked-token losses) */
+int magic_add(const void* a, const void* b, const void* c, void* out, long long n, int dtype, cudaStream_t st);
+int magic_copy2d(const void* src, long src_ld, void* dst, long dst_ld, int rows, int cols, int dtype,
+                 cudaStream_t st);
+int magic_segsum(const float* vals, const long long* seg, const float* seg_scale, float* out, int R, int n_seg,
+                 cudaStream_t st);
+/* MKTD sample weights: exponential_decay (kd_loss.py:43-44), invert_normalized_losses (kd_loss.py:46-54) */
+int magic_exp_decay(const float* in, float* out, int n, float rate, cudaStream_t st);
+int magic_invert_norm(const float* in, float* out, int n, cudaStream_t st);
+/* dz = dy * dropscale * act'(pre): backward of a stand-alone Linear+activation (ClsPrediction, MLM transform) */
+int magic_act_bwd(const void* dy, const void* pre, void* dz, long long n, int act, int dtype, float drop_p,
+                  unsigned salt, const unsigned long long* seed_ptr, cudaStream_t st);
+
+/* ---- gmap node features (DUET-lineage _aggregate_gmap_features) -------------------- */
+int magic_gmap_aggregate_fwd(const void* tokens, const void* fused, const int* node_ptr, const int* entries,
+                             void* out, int n_nodes, int h, int dtype, cudaStream_t st);
+int magic_gmap_aggregate_bwd(const void* dout, const int* src_ids, const int* src_ptr, const int* src_nodes,
+                             const float* src_w, void* dtokens, long long n_token_rows, void* dfused,
+                             long long n_fused_rows, int n_src, int h, int dtype, cudaStream_t st);
+
+/* ---- SAP logits: gate, -inf masks, local->global scatter (outputs pinned train_r2r_magic.py:510-518) */
+int magic_sap_fuse_fwd(const float* g_raw, const float* l_raw, const float* gate_raw, const unsigned char* g_valid,
+                       const unsigned char* l_valid, const int* node2cand, const unsigned char* bw_mask, float* gl,
+                       float* ll, float* fl, int B, int G, int Vp, cudaStream_t st);
+int magic_sap_fuse_bwd(const float* dgl, const float* dll, const float* dfl, const float* g_raw, const float* l_raw,
+                       const float* gate_raw, const unsigned char* g_valid, const unsigned char* l_valid,
+                       const int* node2cand, const unsigned char* bw_mask, float* dg_raw, float* dl_raw,
+                       float* dgate_raw, int B, int G, int Vp, cudaStream_t st);
+
+/* ---- cross-entropy rows (F.cross_entropy(reduction='none', ignore_index)) ------------------------- */
+int magic_ce_fwd(const void* logits, const long long* labels, float* loss, float* lse, int R, int C, long ld,
+                 long long ignore_index, int dtype, cudaStream_t st);
+int magic_ce_bwd(const void* logits, const long long* labels, const float* lse, const float* dloss, void* dlogits,
+                 int R, int C, long ld, long long ignore_index, int dtype, cudaStream_t st);
+
+/* ---- MAKD losses (pretrain_src/optim/kd_loss.py:5-41; aggregation map_nav_src/r2r/agent.py:546-719) */
+typedef struct MagicMseSeg {
+  const void* s;      /* student (already projected to the teacher width) */
+  const void* t;      /* teacher */
+  void* ds;           /* backward: gradient wrt s, same layout as s (may be NULL in forward) */
+  const float* w;     /* per-row MKTD weights (kd_loss.py:11-13) or NULL */
+  long long rows, inner, s_rs, t_rs; /* rows x inner elements, row strides in elements */
+  float scale;        /* MKRW weight / (rows*inner)  (mean reduction, kd_loss.py:8,14) */
+  int s_dt, t_dt;
+  int vec_ok;         /* filled by the library */
+} MagicMseSeg;
+/* loss[0..nseg) per-segment, loss[MAGIC_MAKD_MAX_SEGS] = sum of all segments (buffer of MAX_SEGS+1, zeroed here) */
+int magic_makd_mse_fwd(const MagicMseSeg* segs, int nseg, float* loss, cudaStream_t st);
+/* upstream gradient of segment i = gseg[i] (nullable) + gtot[0] (nullable) */
+int magic_makd_mse_bwd(const MagicMseSeg* segs, int nseg, const float* gseg, const float* gtot, cudaStream_t st);
+/* total = alpha*(mse_total + kl) + (1-alpha)*mean(sup[0..n))  (agent.py:1119); out = [total, sup_mean, kd] */
+int magic_loss_mix_fwd(const float* mse_total, const float* kl, const float* sup, int n, float alpha, float* out,
+                       cudaStream_t st);
+int magic_loss_mix_bwd(const float* g, int n, float alpha, float* d_mse, float* d_kl, float* d_sup,
+                       cudaStream_t st);
+int magic_makd_kl_fwd(const void* s, const void* t, int R, int C, long ld, float temperature, const float* w,
+                      float scale, float* stats /* [R,2] */, float* loss /* [1], zeroed here */, int dtype,
+                      cudaStream_t st);
+int magic_makd_kl_bwd(const void* s, const void* t, void* ds, int R, int C, long ld, float temperature,
+                      const float* w, float scale, const float* stats, const float* gout, int dtype,
+                      cudaStream_t st);
+
+/* ---- optimizer (pretrain_src/optim/adamw.py:53-112, clip grad_norm r2r_magic_pretrain.json:22) ----- */
+int magic_sumsq(const float* g, long long n, float* out, int zero_first, cudaStream_t st);
+int magic_adamw(float* p, const float* g, float* m, float* v, void* bf16_shadow, long long n, const float* hyper,
+                float weight_decay, const float* sumsq, cudaStream_t st);
+int magic_scale(float* x, long long n, float s, cudaStream_t st);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MAGIC_B200_H_ */

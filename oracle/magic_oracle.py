@@ -655,6 +655,9 @@ def makd_losses(student, s_out, t_out, task, rw, t_w, kdl=None):
     L = {}
     z = s_out["txt_embeds"].new_zeros(())
     min_len = min(s_out["txt_attns"].shape[1], t_out["txt_attns"].shape[1])  # agent.py:560
+    # [DECISION] x-layer maps are additionally clipped to their own common depth (the reference expression
+    # `[:, :min_len]` would raise on teacher/student pairs with different num_x_layers, e.g. 4 vs 3)
+    nx = min(min_len, s_out["gmap_attns"].shape[1], t_out["gmap_attns"].shape[1])
     if "txt" in k["kdl_tasks"]:
         L["txt_emb_loss"] = KD.mse_loss(bert.txt_emb_w(s_out["txt_embeds"]), t_out["txt_embeds"].detach(), t_w) * rw[0] if emb else z
         L["txt_attn_loss"] = KD.mse_loss(s_out["txt_attns"][:, :min_len], t_out["txt_attns"][:, :min_len].detach(), t_w) * rw[0] if att else z
@@ -666,10 +669,10 @@ def makd_losses(student, s_out, t_out, task, rw, t_w, kdl=None):
     gw, lw = (bert.gmap_txt_w, bert.vp_txt_w) if task.startswith("mlm") else (bert.global_cross_w, bert.local_cross_w)
     if "global" in k["kdl_tasks"]:
         L["global_emb_loss"] = KD.mse_loss(gw(s_out["gmap_embeds"]), t_out["gmap_embeds"].detach(), t_w) * rw[2] if emb else z
-        L["global_attn_loss"] = KD.mse_loss(s_out["gmap_attns"][:, :min_len], t_out["gmap_attns"][:, :min_len].detach(), t_w) * rw[2] if att else z
+        L["global_attn_loss"] = KD.mse_loss(s_out["gmap_attns"][:, :nx], t_out["gmap_attns"][:, :nx].detach(), t_w) * rw[2] if att else z
     if "local" in k["kdl_tasks"]:
         L["local_emb_loss"] = KD.mse_loss(lw(s_out["vp_embeds"]), t_out["vp_embeds"].detach(), t_w) * rw[3] if emb else z
-        L["local_attn_loss"] = KD.mse_loss(s_out["vp_attns"][:, :min_len], t_out["vp_attns"][:, :min_len].detach(), t_w) * rw[3] if att else z
+        L["local_attn_loss"] = KD.mse_loss(s_out["vp_attns"][:, :nx], t_out["vp_attns"][:, :nx].detach(), t_w) * rw[3] if att else z
     if "predict" in k["kdl_tasks"]:
         w = t_w
         if w is not None and task.startswith("mlm"):

@@ -1,0 +1,176 @@
+"""GPU parity of the full hot path (model forward/backward + MAKD losses) against the fp32 oracle on identical
+synthetic inputs and weights.  Tolerances are the north-star's: masks / gather indices / argmax bit-exact,
+losses and logits 1e-4 relative in fp32 mode, 2e-2 relative in bf16 mode."""
+import copy
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+import magic_b200  # noqa: E402
+from magic_b200 import makd, ops, synth  # noqa: E402
+from magic_b200.graph_index import prepare_batch, batch_to_device  # noqa: E402
+from oracle import magic_oracle as O  # noqa: E402
+
+DEV = "cuda"
+
+
+def rel(a, b):
+    a, b = a.float(), b.float()
+    return ((a - b).norm() / (b.norm() + 1e-20)).item()
+
+
+def build_pair(h, ht=None, role="student", seed=0, **kw):
+    cfg = O.make_config(h, role=role, teacher_hidden_size=ht, hidden_dropout_prob=0.0,
+                        attention_probs_dropout_prob=0.0, **kw)
+    torch.manual_seed(seed)
+    oracle = O.GlocalTextPathCMTPreTraining(cfg)
+    # make the test non-trivial: random biases / LN params (init leaves them at 0 / 1)
+    g = torch.Generator().manual_seed(seed + 100)
+    for n, p in oracle.named_parameters():
+        if n.endswith("bias") or "LayerNorm" in n or "norm" in n or "layer_norm" in n:
+            p.data.add_(torch.randn(p.shape, generator=g) * 0.05)
+        elif "sprel_linear.weight" in n:
+            p.data.fill_(-0.07)
+    oracle = oracle.to(DEV).eval()
+    prod = magic_b200.GlocalTextPathCMTPreTraining.from_pretrained(None, config=copy.copy(cfg),
+                                                                   state_dict=oracle.state_dict()).to(DEV).eval()
+    return oracle, prod
+
+
+def get_batch(task, B=8, seed=1234, **kw):
+    b = synth.make_batch(task, B, seed=seed, **kw)
+    prepare_batch(b)
+    return batch_to_device(b, DEV)
+
+
+def oracle_batch(b):
+    return {k: v for k, v in b.items() if k != magic_b200.INDEX_KEY}
+
+
+@pytest.mark.parametrize("task", ["sap", "mlm"])
+def test_forward_outputs_fp32(task):
+    oracle, prod = build_pair(128, ht=256)
+    prod.output_kd = True
+    b = get_batch(task)
+    with torch.no_grad():
+        ro = oracle(oracle_batch(b), task, True)
+        po = prod(b, task, True)
+    for k in ("txt_embeds", "pano_embeds", "pano_fused_embeds", "gmap_embeds", "vp_embeds", "loss", "logits",
+              "sample_loss"):
+        fin = torch.isfinite(ro[k])
+        assert torch.equal(fin, torch.isfinite(po[k].float())), k
+        r = rel(po[k].float()[fin], ro[k][fin])
+        assert r < 1e-4, (k, r)
+    for k, lk in (("txt_attns", "txt_attn_list"), ("img_attns", "img_attn_list"), ("gmap_attns", "gmap_attn_list"),
+                  ("vp_attns", "vp_attn_list")):
+        r = rel(magic_b200.stack_attns(po[lk]), ro[k])
+        assert r < 1e-4, (k, r)
+    if task == "sap":
+        for k in ("global_logits", "local_logits", "fused_logits"):
+            assert torch.equal(torch.isinf(po[k]), torch.isinf(ro[k])), k      # masks bit-exact
+            assert torch.equal(po[k].argmax(1), ro[k].argmax(1)), k            # argmax actions bit-exact
+    # validation-mode outputs (train_r2r_magic.py:448, 510-512)
+    with torch.no_grad():
+        rv, pv = oracle(oracle_batch(b), task, False), prod(b, task, False)
+    if task == "mlm":
+        assert pv["predict"].shape == rv["predict"].shape
+        assert rel(pv["predict"], rv["predict"]) < 1e-4
+        assert torch.equal(pv["predict"].argmax(-1), rv["predict"].argmax(-1))
+    else:
+        assert set(pv.keys()) == {"global_logits", "local_logits", "fused_logits", "global_act_labels",
+                                  "local_act_labels"}
+
+
+@pytest.mark.parametrize("task", ["sap", "mlm"])
+def test_distill_step_loss_and_grads_fp32(task):
+    t_oracle, t_prod = build_pair(256, role="teacher", seed=3)
+    s_oracle, s_prod = build_pair(128, ht=256, seed=4)
+    s_oracle.train()
+    s_prod.train()
+    b = get_batch(task, seed=77)
+    rw = [1.3, 0.6, 1.1, 0.9, 1.1]
+    total_o, sup_o, kd_o, L_o, _, _ = O.distill_step_loss(s_oracle, t_oracle, oracle_batch(b), task,
+                                                          torch.tensor(rw, device=DEV))
+    total_o.backward()
+    mix, res, s_out, t_out = makd.distill_step_loss(s_prod, t_prod, b, task, rw)
+    mix[0].backward()
+    assert abs(mix[0].item() - total_o.item()) <= 1e-4 * abs(total_o.item()), (mix[0].item(), total_o.item())
+    assert abs(mix[1].item() - sup_o.item()) <= 1e-4 * abs(sup_o.item())
+    assert abs(mix[2].item() - kd_o.item()) <= 1e-4 * abs(kd_o.item())
+    named = makd.named_losses(res)
+    for k, v in L_o.items():
+        assert abs(named[k] - v.item()) <= 1e-4 * abs(v.item()) + 1e-7, (k, named[k], v.item())
+    go = dict(s_oracle.named_parameters())
+    bad = []
+    for n, p in s_prod.named_parameters():
+        ref = go[n].grad
+        if ref is None:
+            assert p.grad is None or p.grad.abs().max() == 0, n
+            continue
+        assert p.grad is not None, n
+        r = rel(p.grad, ref)
+        if r > 2e-3 and ref.norm() > 1e-7:
+            bad.append((n, r, ref.norm().item()))
+    assert not bad, bad[:10]
+
+
+@pytest.mark.parametrize("task", ["sap", "mlm"])
+def test_bf16_mode(task):
+    oracle, prod = build_pair(128, ht=256, seed=5)
+    prod.set_compute_dtype(torch.bfloat16)
+    prod.train()
+    oracle.train()
+    b = get_batch(task, seed=5)
+    ro = oracle(oracle_batch(b), task, True)
+    po = prod(b, task, True)
+    lo, lp = ro["loss"].mean(), po["loss"].mean()
+    assert abs(lp.item() - lo.item()) <= 2e-2 * abs(lo.item()), (lp.item(), lo.item())
+    fin = torch.isfinite(ro["logits"])
+    assert torch.equal(fin, torch.isfinite(po["logits"].float()))
+    assert rel(po["logits"].float()[fin], ro["logits"][fin]) < 2e-2
+    lo.backward()
+    lp.backward()
+    go = dict(oracle.named_parameters())
+    worst = 0.0
+    for n, p in prod.named_parameters():
+        if go[n].grad is None or go[n].grad.norm() < 1e-6:
+            continue
+        worst = max(worst, rel(p.grad, go[n].grad))
+    assert worst < 0.1, worst
+
+
+def test_teacher_width_768_forward():
+    """Config-3-shaped teacher (9 text / 2 pano / 4 cross layers, h=768), small batch."""
+    oracle, prod = build_pair(768, role="teacher", seed=6, num_l_layers=9, num_x_layers=4)
+    b = get_batch("sap", B=4, seed=9)
+    with torch.no_grad():
+        ro, po = oracle(oracle_batch(b), "sap", True), prod(b, "sap", True)
+    for k in ("gmap_embeds", "vp_embeds", "loss"):
+        assert rel(po[k], ro[k]) < 1e-4, k
+    assert torch.equal(po["fused_logits"].argmax(1), ro["fused_logits"].argmax(1))
+
+
+def test_rxr_shape_long_instruction():
+    """Config-5 shape: L=160, G=50, T_max=12."""
+    oracle, prod = build_pair(128, seed=7)
+    b = get_batch("sap", B=4, seed=11, L=160, T_max=12, G_max=50)
+    assert b["gmap_step_ids"].shape[1] == 50 and b["txt_ids"].shape[1] == 160
+    with torch.no_grad():
+        ro, po = oracle(oracle_batch(b), "sap", True), prod(b, "sap", True)
+    assert rel(po["loss"], ro["loss"]) < 1e-4
+    assert torch.equal(po["fused_logits"].argmax(1), ro["fused_logits"].argmax(1))
+
+
+def test_ignore_labels_and_no_cpu_fallback():
+    oracle, prod = build_pair(128, seed=8)
+    b = get_batch("sap", B=4, seed=13)
+    b["global_act_labels"][1] = -100
+    b["local_act_labels"][2] = -100
+    with torch.no_grad():
+        ro, po = oracle(oracle_batch(b), "sap", True), prod(b, "sap", True)
+    assert rel(po["loss"], ro["loss"]) < 1e-4
+    cpu_b = synth.make_batch("sap", 2)
+    with pytest.raises(Exception):
+        prod(cpu_b, "sap", True)

@@ -1,0 +1,106 @@
+"""ctypes binding of libmagic_b200.so (the C ABI declared in include/magic_b200.h).
+
+The argtypes of every entry point are derived from the header itself, so the header is the single
+source of truth for the boundary.  There is NO fallback: if the shared library is missing the import
+of any compute op raises (the product path must fail loudly without its CUDA extension).
+"""
+import ctypes
+import os
+import re
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+HEADER = os.path.join(os.path.dirname(_HERE), "include", "magic_b200.h")
+LIB_PATH = os.path.join(_HERE, "lib", "libmagic_b200.so")
+
+F32, BF16 = 0, 1
+ACT_NONE, ACT_GELU, ACT_RELU = 0, 1, 2
+MAKD_MAX_SEGS = 32
+
+_CT = {
+    "int": ctypes.c_int, "long": ctypes.c_long, "long long": ctypes.c_longlong, "float": ctypes.c_float,
+    "unsigned": ctypes.c_uint, "cudaStream_t": ctypes.c_void_p,
+}
+
+
+class MagicMseSeg(ctypes.Structure):
+    _fields_ = [("s", ctypes.c_void_p), ("t", ctypes.c_void_p), ("ds", ctypes.c_void_p), ("w", ctypes.c_void_p),
+                ("rows", ctypes.c_longlong), ("inner", ctypes.c_longlong), ("s_rs", ctypes.c_longlong),
+                ("t_rs", ctypes.c_longlong), ("scale", ctypes.c_float), ("s_dt", ctypes.c_int),
+                ("t_dt", ctypes.c_int), ("vec_ok", ctypes.c_int)]
+
+
+def parse_header(path=HEADER):
+    """-> {name: (restype, [argtypes])} for every function the header declares."""
+    src = open(path).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    decls = {}
+    for m in re.finditer(r"^(const char\*|int)\s+(magic_\w+)\s*\(([^;{]*?)\)\s*;", src, flags=re.M | re.S):
+        ret, name, args = m.group(1), m.group(2), m.group(3)
+        argtypes = []
+        for a in [x.strip() for x in args.replace("\n", " ").split(",")]:
+            if a in ("void", ""):
+                continue
+            if "*" in a:
+                argtypes.append(ctypes.c_void_p)
+                continue
+            toks = a.split()
+            ty = " ".join(toks[:-1]) if len(toks) > 1 else toks[0]
+            ty = ty.replace("const ", "").strip()
+            argtypes.append(_CT[ty])
+        decls[name] = (ctypes.c_char_p if ret.startswith("const char") else ctypes.c_int, argtypes)
+    return decls
+
+
+_lib = None
+
+
+def load():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"libmagic_b200.so not found at {LIB_PATH}: build it with `python -c 'import __graft_entry__ as g; "
+            f"g.build()'` (or python vln-magic_b200/build.py). There is no CPU / PyTorch fallback.")
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (ret, argtypes) in parse_header().items():
+        fn = getattr(lib, name)  # AttributeError if the header declares something the library lacks
+        fn.restype = ret
+        fn.argtypes = argtypes
+    _lib = lib
+    return lib
+
+
+class MagicError(RuntimeError):
+    pass
+
+
+def call(name, *args):
+    lib = load()
+    rc = getattr(lib, name)(*args)
+    if rc != 0:
+        raise MagicError(f"{name} failed (rc={rc}): {lib.magic_last_error().decode()}")
+
+
+def ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def dt(t):
+    if t.dtype == torch.float32:
+        return F32
+    if t.dtype == torch.bfloat16:
+        return BF16
+    raise MagicError(f"unsupported dtype {t.dtype}")
+
+
+def stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise MagicError("magic_b200 ops need CUDA tensors (no CPU fallback exists)")

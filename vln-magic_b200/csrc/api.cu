@@ -1,0 +1,59 @@
+// Error channel, version and the GEMM dispatcher (tcgen05 path vs fp32 FFMA path).
+#include <stdarg.h>
+#include <string.h>
+
+#include "common.cuh"
+#include "gemm_epi.cuh"
+#include "../../include/magic_b200.h"
+
+static thread_local char g_err[512] = "";
+
+void magic_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int gemm_simt_dispatch(const void* A, int a_dt, const void* B, int b_dt, void* C, int c_dt, int M, int N, int K,
+                       long sam, long sak, long sbk, long sbn, long ldc, const GemmEpi& epi, cudaStream_t st);
+// returns MAGIC_ERR_UNSUPPORTED when the operand layout is not one the tcgen05 kernel takes
+int gemm_tc_dispatch(const void* A, const void* B, void* C, int c_dt, int M, int N, int K, long sam, long sak,
+                     long sbk, long sbn, long ldc, const GemmEpi& epi, cudaStream_t st);
+int gemm_tc_shape_ok(int M, int N, int K);
+
+extern "C" {
+
+const char* magic_last_error(void) { return g_err; }
+int magic_version(void) { return 100; }
+int magic_gemm_tc_supported(int M, int N, int K) { return gemm_tc_shape_ok(M, N, K); }
+
+int magic_gemm(const void* A, int a_dt, long sam, long sak, const void* B, int b_dt, long sbk, long sbn, void* C,
+               int c_dt, long ldc, int M, int N, int K, const float* bias, int act, void* pre_out,
+               const void* dact_pre, int dact_dt, long dact_ld, const void* residual, long res_ld, float alpha,
+               float beta, float drop_p, unsigned salt, const unsigned long long* seed_ptr, int allow_tc,
+               cudaStream_t st) {
+  MAGIC_CHECK_ARG(M >= 0 && N >= 0 && K >= 0, "magic_gemm: negative shape");
+  if (M == 0 || N == 0) return MAGIC_OK;
+  GemmEpi epi;
+  epi.bias = bias;
+  epi.act = act;
+  epi.pre_out = pre_out;
+  epi.dact_pre = dact_pre;
+  epi.dact_dt = dact_dt;
+  epi.dact_ld = dact_ld;
+  epi.residual = residual;
+  epi.res_ld = res_ld;
+  epi.alpha = alpha;
+  epi.beta = beta;
+  epi.drop_p = drop_p;
+  epi.seed_ptr = seed_ptr;
+  epi.salt = salt;
+  if (allow_tc && a_dt == MAGIC_BF16 && b_dt == MAGIC_BF16) {
+    const int rc = gemm_tc_dispatch(A, B, C, c_dt, M, N, K, sam, sak, sbk, sbn, ldc, epi, st);
+    if (rc != MAGIC_ERR_UNSUPPORTED) return rc;
+  }
+  return gemm_simt_dispatch(A, a_dt, B, b_dt, C, c_dt, M, N, K, sam, sak, sbk, sbn, ldc, epi, st);
+}
+
+}  // extern "C"

@@ -1,0 +1,139 @@
+// Shared device/host helpers for libmagic_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <math.h>
+
+#define MAGIC_F32 0
+#define MAGIC_BF16 1
+
+#define MAGIC_OK 0
+#define MAGIC_ERR_ARG 1
+#define MAGIC_ERR_CUDA 2
+#define MAGIC_ERR_UNSUPPORTED 3
+
+void magic_set_error(const char* fmt, ...);
+
+#define MAGIC_CHECK_ARG(cond, ...)            \
+  do {                                        \
+    if (!(cond)) {                            \
+      magic_set_error(__VA_ARGS__);           \
+      return MAGIC_ERR_ARG;                   \
+    }                                         \
+  } while (0)
+
+#define MAGIC_CHECK_LAUNCH(name)                                                      \
+  do {                                                                                \
+    cudaError_t e__ = cudaGetLastError();                                             \
+    if (e__ != cudaSuccess) {                                                         \
+      magic_set_error("%s: CUDA launch failed: %s", name, cudaGetErrorString(e__));   \
+      return MAGIC_ERR_CUDA;                                                          \
+    }                                                                                 \
+  } while (0)
+
+#define MAGIC_CUDA(call, name)                                                        \
+  do {                                                                                \
+    cudaError_t e__ = (call);                                                         \
+    if (e__ != cudaSuccess) {                                                         \
+      magic_set_error("%s: %s", name, cudaGetErrorString(e__));                       \
+      return MAGIC_ERR_CUDA;                                                          \
+    }                                                                                 \
+  } while (0)
+
+static inline int magic_num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+// ---------------------------------------------------------------------------------------------
+// element access: activations are f32 or bf16; math is always fp32
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float ldf(const float* p, size_t i) { return p[i]; }
+__device__ __forceinline__ float ldf(const __nv_bfloat16* p, size_t i) { return __bfloat162float(p[i]); }
+__device__ __forceinline__ void stf(float* p, size_t i, float v) { p[i] = v; }
+__device__ __forceinline__ void stf(__nv_bfloat16* p, size_t i, float v) { p[i] = __float2bfloat16_rn(v); }
+
+// round-trip through the storage type (so fwd and bwd recomputation see identical values)
+__device__ __forceinline__ float rt(const float*, float v) { return v; }
+__device__ __forceinline__ float rt(const __nv_bfloat16*, float v) { return __bfloat162float(__float2bfloat16_rn(v)); }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// block-wide sum; `red` is >= 32 floats of shared memory; all threads get the result
+__device__ __forceinline__ float block_sum(float v, float* red) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  v = warp_sum(v);
+  __syncthreads();
+  if (lane == 0) red[w] = v;
+  __syncthreads();
+  float r = (lane < nw) ? red[lane] : 0.f;
+  r = warp_sum(r);
+  return r;
+}
+__device__ __forceinline__ float block_max(float v, float* red) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  v = warp_max(v);
+  __syncthreads();
+  if (lane == 0) red[w] = v;
+  __syncthreads();
+  float r = (lane < nw) ? red[lane] : -INFINITY;
+  r = warp_max(r);
+  return r;
+}
+
+// ---------------------------------------------------------------------------------------------
+// stateless dropout RNG: keep(idx) is a pure function of (seed, salt, idx) so backward regenerates
+// the forward mask instead of storing it.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t magic_hash(uint64_t seed, uint32_t salt, uint64_t idx) {
+  uint64_t z = seed + 0x9E3779B97F4A7C15ull * (uint64_t)(salt + 1) + idx * 0xD1342543DE82EF95ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  z = z ^ (z >> 31);
+  return (uint32_t)(z >> 32);
+}
+struct Dropout {
+  float p;           // drop probability (0 = disabled)
+  float inv_keep;    // 1 / (1 - p)
+  uint32_t thresh;   // drop iff hash < thresh
+  uint32_t salt;
+  uint64_t seed;
+  __device__ __forceinline__ float scale(uint64_t idx) const {
+    if (p <= 0.f) return 1.f;
+    return magic_hash(seed, salt, idx) < thresh ? 0.f : inv_keep;
+  }
+};
+// host+device constructor; seed_ptr is DEVICE memory (so a captured CUDA graph sees fresh seeds)
+__device__ __forceinline__ Dropout make_dropout(float p, const unsigned long long* seed_ptr, uint32_t salt) {
+  Dropout d;
+  d.p = p;
+  d.inv_keep = p > 0.f ? 1.f / (1.f - p) : 1.f;
+  d.thresh = p > 0.f ? (uint32_t)fminf(4294967295.f, p * 4294967296.f) : 0u;
+  d.salt = salt;
+  d.seed = (p > 0.f && seed_ptr) ? *seed_ptr : 0ull;
+  return d;
+}
+
+__device__ __forceinline__ float gelu_f(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752f)); }
+__device__ __forceinline__ float gelu_grad_f(float x) {
+  const float cdf = 0.5f * (1.f + erff(x * 0.70710678118654752f));
+  const float pdf = 0.3989422804014327f * expf(-0.5f * x * x);
+  return cdf + x * pdf;
+}

@@ -1,0 +1,301 @@
+// Fused MAKD (meta-ability knowledge distillation) losses -- HBM-streaming kernels.
+//
+//  * magic_makd_mse_{fwd,bwd}: ONE launch covers every hidden-state / attention-map MSE of a step
+//    (up to 16 segments: txt, pano, pano-fused, global, local embeddings + 4 attention maps).  Each
+//    segment is `rows` x `inner` with independent row strides for student and teacher (so the
+//    `[:, :min_len]` layer slices of agent.py:560-671 need no copies), an optional per-row MKTD
+//    weight w[row] (kd_loss.py:11-13) and a scalar scale = MKRW weight / numel (kd_loss.py:8,14 mean).
+//  * magic_makd_kl_{fwd,bwd}: temperature-scaled KL on action / MLM logits with the -inf -> -1e6 rule
+//    (kd_loss.py:21-22), mean over B*C (unweighted, :29) or over rows after the per-row weight (:31-40).
+//
+// Algorithmic bytes: fwd reads |S|+|T| once; bwd reads |S|+|T| once and writes |dS|.
+#include "common.cuh"
+#include "../../include/magic_b200.h"
+
+namespace {
+
+constexpr int CH = 4096;        // elements per chunk
+constexpr int NT = 256;         // threads per CTA
+
+struct Args {
+  MagicMseSeg seg[MAGIC_MAKD_MAX_SEGS];
+  long long chunk0[MAGIC_MAKD_MAX_SEGS + 1];
+  int nseg;
+};
+
+__device__ __forceinline__ float ld_any(const void* p, int dt, size_t i) {
+  return dt == MAGIC_BF16 ? __bfloat162float(((const __nv_bfloat16*)p)[i]) : ((const float*)p)[i];
+}
+__device__ __forceinline__ void st_any(void* p, int dt, size_t i, float v) {
+  if (dt == MAGIC_BF16) ((__nv_bfloat16*)p)[i] = __float2bfloat16_rn(v);
+  else ((float*)p)[i] = v;
+}
+
+template <bool BWD>
+__global__ void __launch_bounds__(NT) makd_mse_kernel(const __grid_constant__ Args A, float* __restrict__ loss,
+                                                      const float* __restrict__ gseg,
+                                                      const float* __restrict__ gtot) {
+  __shared__ float red[32];
+  const long long total = A.chunk0[A.nseg];
+  for (long long ch = blockIdx.x; ch < total; ch += gridDim.x) {
+    int si = 0;
+    while (si + 1 < A.nseg && ch >= A.chunk0[si + 1]) si++;
+    const MagicMseSeg& S = A.seg[si];
+    const long long cpr = (S.inner + CH - 1) / CH;
+    const long long local = ch - A.chunk0[si];
+    const long long row = local / cpr;
+    const long long c0 = (local % cpr) * CH;
+    const long long c1 = min(S.inner, c0 + CH);
+    const float wr = S.w ? S.w[row] : 1.f;
+    const size_t sb = (size_t)row * S.s_rs, tb = (size_t)row * S.t_rs;
+    const float coef = BWD ? 2.f * S.scale * wr * ((gseg ? gseg[si] : 0.f) + (gtot ? gtot[0] : 0.f)) : 0.f;
+    float acc = 0.f;
+    const bool vec = S.vec_ok && (c1 - c0) == CH;
+    if (vec && S.s_dt == MAGIC_F32) {
+      const float4* s4 = reinterpret_cast<const float4*>((const float*)S.s + sb + c0);
+      const float4* t4 = reinterpret_cast<const float4*>((const float*)S.t + tb + c0);
+      float4* d4 = BWD ? reinterpret_cast<float4*>((float*)S.ds + sb + c0) : nullptr;
+      float4 a[4], b[4];
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        a[k] = __ldcs(s4 + threadIdx.x + k * NT);
+        b[k] = __ldcs(t4 + threadIdx.x + k * NT);
+      }
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        const float dx = a[k].x - b[k].x, dy = a[k].y - b[k].y, dz = a[k].z - b[k].z, dw = a[k].w - b[k].w;
+        if (BWD) d4[threadIdx.x + k * NT] = make_float4(coef * dx, coef * dy, coef * dz, coef * dw);
+        else acc += dx * dx + dy * dy + dz * dz + dw * dw;
+      }
+    } else if (vec && S.s_dt == MAGIC_BF16) {
+      const uint4* s4 = reinterpret_cast<const uint4*>((const __nv_bfloat16*)S.s + sb + c0);
+      const uint4* t4 = reinterpret_cast<const uint4*>((const __nv_bfloat16*)S.t + tb + c0);
+      uint4* d4 = BWD ? reinterpret_cast<uint4*>((__nv_bfloat16*)S.ds + sb + c0) : nullptr;
+      uint4 a[2], b[2];
+#pragma unroll
+      for (int k = 0; k < 2; k++) {
+        a[k] = __ldcs(s4 + threadIdx.x + k * NT);
+        b[k] = __ldcs(t4 + threadIdx.x + k * NT);
+      }
+#pragma unroll
+      for (int k = 0; k < 2; k++) {
+        const __nv_bfloat162* ah = reinterpret_cast<const __nv_bfloat162*>(&a[k]);
+        const __nv_bfloat162* bh = reinterpret_cast<const __nv_bfloat162*>(&b[k]);
+        uint4 o;
+        __nv_bfloat162* oh = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+          const float2 fa = __bfloat1622float2(ah[e]), fb = __bfloat1622float2(bh[e]);
+          const float dx = fa.x - fb.x, dy = fa.y - fb.y;
+          if (BWD) oh[e] = __floats2bfloat162_rn(coef * dx, coef * dy);
+          else acc += dx * dx + dy * dy;
+        }
+        if (BWD) d4[threadIdx.x + k * NT] = o;
+      }
+    } else {
+      for (long long c = c0 + threadIdx.x; c < c1; c += NT) {
+        const float d = ld_any(S.s, S.s_dt, sb + c) - ld_any(S.t, S.t_dt, tb + c);
+        if (BWD) st_any(S.ds, S.s_dt, sb + c, coef * d);
+        else acc += d * d;
+      }
+    }
+    if (!BWD) {
+      acc = block_sum(acc, red);
+      if (threadIdx.x == 0) {
+        atomicAdd(loss + si, acc * wr * S.scale);
+        atomicAdd(loss + MAGIC_MAKD_MAX_SEGS, acc * wr * S.scale);  // running total of all segments
+      }
+    }
+  }
+}
+
+// ---- KL on logits: one CTA per row -----------------------------------------------------------------
+__device__ __forceinline__ float fix_inf(float v, float invT) { return (v == -INFINITY ? -1e6f : v) * invT; }
+
+template <typename T>
+__global__ void __launch_bounds__(NT)
+    makd_kl_fwd_kernel(const T* __restrict__ s, const T* __restrict__ t, int C, long ld, float invT,
+                       const float* __restrict__ w, float scale, float* __restrict__ stats,
+                       float* __restrict__ loss) {
+  __shared__ float red[32];
+  const int r = blockIdx.x;
+  const T* sr = s + (size_t)r * ld;
+  const T* tr = t + (size_t)r * ld;
+  float ms = -INFINITY, mt = -INFINITY;
+  for (int c = threadIdx.x; c < C; c += NT) {
+    ms = fmaxf(ms, fix_inf(ldf(sr, c), invT));
+    mt = fmaxf(mt, fix_inf(ldf(tr, c), invT));
+  }
+  ms = block_max(ms, red);
+  mt = block_max(mt, red);
+  float zs = 0.f, zt = 0.f;
+  for (int c = threadIdx.x; c < C; c += NT) {
+    zs += expf(fix_inf(ldf(sr, c), invT) - ms);
+    zt += expf(fix_inf(ldf(tr, c), invT) - mt);
+  }
+  zs = block_sum(zs, red);
+  zt = block_sum(zt, red);
+  const float lse_s = ms + logf(zs), lse_t = mt + logf(zt);
+  float kl = 0.f;
+  for (int c = threadIdx.x; c < C; c += NT) {
+    const float a = fix_inf(ldf(sr, c), invT) - lse_s, b = fix_inf(ldf(tr, c), invT) - lse_t;
+    const float p = expf(b);
+    if (p > 0.f) kl += p * (b - a);  // xlogy(p,p) - p*logq ; p == 0 contributes exactly 0
+  }
+  kl = block_sum(kl, red);
+  if (threadIdx.x == 0) {
+    stats[2 * r] = lse_s;
+    stats[2 * r + 1] = lse_t;
+    atomicAdd(loss, kl * (w ? w[r] : 1.f) * scale);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(NT)
+    makd_kl_bwd_kernel(const T* __restrict__ s, const T* __restrict__ t, T* __restrict__ ds, int C, long ld,
+                       float invT, const float* __restrict__ w, float scale, const float* __restrict__ stats,
+                       const float* __restrict__ gout) {
+  const int r = blockIdx.x;
+  const T* sr = s + (size_t)r * ld;
+  const T* tr = t + (size_t)r * ld;
+  T* dr = ds + (size_t)r * ld;
+  const float lse_s = stats[2 * r], lse_t = stats[2 * r + 1];
+  const float coef = gout[0] * scale * (w ? w[r] : 1.f) * invT;
+  for (int c = threadIdx.x; c < C; c += NT) {
+    const float sv = ldf(sr, c);
+    float g = 0.f;
+    if (sv != -INFINITY) g = coef * (expf(sv * invT - lse_s) - expf(fix_inf(ldf(tr, c), invT) - lse_t));
+    stf(dr, c, g);
+  }
+}
+
+// total = alpha * (mse_total + kl) + (1 - alpha) * mean(sup)      (agent.py:1119)
+__global__ void __launch_bounds__(256)
+    mix_fwd_kernel(const float* __restrict__ mse_total, const float* __restrict__ kl, const float* __restrict__ sup,
+                   int n, float alpha, float* __restrict__ out) {
+  __shared__ float red[32];
+  float a = 0.f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) a += sup[i];
+  a = block_sum(a, red);
+  if (threadIdx.x == 0) {
+    const float sm = n > 0 ? a / (float)n : 0.f;
+    const float kd = (mse_total ? mse_total[0] : 0.f) + (kl ? kl[0] : 0.f);
+    out[0] = alpha * kd + (1.f - alpha) * sm;
+    out[1] = sm;
+    out[2] = kd;
+  }
+}
+__global__ void mix_bwd_kernel(const float* __restrict__ g, int n, float alpha, float* __restrict__ d_mse,
+                               float* __restrict__ d_kl, float* __restrict__ d_sup) {
+  const float gv = g[0];
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    if (d_mse) d_mse[0] = alpha * gv;
+    if (d_kl) d_kl[0] = alpha * gv;
+  }
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    d_sup[i] = (1.f - alpha) * gv / (float)n;
+}
+
+int build_args(const MagicMseSeg* segs, int nseg, Args& A, const char* name) {
+  MAGIC_CHECK_ARG(nseg >= 0 && nseg <= MAGIC_MAKD_MAX_SEGS, "%s: nseg=%d out of range", name, nseg);
+  A.nseg = nseg;
+  long long c = 0;
+  for (int i = 0; i < nseg; i++) {
+    A.seg[i] = segs[i];
+    A.chunk0[i] = c;
+    MAGIC_CHECK_ARG(segs[i].rows >= 0 && segs[i].inner >= 0, "%s: negative extent in segment %d", name, i);
+    c += segs[i].rows * ((segs[i].inner + CH - 1) / CH);
+    // 128-bit path: same dtype, 16-byte aligned bases and row strides
+    const int esz = segs[i].s_dt == MAGIC_BF16 ? 2 : 4;
+    const int v = 16 / esz;
+    bool ok = segs[i].s_dt == segs[i].t_dt && segs[i].s_rs % v == 0 && segs[i].t_rs % v == 0 &&
+              ((uintptr_t)segs[i].s % 16 == 0) && ((uintptr_t)segs[i].t % 16 == 0) &&
+              (segs[i].ds == nullptr || (uintptr_t)segs[i].ds % 16 == 0);
+    A.seg[i].vec_ok = ok ? 1 : 0;
+  }
+  A.chunk0[nseg] = c;
+  return MAGIC_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int magic_makd_mse_fwd(const MagicMseSeg* segs, int nseg, float* loss, cudaStream_t st) {
+  Args A;
+  int rc = build_args(segs, nseg, A, "magic_makd_mse_fwd");
+  if (rc) return rc;
+  MAGIC_CUDA(cudaMemsetAsync(loss, 0, sizeof(float) * (MAGIC_MAKD_MAX_SEGS + 1), st), "magic_makd_mse_fwd");
+  const long long total = A.chunk0[nseg];
+  if (total == 0) return MAGIC_OK;
+  const long long cap = 16LL * magic_num_sms();
+  makd_mse_kernel<false><<<(int)(total < cap ? total : cap), NT, 0, st>>>(A, loss, nullptr, nullptr);
+  MAGIC_CHECK_LAUNCH("magic_makd_mse_fwd");
+  return MAGIC_OK;
+}
+
+int magic_makd_mse_bwd(const MagicMseSeg* segs, int nseg, const float* gseg, const float* gtot, cudaStream_t st) {
+  Args A;
+  int rc = build_args(segs, nseg, A, "magic_makd_mse_bwd");
+  if (rc) return rc;
+  for (int i = 0; i < nseg; i++) MAGIC_CHECK_ARG(segs[i].ds != nullptr, "magic_makd_mse_bwd: segment %d has no ds", i);
+  const long long total = A.chunk0[nseg];
+  if (total == 0) return MAGIC_OK;
+  const long long cap = 16LL * magic_num_sms();
+  makd_mse_kernel<true><<<(int)(total < cap ? total : cap), NT, 0, st>>>(A, nullptr, gseg, gtot);
+  MAGIC_CHECK_LAUNCH("magic_makd_mse_bwd");
+  return MAGIC_OK;
+}
+
+int magic_loss_mix_fwd(const float* mse_total, const float* kl, const float* sup, int n, float alpha, float* out,
+                       cudaStream_t st) {
+  mix_fwd_kernel<<<1, 256, 0, st>>>(mse_total, kl, sup, n, alpha, out);
+  MAGIC_CHECK_LAUNCH("magic_loss_mix_fwd");
+  return MAGIC_OK;
+}
+
+int magic_loss_mix_bwd(const float* g, int n, float alpha, float* d_mse, float* d_kl, float* d_sup,
+                       cudaStream_t st) {
+  mix_bwd_kernel<<<(n + 255) / 256 > 0 ? (n + 255) / 256 : 1, 256, 0, st>>>(g, n, alpha, d_mse, d_kl, d_sup);
+  MAGIC_CHECK_LAUNCH("magic_loss_mix_bwd");
+  return MAGIC_OK;
+}
+
+int magic_makd_kl_fwd(const void* s, const void* t, int R, int C, long ld, float temperature, const float* w,
+                      float scale, float* stats, float* loss, int dtype, cudaStream_t st) {
+  MAGIC_CUDA(cudaMemsetAsync(loss, 0, sizeof(float), st), "magic_makd_kl_fwd");
+  if (R <= 0) return MAGIC_OK;
+  const float invT = 1.f / temperature;
+  if (dtype == MAGIC_F32)
+    makd_kl_fwd_kernel<float><<<R, NT, 0, st>>>((const float*)s, (const float*)t, C, ld, invT, w, scale, stats, loss);
+  else if (dtype == MAGIC_BF16)
+    makd_kl_fwd_kernel<__nv_bfloat16><<<R, NT, 0, st>>>((const __nv_bfloat16*)s, (const __nv_bfloat16*)t, C, ld, invT,
+                                                       w, scale, stats, loss);
+  else {
+    magic_set_error("magic_makd_kl_fwd: bad dtype");
+    return MAGIC_ERR_ARG;
+  }
+  MAGIC_CHECK_LAUNCH("magic_makd_kl_fwd");
+  return MAGIC_OK;
+}
+
+int magic_makd_kl_bwd(const void* s, const void* t, void* ds, int R, int C, long ld, float temperature,
+                      const float* w, float scale, const float* stats, const float* gout, int dtype,
+                      cudaStream_t st) {
+  if (R <= 0) return MAGIC_OK;
+  const float invT = 1.f / temperature;
+  if (dtype == MAGIC_F32)
+    makd_kl_bwd_kernel<float><<<R, NT, 0, st>>>((const float*)s, (const float*)t, (float*)ds, C, ld, invT, w, scale,
+                                                stats, gout);
+  else if (dtype == MAGIC_BF16)
+    makd_kl_bwd_kernel<__nv_bfloat16><<<R, NT, 0, st>>>((const __nv_bfloat16*)s, (const __nv_bfloat16*)t,
+                                                       (__nv_bfloat16*)ds, C, ld, invT, w, scale, stats, gout);
+  else {
+    magic_set_error("magic_makd_kl_bwd: bad dtype");
+    return MAGIC_ERR_ARG;
+  }
+  MAGIC_CHECK_LAUNCH("magic_makd_kl_bwd");
+  return MAGIC_OK;
+}
+
+}  // extern "C"

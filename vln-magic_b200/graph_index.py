@@ -1,0 +1,145 @@
+"""Host-side conversion of the batch's viewpoint-id STRING lists into integer index tables (once per
+batch, on the CPU copy of the batch -- ideally inside the data loader, before the H2D move).
+
+Spec: SURVEY.md A.4; semantics follow the reference data pipeline
+(pretrain_src/data/dataset.py:513-549 node order / visited masks, :742-756 candidate-first view order)
+and the DUET-lineage model loops the reference's missing `pretrain_goat.py` runs on strings
+(gmap feature aggregation; global/local logit fusion).  Everything here is exact integer logic.
+"""
+import numpy as np
+import torch
+
+INDEX_KEY = "_magic_index"
+
+
+def _cpu(t):
+    return t.detach().cpu() if torch.is_tensor(t) else t
+
+
+def build_index(batch):
+    """-> dict of CPU tensors (int32 / uint8 / int64 / float32) + python ints."""
+    steps = batch["traj_step_lens"]
+    B = len(steps)
+    V = batch["traj_view_img_fts"].shape[1]
+    G = batch["gmap_step_ids"].shape[1]
+    Vp = batch["vp_pos_fts"].shape[1]
+    gmap_lens = _cpu(batch["gmap_lens"]).tolist()
+    visited_masks = _cpu(batch["gmap_visited_masks"]).numpy().astype(bool)
+    vp_lens = _cpu(batch["vp_lens"]).tolist()
+    nav_types = _cpu(batch["traj_nav_types"]).numpy()
+
+    node_ptr, entries = [0], []
+    last_rows = []
+    row0 = 0
+    for b in range(B):
+        T = steps[b]
+        visited_row, cand_tokens = {}, {}
+        for t in range(T):
+            visited_row[batch["traj_vpids"][b][t]] = row0 + t  # last occurrence wins (dict overwrite)
+            for j, c in enumerate(batch["traj_cand_vpids"][b][t]):
+                cand_tokens.setdefault(c, []).append((row0 + t) * V + j)
+        vps = batch["gmap_vpids"][b]
+        for n in range(G):
+            if 1 <= n < len(vps):
+                v = vps[n]
+                if v in visited_row:
+                    entries.append(-(visited_row[v] + 1))
+                else:
+                    entries.extend(cand_tokens[v])
+            node_ptr.append(len(entries))
+        row0 += T
+        last_rows.append(row0 - 1)
+    n_rows = row0
+
+    # reverse CSR (unique source -> nodes, weights 1/count(node)) for the deterministic backward
+    node_of_entry = np.repeat(np.arange(B * G), np.diff(np.asarray(node_ptr)))
+    cnt = np.diff(np.asarray(node_ptr))
+    ent = np.asarray(entries, dtype=np.int64)
+    order = np.argsort(ent, kind="stable")
+    ent_sorted = ent[order]
+    src_ids, starts = np.unique(ent_sorted, return_index=True)
+    src_ptr = np.append(starts, len(ent_sorted))
+    src_nodes = node_of_entry[order]
+    src_w = (1.0 / cnt[src_nodes]).astype(np.float32)
+
+    # local branch: [stop] + the last step's views
+    vp_gather = np.full((B, Vp), -1, dtype=np.int64)
+    l_valid = np.zeros((B, Vp), dtype=np.uint8)
+    for b in range(B):
+        n = min(Vp - 1, V)
+        vp_gather[b, 1:1 + n] = last_rows[b] * V + np.arange(n)
+        l_valid[b, 0] = 1
+        nt = nav_types[last_rows[b]]
+        for j in range(1, min(Vp, vp_lens[b])):
+            if j - 1 < V and nt[j - 1] == 1:
+                l_valid[b, j] = 1
+
+    # SAP masks + local->global scatter table
+    g_valid = np.zeros((B, G), dtype=np.uint8)
+    node2cand = np.full((B, G), -1, dtype=np.int32)
+    bw_mask = np.zeros((B, Vp), dtype=np.uint8)
+    for b in range(B):
+        vps = batch["gmap_vpids"][b]
+        vis = visited_masks[b]
+        for n in range(min(G, gmap_lens[b])):
+            if not vis[n]:
+                g_valid[b, n] = 1
+        visited_nodes = set(vp for vp, m in zip(vps, vis.tolist()) if m)
+        tmp = {}
+        for j, c in enumerate(batch["traj_cand_vpids"][b][-1]):
+            if j + 1 >= Vp:
+                break
+            if c in visited_nodes:
+                bw_mask[b, j + 1] = 1
+            else:
+                tmp[c] = j + 1  # last candidate with this id wins (dict overwrite)
+        for n, vp in enumerate(vps):
+            if n > 0 and vp not in visited_nodes and vp in tmp:
+                node2cand[b, n] = tmp[vp]
+
+    idx = dict(
+        node_ptr=torch.from_numpy(np.asarray(node_ptr, dtype=np.int32)),
+        entries=torch.from_numpy(np.asarray(entries, dtype=np.int32).reshape(-1)),
+        src_ids=torch.from_numpy(src_ids.astype(np.int32)), src_ptr=torch.from_numpy(src_ptr.astype(np.int32)),
+        src_nodes=torch.from_numpy(src_nodes.astype(np.int32)), src_w=torch.from_numpy(src_w),
+        vp_gather=torch.from_numpy(vp_gather.reshape(-1)), l_valid=torch.from_numpy(l_valid),
+        g_valid=torch.from_numpy(g_valid), node2cand=torch.from_numpy(node2cand), bw_mask=torch.from_numpy(bw_mask),
+        last_rows=torch.from_numpy(np.asarray(last_rows, dtype=np.int64)),
+        stop_rows_g=torch.arange(B, dtype=torch.int64) * G, stop_rows_v=torch.arange(B, dtype=torch.int64) * Vp,
+        key_lens_txt=_cpu(batch["txt_lens"]).to(torch.int32), key_lens_gmap=_cpu(batch["gmap_lens"]).to(torch.int32),
+        key_lens_vp=_cpu(batch["vp_lens"]).to(torch.int32), key_lens_pano=_cpu(batch["traj_vp_view_lens"]).to(torch.int32),
+        n_nodes=B * G, n_src=int(len(src_ids)), n_rows=n_rows,
+    )
+    if "txt_labels" in batch:
+        lab = _cpu(batch["txt_labels"])
+        sel = (lab != -1)
+        pos = sel.reshape(-1).nonzero()[:, 0]          # row-major (b, position) order
+        idx["mlm_rows"] = pos.to(torch.int64)
+        idx["mlm_labels"] = lab[sel].to(torch.int64)
+        idx["mlm_row_sample"] = (pos // lab.shape[1]).to(torch.int64)
+        counts = sel.sum(1).clamp(min=1).to(torch.float32)
+        idx["mlm_inv_count"] = (1.0 / counts)
+    return idx
+
+
+def prepare_batch(batch):
+    """Attach the index tables to a (CPU) collate batch.  Call before moving the batch to the GPU."""
+    if INDEX_KEY not in batch:
+        batch[INDEX_KEY] = build_index(batch)
+    return batch
+
+
+def index_to(idx, device, non_blocking=False):
+    return {k: (v.to(device, non_blocking=non_blocking) if torch.is_tensor(v) else v) for k, v in idx.items()}
+
+
+def batch_to_device(batch, device, non_blocking=False):
+    out = {}
+    for k, v in batch.items():
+        if k == INDEX_KEY:
+            out[k] = index_to(v, device, non_blocking)
+        elif torch.is_tensor(v):
+            out[k] = v.to(device, non_blocking=non_blocking)
+        else:
+            out[k] = v
+    return out

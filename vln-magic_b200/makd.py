@@ -1,0 +1,128 @@
+"""MAKD aggregation for pretraining: the composition of map_nav_src/r2r/agent.py:546-719
+(`compute_kd_losses`, role 't2s') with the `mean` reductions of pretrain_src/optim/kd_loss.py, MKRW ability
+weights (agent.py:866-869) and MKTD per-sample weights (agent.py:1013-1020).  Every MSE term of a step
+(5 hidden-state pairs + all attention-map pairs) goes through ONE fused kernel launch, the logit KL through
+a second, and the alpha mix (agent.py:1119) through a third."""
+import torch
+
+from . import ops
+from .kd_loss import exponential_decay
+
+KDL_DEFAULT = dict(kd_alpha=0.5, kd_temperature=2.0, rw_temp=4.0, t_sample_preprocess_exp_decay=0.7,
+                   teacher_sample_hard_mining=True, kdl_tasks=("txt", "img", "local", "global", "predict"),
+                   kdl_task_types=("emb", "attn"))
+
+NAMES = ("txt_emb_loss", "txt_attn_loss", "img_emb_loss", "avg_img_emb_loss", "img_attn_loss", "global_emb_loss",
+         "global_attn_loss", "local_emb_loss", "local_attn_loss", "predict_loss")
+
+
+def kdl_config(kdl=None):
+    k = dict(KDL_DEFAULT)
+    if kdl:
+        k.update({kk: kdl[kk] for kk in kdl.keys()} if hasattr(kdl, "keys") else vars(kdl))
+    return k
+
+
+def mkrw_weights(rw_temp=4.0, device="cuda", generator=None):
+    """softmax(randn(5)/rw_temp)*5, order [txt, img, global, local, predict] (agent.py:866-869).
+    Returned as python floats (they scale kernel arguments; drawn per step per rank like the reference)."""
+    r = torch.randn(5, generator=generator)
+    return (torch.softmax(r / rw_temp, 0) * 5).tolist()
+
+
+def mktd_weights(t_sample_loss, decay=0.7):
+    return exponential_decay(t_sample_loss, decay_rate=decay)
+
+
+def _w_for(x, w):
+    return w if (w is not None and x.shape[0] == w.shape[0]) else None
+
+
+def compute_kd_losses(student, s_out, t_out, task, rw, t_w, kdl=None):
+    """-> (named dict of per-ability scalars as a [10] tensor view, mse_total scalar, kl scalar or None)."""
+    k = kdl_config(kdl)
+    bert = student.bert
+    emb, att = "emb" in k["kdl_task_types"], "attn" in k["kdl_task_types"]
+    tasks = k["kdl_tasks"]
+    pairs, owner = [], []
+
+    def add_emb(name, proj, s, t, rwi):
+        if not emb:
+            return
+        ps = ops.linear(s, proj.weight, proj.bias)
+        t = t.detach()
+        pairs.append((ps, t, _w_for(ps, t_w), rwi / ps.numel()))
+        owner.append(name)
+
+    def add_attn(name, s_list, t_list, rwi, n_layers):
+        if not att or not s_list:
+            return
+        items = []
+        for sl, tl in zip(s_list[:n_layers], t_list[:n_layers]):
+            if isinstance(sl, tuple):
+                items += [(sl[0], tl[0]), (sl[1], tl[1])]
+            else:
+                items.append((sl, tl))
+        numel = sum(a.numel() for a, _ in items)
+        for a, b in items:
+            pairs.append((a, b.detach(), _w_for(a, t_w), rwi / numel))
+            owner.append(name)
+
+    # agent.py:560 -- the attention maps are compared on their first min(layers) layers
+    min_len = min(len(s_out["txt_attn_list"]), len(t_out["txt_attn_list"])) if att else 0
+    if "txt" in tasks:
+        add_emb("txt_emb_loss", bert.txt_emb_w, s_out["txt_embeds"], t_out["txt_embeds"], rw[0])
+        add_attn("txt_attn_loss", s_out["txt_attn_list"], t_out["txt_attn_list"], rw[0], min_len)
+    if "img" in tasks:
+        add_emb("img_emb_loss", bert.kdl_img_w, s_out["pano_embeds"], t_out["pano_embeds"], rw[1])
+        add_emb("avg_img_emb_loss", bert.kdl_avg_img_w, s_out["pano_fused_embeds"], t_out["pano_fused_embeds"], rw[1])
+        if att and len(s_out["img_attn_list"]) != len(t_out["img_attn_list"]):
+            raise ValueError("img_attns of teacher and student must have the same shape (agent.py:628)")
+        add_attn("img_attn_loss", s_out["img_attn_list"], t_out["img_attn_list"], rw[1], len(s_out["img_attn_list"]))
+    mlm = task.startswith("mlm")
+    gw, lw = (bert.gmap_txt_w, bert.vp_txt_w) if mlm else (bert.global_cross_w, bert.local_cross_w)
+    nx = min(len(s_out["gmap_attn_list"]), len(t_out["gmap_attn_list"]), max(min_len, 0)) if att else 0
+    if "global" in tasks:
+        add_emb("global_emb_loss", gw, s_out["gmap_embeds"], t_out["gmap_embeds"], rw[2])
+        add_attn("global_attn_loss", s_out["gmap_attn_list"], t_out["gmap_attn_list"], rw[2], nx)
+    if "local" in tasks:
+        add_emb("local_emb_loss", lw, s_out["vp_embeds"], t_out["vp_embeds"], rw[3])
+        add_attn("local_attn_loss", s_out["vp_attn_list"], t_out["vp_attn_list"], rw[3], nx)
+    per_seg, mse_total = ops.makd_mse(pairs) if pairs else (None, None)
+    kl = None
+    if "predict" in tasks:
+        w = t_w
+        if w is not None and mlm:
+            w = ops.gather_rows(t_w.reshape(-1, 1), s_out["row_sample"]).reshape(-1)  # per-row weights
+        s_log, t_log = s_out["logits"], t_out["logits"].detach()
+        R, C = s_log.shape
+        T = float(k["kd_temperature"])
+        scale = (T * T / R if w is not None else T * T / (R * C)) * rw[4]
+        kl = ops.makd_kl(s_log, t_log, T, w, scale)
+    return dict(per_seg=per_seg, owner=owner, mse_total=mse_total, kl=kl)
+
+
+def named_losses(res):
+    """Host-side (logging / tests): fold the per-segment vector into the reference's 10 named scalars."""
+    out = {n: 0.0 for n in NAMES}
+    if res["per_seg"] is not None:
+        vals = res["per_seg"].detach().float().cpu().tolist()
+        for name, v in zip(res["owner"], vals):
+            out[name] += v
+    if res["kl"] is not None:
+        out["predict_loss"] = float(res["kl"].detach())
+    return out
+
+
+def distill_step_loss(student, teacher, batch, task, rw, kdl=None):
+    """Forward of the (missing upstream) distillation step, SURVEY.md 3.2.
+    Returns (mix [total, sup_mean, kd_total], kd result dict, s_out, t_out)."""
+    k = kdl_config(kdl)
+    with torch.no_grad():
+        t_out = teacher(batch, task, True)
+    s_out = student(batch, task, True)
+    t_w = mktd_weights(t_out["sample_loss"], k["t_sample_preprocess_exp_decay"]) if k["teacher_sample_hard_mining"] \
+        else None
+    res = compute_kd_losses(student, s_out, t_out, task, rw, t_w, k)
+    mix = ops.loss_mix(res["mse_total"], res["kl"], s_out["loss"], k["kd_alpha"])
+    return mix, res, s_out, t_out
