@@ -251,7 +251,8 @@ def test_attention(dtype, tol, cfg):
         close(kv.grad, rkv.grad, tol * 4, "attn dkv")
     if dists is not None:
         close(sw.grad, sw2.grad, tol * 10, "attn dsprel_w")
-        close(sb.grad, sb2.grad, tol * 10 + 1e-4, "attn dsprel_b")
+        # d(bias) is analytically zero (softmax is shift invariant): compare absolutely against the scale of dw
+        assert (sb.grad - sb2.grad).abs().max().item() <= 1e-3 * max(1.0, sw2.grad.abs().max().item())
 
 
 def test_ce_and_sap_fuse():

@@ -133,12 +133,15 @@ def test_bf16_mode(task):
     lo.backward()
     lp.backward()
     go = dict(oracle.named_parameters())
-    worst = 0.0
+    bad = []
+    gmax = max(g.grad.norm().item() for g in go.values() if g.grad is not None)
     for n, p in prod.named_parameters():
-        if go[n].grad is None or go[n].grad.norm() < 1e-6:
-            continue
-        worst = max(worst, rel(p.grad, go[n].grad))
-    assert worst < 0.1, worst
+        if go[n].grad is None or go[n].grad.norm() < 1e-4 * gmax:
+            continue  # (near-)zero-gradient parameters (key biases, sprel bias): pure rounding noise
+        r = rel(p.grad, go[n].grad)
+        if r > 0.1:
+            bad.append((n, round(r, 3), go[n].grad.norm().item()))
+    assert not bad, bad[:10]
 
 
 def test_teacher_width_768_forward():

@@ -77,9 +77,35 @@ class MagicError(RuntimeError):
     pass
 
 
+# kernels launched per C-ABI call (for the launch counter bench.py reports as gpu_launches)
+_LAUNCHES = {"magic_attn_bwd": 2, "magic_scatter_rows": 1, "magic_gmap_aggregate_bwd": 1}
+COUNTERS = {"calls": 0, "launches": 0}
+_PROFILE = None  # {name: [(start_event, end_event, args)]} when bench.py profiles kernel families
+
+
+def profile_start():
+    global _PROFILE
+    _PROFILE = {}
+
+
+def profile_stop():
+    global _PROFILE
+    p, _PROFILE = _PROFILE, None
+    return p
+
+
 def call(name, *args):
     lib = load()
-    rc = getattr(lib, name)(*args)
+    COUNTERS["calls"] += 1
+    COUNTERS["launches"] += _LAUNCHES.get(name, 1)
+    if _PROFILE is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = getattr(lib, name)(*args)
+        e1.record()
+        _PROFILE.setdefault(name, []).append((e0, e1, args))
+    else:
+        rc = getattr(lib, name)(*args)
     if rc != 0:
         raise MagicError(f"{name} failed (rc={rc}): {lib.magic_last_error().decode()}")
 

@@ -119,8 +119,8 @@ def distill_step_loss(student, teacher, batch, task, rw, kdl=None):
     Returns (mix [total, sup_mean, kd_total], kd result dict, s_out, t_out)."""
     k = kdl_config(kdl)
     with torch.no_grad():
-        t_out = teacher(batch, task, True)
-    s_out = student(batch, task, True)
+        t_out = teacher(batch, task, True, output_kd=True)
+    s_out = student(batch, task, True, output_kd=True)
     t_w = mktd_weights(t_out["sample_loss"], k["t_sample_preprocess_exp_decay"]) if k["teacher_sample_hard_mining"] \
         else None
     res = compute_kd_losses(student, s_out, t_out, task, rw, t_w, k)

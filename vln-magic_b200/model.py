@@ -459,7 +459,14 @@ class GlocalTextPathCMTPreTraining(nn.Module):
             batch[INDEX_KEY] = ix
         return ix
 
-    def forward(self, batch, task, compute_loss=True):
+    def forward(self, batch, task, compute_loss=True, output_kd=None):
+        """`output_kd` (ours): also return the KD attention maps; default = config.kd (train_r2r_magic.py:134,159)."""
+        if output_kd is not None:
+            prev, self.output_kd = self.output_kd, bool(output_kd)
+            try:
+                return self.forward(batch, task, compute_loss)
+            finally:
+                self.output_kd = prev
         if task.startswith("mlm"):
             return self.forward_mlm(batch, compute_loss)
         if task.startswith("sap"):

@@ -1,0 +1,114 @@
+"""The training step the reference's `train_r2r_magic.py` builds everything for but does not ship
+(its loop body is missing after :399-401): teacher forward (no grad), student forward,
+supervised task loss, MAKD losses, alpha mix, backward, gradient all-reduce, clip + AdamW.
+
+Optionally the whole device side of a step is captured into a CUDA graph per (task, shape signature) and
+replayed: at MAGIC-S sizes (h = 128) the step is launch-bound, so removing the per-kernel host cost is the
+single largest win."""
+import torch
+import torch.distributed as dist
+
+from . import _lib, makd, ops
+from .graph_index import INDEX_KEY
+from .optim import FusedAdamW
+from .arena import ParamArena
+
+
+class PretrainStepper:
+    def __init__(self, student, teacher=None, kdl=None, lr=5e-5, betas=(0.9, 0.98), weight_decay=0.01,
+                 max_grad_norm=5.0, use_graphs=False, rw_generator=None):
+        self.student, self.teacher = student, teacher
+        self.kdl = makd.kdl_config(kdl)
+        lowp = student.compute_dtype == torch.bfloat16
+        self.arena = ParamArena(student, lowp=lowp)
+        if teacher is not None and lowp:
+            self.t_arena = ParamArena(teacher, lowp=True, requires_grad_only=False, with_grads=False)
+            for p in teacher.parameters():
+                p.requires_grad_(False)
+        self.opt = FusedAdamW(self.arena, lr=lr, betas=betas, weight_decay=weight_decay, max_grad_norm=max_grad_norm)
+        self.use_graphs = use_graphs
+        self.graphs = {}
+        self.rw_generator = rw_generator
+        self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+        self.device = self.arena.device
+        self.launches_per_step = None
+
+    # -- the device side of one step -------------------------------------------------------------
+    def _device_step(self, task, batch, rw):
+        self.arena.zero_grad()
+        if self.teacher is not None:
+            mix, res, s_out, t_out = makd.distill_step_loss(self.student, self.teacher, batch, task, rw, self.kdl)
+        else:
+            s_out = self.student(batch, task, True)
+            mix = ops.loss_mix(None, None, s_out["loss"], 0.0)
+        mix[0].backward()
+        if self.world > 1:
+            dist.all_reduce(self.arena.flat_g, op=dist.ReduceOp.AVG)
+        self.opt.apply()
+        return mix
+
+    def step(self, task, batch, lr=None):
+        """batch: device batch with index tables (graph_index.prepare_batch + batch_to_device).
+        Returns the device tensor [total, supervised_mean, kd_total] (no host sync)."""
+        rw = makd.mkrw_weights(self.kdl["rw_temp"], generator=self.rw_generator) if self.teacher is not None else None
+        self.opt.set_hyper(lr)
+        ops.bump_seed(self.device)
+        if not self.use_graphs:
+            return self._device_step(task, batch, rw)
+        return self._graph_step(task, batch, rw)
+
+    # -- CUDA-graph replay ------------------------------------------------------------------------
+    @staticmethod
+    def _signature(task, batch):
+        sig = [task]
+        for k in sorted(batch.keys()):
+            v = batch[k]
+            if torch.is_tensor(v):
+                sig.append((k, tuple(v.shape)))
+            elif k == INDEX_KEY:
+                sig.append(tuple((kk, tuple(vv.shape) if torch.is_tensor(vv) else vv) for kk, vv in sorted(v.items())))
+        return tuple(sig)
+
+    @staticmethod
+    def _copy_into(dst, src):
+        for k, v in src.items():
+            if torch.is_tensor(v):
+                dst[k].copy_(v, non_blocking=True)
+            elif k == INDEX_KEY:
+                for kk, vv in v.items():
+                    if torch.is_tensor(vv):
+                        dst[k][kk].copy_(vv, non_blocking=True)
+
+    def _graph_step(self, task, batch, rw):
+        if self.teacher is not None:
+            raise NotImplementedError("graph replay with MAKD needs device-resident MKRW weights (round 2)")
+        sig = self._signature(task, batch)
+        entry = self.graphs.get(sig)
+        if entry is None:
+            static = {k: (v.clone() if torch.is_tensor(v) else
+                          ({kk: (vv.clone() if torch.is_tensor(vv) else vv) for kk, vv in v.items()}
+                           if k == INDEX_KEY else v)) for k, v in batch.items()}
+            s = torch.cuda.Stream()
+            s.wait_stream(torch.cuda.current_stream())
+            # warm-up on a side stream (allocator, cudaFuncSetAttribute, lazy init) WITHOUT changing the
+            # training state: parameters and moments are restored afterwards
+            snap = (self.arena.flat_p.clone(), self.opt.m.clone(), self.opt.v.clone())
+            with torch.cuda.stream(s):
+                for _ in range(2):
+                    self._device_step(task, static, rw)
+                self.arena.flat_p.copy_(snap[0])
+                self.opt.m.copy_(snap[1])
+                self.opt.v.copy_(snap[2])
+                self.arena.refresh_lowp()
+            torch.cuda.current_stream().wait_stream(s)
+            g = torch.cuda.CUDAGraph()
+            n0 = _lib.COUNTERS["launches"]
+            with torch.cuda.graph(g):
+                out = self._device_step(task, static, rw)
+            entry = (g, static, out, _lib.COUNTERS["launches"] - n0)
+            self.graphs[sig] = entry
+        g, static, out, n_launch = entry
+        self._copy_into(static, batch)
+        g.replay()
+        _lib.COUNTERS["launches"] += n_launch  # kernels replayed inside the graph
+        return out
