@@ -163,11 +163,14 @@ typedef struct MagicMseSeg {
 int magic_makd_mse_fwd(const MagicMseSeg* segs, int nseg, float* loss, cudaStream_t st);
 /* upstream gradient of segment i = gseg[i] (nullable) + gtot[0] (nullable) */
 int magic_makd_mse_bwd(const MagicMseSeg* segs, int nseg, const float* gseg, const float* gtot, cudaStream_t st);
-/* total = alpha*(mse_total + kl) + (1-alpha)*mean(sup[0..n))  (agent.py:1119); out = [total, sup_mean, kd] */
-int magic_loss_mix_fwd(const float* mse_total, const float* kl, const float* sup, int n, float alpha, float* out,
-                       cudaStream_t st);
-int magic_loss_mix_bwd(const float* g, int n, float alpha, float* d_mse, float* d_kl, float* d_sup,
-                       cudaStream_t st);
+/* total = alpha*(mse_total + kl) + (1-alpha)*mean(sup[0..n))  (agent.py:1119); out = [total, sup_mean, kd].
+ * inv_n (nullable, device): 1/(number of real rows) when sup is padded with zero rows for CUDA-graph replay */
+int magic_loss_mix_fwd(const float* mse_total, const float* kl, const float* sup, int n, float alpha,
+                       const float* inv_n, float* out, cudaStream_t st);
+int magic_loss_mix_bwd(const float* g, int n, float alpha, const float* inv_n, float* d_mse, float* d_kl,
+                       float* d_sup, cudaStream_t st);
+/* measurement aid: keeps the stream busy for ~cycles SM clocks so the host can queue launches ahead of the GPU */
+int magic_delay(long long cycles, cudaStream_t st);
 int magic_makd_kl_fwd(const void* s, const void* t, int R, int C, long ld, float temperature, const float* w,
                       float scale, float* stats /* [R,2] */, float* loss /* [1], zeroed here */, int dtype,
                       cudaStream_t st);

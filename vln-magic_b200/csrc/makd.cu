@@ -172,28 +172,28 @@ __global__ void __launch_bounds__(NT)
 // total = alpha * (mse_total + kl) + (1 - alpha) * mean(sup)      (agent.py:1119)
 __global__ void __launch_bounds__(256)
     mix_fwd_kernel(const float* __restrict__ mse_total, const float* __restrict__ kl, const float* __restrict__ sup,
-                   int n, float alpha, float* __restrict__ out) {
+                   int n, float alpha, const float* __restrict__ inv_n, float* __restrict__ out) {
   __shared__ float red[32];
   float a = 0.f;
   for (int i = threadIdx.x; i < n; i += blockDim.x) a += sup[i];
   a = block_sum(a, red);
   if (threadIdx.x == 0) {
-    const float sm = n > 0 ? a / (float)n : 0.f;
+    const float sm = inv_n ? a * inv_n[0] : (n > 0 ? a / (float)n : 0.f);
     const float kd = (mse_total ? mse_total[0] : 0.f) + (kl ? kl[0] : 0.f);
     out[0] = alpha * kd + (1.f - alpha) * sm;
     out[1] = sm;
     out[2] = kd;
   }
 }
-__global__ void mix_bwd_kernel(const float* __restrict__ g, int n, float alpha, float* __restrict__ d_mse,
-                               float* __restrict__ d_kl, float* __restrict__ d_sup) {
+__global__ void mix_bwd_kernel(const float* __restrict__ g, int n, float alpha, const float* __restrict__ inv_n,
+                               float* __restrict__ d_mse, float* __restrict__ d_kl, float* __restrict__ d_sup) {
   const float gv = g[0];
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     if (d_mse) d_mse[0] = alpha * gv;
     if (d_kl) d_kl[0] = alpha * gv;
   }
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
-    d_sup[i] = (1.f - alpha) * gv / (float)n;
+    d_sup[i] = inv_n ? (1.f - alpha) * gv * inv_n[0] : (1.f - alpha) * gv / (float)n;
 }
 
 int build_args(const MagicMseSeg* segs, int nseg, Args& A, const char* name) {
@@ -247,16 +247,16 @@ int magic_makd_mse_bwd(const MagicMseSeg* segs, int nseg, const float* gseg, con
   return MAGIC_OK;
 }
 
-int magic_loss_mix_fwd(const float* mse_total, const float* kl, const float* sup, int n, float alpha, float* out,
-                       cudaStream_t st) {
-  mix_fwd_kernel<<<1, 256, 0, st>>>(mse_total, kl, sup, n, alpha, out);
+int magic_loss_mix_fwd(const float* mse_total, const float* kl, const float* sup, int n, float alpha,
+                       const float* inv_n, float* out, cudaStream_t st) {
+  mix_fwd_kernel<<<1, 256, 0, st>>>(mse_total, kl, sup, n, alpha, inv_n, out);
   MAGIC_CHECK_LAUNCH("magic_loss_mix_fwd");
   return MAGIC_OK;
 }
 
-int magic_loss_mix_bwd(const float* g, int n, float alpha, float* d_mse, float* d_kl, float* d_sup,
-                       cudaStream_t st) {
-  mix_bwd_kernel<<<(n + 255) / 256 > 0 ? (n + 255) / 256 : 1, 256, 0, st>>>(g, n, alpha, d_mse, d_kl, d_sup);
+int magic_loss_mix_bwd(const float* g, int n, float alpha, const float* inv_n, float* d_mse, float* d_kl,
+                       float* d_sup, cudaStream_t st) {
+  mix_bwd_kernel<<<(n + 255) / 256 > 0 ? (n + 255) / 256 : 1, 256, 0, st>>>(g, n, alpha, inv_n, d_mse, d_kl, d_sup);
   MAGIC_CHECK_LAUNCH("magic_loss_mix_bwd");
   return MAGIC_OK;
 }

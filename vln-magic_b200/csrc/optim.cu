@@ -55,9 +55,22 @@ __global__ void scale_kernel(float* __restrict__ x, long long n, float s) {
     x[i] *= s;
 }
 
+__global__ void delay_kernel(long long cycles) {
+  const long long t0 = clock64();
+  while (clock64() - t0 < cycles) {
+  }
+}
+
 }  // namespace
 
 extern "C" {
+
+int magic_delay(long long cycles, cudaStream_t st) {
+  delay_kernel<<<1, 1, 0, st>>>(cycles);
+  MAGIC_CHECK_LAUNCH("magic_delay");
+  return MAGIC_OK;
+}
+
 
 int magic_sumsq(const float* g, long long n, float* out, int zero_first, cudaStream_t st) {
   if (zero_first) MAGIC_CUDA(cudaMemsetAsync(out, 0, sizeof(float), st), "magic_sumsq");

@@ -122,6 +122,38 @@ def build_index(batch):
     return idx
 
 
+def pad_batch(batch, n_panos=None, n_masked=None):
+    """Pad a prepared CPU batch to fixed capacities so every batch of a task has the same tensor shapes
+    (one CUDA graph per task).  Padded panoramas have a single all-zero view and are referenced by no index
+    table; padded masked-token rows gather a zero row, carry label -1 (ignored) and are excluded from the
+    mean through `mlm_inv_n`."""
+    ix = batch[INDEX_KEY]
+    if n_panos is not None:
+        R = batch["traj_view_img_fts"].shape[0]
+        if n_panos < R:
+            raise ValueError(f"pano capacity {n_panos} < {R}")
+        if n_panos > R:
+            def padr(t, value=0):
+                pad = torch.full((n_panos - R, *t.shape[1:]), value, dtype=t.dtype)
+                return torch.cat([t, pad], 0)
+            for k in ("traj_view_img_fts", "traj_loc_fts", "traj_nav_types"):
+                batch[k] = padr(batch[k])
+            batch["traj_vp_view_lens"] = padr(batch["traj_vp_view_lens"], 1)
+            ix["key_lens_pano"] = padr(ix["key_lens_pano"], 1)
+    if "mlm_rows" in ix:
+        n = ix["mlm_rows"].numel()
+        ix["mlm_inv_n"] = torch.tensor([1.0 / max(n, 1)], dtype=torch.float32)
+        if n_masked is not None:
+            if n_masked < n:
+                raise ValueError(f"masked-token capacity {n_masked} < {n}")
+            if n_masked > n:
+                pad = n_masked - n
+                ix["mlm_rows"] = torch.cat([ix["mlm_rows"], torch.full((pad,), -1, dtype=torch.int64)])
+                ix["mlm_labels"] = torch.cat([ix["mlm_labels"], torch.full((pad,), -1, dtype=torch.int64)])
+                ix["mlm_row_sample"] = torch.cat([ix["mlm_row_sample"], torch.zeros(pad, dtype=torch.int64)])
+    return batch
+
+
 def prepare_batch(batch):
     """Attach the index tables to a (CPU) collate batch.  Call before moving the batch to the GPU."""
     if INDEX_KEY not in batch:

@@ -124,5 +124,5 @@ def distill_step_loss(student, teacher, batch, task, rw, kdl=None):
     t_w = mktd_weights(t_out["sample_loss"], k["t_sample_preprocess_exp_decay"]) if k["teacher_sample_hard_mining"] \
         else None
     res = compute_kd_losses(student, s_out, t_out, task, rw, t_w, k)
-    mix = ops.loss_mix(res["mse_total"], res["kl"], s_out["loss"], k["kd_alpha"])
+    mix = ops.loss_mix(res["mse_total"], res["kl"], s_out["loss"], k["kd_alpha"], s_out.get("loss_inv_n"))
     return mix, res, s_out, t_out

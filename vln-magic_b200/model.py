@@ -494,11 +494,12 @@ class GlocalTextPathCMTPreTraining(nn.Module):
         t = ops.linear(x, head.transform.dense.weight, head.transform.dense.bias, act=L.ACT_GELU)
         t = ops.layer_norm(t, head.transform.LayerNorm.weight, head.transform.LayerNorm.bias,
                            head.transform.LayerNorm.eps)
-        logits = ops.linear(t, head.decoder.weight, head.bias)
+        logits = ops.linear(t, head.decoder.weight, head.bias, pad_out=True)
         if not compute_loss:
             return {"predict": logits.float() if logits.dtype != torch.float32 else logits}
         loss = ops.cross_entropy(logits, ix["mlm_labels"], -1)
         o.update(loss=loss, logits=logits, predict=logits, row_sample=ix["mlm_row_sample"],
+                 loss_inv_n=ix.get("mlm_inv_n"),
                  sample_loss=ops.segment_mean(loss.detach(), ix["mlm_row_sample"], ix["mlm_inv_count"], B))
         return o
 
@@ -507,7 +508,7 @@ class GlocalTextPathCMTPreTraining(nn.Module):
         t = ops.linear(x, n[0].weight, n[0].bias, act=L.ACT_RELU)
         t = ops.layer_norm(t, n[2].weight, n[2].bias, n[2].eps)
         if n[3].weight.shape[0] == 1:
-            return ops.rowdot(t, n[3].weight.reshape(-1), n[3].bias)
+            return ops.rowdot(t, n[3].weight, n[3].bias)
         return ops.linear(t, n[3].weight, n[3].bias)
 
     def sap_logits(self, o, ix):

@@ -76,11 +76,19 @@ def _lin_fwd(x2, w, bias, out, act=0, pre_out=None, residual=None, drop_p=0.0, s
          salt=salt, seed=seed)
 
 
+def _rows2d(t):
+    """2-D view usable as a GEMM operand without a copy when the rows are unit-stride (padded ld allowed)."""
+    if t.dim() == 2 and t.stride(1) == 1 and t.stride(0) >= t.shape[1]:
+        return t
+    return t.reshape(-1, t.shape[-1]).contiguous()
+
+
 def _lin_dgrad(dy2, w, dx, act=0, dact_pre=None, drop_p=0.0, salt=0, seed=None):
     M, N = dy2.shape
     K = w.shape[1]
     wo = _wop(w)
-    gemm(dy2, N, 1, wo, K, 1, dx, M, K, N, act=act, dact_pre=dact_pre, drop_p=drop_p, salt=salt, seed=seed)
+    gemm(dy2, dy2.stride(0), 1, wo, K, 1, dx, M, K, N, act=act, dact_pre=dact_pre, drop_p=drop_p, salt=salt,
+         seed=seed)
 
 
 def _lin_wgrad(dy2, x2, w, bias):
@@ -88,7 +96,7 @@ def _lin_wgrad(dy2, x2, w, bias):
     M, N = dy2.shape
     K = x2.shape[1]
     gw, rw, beta = _sink(w)
-    gemm(dy2, 1, N, x2, K, 1, gw, N, K, M, beta=beta)
+    gemm(dy2, 1, dy2.stride(0), x2, K, 1, gw, N, K, M, beta=beta)
     rb = None
     if bias is not None:
         gb, rb, _ = _sink(bias)
@@ -100,23 +108,27 @@ class LinearFn(torch.autograd.Function):
     """y = drop(act(x W^T + b)) (+ residual)."""
 
     @staticmethod
-    def forward(ctx, x, w, bias, act, residual, drop_p, salt):
+    def forward(ctx, x, w, bias, act, residual, drop_p, salt, pad_out=False):
         x2 = x.reshape(-1, x.shape[-1]).contiguous()
         M, N = x2.shape[0], w.shape[0]
-        out = torch.empty(M, N, dtype=x.dtype, device=x.device)
+        if pad_out and N % 8 != 0:
+            # leading dimension padded to 16 bytes so the gradient of this output is a legal TMA operand
+            out = torch.empty(M, (N + 7) // 8 * 8, dtype=x.dtype, device=x.device)[:, :N]
+        else:
+            out = torch.empty(M, N, dtype=x.dtype, device=x.device)
         pre = torch.empty_like(out) if act != 0 else None
         seed = seed_tensor(x.device) if drop_p > 0 else None
         res2 = residual.reshape(-1, N).contiguous() if residual is not None else None
         _lin_fwd(x2, w, bias, out, act, pre, res2, drop_p, salt, seed)
         ctx.save_for_backward(x2, w, bias, pre)
         ctx.meta = (act, drop_p, salt, x.shape, residual is not None)
-        return out.view(*x.shape[:-1], N)
+        return out if x.dim() == 2 else out.view(*x.shape[:-1], N)
 
     @staticmethod
     def backward(ctx, dy):
         x2, w, bias, pre = ctx.saved_tensors
         act, drop_p, salt, xshape, has_res = ctx.meta
-        dy2 = dy.reshape(-1, dy.shape[-1]).contiguous()
+        dy2 = _rows2d(dy) if (act == 0 and drop_p == 0) else dy.reshape(-1, dy.shape[-1]).contiguous()
         dres = dy if has_res else None
         if act != 0 or drop_p > 0:
             dz = torch.empty_like(dy2)
@@ -131,11 +143,11 @@ class LinearFn(torch.autograd.Function):
             _lin_dgrad(dz, w, dx)
             dx = dx.view(xshape)
         rw, rb = _lin_wgrad(dz, x2, w, bias)
-        return dx, rw, rb, None, dres, None, None
+        return dx, rw, rb, None, dres, None, None, None
 
 
-def linear(x, w, bias=None, act=0, residual=None, drop_p=0.0, salt=0):
-    return LinearFn.apply(x, w, bias, act, residual, drop_p if _DROP_ON else 0.0, salt)
+def linear(x, w, bias=None, act=0, residual=None, drop_p=0.0, salt=0, pad_out=False):
+    return LinearFn.apply(x, w, bias, act, residual, drop_p if _DROP_ON else 0.0, salt, pad_out)
 
 
 def _adjacent(ts):
@@ -454,6 +466,8 @@ class RowDotFn(torch.autograd.Function):
         h = x.shape[-1]
         x2 = x.reshape(-1, h).contiguous()
         y = torch.empty(x2.shape[0], dtype=torch.float32, device=x.device)
+        if w.numel() != h:
+            raise L.MagicError("rowdot: weight must have h elements")
         call("magic_rowdot_fwd", ptr(x2), ptr(w), ptr(bias), ptr(y), x2.shape[0], h, dt(x2), stream())
         ctx.save_for_backward(x2, w, bias)
         ctx.xshape = x.shape
@@ -616,7 +630,7 @@ class CrossEntropyFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, logits, labels, ignore_index):
         R, C = logits.shape
-        logits = logits.contiguous()
+        logits = _rows2d(logits)
         labels = labels.contiguous()
         loss = torch.empty(R, dtype=torch.float32, device=logits.device)
         lse = torch.empty(R, dtype=torch.float32, device=logits.device)
@@ -631,7 +645,7 @@ class CrossEntropyFn(torch.autograd.Function):
         logits, labels, lse = ctx.saved_tensors
         R, C = logits.shape
         dloss = dloss.contiguous().float()
-        dlogits = torch.empty_like(logits)
+        dlogits = torch.empty_strided(logits.shape, logits.stride(), dtype=logits.dtype, device=logits.device)
         call("magic_ce_bwd", ptr(logits), ptr(labels), ptr(lse), ptr(dloss), ptr(dlogits), R, C, logits.stride(0),
              ctx.ignore_index, dt(logits), stream())
         return dlogits, None, None
@@ -706,11 +720,13 @@ class LossMixFn(torch.autograd.Function):
     """total = alpha*(mse_total + kl) + (1-alpha)*mean(sup).  Returns [total, sup_mean, kd] (grad flows via [0])."""
 
     @staticmethod
-    def forward(ctx, mse_total, kl, sup, alpha):
+    def forward(ctx, mse_total, kl, sup, alpha, inv_n):
         sup = sup.contiguous().float()
         out = torch.empty(3, dtype=torch.float32, device=sup.device)
-        call("magic_loss_mix_fwd", ptr(mse_total), ptr(kl), ptr(sup), sup.numel(), alpha, ptr(out), stream())
+        call("magic_loss_mix_fwd", ptr(mse_total), ptr(kl), ptr(sup), sup.numel(), alpha, ptr(inv_n), ptr(out),
+             stream())
         ctx.meta = (mse_total is not None, kl is not None, sup.numel(), alpha)
+        ctx.inv_n = inv_n
         return out
 
     @staticmethod
@@ -720,21 +736,23 @@ class LossMixFn(torch.autograd.Function):
         d_mse = torch.empty((), dtype=torch.float32, device=dout.device) if has_mse else None
         d_kl = torch.empty((), dtype=torch.float32, device=dout.device) if has_kl else None
         d_sup = torch.empty(n, dtype=torch.float32, device=dout.device)
-        call("magic_loss_mix_bwd", ptr(g), n, alpha, ptr(d_mse), ptr(d_kl), ptr(d_sup), stream())
-        return d_mse, d_kl, d_sup, None
+        call("magic_loss_mix_bwd", ptr(g), n, alpha, ptr(ctx.inv_n), ptr(d_mse), ptr(d_kl), ptr(d_sup), stream())
+        return d_mse, d_kl, d_sup, None, None
 
 
-def loss_mix(mse_total, kl, sup, alpha):
-    return LossMixFn.apply(mse_total, kl, sup, float(alpha))
+def loss_mix(mse_total, kl, sup, alpha, inv_n=None):
+    return LossMixFn.apply(mse_total, kl, sup, float(alpha), inv_n)
 
 
 class MakdKlFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, s, t, temperature, w, scale):
         R, C = s.shape
-        s, t = s.contiguous(), t.contiguous()
+        s, t = _rows2d(s), _rows2d(t)
         if t.dtype != s.dtype:
             t = t.to(s.dtype)
+        if t.stride(0) != s.stride(0):
+            s, t = s.contiguous(), t.contiguous()
         if w is not None:
             w = w.contiguous().float()
         stats = torch.empty(R, 2, dtype=torch.float32, device=s.device)
@@ -751,7 +769,7 @@ class MakdKlFn(torch.autograd.Function):
         temperature, scale = ctx.meta
         R, C = s.shape
         g = dloss.reshape(1).contiguous().float()
-        ds = torch.empty_like(s)
+        ds = torch.empty_strided(s.shape, s.stride(), dtype=s.dtype, device=s.device)
         call("magic_makd_kl_bwd", ptr(s), ptr(t), ptr(ds), R, C, s.stride(0), temperature, ptr(w), scale, ptr(stats),
              ptr(g), dt(s), stream())
         return ds, None, None, None, None

@@ -40,7 +40,7 @@ class PretrainStepper:
             mix, res, s_out, t_out = makd.distill_step_loss(self.student, self.teacher, batch, task, rw, self.kdl)
         else:
             s_out = self.student(batch, task, True)
-            mix = ops.loss_mix(None, None, s_out["loss"], 0.0)
+            mix = ops.loss_mix(None, None, s_out["loss"], 0.0, s_out.get("loss_inv_n"))
         mix[0].backward()
         if self.world > 1:
             dist.all_reduce(self.arena.flat_g, op=dist.ReduceOp.AVG)
@@ -85,8 +85,9 @@ class PretrainStepper:
         sig = self._signature(task, batch)
         entry = self.graphs.get(sig)
         if entry is None:
-            static = {k: (v.clone() if torch.is_tensor(v) else
-                          ({kk: (vv.clone() if torch.is_tensor(vv) else vv) for kk, vv in v.items()}
+            dev = self.device
+            static = {k: (v.to(dev, copy=True) if torch.is_tensor(v) else
+                          ({kk: (vv.to(dev, copy=True) if torch.is_tensor(vv) else vv) for kk, vv in v.items()}
                            if k == INDEX_KEY else v)) for k, v in batch.items()}
             s = torch.cuda.Stream()
             s.wait_stream(torch.cuda.current_stream())
