@@ -109,7 +109,10 @@ def make_pool(task, n, w, seed0):
     if task == "mlm":
         mcap = max(b[magic_b200.INDEX_KEY]["mlm_rows"].numel() for b in out)
         mcap = (mcap + 63) // 64 * 64
-    return [pad_batch(b, rcap, mcap) for b in out]
+    K = magic_b200.INDEX_KEY
+    ecap = (max(b[K]["entries"].numel() for b in out) + 255) // 256 * 256
+    scap = (max(b[K]["src_ids"].numel() for b in out) + 255) // 256 * 256
+    return [pad_batch(b, rcap, mcap, ecap, scap) for b in out]
 
 
 def host_pin(batch):

@@ -19,6 +19,7 @@ for i in range(4):
     stepper.step("mlm" if i % 2 == 0 else "sap", pools["mlm" if i % 2 == 0 else "sap"][0])
 torch.cuda.synchronize()
 _lib.profile_start()
+_lib.call("magic_delay", int(60e6), _lib.stream())
 for i in range(4):
     stepper.step("mlm" if i % 2 == 0 else "sap", pools["mlm" if i % 2 == 0 else "sap"][1])
 torch.cuda.synchronize()

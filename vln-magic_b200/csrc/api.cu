@@ -46,6 +46,7 @@ int magic_gemm(const void* A, int a_dt, long sam, long sak, const void* B, int b
   epi.res_ld = res_ld;
   epi.alpha = alpha;
   epi.beta = beta;
+  epi.atomic = 0;
   epi.drop_p = drop_p;
   epi.seed_ptr = seed_ptr;
   epi.salt = salt;

@@ -16,6 +16,7 @@ struct GemmEpi {
   const void* residual;                // forward: optional residual[m,n] (dtype of C) added after act/dropout
   long res_ld;
   float alpha, beta;                   // C = epi(alpha*acc) + residual + beta*C
+  int atomic;                          // split-K: accumulate with atomicAdd (fp32 C, linear epilogue only)
   float drop_p;                        // dropout applied to the activation OUTPUT (forward) / its gradient (backward)
   const unsigned long long* seed_ptr;  // device pointer
   uint32_t salt;
@@ -32,9 +33,10 @@ __device__ __forceinline__ float act_bwd(int act, float pre) {
   return 1.f;
 }
 
+// bias_n = bias[n] hoisted by the caller (column-invariant)
 template <typename TC>
 __device__ __forceinline__ void epi_store(const GemmEpi& epi, const Dropout& dr, TC* C, float acc, int m, int n,
-                                          long ldc) {
+                                          long ldc, float bias_n) {
   float v = epi.alpha * acc;
   const size_t off = (size_t)m * ldc + n;
   if (epi.dact_pre != nullptr) {  // backward: dz = dh * dropscale * act'(z)
@@ -43,7 +45,7 @@ __device__ __forceinline__ void epi_store(const GemmEpi& epi, const Dropout& dr,
                                                 : ldf((const float*)epi.dact_pre, poff);
     v *= dr.scale(poff) * act_bwd(epi.act, pre);
   } else {
-    if (epi.bias) v += epi.bias[n];
+    v += bias_n;
     if (epi.pre_out) {
       stf((TC*)epi.pre_out, off, v);
       v = rt((const TC*)nullptr, v);  // activation sees what backward will re-read
@@ -51,6 +53,10 @@ __device__ __forceinline__ void epi_store(const GemmEpi& epi, const Dropout& dr,
     v = act_fwd(epi.act, v);
     v *= dr.scale(off);
     if (epi.residual) v += ldf((const TC*)epi.residual, (size_t)m * epi.res_ld + n);
+  }
+  if (epi.atomic) {
+    atomicAdd(reinterpret_cast<float*>(C) + off, v);
+    return;
   }
   if (epi.beta != 0.f) v += epi.beta * ldf(C, off);
   stf(C, off, v);

@@ -66,7 +66,7 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const TA* __restrict__ A
     for (int j = 0; j < 4; j++) {
       const int gn = n0 + tx * 4 + j;
       if (gn >= N) continue;
-      epi_store<TC>(epi, dr, C, acc[i][j], gm, gn, ldc);
+      epi_store<TC>(epi, dr, C, acc[i][j], gm, gn, ldc, epi.bias ? epi.bias[gn] : 0.f);
     }
   }
 }

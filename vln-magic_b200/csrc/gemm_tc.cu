@@ -119,12 +119,123 @@ __host__ __device__ constexpr uint32_t make_idesc(int m, int n, int a_mn_major, 
          ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
+// ---- vectorised row-per-thread epilogue (the common, dropout-free modes) ---------------------------------
+// Each epilogue thread owns one accumulator row and 32 consecutive columns: 64 B (bf16) / 128 B (fp32) of
+// contiguous output per chunk, moved with 128-bit loads/stores (full 32 B sectors, ~20x fewer instructions
+// than an element-wise loop -- the epilogue runs one warp per scheduler, so instruction count is latency).
+__device__ __forceinline__ void ld_row32(const float* p, float (&v)[32]) {
+  const float4* q = reinterpret_cast<const float4*>(p);
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    const float4 t = q[i];
+    v[4 * i] = t.x; v[4 * i + 1] = t.y; v[4 * i + 2] = t.z; v[4 * i + 3] = t.w;
+  }
+}
+__device__ __forceinline__ void ld_row32(const __nv_bfloat16* p, float (&v)[32]) {
+  const uint4* q = reinterpret_cast<const uint4*>(p);
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    const uint4 t = q[i];
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&t);
+#pragma unroll
+    for (int e = 0; e < 4; e++) {
+      const float2 f = __bfloat1622float2(h[e]);
+      v[8 * i + 2 * e] = f.x; v[8 * i + 2 * e + 1] = f.y;
+    }
+  }
+}
+__device__ __forceinline__ void st_row32(float* p, const float (&v)[32]) {
+  float4* q = reinterpret_cast<float4*>(p);
+#pragma unroll
+  for (int i = 0; i < 8; i++) q[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+}
+__device__ __forceinline__ void st_row32(__nv_bfloat16* p, const float (&v)[32]) {
+  uint4* q = reinterpret_cast<uint4*>(p);
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    uint4 t;
+    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&t);
+#pragma unroll
+    for (int e = 0; e < 4; e++) h[e] = __floats2bfloat162_rn(v[8 * i + 2 * e], v[8 * i + 2 * e + 1]);
+    q[i] = t;
+  }
+}
+template <typename T>
+__device__ __forceinline__ void rt_row32(float (&v)[32]) {
+  if (sizeof(T) == 2) {
+#pragma unroll
+    for (int j = 0; j < 32; j++) v[j] = __bfloat162float(__float2bfloat16_rn(v[j]));
+  }
+}
+
+template <typename TC, int ACT>
+__device__ __forceinline__ void epi_fast_chunk(const GemmEpi& epi, TC* C, const uint32_t (&r)[32], int m, int nb,
+                                               long ldc) {
+  float v[32];
+#pragma unroll
+  for (int j = 0; j < 32; j++) v[j] = epi.alpha * __uint_as_float(r[j]);
+  const size_t off = (size_t)m * ldc + nb;
+  if (epi.dact_pre != nullptr) {
+    float pre[32];
+    const size_t poff = (size_t)m * epi.dact_ld + nb;
+    if (epi.dact_dt == MAGIC_BF16) ld_row32((const __nv_bfloat16*)epi.dact_pre + poff, pre);
+    else ld_row32((const float*)epi.dact_pre + poff, pre);
+#pragma unroll
+    for (int j = 0; j < 32; j++) v[j] *= act_bwd(ACT, pre[j]);
+  } else {
+    if (epi.bias) {
+      float b[32];
+      ld_row32(epi.bias + nb, b);
+#pragma unroll
+      for (int j = 0; j < 32; j++) v[j] += b[j];
+    }
+    if (epi.pre_out) {
+      st_row32((TC*)epi.pre_out + off, v);
+      rt_row32<TC>(v);
+    }
+    if (ACT != 0) {
+#pragma unroll
+      for (int j = 0; j < 32; j++) v[j] = act_fwd(ACT, v[j]);
+    }
+    if (epi.residual) {
+      float rs[32];
+      ld_row32((const TC*)epi.residual + (size_t)m * epi.res_ld + nb, rs);
+#pragma unroll
+      for (int j = 0; j < 32; j++) v[j] += rs[j];
+    }
+  }
+  if (epi.atomic) {
+#pragma unroll
+    for (int j = 0; j < 32; j++) atomicAdd(reinterpret_cast<float*>(C) + off + j, v[j]);
+    return;
+  }
+  if (epi.beta != 0.f) {
+    float c[32];
+    ld_row32(C + off, c);
+#pragma unroll
+    for (int j = 0; j < 32; j++) v[j] += epi.beta * c[j];
+  }
+  st_row32(C + off, v);
+}
+
 struct TcParams {
   int M, N, K;
+  int kb_per_split;  // k-blocks handled by one CTA along gridDim.z (split-K)
   int a_mn, b_mn;  // 1 = MN-major operand
   long ldc;
   GemmEpi epi;
+  int fast_epi;             // 1: vectorised row-per-thread epilogue is legal (alignment, no dropout)
+  unsigned long long* dbg;  // optional per-CTA timestamps (MAGIC_TC_DEBUG), else null
 };
+
+__device__ __forceinline__ unsigned long long gtime() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+#define DBG(slot)                                                                            \
+  if (P.dbg && (threadIdx.x & 31) == 0)                                                      \
+    P.dbg[((size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 8 + (slot))] = gtime();
 
 template <int BN, typename TC>
 __global__ void __launch_bounds__(NTHREADS, 1)
@@ -141,10 +252,14 @@ __global__ void __launch_bounds__(NTHREADS, 1)
   uint64_t* empty = full + STAGES;
   uint64_t* tmem_full = empty + STAGES;
   uint32_t* tmem_ptr = (uint32_t*)(tmem_full + 1);
+  float* stage = (float*)(tmem_ptr + 4);  // [4 epilogue warps][32][33] fp32 staging for coalesced stores
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
-  const int num_kb = (P.K + BK - 1) / BK;
+  if (threadIdx.x == 0) { DBG(0) }
+  const int total_kb = (P.K + BK - 1) / BK;
+  const int kb0 = blockIdx.z * P.kb_per_split;
+  const int num_kb = min(P.kb_per_split, total_kb - kb0);
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmap_a);
@@ -161,6 +276,7 @@ __global__ void __launch_bounds__(NTHREADS, 1)
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  if (threadIdx.x == 0) { DBG(1) }
 
   if (warp == 0) {
     if (lane == 0) {
@@ -172,7 +288,7 @@ __global__ void __launch_bounds__(NTHREADS, 1)
         mbar_expect_tx(&full[s], A_BYTES + B_BYTES);
         uint8_t* a_dst = sA + s * A_BYTES;
         uint8_t* b_dst = sB + s * B_BYTES;
-        const int k0 = kb * BK;
+        const int k0 = (kb0 + kb) * BK;
         if (!P.a_mn) {
           tma_load_2d(&tmap_a, &full[s], a_dst, k0, m0);                       // box {64 k, 128 rows}
         } else {
@@ -196,6 +312,7 @@ __global__ void __launch_bounds__(NTHREADS, 1)
         const uint32_t ph = (kb / STAGES) & 1;
         mbar_wait(&full[s], ph);
         tc_fence_after();
+        if (kb == 0) { DBG(2) }
         const uint32_t a_base = smem_u32(sA + s * A_BYTES), b_base = smem_u32(sB + s * B_BYTES);
 #pragma unroll
         for (int k = 0; k < BK / 16; k++) {
@@ -210,29 +327,48 @@ __global__ void __launch_bounds__(NTHREADS, 1)
     }
   } else {
     // ===== epilogue: warps 2..5, TMEM lane quarter = warp % 4 =====
+    // TMEM -> registers (row = lane) -> padded smem -> rolled loop with lane = column, so the code stays
+    // small (instruction cache) and every global access of a warp is one contiguous row segment.
     const int q = warp & 3;
+    float* st = stage + q * (32 * 33);
     mbar_wait(tmem_full, 0);
     tc_fence_after();
-    const int m = m0 + q * 32 + lane;
+    if (warp == 2) { DBG(3) }
     const Dropout dr = make_dropout(P.epi.drop_p, P.epi.seed_ptr, P.epi.salt);
-#pragma unroll
+#pragma unroll 1
     for (int c0 = 0; c0 < BN; c0 += 32) {
       uint32_t r[32];
       tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
-      if (m < P.M) {
-#pragma unroll
-        for (int j = 0; j < 32; j++) {
-          const int n = n0 + c0 + j;
-          if (n < P.N) epi_store<TC>(P.epi, dr, C, __uint_as_float(r[j]), m, n, P.ldc);
+      if (P.fast_epi && n0 + c0 + 32 <= P.N) {  // warp-uniform
+        const int m = m0 + q * 32 + lane;
+        if (m < P.M) {
+          if (P.epi.act == MAGIC_ACT_GELU) epi_fast_chunk<TC, MAGIC_ACT_GELU>(P.epi, C, r, m, n0 + c0, P.ldc);
+          else if (P.epi.act == MAGIC_ACT_RELU) epi_fast_chunk<TC, MAGIC_ACT_RELU>(P.epi, C, r, m, n0 + c0, P.ldc);
+          else epi_fast_chunk<TC, MAGIC_ACT_NONE>(P.epi, C, r, m, n0 + c0, P.ldc);
         }
+        continue;
       }
+#pragma unroll
+      for (int j = 0; j < 32; j++) st[lane * 33 + j] = __uint_as_float(r[j]);
+      __syncwarp();
+      const int n = n0 + c0 + lane;
+      if (n < P.N) {
+        const float bias_n = P.epi.bias ? __ldg(P.epi.bias + n) : 0.f;
+        const int rows = min(32, P.M - (m0 + q * 32));
+#pragma unroll 4
+        for (int rr = 0; rr < rows; rr++)
+          epi_store<TC>(P.epi, dr, C, st[rr * 33 + lane], m0 + q * 32 + rr, n, P.ldc, bias_n);
+      }
+      __syncwarp();
     }
+    if (warp == 2) { DBG(4) }
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, BN);
+    DBG(5)
   }
 }
 
@@ -275,6 +411,7 @@ struct MapHash {
   }
 };
 
+unsigned long long* g_dbg_buf = nullptr;
 std::mutex g_mu;
 std::unordered_map<MapKey, CUtensorMap, MapHash> g_maps;
 
@@ -319,14 +456,16 @@ int get_map(const void* ptr, uint64_t inner, uint64_t outer, uint64_t stride, ui
 
 template <int BN, typename TC>
 int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, void* C, const TcParams& P, cudaStream_t st) {
-  constexpr size_t smem = 1024 + (size_t)STAGES * (BM * BK * 2 + BN * BK * 2) + (2 * STAGES + 1) * 8 + 16;
+  constexpr size_t smem = 1024 + (size_t)STAGES * (BM * BK * 2 + BN * BK * 2) + (2 * STAGES + 1) * 8 + 16 +
+                          4 * 32 * 33 * sizeof(float);
   static bool attr_set = false;
   if (!attr_set) {
     MAGIC_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, TC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
                "magic_gemm(tc)");
     attr_set = true;
   }
-  dim3 grid((P.N + BN - 1) / BN, (P.M + BM - 1) / BM);
+  const int total_kb = (P.K + BK - 1) / BK;
+  dim3 grid((P.N + BN - 1) / BN, (P.M + BM - 1) / BM, (total_kb + P.kb_per_split - 1) / P.kb_per_split);
   gemm_tc_kernel<BN, TC><<<grid, NTHREADS, smem, st>>>(ta, tb, (TC*)C, P);
   MAGIC_CHECK_LAUNCH("magic_gemm(tc)");
   return MAGIC_OK;
@@ -342,6 +481,8 @@ bool tc_disabled() {
 }
 
 }  // namespace
+
+extern "C" unsigned long long* magic_tc_debug_buffer(void) { return g_dbg_buf; }
 
 int gemm_tc_shape_ok(int M, int N, int K) { return (!tc_disabled() && M > 0 && N > 0 && K > 0) ? 1 : 0; }
 
@@ -369,7 +510,50 @@ int gemm_tc_dispatch(const void* A, const void* B, void* C, int c_dt, int M, int
   else rc = get_map(B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, 64, 64, &tb);
   if (rc) return rc;
   TcParams P;
+  {
+    static unsigned long long* dbg_buf = nullptr;
+    static int dbg_on = -1;
+    if (dbg_on < 0) {
+      const char* e = getenv("MAGIC_TC_DEBUG");
+      dbg_on = (e && e[0] == '1') ? 1 : 0;
+      if (dbg_on) cudaMalloc(&dbg_buf, 8 * 8 * 65536);
+    }
+    P.dbg = dbg_on ? dbg_buf : nullptr;
+    if (dbg_on) g_dbg_buf = dbg_buf;
+  }
   P.M = M; P.N = N; P.K = K; P.a_mn = a_mn; P.b_mn = b_mn; P.ldc = ldc; P.epi = epi;
+  {
+    const int cesz = c_dt == MAGIC_BF16 ? 2 : 4;
+    auto al16 = [](const void* p) { return ((uintptr_t)p & 15) == 0; };
+    bool ok = epi.drop_p == 0.f && al16(C) && (ldc * cesz) % 16 == 0;
+    if (epi.bias) ok = ok && al16(epi.bias);
+    if (epi.pre_out) ok = ok && al16(epi.pre_out);
+    if (epi.residual) ok = ok && al16(epi.residual) && (epi.res_ld * cesz) % 16 == 0;
+    if (epi.dact_pre) ok = ok && al16(epi.dact_pre) && (epi.dact_ld * (epi.dact_dt == MAGIC_BF16 ? 2 : 4)) % 16 == 0;
+    P.fast_epi = ok ? 1 : 0;
+  }
+  // split-K for skinny outputs with a long reduction (weight gradients): fp32 C, purely linear epilogue
+  const int total_kb = (K + BK - 1) / BK;
+  P.kb_per_split = total_kb;
+  const long tiles = (long)((M + BM - 1) / BM) * ((N + BN - 1) / BN);
+  const bool linear_epi = c_dt == MAGIC_F32 && !epi.bias && epi.act == 0 && !epi.pre_out && !epi.dact_pre &&
+                          !epi.residual && epi.drop_p == 0.f && (epi.beta == 0.f || epi.beta == 1.f);
+  if (linear_epi && tiles * 2 <= magic_num_sms() && total_kb >= 8) {
+    int splits = (int)(magic_num_sms() / tiles);
+    if (splits > total_kb / 4) splits = total_kb / 4;
+    if (splits > 1) {
+      P.kb_per_split = (total_kb + splits - 1) / splits;
+      P.epi.atomic = 1;
+      if (epi.beta == 0.f) {
+        if (ldc == N) {
+          MAGIC_CUDA(cudaMemsetAsync(C, 0, (size_t)M * N * sizeof(float), st), "magic_gemm(tc) split-K memset");
+        } else {
+          MAGIC_CUDA(cudaMemset2DAsync(C, (size_t)ldc * sizeof(float), 0, (size_t)N * sizeof(float), (size_t)M, st),
+                     "magic_gemm(tc) split-K memset");
+        }
+      }
+    }
+  }
   typedef __nv_bfloat16 bf;
   if (BN == 64) {
     if (c_dt == MAGIC_BF16) return launch_tc<64, bf>(ta, tb, C, P, st);

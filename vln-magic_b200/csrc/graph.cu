@@ -37,6 +37,7 @@ __global__ void __launch_bounds__(256)
   for (int i = blockIdx.x * 8 + w; i < n_src; i += gridDim.x * 8) {
     const int s = src_ids[i];
     const int e0 = src_ptr[i], e1 = src_ptr[i + 1];
+    if (e1 <= e0) continue;  // padding entry (fixed-capacity tables for CUDA-graph replay)
     for (int c = lane; c < h; c += 32) {
       float a = 0.f;
       for (int e = e0; e < e1; e++) a = fmaf(src_w[e], ldf(dout, (size_t)src_nodes[e] * h + c), a);

@@ -122,7 +122,13 @@ def build_index(batch):
     return idx
 
 
-def pad_batch(batch, n_panos=None, n_masked=None):
+def _pad1(t, n, value=0):
+    if t.numel() >= n:
+        return t
+    return torch.cat([t, torch.full((n - t.numel(),), value, dtype=t.dtype)])
+
+
+def pad_batch(batch, n_panos=None, n_masked=None, n_entries=None, n_sources=None):
     """Pad a prepared CPU batch to fixed capacities so every batch of a task has the same tensor shapes
     (one CUDA graph per task).  Padded panoramas have a single all-zero view and are referenced by no index
     table; padded masked-token rows gather a zero row, carry label -1 (ignored) and are excluded from the
@@ -140,6 +146,20 @@ def pad_batch(batch, n_panos=None, n_masked=None):
                 batch[k] = padr(batch[k])
             batch["traj_vp_view_lens"] = padr(batch["traj_vp_view_lens"], 1)
             ix["key_lens_pano"] = padr(ix["key_lens_pano"], 1)
+    if n_entries is not None:
+        if ix["entries"].numel() > n_entries:
+            raise ValueError("gmap entry capacity too small")
+        ix["entries"] = _pad1(ix["entries"], n_entries)
+        ix["src_nodes"] = _pad1(ix["src_nodes"], n_entries)
+        ix["src_w"] = _pad1(ix["src_w"], n_entries)
+    if n_sources is not None:
+        ns = ix["src_ids"].numel()
+        if ns > n_sources:
+            raise ValueError("gmap source capacity too small")
+        last = int(ix["src_ptr"][-1]) if ix["src_ptr"].numel() else 0
+        ix["src_ids"] = _pad1(ix["src_ids"], n_sources)
+        ix["src_ptr"] = _pad1(ix["src_ptr"], n_sources + 1, last)  # empty ranges -> skipped by the kernel
+        ix["n_src"] = n_sources
     if "mlm_rows" in ix:
         n = ix["mlm_rows"].numel()
         ix["mlm_inv_n"] = torch.tensor([1.0 / max(n, 1)], dtype=torch.float32)
