@@ -169,6 +169,8 @@ def family_cost(name, a):
 def summarise_profile(prof, n_steps, pk):
     fam = {}
     for name, recs in prof.items():
+        if name == "magic_delay":
+            continue
         ms = sum(e0.elapsed_time(e1) for e0, e1, _ in recs)
         fl = by = 0.0
         for _, _, a in recs:

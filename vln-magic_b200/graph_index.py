@@ -108,7 +108,7 @@ def build_index(batch):
         stop_rows_g=torch.arange(B, dtype=torch.int64) * G, stop_rows_v=torch.arange(B, dtype=torch.int64) * Vp,
         key_lens_txt=_cpu(batch["txt_lens"]).to(torch.int32), key_lens_gmap=_cpu(batch["gmap_lens"]).to(torch.int32),
         key_lens_vp=_cpu(batch["vp_lens"]).to(torch.int32), key_lens_pano=_cpu(batch["traj_vp_view_lens"]).to(torch.int32),
-        n_nodes=B * G, n_src=int(len(src_ids)), n_rows=n_rows,
+        n_nodes=B * G, n_src=int(len(src_ids)),
     )
     if "txt_labels" in batch:
         lab = _cpu(batch["txt_labels"])
