@@ -344,6 +344,14 @@ def aggregate_gmap_features(pano_embeds, pano_fused, batch):
     return torch.stack(out, 0)
 
 
+def vp_lens_of(batch):
+    """Number of valid local tokens = views of the LAST step + 1 ([stop]) -- DUET lineage computes this inside
+    the model from traj_vp_view_lens.  NB the reference collate's own batch['vp_lens'] is `len(x[-1])` of a
+    [Vp,14] tensor, i.e. the constant 14 (pretrain_src/data/tasks.py:153); it is not usable as a length."""
+    rows = last_step_rows(batch)
+    return batch["traj_vp_view_lens"][rows] + 1
+
+
 def last_step_rows(batch):
     rows, r = [], 0
     for T in batch["traj_step_lens"]:
@@ -424,7 +432,7 @@ class GlocalTextPathCMT(nn.Module):
         Vp = batch["vp_pos_fts"].shape[1]
         x = torch.cat([torch.zeros_like(last[:, :1]), last], 1)[:, :Vp]
         x = x + self.local_encoder.vp_pos_embeddings(batch["vp_pos_fts"])
-        mask = gen_seq_masks(batch["vp_lens"], Vp)
+        mask = gen_seq_masks(vp_lens_of(batch), Vp)
         return x, mask
 
     def forward(self, batch, mode):
@@ -567,7 +575,7 @@ class GlocalTextPathCMTPreTraining(nn.Module):
         Vp = v.shape[1]
         nav = torch.cat([torch.ones_like(batch["traj_nav_types"][rows][:, :1], dtype=torch.bool),
                          batch["traj_nav_types"][rows] == 1], 1)[:, :Vp]
-        nav = nav & gen_seq_masks(batch["vp_lens"], Vp)
+        nav = nav & gen_seq_masks(vp_lens_of(batch), Vp)
         ll = ll.masked_fill(~nav, float("-inf"))
         fl = fuse_sap_logits(gl, ll, batch)
         return gl, ll, fl

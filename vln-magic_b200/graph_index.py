@@ -25,7 +25,7 @@ def build_index(batch):
     Vp = batch["vp_pos_fts"].shape[1]
     gmap_lens = _cpu(batch["gmap_lens"]).tolist()
     visited_masks = _cpu(batch["gmap_visited_masks"]).numpy().astype(bool)
-    vp_lens = _cpu(batch["vp_lens"]).tolist()
+    view_lens = _cpu(batch["traj_vp_view_lens"])
     nav_types = _cpu(batch["traj_nav_types"]).numpy()
 
     node_ptr, entries = [0], []
@@ -50,6 +50,10 @@ def build_index(batch):
         row0 += T
         last_rows.append(row0 - 1)
     n_rows = row0
+    # valid local tokens = views of the last step + [stop] (DUET lineage; the reference collate's 'vp_lens' key is
+    # the constant 14 = len(x[-1]) of a [Vp,14] tensor, pretrain_src/data/tasks.py:153, and is not a length)
+    vp_lens_t = view_lens[torch.as_tensor(last_rows, dtype=torch.int64)] + 1
+    vp_lens = vp_lens_t.tolist()
 
     # reverse CSR (unique source -> nodes, weights 1/count(node)) for the deterministic backward
     node_of_entry = np.repeat(np.arange(B * G), np.diff(np.asarray(node_ptr)))
@@ -107,7 +111,7 @@ def build_index(batch):
         last_rows=torch.from_numpy(np.asarray(last_rows, dtype=np.int64)),
         stop_rows_g=torch.arange(B, dtype=torch.int64) * G, stop_rows_v=torch.arange(B, dtype=torch.int64) * Vp,
         key_lens_txt=_cpu(batch["txt_lens"]).to(torch.int32), key_lens_gmap=_cpu(batch["gmap_lens"]).to(torch.int32),
-        key_lens_vp=_cpu(batch["vp_lens"]).to(torch.int32), key_lens_pano=_cpu(batch["traj_vp_view_lens"]).to(torch.int32),
+        key_lens_vp=vp_lens_t.to(torch.int32), key_lens_pano=_cpu(batch["traj_vp_view_lens"]).to(torch.int32),
         n_nodes=B * G, n_src=int(len(src_ids)),
     )
     if "txt_labels" in batch:

@@ -205,7 +205,9 @@ def collate(samples):
     for i, x in enumerate(batch["gmap_pair_dists"]):
         d[i, :x.shape[0], :x.shape[1]] = x
     batch["gmap_pair_dists"] = d
-    batch["vp_lens"] = torch.LongTensor([len(x) for x in batch["vp_pos_fts"]])
+    # literal reference behaviour (tasks.py:153): len(x[-1]) of a [Vp,14] tensor == 14; models derive the real
+    # local length from traj_vp_view_lens (see graph_index.build_index)
+    batch["vp_lens"] = torch.LongTensor([len(x[-1]) for x in batch["vp_pos_fts"]])
     batch["vp_pos_fts"] = pad_tensors(batch["vp_pos_fts"])
     if "global_act_labels" in batch:
         batch["local_act_labels"] = torch.LongTensor(batch["local_act_labels"])
