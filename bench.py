@@ -284,13 +284,10 @@ def run_ours(args):
     from magic_b200.graph_index import batch_to_device
     from magic_b200.train_step import PretrainStepper
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
+    from magic_b200.parallel import init_distributed
+    rank, world, local = init_distributed()
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
     w = WORKLOADS[args.workload]
     pk = peaks()
     cfg_s, cfg_t = make_cfgs(w, args.dropout)

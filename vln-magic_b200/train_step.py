@@ -12,6 +12,7 @@ from . import _lib, makd, ops
 from .graph_index import INDEX_KEY
 from .optim import FusedAdamW
 from .arena import ParamArena
+from .parallel import FlatAllReduce, broadcast_flat
 
 
 class PretrainStepper:
@@ -31,10 +32,20 @@ class PretrainStepper:
         self.rw_generator = rw_generator
         self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
         self.device = self.arena.device
+        self.allreduce = FlatAllReduce(self.arena.flat_g) if self.world > 1 else None
+        if self.world > 1:
+            broadcast_flat(self.arena.flat_p, 0)  # DDP's wrap-time parameter broadcast (utils/misc.py:63-66)
+            self.arena.refresh_lowp()
         self.launches_per_step = None
 
     # -- the device side of one step -------------------------------------------------------------
-    def _device_step(self, task, batch, rw):
+    def _finish(self):
+        """Gradient exchange + optimizer (kept outside the captured graph when world > 1)."""
+        if self.allreduce is not None:
+            self.allreduce()
+        self.opt.apply()
+
+    def _device_step(self, task, batch, rw, finish=True):
         self.arena.zero_grad()
         if self.teacher is not None:
             mix, res, s_out, t_out = makd.distill_step_loss(self.student, self.teacher, batch, task, rw, self.kdl)
@@ -42,9 +53,8 @@ class PretrainStepper:
             s_out = self.student(batch, task, True)
             mix = ops.loss_mix(None, None, s_out["loss"], 0.0, s_out.get("loss_inv_n"))
         mix[0].backward()
-        if self.world > 1:
-            dist.all_reduce(self.arena.flat_g, op=dist.ReduceOp.AVG)
-        self.opt.apply()
+        if finish:
+            self._finish()
         return mix
 
     def step(self, task, batch, lr=None):
@@ -96,7 +106,9 @@ class PretrainStepper:
             snap = (self.arena.flat_p.clone(), self.opt.m.clone(), self.opt.v.clone())
             with torch.cuda.stream(s):
                 for _ in range(2):
-                    self._device_step(task, static, rw)
+                    self._device_step(task, static, rw, finish=self.world == 1)
+                    if self.world > 1:
+                        self.opt.apply()
                 self.arena.flat_p.copy_(snap[0])
                 self.opt.m.copy_(snap[1])
                 self.opt.v.copy_(snap[2])
@@ -105,11 +117,13 @@ class PretrainStepper:
             g = torch.cuda.CUDAGraph()
             n0 = _lib.COUNTERS["launches"]
             with torch.cuda.graph(g):
-                out = self._device_step(task, static, rw)
+                out = self._device_step(task, static, rw, finish=self.world == 1)
             entry = (g, static, out, _lib.COUNTERS["launches"] - n0)
             self.graphs[sig] = entry
         g, static, out, n_launch = entry
         self._copy_into(static, batch)
         g.replay()
         _lib.COUNTERS["launches"] += n_launch  # kernels replayed inside the graph
+        if self.world > 1:
+            self._finish()
         return out
