@@ -312,9 +312,14 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def run_steps(n, first, from_host):
+    def run_steps(n, first, from_host, delay_cycles=0):
         out = None
         for i in range(first, first + n):
+            if delay_cycles:
+                # keep the GPU busy while the host queues this step's launches, so per-call CUDA events bracket
+                # back-to-back device execution rather than host launch latency
+                _lib.COUNTERS["launches"] -= 1
+                _lib.call("magic_delay", int(delay_cycles), _lib.stream())
             task = "mlm" if i % 2 == 0 else "sap"
             j = (i // 2) % pool_n
             if from_host and stepper.use_graphs:
@@ -371,10 +376,7 @@ def run_ours(args):
         torch.cuda.synchronize()
         _lib.profile_start()
         nprof = 4
-        # keep the GPU busy while the host queues the first launches, so the per-call CUDA events bracket
-        # back-to-back device execution rather than host launch latency
-        _lib.call("magic_delay", int(40e6), _lib.stream())
-        run_steps(nprof, 100, False)
+        run_steps(nprof, 100, False, delay_cycles=60e6)
         torch.cuda.synchronize()
         roof, fams = summarise_profile(_lib.profile_stop(), nprof, pk)
         stepper.use_graphs = g

@@ -169,8 +169,8 @@ __device__ __forceinline__ void rt_row32(float (&v)[32]) {
 }
 
 template <typename TC, int ACT>
-__device__ __forceinline__ void epi_fast_chunk(const GemmEpi& epi, TC* C, const uint32_t (&r)[32], int m, int nb,
-                                               long ldc) {
+__device__ __forceinline__ void epi_fast_chunk(const GemmEpi& epi, const Dropout& dr, TC* C, const uint32_t (&r)[32],
+                                               int m, int nb, long ldc) {
   float v[32];
 #pragma unroll
   for (int j = 0; j < 32; j++) v[j] = epi.alpha * __uint_as_float(r[j]);
@@ -182,6 +182,10 @@ __device__ __forceinline__ void epi_fast_chunk(const GemmEpi& epi, TC* C, const 
     else ld_row32((const float*)epi.dact_pre + poff, pre);
 #pragma unroll
     for (int j = 0; j < 32; j++) v[j] *= act_bwd(ACT, pre[j]);
+    if (dr.p > 0.f) {
+#pragma unroll
+      for (int j = 0; j < 32; j++) v[j] *= dr.scale(poff + j);
+    }
   } else {
     if (epi.bias) {
       float b[32];
@@ -196,6 +200,10 @@ __device__ __forceinline__ void epi_fast_chunk(const GemmEpi& epi, TC* C, const 
     if (ACT != 0) {
 #pragma unroll
       for (int j = 0; j < 32; j++) v[j] = act_fwd(ACT, v[j]);
+    }
+    if (dr.p > 0.f) {
+#pragma unroll
+      for (int j = 0; j < 32; j++) v[j] *= dr.scale(off + j);
     }
     if (epi.residual) {
       float rs[32];
@@ -342,9 +350,9 @@ __global__ void __launch_bounds__(NTHREADS, 1)
       if (P.fast_epi && n0 + c0 + 32 <= P.N) {  // warp-uniform
         const int m = m0 + q * 32 + lane;
         if (m < P.M) {
-          if (P.epi.act == MAGIC_ACT_GELU) epi_fast_chunk<TC, MAGIC_ACT_GELU>(P.epi, C, r, m, n0 + c0, P.ldc);
-          else if (P.epi.act == MAGIC_ACT_RELU) epi_fast_chunk<TC, MAGIC_ACT_RELU>(P.epi, C, r, m, n0 + c0, P.ldc);
-          else epi_fast_chunk<TC, MAGIC_ACT_NONE>(P.epi, C, r, m, n0 + c0, P.ldc);
+          if (P.epi.act == MAGIC_ACT_GELU) epi_fast_chunk<TC, MAGIC_ACT_GELU>(P.epi, dr, C, r, m, n0 + c0, P.ldc);
+          else if (P.epi.act == MAGIC_ACT_RELU) epi_fast_chunk<TC, MAGIC_ACT_RELU>(P.epi, dr, C, r, m, n0 + c0, P.ldc);
+          else epi_fast_chunk<TC, MAGIC_ACT_NONE>(P.epi, dr, C, r, m, n0 + c0, P.ldc);
         }
         continue;
       }
@@ -525,7 +533,7 @@ int gemm_tc_dispatch(const void* A, const void* B, void* C, int c_dt, int M, int
   {
     const int cesz = c_dt == MAGIC_BF16 ? 2 : 4;
     auto al16 = [](const void* p) { return ((uintptr_t)p & 15) == 0; };
-    bool ok = epi.drop_p == 0.f && al16(C) && (ldc * cesz) % 16 == 0;
+    bool ok = al16(C) && (ldc * cesz) % 16 == 0;
     if (epi.bias) ok = ok && al16(epi.bias);
     if (epi.pre_out) ok = ok && al16(epi.pre_out);
     if (epi.residual) ok = ok && al16(epi.residual) && (epi.res_ld * cesz) % 16 == 0;

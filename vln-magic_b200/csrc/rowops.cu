@@ -18,16 +18,17 @@ __host__ int row_grid(int M) {
 }
 
 // ---- LayerNorm math on a register-resident row ------------------------------------------------
-__device__ __forceinline__ void row_stats(const float (&v)[MAXE], int h, int lane, float eps, float& mean,
+template <int NE>
+__device__ __forceinline__ void row_stats(const float (&v)[NE], int h, int lane, float eps, float& mean,
                                           float& rstd) {
   float s = 0.f;
 #pragma unroll
-  for (int i = 0; i < MAXE; i++)
+  for (int i = 0; i < NE; i++)
     if (lane + 32 * i < h) s += v[i];
   mean = warp_sum(s) / (float)h;
   float q = 0.f;
 #pragma unroll
-  for (int i = 0; i < MAXE; i++)
+  for (int i = 0; i < NE; i++)
     if (lane + 32 * i < h) {
       const float d = v[i] - mean;
       q += d * d;
@@ -36,10 +37,11 @@ __device__ __forceinline__ void row_stats(const float (&v)[MAXE], int h, int lan
 }
 
 // given xhat (in v) and dxhat = g*gamma (in d): dv = rstd * (dxhat - mean(dxhat) - xhat * mean(dxhat*xhat))
-__device__ __forceinline__ void ln_bwd_row(const float (&xhat)[MAXE], float (&d)[MAXE], int h, int lane, float rstd) {
+template <int NE>
+__device__ __forceinline__ void ln_bwd_row(const float (&xhat)[NE], float (&d)[NE], int h, int lane, float rstd) {
   float c1 = 0.f, c2 = 0.f;
 #pragma unroll
-  for (int i = 0; i < MAXE; i++)
+  for (int i = 0; i < NE; i++)
     if (lane + 32 * i < h) {
       c1 += d[i];
       c2 += d[i] * xhat[i];
@@ -47,7 +49,7 @@ __device__ __forceinline__ void ln_bwd_row(const float (&xhat)[MAXE], float (&d)
   c1 = warp_sum(c1) / (float)h;
   c2 = warp_sum(c2) / (float)h;
 #pragma unroll
-  for (int i = 0; i < MAXE; i++)
+  for (int i = 0; i < NE; i++)
     if (lane + 32 * i < h) d[i] = rstd * (d[i] - c1 - xhat[i] * c2);
 }
 
@@ -63,7 +65,7 @@ __device__ __forceinline__ void flush_cols(float* smem_acc, float* gout, int h) 
 // =================================================================================================
 // LayerNorm forward:  y = drop_out( LN( drop_in(x) + res ) * gamma + beta )
 // =================================================================================================
-template <typename T>
+template <typename T, int NE>
 __global__ void __launch_bounds__(ROW_WARPS * 32)
     ln_fwd_kernel(const T* __restrict__ x, const T* __restrict__ res, const float* __restrict__ gamma,
                   const float* __restrict__ beta, T* __restrict__ y, float* __restrict__ stats, int M, int h,
@@ -73,9 +75,9 @@ __global__ void __launch_bounds__(ROW_WARPS * 32)
   const Dropout din = make_dropout(p_in, seed_ptr, salt_in), dout = make_dropout(p_out, seed_ptr, salt_out);
   for (int r = blockIdx.x * ROW_WARPS + w; r < M; r += gridDim.x * ROW_WARPS) {
     const size_t base = (size_t)r * h;
-    float v[MAXE];
+    float v[NE];
 #pragma unroll
-    for (int i = 0; i < MAXE; i++) {
+    for (int i = 0; i < NE; i++) {
       const int c = lane + 32 * i;
       v[i] = 0.f;
       if (c < h) {
@@ -87,7 +89,7 @@ __global__ void __launch_bounds__(ROW_WARPS * 32)
     float mean, rstd;
     row_stats(v, h, lane, eps, mean, rstd);
 #pragma unroll
-    for (int i = 0; i < MAXE; i++) {
+    for (int i = 0; i < NE; i++) {
       const int c = lane + 32 * i;
       if (c < h) stf(y, base + c, ((v[i] - mean) * rstd * gamma[c] + beta[c]) * dout.scale(base + c));
     }
@@ -98,7 +100,7 @@ __global__ void __launch_bounds__(ROW_WARPS * 32)
   }
 }
 
-template <typename T>
+template <typename T, int NE>
 __global__ void __launch_bounds__(ROW_WARPS * 32)
     ln_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T* __restrict__ res,
                   const float* __restrict__ gamma, const float* __restrict__ stats, T* __restrict__ dx,
@@ -110,15 +112,15 @@ __global__ void __launch_bounds__(ROW_WARPS * 32)
   for (int c = threadIdx.x; c < 2 * h; c += blockDim.x) sm[c] = 0.f;
   __syncthreads();
   const Dropout din = make_dropout(p_in, seed_ptr, salt_in), dout = make_dropout(p_out, seed_ptr, salt_out);
-  float pg[MAXE], pb[MAXE];
+  float pg[NE], pb[NE];
 #pragma unroll
-  for (int i = 0; i < MAXE; i++) pg[i] = pb[i] = 0.f;
+  for (int i = 0; i < NE; i++) pg[i] = pb[i] = 0.f;
   for (int r = blockIdx.x * ROW_WARPS + w; r < M; r += gridDim.x * ROW_WARPS) {
     const size_t base = (size_t)r * h;
     const float mean = stats[2 * r], rstd = stats[2 * r + 1];
-    float xh[MAXE], d[MAXE];
+    float xh[NE], d[NE];
 #pragma unroll
-    for (int i = 0; i < MAXE; i++) {
+    for (int i = 0; i < NE; i++) {
       const int c = lane + 32 * i;
       xh[i] = d[i] = 0.f;
       if (c < h) {
@@ -133,7 +135,7 @@ __global__ void __launch_bounds__(ROW_WARPS * 32)
     }
     ln_bwd_row(xh, d, h, lane, rstd);
 #pragma unroll
-    for (int i = 0; i < MAXE; i++) {
+    for (int i = 0; i < NE; i++) {
       const int c = lane + 32 * i;
       if (c < h) {
         if (dres) stf(dres, base + c, d[i]);
@@ -142,7 +144,7 @@ __global__ void __launch_bounds__(ROW_WARPS * 32)
     }
   }
 #pragma unroll
-  for (int i = 0; i < MAXE; i++) {
+  for (int i = 0; i < NE; i++) {
     const int c = lane + 32 * i;
     if (c < h) {
       atomicAdd(&sm[c], pg[i]);
@@ -159,7 +161,7 @@ __global__ void __launch_bounds__(ROW_WARPS * 32)
 // =================================================================================================
 // text embedding + LayerNorm:  y[r] = drop_out( LN(word[ids[r]] + pos[r % L] + type0) )
 // =================================================================================================
-template <typename T>
+template <typename T, int NE>
 __global__ void __launch_bounds__(ROW_WARPS * 32)
     embed_ln_fwd_kernel(const long long* __restrict__ ids, const float* __restrict__ word,
                         const float* __restrict__ pos, const float* __restrict__ type0,
@@ -171,16 +173,16 @@ __global__ void __launch_bounds__(ROW_WARPS * 32)
   for (int r = blockIdx.x * ROW_WARPS + w; r < M; r += gridDim.x * ROW_WARPS) {
     const size_t base = (size_t)r * h;
     const size_t wb = (size_t)ids[r] * h, pb = (size_t)(r % L) * h;
-    float v[MAXE];
+    float v[NE];
 #pragma unroll
-    for (int i = 0; i < MAXE; i++) {
+    for (int i = 0; i < NE; i++) {
       const int c = lane + 32 * i;
       v[i] = (c < h) ? (word[wb + c] + pos[pb + c] + type0[c]) : 0.f;
     }
     float mean, rstd;
     row_stats(v, h, lane, eps, mean, rstd);
 #pragma unroll
-    for (int i = 0; i < MAXE; i++) {
+    for (int i = 0; i < NE; i++) {
       const int c = lane + 32 * i;
       if (c < h) stf(y, base + c, ((v[i] - mean) * rstd * gamma[c] + beta[c]) * dout.scale(base + c));
     }
@@ -191,7 +193,7 @@ __global__ void __launch_bounds__(ROW_WARPS * 32)
   }
 }
 
-template <typename T>
+template <typename T, int NE>
 __global__ void __launch_bounds__(ROW_WARPS * 32)
     embed_ln_bwd_kernel(const T* __restrict__ dy, const long long* __restrict__ ids, const float* __restrict__ word,
                         const float* __restrict__ pos, const float* __restrict__ type0,
@@ -204,16 +206,16 @@ __global__ void __launch_bounds__(ROW_WARPS * 32)
   for (int c = threadIdx.x; c < 3 * h; c += blockDim.x) sm[c] = 0.f;
   __syncthreads();
   const Dropout dout = make_dropout(p_out, seed_ptr, salt_out);
-  float pg[MAXE], pbt[MAXE], pt[MAXE];
+  float pg[NE], pbt[NE], pt[NE];
 #pragma unroll
-  for (int i = 0; i < MAXE; i++) pg[i] = pbt[i] = pt[i] = 0.f;
+  for (int i = 0; i < NE; i++) pg[i] = pbt[i] = pt[i] = 0.f;
   for (int r = blockIdx.x * ROW_WARPS + w; r < M; r += gridDim.x * ROW_WARPS) {
     const size_t base = (size_t)r * h;
     const size_t wb = (size_t)ids[r] * h, pb = (size_t)(r % L) * h;
     const float mean = stats[2 * r], rstd = stats[2 * r + 1];
-    float xh[MAXE], d[MAXE];
+    float xh[NE], d[NE];
 #pragma unroll
-    for (int i = 0; i < MAXE; i++) {
+    for (int i = 0; i < NE; i++) {
       const int c = lane + 32 * i;
       xh[i] = d[i] = 0.f;
       if (c < h) {
@@ -226,7 +228,7 @@ __global__ void __launch_bounds__(ROW_WARPS * 32)
     }
     ln_bwd_row(xh, d, h, lane, rstd);
 #pragma unroll
-    for (int i = 0; i < MAXE; i++) {
+    for (int i = 0; i < NE; i++) {
       const int c = lane + 32 * i;
       if (c < h) {
         atomicAdd(dword + wb + c, d[i]);
@@ -236,7 +238,7 @@ __global__ void __launch_bounds__(ROW_WARPS * 32)
     }
   }
 #pragma unroll
-  for (int i = 0; i < MAXE; i++) {
+  for (int i = 0; i < NE; i++) {
     const int c = lane + 32 * i;
     if (c < h) {
       atomicAdd(&sm[c], pg[i]);
@@ -257,7 +259,7 @@ __global__ void __launch_bounds__(ROW_WARPS * 32)
 // =================================================================================================
 constexpr int MAXK = 16;
 
-template <typename T>
+template <typename T, int NE>
 __global__ void __launch_bounds__(ROW_WARPS * 32)
     posfuse_fwd_kernel(const T* __restrict__ xin, const long long* __restrict__ idx, const float* __restrict__ emb,
                        const float* __restrict__ cst, const float* __restrict__ f, const float* __restrict__ W,
@@ -269,9 +271,9 @@ __global__ void __launch_bounds__(ROW_WARPS * 32)
     float fr[MAXK];
 #pragma unroll
     for (int k = 0; k < MAXK; k++) fr[k] = (k < K) ? f[(size_t)r * K + k] : 0.f;
-    float v[MAXE];
+    float v[NE];
 #pragma unroll
-    for (int i = 0; i < MAXE; i++) {
+    for (int i = 0; i < NE; i++) {
       const int c = lane + 32 * i;
       v[i] = 0.f;
       if (c < h) {
@@ -286,7 +288,7 @@ __global__ void __launch_bounds__(ROW_WARPS * 32)
     row_stats(v, h, lane, eps, mean, rstd);
     const size_t eb = idx ? (size_t)idx[r] * h : 0;
 #pragma unroll
-    for (int i = 0; i < MAXE; i++) {
+    for (int i = 0; i < NE; i++) {
       const int c = lane + 32 * i;
       if (c < h) {
         float o = (v[i] - mean) * rstd * gamma[c] + beta[c];
@@ -304,7 +306,7 @@ __global__ void __launch_bounds__(ROW_WARPS * 32)
 }
 
 // backward: dxin == dy (handled by the caller).  smem: [h*K] dW | [h] db | [h] dgamma | [h] dbeta | [h] dcst
-template <typename T>
+template <typename T, int NE>
 __global__ void __launch_bounds__(ROW_WARPS * 32)
     posfuse_bwd_kernel(const T* __restrict__ dy, const long long* __restrict__ idx, const float* __restrict__ f,
                        const float* __restrict__ W, const float* __restrict__ b, const float* __restrict__ gamma,
@@ -321,9 +323,9 @@ __global__ void __launch_bounds__(ROW_WARPS * 32)
   for (int c = threadIdx.x; c < tot; c += blockDim.x) sm[c] = 0.f;
   __syncthreads();
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  float pg[MAXE], pbt[MAXE], pdb[MAXE];
+  float pg[NE], pbt[NE], pdb[NE];
 #pragma unroll
-  for (int i = 0; i < MAXE; i++) pg[i] = pbt[i] = pdb[i] = 0.f;
+  for (int i = 0; i < NE; i++) pg[i] = pbt[i] = pdb[i] = 0.f;
   for (int r = blockIdx.x * ROW_WARPS + w; r < M; r += gridDim.x * ROW_WARPS) {
     const size_t base = (size_t)r * h;
     float fr[MAXK];
@@ -331,9 +333,9 @@ __global__ void __launch_bounds__(ROW_WARPS * 32)
     for (int k = 0; k < MAXK; k++) fr[k] = (k < K) ? f[(size_t)r * K + k] : 0.f;
     const float mean = stats[2 * r], rstd = stats[2 * r + 1];
     const size_t eb = idx ? (size_t)idx[r] * h : 0;
-    float xh[MAXE], d[MAXE];
+    float xh[NE], d[NE];
 #pragma unroll
-    for (int i = 0; i < MAXE; i++) {
+    for (int i = 0; i < NE; i++) {
       const int c = lane + 32 * i;
       xh[i] = d[i] = 0.f;
       if (c < h) {
@@ -351,7 +353,7 @@ __global__ void __launch_bounds__(ROW_WARPS * 32)
     }
     ln_bwd_row(xh, d, h, lane, rstd);
 #pragma unroll
-    for (int i = 0; i < MAXE; i++) {
+    for (int i = 0; i < NE; i++) {
       const int c = lane + 32 * i;
       if (c < h) {
         pdb[i] += d[i];
@@ -362,7 +364,7 @@ __global__ void __launch_bounds__(ROW_WARPS * 32)
     }
   }
 #pragma unroll
-  for (int i = 0; i < MAXE; i++) {
+  for (int i = 0; i < NE; i++) {
     const int c = lane + 32 * i;
     if (c < h) {
       atomicAdd(&s_dg[c], pg[i]);
@@ -528,7 +530,7 @@ __global__ void __launch_bounds__(ROW_WARPS * 32)
     if (lane == 0) y[r] = a + (bias ? bias[0] : 0.f);
   }
 }
-template <typename T>
+template <typename T, int NE>
 __global__ void __launch_bounds__(ROW_WARPS * 32)
     rowdot_bwd_kernel(const float* __restrict__ dy, const T* __restrict__ x, const float* __restrict__ wv,
                       T* __restrict__ dx, float* __restrict__ dw, float* __restrict__ dbias, int M, int h) {
@@ -536,15 +538,15 @@ __global__ void __launch_bounds__(ROW_WARPS * 32)
   for (int c = threadIdx.x; c < h + 1; c += blockDim.x) sm[c] = 0.f;
   __syncthreads();
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  float pw[MAXE];
+  float pw[NE];
 #pragma unroll
-  for (int i = 0; i < MAXE; i++) pw[i] = 0.f;
+  for (int i = 0; i < NE; i++) pw[i] = 0.f;
   float pb = 0.f;
   for (int r = blockIdx.x * ROW_WARPS + w; r < M; r += gridDim.x * ROW_WARPS) {
     const float g = dy[r];
     pb += g;
 #pragma unroll
-    for (int i = 0; i < MAXE; i++) {
+    for (int i = 0; i < NE; i++) {
       const int c = lane + 32 * i;
       if (c < h) {
         pw[i] = fmaf(g, ldf(x, (size_t)r * h + c), pw[i]);
@@ -553,7 +555,7 @@ __global__ void __launch_bounds__(ROW_WARPS * 32)
     }
   }
 #pragma unroll
-  for (int i = 0; i < MAXE; i++) {
+  for (int i = 0; i < NE; i++) {
     const int c = lane + 32 * i;
     if (c < h) atomicAdd(&sm[c], pw[i]);
   }
@@ -669,6 +671,36 @@ __global__ void __launch_bounds__(256) invert_norm_kernel(const float* __restric
     return MAGIC_ERR_ARG;                                      \
   }
 
+#define DISPATCH_NE(h, ...)            \
+  if ((h) <= 64) {                     \
+    constexpr int NE = 2;              \
+    __VA_ARGS__;                       \
+  } else if ((h) <= 128) {             \
+    constexpr int NE = 4;              \
+    __VA_ARGS__;                       \
+  } else if ((h) <= 256) {             \
+    constexpr int NE = 8;              \
+    __VA_ARGS__;                       \
+  } else if ((h) <= 384) {             \
+    constexpr int NE = 12;             \
+    __VA_ARGS__;                       \
+  } else {                             \
+    constexpr int NE = 24;             \
+    __VA_ARGS__;                       \
+  }
+
+template <typename T, int NE>
+int launch_posfuse_bwd(int grid, size_t smem, cudaStream_t st, const void* dy, const long long* idx, const float* f,
+                       const float* W, const float* b, const float* gamma, const float* stats, float* demb,
+                       float* dcst, float* dW, float* db, float* dgamma, float* dbeta, int M, int h, int K) {
+  if (smem > 48 * 1024)
+    MAGIC_CUDA(cudaFuncSetAttribute(posfuse_bwd_kernel<T, NE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+               "magic_posfuse_bwd");
+  posfuse_bwd_kernel<T, NE><<<grid, ROW_WARPS * 32, smem, st>>>((const T*)dy, idx, f, W, b, gamma, stats, demb, dcst, dW,
+                                                                 db, dgamma, dbeta, M, h, K);
+  return MAGIC_OK;
+}
+
 extern "C" {
 
 int magic_ln_fwd(const void* x, const void* res, const float* gamma, const float* beta, void* y, float* stats,
@@ -676,9 +708,9 @@ int magic_ln_fwd(const void* x, const void* res, const float* gamma, const float
                  const unsigned long long* seed_ptr, cudaStream_t st) {
   MAGIC_CHECK_ARG(h > 0 && h <= MAXE * 32, "magic_ln_fwd: hidden size %d unsupported (max %d)", h, MAXE * 32);
   if (M <= 0) return MAGIC_OK;
-  DISPATCH_T(dtype, (ln_fwd_kernel<T><<<row_grid(M), ROW_WARPS * 32, 0, st>>>(
+  DISPATCH_T(dtype, DISPATCH_NE(h, (ln_fwd_kernel<T, NE><<<row_grid(M), ROW_WARPS * 32, 0, st>>>(
                         (const T*)x, (const T*)res, gamma, beta, (T*)y, stats, M, h, eps, p_in, salt_in, p_out,
-                        salt_out, seed_ptr)));
+                        salt_out, seed_ptr))));
   MAGIC_CHECK_LAUNCH("magic_ln_fwd");
   return MAGIC_OK;
 }
@@ -689,9 +721,9 @@ int magic_ln_bwd(const void* dy, const void* x, const void* res, const float* ga
   MAGIC_CHECK_ARG(h > 0 && h <= MAXE * 32, "magic_ln_bwd: hidden size %d unsupported", h);
   if (M <= 0) return MAGIC_OK;
   const size_t smem = 2 * (size_t)h * sizeof(float);
-  DISPATCH_T(dtype, (ln_bwd_kernel<T><<<row_grid(M), ROW_WARPS * 32, smem, st>>>(
+  DISPATCH_T(dtype, DISPATCH_NE(h, (ln_bwd_kernel<T, NE><<<row_grid(M), ROW_WARPS * 32, smem, st>>>(
                         (const T*)dy, (const T*)x, (const T*)res, gamma, stats, (T*)dx, (T*)dres, dgamma, dbeta, M, h,
-                        p_in, salt_in, p_out, salt_out, seed_ptr)));
+                        p_in, salt_in, p_out, salt_out, seed_ptr))));
   MAGIC_CHECK_LAUNCH("magic_ln_bwd");
   return MAGIC_OK;
 }
@@ -702,8 +734,8 @@ int magic_embed_ln_fwd(const long long* ids, const float* word, const float* pos
                        cudaStream_t st) {
   MAGIC_CHECK_ARG(h > 0 && h <= MAXE * 32, "magic_embed_ln_fwd: hidden size %d unsupported", h);
   if (M <= 0) return MAGIC_OK;
-  DISPATCH_T(dtype, (embed_ln_fwd_kernel<T><<<row_grid(M), ROW_WARPS * 32, 0, st>>>(
-                        ids, word, pos, type0, gamma, beta, (T*)y, stats, M, L, h, eps, p_out, salt_out, seed_ptr)));
+  DISPATCH_T(dtype, DISPATCH_NE(h, (embed_ln_fwd_kernel<T, NE><<<row_grid(M), ROW_WARPS * 32, 0, st>>>(
+                        ids, word, pos, type0, gamma, beta, (T*)y, stats, M, L, h, eps, p_out, salt_out, seed_ptr))));
   MAGIC_CHECK_LAUNCH("magic_embed_ln_fwd");
   return MAGIC_OK;
 }
@@ -715,9 +747,9 @@ int magic_embed_ln_bwd(const void* dy, const long long* ids, const float* word, 
   MAGIC_CHECK_ARG(h > 0 && h <= MAXE * 32, "magic_embed_ln_bwd: hidden size %d unsupported", h);
   if (M <= 0) return MAGIC_OK;
   const size_t smem = 3 * (size_t)h * sizeof(float);
-  DISPATCH_T(dtype, (embed_ln_bwd_kernel<T><<<row_grid(M), ROW_WARPS * 32, smem, st>>>(
+  DISPATCH_T(dtype, DISPATCH_NE(h, (embed_ln_bwd_kernel<T, NE><<<row_grid(M), ROW_WARPS * 32, smem, st>>>(
                         (const T*)dy, ids, word, pos, type0, gamma, stats, dword, dpos, dtype0, dgamma, dbeta, M, L, h,
-                        p_out, salt_out, seed_ptr)));
+                        p_out, salt_out, seed_ptr))));
   MAGIC_CHECK_LAUNCH("magic_embed_ln_bwd");
   return MAGIC_OK;
 }
@@ -727,8 +759,8 @@ int magic_posfuse_fwd(const void* xin, const long long* idx, const float* emb, c
                       int M, int h, int K, float eps, int dtype, cudaStream_t st) {
   MAGIC_CHECK_ARG(h > 0 && h <= MAXE * 32 && K > 0 && K <= MAXK, "magic_posfuse_fwd: h=%d K=%d unsupported", h, K);
   if (M <= 0) return MAGIC_OK;
-  DISPATCH_T(dtype, (posfuse_fwd_kernel<T><<<row_grid(M), ROW_WARPS * 32, 0, st>>>(
-                        (const T*)xin, idx, emb, cst, f, W, b, gamma, beta, (T*)y, stats, M, h, K, eps)));
+  DISPATCH_T(dtype, DISPATCH_NE(h, (posfuse_fwd_kernel<T, NE><<<row_grid(M), ROW_WARPS * 32, 0, st>>>(
+                        (const T*)xin, idx, emb, cst, f, W, b, gamma, beta, (T*)y, stats, M, h, K, eps))));
   MAGIC_CHECK_LAUNCH("magic_posfuse_fwd");
   return MAGIC_OK;
 }
@@ -741,22 +773,10 @@ int magic_posfuse_bwd(const void* dy, const long long* idx, const float* f, cons
   const size_t smem = ((size_t)h * K + 4 * (size_t)h) * sizeof(float);
   int grid = row_grid(M);
   if (grid > magic_num_sms()) grid = magic_num_sms();
-  if (dtype == MAGIC_F32) {
-    if (smem > 48 * 1024)
-      MAGIC_CUDA(cudaFuncSetAttribute(posfuse_bwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)smem), "magic_posfuse_bwd");
-    posfuse_bwd_kernel<float><<<grid, ROW_WARPS * 32, smem, st>>>((const float*)dy, idx, f, W, b, gamma, stats, demb,
-                                                                  dcst, dW, db, dgamma, dbeta, M, h, K);
-  } else if (dtype == MAGIC_BF16) {
-    if (smem > 48 * 1024)
-      MAGIC_CUDA(cudaFuncSetAttribute(posfuse_bwd_kernel<__nv_bfloat16>,
-                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "magic_posfuse_bwd");
-    posfuse_bwd_kernel<__nv_bfloat16><<<grid, ROW_WARPS * 32, smem, st>>>(
-        (const __nv_bfloat16*)dy, idx, f, W, b, gamma, stats, demb, dcst, dW, db, dgamma, dbeta, M, h, K);
-  } else {
-    magic_set_error("magic_posfuse_bwd: bad dtype");
-    return MAGIC_ERR_ARG;
-  }
+  int rc = MAGIC_OK;
+  DISPATCH_T(dtype, DISPATCH_NE(h, (rc = launch_posfuse_bwd<T, NE>(grid, smem, st, dy, idx, f, W, b, gamma, stats, demb,
+                                                                  dcst, dW, db, dgamma, dbeta, M, h, K))));
+  if (rc) return rc;
   MAGIC_CHECK_LAUNCH("magic_posfuse_bwd");
   return MAGIC_OK;
 }
@@ -811,8 +831,8 @@ int magic_rowdot_bwd(const float* dy, const void* x, const float* w, void* dx, f
   MAGIC_CHECK_ARG(h > 0 && h <= MAXE * 32, "magic_rowdot_bwd: hidden size %d unsupported", h);
   if (M <= 0) return MAGIC_OK;
   const size_t smem = ((size_t)h + 1) * sizeof(float);
-  DISPATCH_T(dtype, (rowdot_bwd_kernel<T><<<row_grid(M), ROW_WARPS * 32, smem, st>>>(dy, (const T*)x, w, (T*)dx, dw,
-                                                                                   dbias, M, h)));
+  DISPATCH_T(dtype, DISPATCH_NE(h, (rowdot_bwd_kernel<T, NE><<<row_grid(M), ROW_WARPS * 32, smem, st>>>(dy, (const T*)x, w, (T*)dx, dw,
+                                                                                   dbias, M, h))));
   MAGIC_CHECK_LAUNCH("magic_rowdot_bwd");
   return MAGIC_OK;
 }
