@@ -6,7 +6,7 @@ import magic_b200
 from magic_b200 import ops, _lib
 
 dev = "cuda"
-shapes = [(1280, 128, 128), (5120, 128, 128), (5120, 512, 128), (5120, 128, 512), (11520, 128, 768), (8192, 8192, 8192)]
+shapes = [(1280, 128, 128), (5120, 128, 128), (5120, 384, 128), (5120, 512, 128), (5120, 128, 512), (11520, 128, 768), (768, 50265, 128), (5120, 768, 768), (5120, 2304, 768), (5120, 3072, 768), (5120, 768, 3072), (8192, 8192, 8192)]
 reps = int(sys.argv[1]) if len(sys.argv) > 1 else 20
 for (M, N, K) in shapes:
     x = torch.randn(M, K, device=dev).bfloat16()
@@ -26,6 +26,16 @@ for (M, N, K) in shapes:
     ref = torch.nn.functional.linear(x.float(), w.float(), b)
     err = ((out.float() - ref).norm() / ref.norm()).item()
     print(f"fwd  {M}x{N}x{K}: {us:8.1f} us  {2.0*M*N*K/us/1e6:8.2f} TFLOP/s  rel_err {err:.2e}")
+    bb = b.bfloat16()
+    for _ in range(3):
+        torch.nn.functional.linear(x, w, bb)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(reps):
+        torch.nn.functional.linear(x, w, bb)
+    e1.record()
+    torch.cuda.synchronize()
+    print(f"     cublas(torch) same shape: {e0.elapsed_time(e1) * 1e3 / reps:8.1f} us")
     if M * N <= 1 << 24:
         # wgrad-shaped: C[N,K] = dy^T x  (both MN-major), fp32 out
         dy = torch.randn(M, N, device=dev).bfloat16()

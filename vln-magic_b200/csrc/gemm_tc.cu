@@ -1,8 +1,19 @@
-// bf16 GEMM on the 5th-generation tensor cores (sm_100a): TMA (cp.async.bulk.tensor) -> 128B-swizzled shared
-// memory -> tcgen05.mma (one elected thread, cta_group::1, UMMA 128 x BN x 16) -> fp32 accumulators in TMEM
-// -> tcgen05.ld -> fused epilogue (bias / GELU / ReLU / activation-derivative / dropout / residual / beta)
-// -> global.  Warp roles: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2..5 = epilogue
-// (one TMEM lane quarter each).  4-stage mbarrier ring, BK = 64 (one 128-byte swizzle atom of bf16).
+// bf16 GEMM on the 5th-generation tensor cores (sm_100a), persistent and warp-specialised:
+//
+//   warp 0      TMA producer   cp.async.bulk.tensor (128B swizzle) -> smem ring (BK = 64, `stages` deep)
+//   warp 1      MMA issuer     tcgen05.mma cta_group::1, UMMA 128 x BN x 16, fp32 accumulators in TMEM;
+//                              TWO accumulator buffers (2*BN columns) so tile i+1 is multiplied while tile i
+//                              is still being drained
+//   warps 2..9  epilogue       tcgen05.ld (one TMEM lane quarter per warp, two warps per quarter splitting the
+//                              columns) -> fused epilogue in registers -> 128B-swizzled smem staging ->
+//                              TMA store (cp.async.bulk.tensor ... global.shared::cta), or TMA reduce-add for
+//                              fp32 accumulation into the gradient arena (beta = 1, split-K)
+//
+// Each CTA walks work items (m tile, n tile, k split) round-robin; the three pipelines (smem full/empty,
+// TMEM full/empty, per-warp staging buffers tracked by bulk async-groups) never meet at a CTA-wide barrier.
+//
+// Fused epilogue: alpha, bias, pre-activation copy-out, GELU / ReLU, activation-derivative (backward),
+// dropout (stateless hash), residual.  M/N edges need no predication on stores: TMA clips the box.
 //
 // Both operands may be K-major (reduce dim contiguous) or MN-major (M / N contiguous), so the SAME kernel
 // serves forward (x W^T), dgrad (dy W) and wgrad (dy^T x) of every nn.Linear without transposed copies:
@@ -23,8 +34,11 @@ namespace {
 
 constexpr int BM = 128;
 constexpr int BK = 64;
-constexpr int STAGES = 4;
-constexpr int NTHREADS = 192;  // 6 warps
+constexpr int NUM_EPI_WARPS = 8;
+constexpr int NTHREADS = 64 + NUM_EPI_WARPS * 32;  // 10 warps
+constexpr int STG_BYTES = 4096;                    // one staging buffer: 32 rows x 128 B
+constexpr int STG_BUFS = 2;                        // per epilogue warp
+constexpr int MAX_STAGES = 8;
 
 // ---- PTX wrappers -------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -34,6 +48,9 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
 }
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   asm volatile(
@@ -58,6 +75,22 @@ __device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* ba
       "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
 }
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map),
+               "r"(smem_u32(src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* map, const void* src, int c0, int c1) {
+  asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map),
+               "r"(smem_u32(src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
@@ -89,6 +122,7 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                : "memory");
 }
+// 32 lanes x 32 consecutive columns -> 32 registers per thread (no wait: pair with tmem_wait_ld)
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -99,8 +133,8 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
         "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
         "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
       : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout), SWIZZLE_128B, version 1
 __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
@@ -119,15 +153,12 @@ __host__ __device__ constexpr uint32_t make_idesc(int m, int n, int a_mn_major, 
          ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
-// ---- vectorised row-per-thread epilogue (the common, dropout-free modes) ---------------------------------
-// Each epilogue thread owns one accumulator row and 32 consecutive columns: 64 B (bf16) / 128 B (fp32) of
-// contiguous output per chunk, moved with 128-bit loads/stores (full 32 B sectors, ~20x fewer instructions
-// than an element-wise loop -- the epilogue runs one warp per scheduler, so instruction count is latency).
+// ---- epilogue helpers: one thread = one accumulator row, 32 consecutive columns per call -------------------
 __device__ __forceinline__ void ld_row32(const float* p, float (&v)[32]) {
   const float4* q = reinterpret_cast<const float4*>(p);
 #pragma unroll
   for (int i = 0; i < 8; i++) {
-    const float4 t = q[i];
+    const float4 t = __ldg(q + i);
     v[4 * i] = t.x; v[4 * i + 1] = t.y; v[4 * i + 2] = t.z; v[4 * i + 3] = t.w;
   }
 }
@@ -135,7 +166,7 @@ __device__ __forceinline__ void ld_row32(const __nv_bfloat16* p, float (&v)[32])
   const uint4* q = reinterpret_cast<const uint4*>(p);
 #pragma unroll
   for (int i = 0; i < 4; i++) {
-    const uint4 t = q[i];
+    const uint4 t = __ldg(q + i);
     const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&t);
 #pragma unroll
     for (int e = 0; e < 4; e++) {
@@ -144,170 +175,198 @@ __device__ __forceinline__ void ld_row32(const __nv_bfloat16* p, float (&v)[32])
     }
   }
 }
-__device__ __forceinline__ void st_row32(float* p, const float (&v)[32]) {
-  float4* q = reinterpret_cast<float4*>(p);
+// guarded (edge) variant: columns >= ncols read as 0
+template <typename T>
+__device__ __forceinline__ void ld_row32_edge(const T* p, float (&v)[32], int ncols) {
 #pragma unroll
-  for (int i = 0; i < 8; i++) q[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+  for (int j = 0; j < 32; j++) v[j] = j < ncols ? ldf(p, j) : 0.f;
 }
-__device__ __forceinline__ void st_row32(__nv_bfloat16* p, const float (&v)[32]) {
-  uint4* q = reinterpret_cast<uint4*>(p);
+
+// 32 fp32 values of row `lane` -> staging buffer in the TMA SWIZZLE_128B layout
+// (row r at r*128 B, 16-byte chunk c at position c ^ (r & 7)); bf16: `half` selects columns 0..31 / 32..63
+__device__ __forceinline__ void stage_row32(uint8_t* buf, int lane, int half, const float (&v)[32],
+                                            const __nv_bfloat16*) {
+  uint8_t* row = buf + lane * 128;
 #pragma unroll
   for (int i = 0; i < 4; i++) {
     uint4 t;
     __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&t);
 #pragma unroll
     for (int e = 0; e < 4; e++) h[e] = __floats2bfloat162_rn(v[8 * i + 2 * e], v[8 * i + 2 * e + 1]);
-    q[i] = t;
+    const int c = half * 4 + i;
+    *reinterpret_cast<uint4*>(row + ((c ^ (lane & 7)) << 4)) = t;
   }
 }
+__device__ __forceinline__ void stage_row32(uint8_t* buf, int lane, int, const float (&v)[32], const float*) {
+  uint8_t* row = buf + lane * 128;
+#pragma unroll
+  for (int c = 0; c < 8; c++)
+    *reinterpret_cast<float4*>(row + ((c ^ (lane & 7)) << 4)) =
+        make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+}
 template <typename T>
-__device__ __forceinline__ void rt_row32(float (&v)[32]) {
+__device__ __forceinline__ void round_trip32(float (&v)[32]) {
   if (sizeof(T) == 2) {
 #pragma unroll
     for (int j = 0; j < 32; j++) v[j] = __bfloat162float(__float2bfloat16_rn(v[j]));
   }
 }
 
+struct TcParams {
+  int M, N, K;
+  int m_tiles, n_tiles, splits;
+  int total_kb, kb_per_split;
+  int stages;
+  int a_mn, b_mn;  // 1 = MN-major operand
+  long ldc;
+  int reduce;      // 1: accumulate into C with TMA reduce-add (fp32 C; beta = 1 and/or split-K)
+  GemmEpi epi;
+};
+
+// fused epilogue math on 32 columns [nb, nb+32) of row m.  `v` in: raw accumulators; out: final values.
+// If epi.pre_out is set, `pre` receives the pre-activation values (already in storage precision).
 template <typename TC, int ACT>
-__device__ __forceinline__ void epi_fast_chunk(const GemmEpi& epi, const Dropout& dr, TC* C, const uint32_t (&r)[32],
-                                               int m, int nb, long ldc) {
-  float v[32];
+__device__ __forceinline__ void epi_math32(const TcParams& P, const Dropout& dr, float (&v)[32], float (&pre)[32],
+                                           int m, int nb, bool row_ok) {
+  const GemmEpi& epi = P.epi;
+  const int ncols = P.N - nb;  // may be < 32 on the N edge (or <= 0: whole chunk clipped by the store)
+  const bool full = ncols >= 32;
 #pragma unroll
-  for (int j = 0; j < 32; j++) v[j] = epi.alpha * __uint_as_float(r[j]);
-  const size_t off = (size_t)m * ldc + nb;
+  for (int j = 0; j < 32; j++) v[j] *= epi.alpha;
   if (epi.dact_pre != nullptr) {
-    float pre[32];
+    float z[32];
     const size_t poff = (size_t)m * epi.dact_ld + nb;
-    if (epi.dact_dt == MAGIC_BF16) ld_row32((const __nv_bfloat16*)epi.dact_pre + poff, pre);
-    else ld_row32((const float*)epi.dact_pre + poff, pre);
+    if (!row_ok || ncols <= 0) {
 #pragma unroll
-    for (int j = 0; j < 32; j++) v[j] *= act_bwd(ACT, pre[j]);
+      for (int j = 0; j < 32; j++) z[j] = 0.f;
+    } else if (epi.dact_dt == MAGIC_BF16) {
+      if (full) ld_row32((const __nv_bfloat16*)epi.dact_pre + poff, z);
+      else ld_row32_edge((const __nv_bfloat16*)epi.dact_pre + poff, z, ncols);
+    } else {
+      if (full) ld_row32((const float*)epi.dact_pre + poff, z);
+      else ld_row32_edge((const float*)epi.dact_pre + poff, z, ncols);
+    }
+#pragma unroll
+    for (int j = 0; j < 32; j++) v[j] *= act_bwd(ACT, z[j]);
     if (dr.p > 0.f) {
 #pragma unroll
       for (int j = 0; j < 32; j++) v[j] *= dr.scale(poff + j);
     }
-  } else {
-    if (epi.bias) {
-      float b[32];
-      ld_row32(epi.bias + nb, b);
-#pragma unroll
-      for (int j = 0; j < 32; j++) v[j] += b[j];
-    }
-    if (epi.pre_out) {
-      st_row32((TC*)epi.pre_out + off, v);
-      rt_row32<TC>(v);
-    }
-    if (ACT != 0) {
-#pragma unroll
-      for (int j = 0; j < 32; j++) v[j] = act_fwd(ACT, v[j]);
-    }
-    if (dr.p > 0.f) {
-#pragma unroll
-      for (int j = 0; j < 32; j++) v[j] *= dr.scale(off + j);
-    }
-    if (epi.residual) {
-      float rs[32];
-      ld_row32((const TC*)epi.residual + (size_t)m * epi.res_ld + nb, rs);
-#pragma unroll
-      for (int j = 0; j < 32; j++) v[j] += rs[j];
-    }
-  }
-  if (epi.atomic) {
-#pragma unroll
-    for (int j = 0; j < 32; j++) atomicAdd(reinterpret_cast<float*>(C) + off + j, v[j]);
     return;
   }
-  if (epi.beta != 0.f) {
-    float c[32];
-    ld_row32(C + off, c);
+  if (epi.bias && ncols > 0) {
+    float b[32];
+    if (full) ld_row32(epi.bias + nb, b);
+    else ld_row32_edge(epi.bias + nb, b, ncols);
 #pragma unroll
-    for (int j = 0; j < 32; j++) v[j] += epi.beta * c[j];
+    for (int j = 0; j < 32; j++) v[j] += b[j];
   }
-  st_row32(C + off, v);
+  if (epi.pre_out) {
+#pragma unroll
+    for (int j = 0; j < 32; j++) pre[j] = v[j];
+    round_trip32<TC>(v);  // the activation sees what backward will re-read
+  }
+  if (ACT != 0) {
+#pragma unroll
+    for (int j = 0; j < 32; j++) v[j] = act_fwd(ACT, v[j]);
+  }
+  if (dr.p > 0.f) {
+    const size_t off = (size_t)m * P.ldc + nb;
+#pragma unroll
+    for (int j = 0; j < 32; j++) v[j] *= dr.scale(off + j);
+  }
+  if (epi.residual && row_ok && ncols > 0) {
+    float rs[32];
+    const TC* rp = (const TC*)epi.residual + (size_t)m * epi.res_ld + nb;
+    if (full) ld_row32(rp, rs);
+    else ld_row32_edge(rp, rs, ncols);
+#pragma unroll
+    for (int j = 0; j < 32; j++) v[j] += rs[j];
+  }
 }
 
-struct TcParams {
-  int M, N, K;
-  int kb_per_split;  // k-blocks handled by one CTA along gridDim.z (split-K)
-  int a_mn, b_mn;  // 1 = MN-major operand
-  long ldc;
-  GemmEpi epi;
-  int fast_epi;             // 1: vectorised row-per-thread epilogue is legal (alignment, no dropout)
-  unsigned long long* dbg;  // optional per-CTA timestamps (MAGIC_TC_DEBUG), else null
-};
-
-__device__ __forceinline__ unsigned long long gtime() {
-  unsigned long long t;
-  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
-  return t;
+template <typename TC>
+__device__ __forceinline__ void epi_math32_dispatch(const TcParams& P, const Dropout& dr, float (&v)[32],
+                                                    float (&pre)[32], int m, int nb, bool row_ok) {
+  if (P.epi.act == MAGIC_ACT_GELU) epi_math32<TC, MAGIC_ACT_GELU>(P, dr, v, pre, m, nb, row_ok);
+  else if (P.epi.act == MAGIC_ACT_RELU) epi_math32<TC, MAGIC_ACT_RELU>(P, dr, v, pre, m, nb, row_ok);
+  else epi_math32<TC, MAGIC_ACT_NONE>(P, dr, v, pre, m, nb, row_ok);
 }
-#define DBG(slot)                                                                            \
-  if (P.dbg && (threadIdx.x & 31) == 0)                                                      \
-    P.dbg[((size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 8 + (slot))] = gtime();
 
 template <int BN, typename TC>
 __global__ void __launch_bounds__(NTHREADS, 1)
     gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                   TC* __restrict__ C, const TcParams P) {
+                   const __grid_constant__ CUtensorMap tmap_c, const __grid_constant__ CUtensorMap tmap_pre,
+                   const TcParams P) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  // carve: [STAGES][A 16 KB][B BN*128 B] (1024-aligned), then barriers
   constexpr int A_BYTES = BM * BK * 2;
   constexpr int B_BYTES = BN * BK * 2;
+  constexpr int UNIT_COLS = 128 / (int)sizeof(TC);  // columns of one 128-byte staging row: 64 (bf16) / 32 (fp32)
+  constexpr int UNITS = BN / UNIT_COLS;             // store units per lane quarter per tile
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  const int stages = P.stages;
   uint8_t* sA = smem;
-  uint8_t* sB = smem + STAGES * A_BYTES;
-  uint64_t* full = (uint64_t*)(sB + STAGES * B_BYTES);
-  uint64_t* empty = full + STAGES;
-  uint64_t* tmem_full = empty + STAGES;
-  uint32_t* tmem_ptr = (uint32_t*)(tmem_full + 1);
-  float* stage = (float*)(tmem_ptr + 4);  // [4 epilogue warps][32][33] fp32 staging for coalesced stores
+  uint8_t* sB = sA + stages * A_BYTES;
+  uint8_t* sStage = sB + stages * B_BYTES;  // [NUM_EPI_WARPS][STG_BUFS][4096], 1024-aligned
+  uint64_t* full = (uint64_t*)(sStage + NUM_EPI_WARPS * STG_BUFS * STG_BYTES);
+  uint64_t* empty = full + MAX_STAGES;
+  uint64_t* tmem_full = empty + MAX_STAGES;  // [2]
+  uint64_t* tmem_empty = tmem_full + 2;      // [2]
+  uint32_t* tmem_ptr = (uint32_t*)(tmem_empty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
-  if (threadIdx.x == 0) { DBG(0) }
-  const int total_kb = (P.K + BK - 1) / BK;
-  const int kb0 = blockIdx.z * P.kb_per_split;
-  const int num_kb = min(P.kb_per_split, total_kb - kb0);
+  const int total_work = P.m_tiles * P.n_tiles * P.splits;
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmap_a);
     prefetch_tmap(&tmap_b);
-    for (int s = 0; s < STAGES; s++) {
+    prefetch_tmap(&tmap_c);
+    if (P.epi.pre_out) prefetch_tmap(&tmap_pre);
+    for (int s = 0; s < stages; s++) {
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], 1);
     }
-    mbar_init(tmem_full, 1);
+    for (int s = 0; s < 2; s++) {
+      mbar_init(&tmem_full[s], 1);
+      mbar_init(&tmem_empty[s], NUM_EPI_WARPS);
+    }
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(tmem_ptr, BN);
+  if (warp == 1) tmem_alloc(tmem_ptr, 2 * BN);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
-  if (threadIdx.x == 0) { DBG(1) }
 
   if (warp == 0) {
     if (lane == 0) {
       // ===== TMA producer =====
-      for (int kb = 0; kb < num_kb; kb++) {
-        const int s = kb % STAGES;
-        const uint32_t ph = (kb / STAGES) & 1;
-        mbar_wait(&empty[s], ph ^ 1);
-        mbar_expect_tx(&full[s], A_BYTES + B_BYTES);
-        uint8_t* a_dst = sA + s * A_BYTES;
-        uint8_t* b_dst = sB + s * B_BYTES;
-        const int k0 = (kb0 + kb) * BK;
-        if (!P.a_mn) {
-          tma_load_2d(&tmap_a, &full[s], a_dst, k0, m0);                       // box {64 k, 128 rows}
-        } else {
-          tma_load_2d(&tmap_a, &full[s], a_dst, m0, k0);                       // box {64 m, 64 k} x 2
-          tma_load_2d(&tmap_a, &full[s], a_dst + 64 * BK * 2, m0 + 64, k0);
-        }
-        if (!P.b_mn) {
-          tma_load_2d(&tmap_b, &full[s], b_dst, k0, n0);                       // box {64 k, BN rows}
-        } else {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int work = blockIdx.x; work < total_work; work += gridDim.x) {
+        const int tile = work % (P.m_tiles * P.n_tiles), ks = work / (P.m_tiles * P.n_tiles);
+        const int m0 = (tile / P.n_tiles) * BM, n0 = (tile % P.n_tiles) * BN;
+        const int kb0 = ks * P.kb_per_split, kb1 = min(P.total_kb, kb0 + P.kb_per_split);
+        for (int kb = kb0; kb < kb1; kb++) {
+          mbar_wait(&empty[s], ph ^ 1);
+          mbar_expect_tx(&full[s], A_BYTES + B_BYTES);
+          uint8_t* a_dst = sA + s * A_BYTES;
+          uint8_t* b_dst = sB + s * B_BYTES;
+          const int k0 = kb * BK;
+          if (!P.a_mn) {
+            tma_load_2d(&tmap_a, &full[s], a_dst, k0, m0);  // box {64 k, 128 rows}
+          } else {
+            tma_load_2d(&tmap_a, &full[s], a_dst, m0, k0);  // box {64 m, 64 k} x 2
+            tma_load_2d(&tmap_a, &full[s], a_dst + 64 * BK * 2, m0 + 64, k0);
+          }
+          if (!P.b_mn) {
+            tma_load_2d(&tmap_b, &full[s], b_dst, k0, n0);  // box {64 k, BN rows}
+          } else {
 #pragma unroll
-          for (int j = 0; j < BN / 64; j++) tma_load_2d(&tmap_b, &full[s], b_dst + j * 64 * BK * 2, n0 + 64 * j, k0);
+            for (int j = 0; j < BN / 64; j++)
+              tma_load_2d(&tmap_b, &full[s], b_dst + j * 64 * BK * 2, n0 + 64 * j, k0);
+          }
+          if (++s == stages) { s = 0; ph ^= 1; }
         }
       }
     }
@@ -315,68 +374,115 @@ __global__ void __launch_bounds__(NTHREADS, 1)
     if (lane == 0) {
       // ===== MMA issuer =====
       const uint32_t idesc = make_idesc(BM, BN, P.a_mn, P.b_mn);
-      for (int kb = 0; kb < num_kb; kb++) {
-        const int s = kb % STAGES;
-        const uint32_t ph = (kb / STAGES) & 1;
-        mbar_wait(&full[s], ph);
+      int s = 0;
+      uint32_t ph = 0;
+      int it = 0;
+      for (int work = blockIdx.x; work < total_work; work += gridDim.x, it++) {
+        const int ks = work / (P.m_tiles * P.n_tiles);
+        const int kb0 = ks * P.kb_per_split, kb1 = min(P.total_kb, kb0 + P.kb_per_split);
+        const int as = it & 1;
+        const uint32_t aph = (it >> 1) & 1;
+        mbar_wait(&tmem_empty[as], aph ^ 1);  // epilogue has drained this accumulator buffer
         tc_fence_after();
-        if (kb == 0) { DBG(2) }
-        const uint32_t a_base = smem_u32(sA + s * A_BYTES), b_base = smem_u32(sB + s * B_BYTES);
+        const uint32_t tmem_c = tmem_base + (uint32_t)(as * BN);
+        for (int kb = kb0; kb < kb1; kb++) {
+          mbar_wait(&full[s], ph);
+          tc_fence_after();
+          const uint32_t a_base = smem_u32(sA + s * A_BYTES), b_base = smem_u32(sB + s * B_BYTES);
 #pragma unroll
-        for (int k = 0; k < BK / 16; k++) {
-          // K-major: +32 B per UMMA_K inside the 128 B swizzle row; MN-major: +16 k-rows * 128 B
-          const uint64_t adesc = P.a_mn ? make_desc(a_base + k * 2048, 8192, 1024) : make_desc(a_base + k * 32, 16, 1024);
-          const uint64_t bdesc = P.b_mn ? make_desc(b_base + k * 2048, 8192, 1024) : make_desc(b_base + k * 32, 16, 1024);
-          umma_bf16(tmem_base, adesc, bdesc, idesc, (kb | k) != 0);
+          for (int k = 0; k < BK / 16; k++) {
+            // K-major: +32 B per UMMA_K inside the 128 B swizzle row; MN-major: +16 k-rows * 128 B
+            const uint64_t adesc =
+                P.a_mn ? make_desc(a_base + k * 2048, 8192, 1024) : make_desc(a_base + k * 32, 16, 1024);
+            const uint64_t bdesc =
+                P.b_mn ? make_desc(b_base + k * 2048, 8192, 1024) : make_desc(b_base + k * 32, 16, 1024);
+            umma_bf16(tmem_c, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty[s]);  // frees this smem stage once the MMAs above have read it
+          if (++s == stages) { s = 0; ph ^= 1; }
         }
-        umma_commit(&empty[s]);  // frees this smem stage once the MMAs above have read it
+        umma_commit(&tmem_full[as]);  // accumulator complete
       }
-      umma_commit(tmem_full);    // accumulator complete
     }
   } else {
-    // ===== epilogue: warps 2..5, TMEM lane quarter = warp % 4 =====
-    // TMEM -> registers (row = lane) -> padded smem -> rolled loop with lane = column, so the code stays
-    // small (instruction cache) and every global access of a warp is one contiguous row segment.
+    // ===== epilogue: warps 2..9; TMEM lane quarter = warp % 4, column half = (warp - 2) / 4 =====
     const int q = warp & 3;
-    float* st = stage + q * (32 * 33);
-    mbar_wait(tmem_full, 0);
-    tc_fence_after();
-    if (warp == 2) { DBG(3) }
+    const int hf = (warp - 2) >> 2;
+    uint8_t* stg = sStage + (warp - 2) * (STG_BUFS * STG_BYTES);
     const Dropout dr = make_dropout(P.epi.drop_p, P.epi.seed_ptr, P.epi.salt);
+    const bool has_pre = P.epi.pre_out != nullptr;
+    int nstore = 0;  // staging buffers used so far by this warp (buffer = nstore & 1)
+    int it = 0;
+    for (int work = blockIdx.x; work < total_work; work += gridDim.x, it++) {
+      const int tile = work % (P.m_tiles * P.n_tiles);
+      const int m0 = (tile / P.n_tiles) * BM, n0 = (tile % P.n_tiles) * BN;
+      const int as = it & 1;
+      const uint32_t aph = (it >> 1) & 1;
+      mbar_wait(&tmem_full[as], aph);
+      tc_fence_after();
+      const int m = m0 + q * 32 + lane;
+      const bool row_ok = m < P.M;
+      const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN);
+      bool released = false;
+      if (UNITS <= hf) {  // nothing to drain for this warp (BN = 64 with bf16 output): just release
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tmem_empty[as]);
+        released = true;
+      }
 #pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 32) {
-      uint32_t r[32];
-      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
-      if (P.fast_epi && n0 + c0 + 32 <= P.N) {  // warp-uniform
-        const int m = m0 + q * 32 + lane;
-        if (m < P.M) {
-          if (P.epi.act == MAGIC_ACT_GELU) epi_fast_chunk<TC, MAGIC_ACT_GELU>(P.epi, dr, C, r, m, n0 + c0, P.ldc);
-          else if (P.epi.act == MAGIC_ACT_RELU) epi_fast_chunk<TC, MAGIC_ACT_RELU>(P.epi, dr, C, r, m, n0 + c0, P.ldc);
-          else epi_fast_chunk<TC, MAGIC_ACT_NONE>(P.epi, dr, C, r, m, n0 + c0, P.ldc);
+      for (int u = hf; u < UNITS; u += 2) {
+        const int nu = n0 + u * UNIT_COLS;
+        uint32_t r0[32], r1[32];
+        tmem_ld32(t_row + (uint32_t)(u * UNIT_COLS), r0);
+        if (sizeof(TC) == 2) tmem_ld32(t_row + (uint32_t)(u * UNIT_COLS + 32), r1);
+        tmem_wait_ld();
+        if (u + 2 >= UNITS && !released) {  // last TMEM read of this warp for this tile: hand the buffer back
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tmem_empty[as]);
+          released = true;
         }
-        continue;
-      }
+        if (nu >= P.N) continue;  // unit entirely beyond the N edge (warp-uniform)
+        // staging buffers: at most one store group may still be reading (the other buffer)
+        if (lane == 0) {
+          if (has_pre) bulk_wait_read<0>();
+          else bulk_wait_read<1>();
+        }
+        __syncwarp();
+        uint8_t* bufc = stg + (nstore & 1) * STG_BYTES;
+        nstore++;
+        uint8_t* bufp = nullptr;
+        if (has_pre) {
+          bufp = stg + (nstore & 1) * STG_BYTES;
+          nstore++;
+        }
 #pragma unroll
-      for (int j = 0; j < 32; j++) st[lane * 33 + j] = __uint_as_float(r[j]);
-      __syncwarp();
-      const int n = n0 + c0 + lane;
-      if (n < P.N) {
-        const float bias_n = P.epi.bias ? __ldg(P.epi.bias + n) : 0.f;
-        const int rows = min(32, P.M - (m0 + q * 32));
-#pragma unroll 4
-        for (int rr = 0; rr < rows; rr++)
-          epi_store<TC>(P.epi, dr, C, st[rr * 33 + lane], m0 + q * 32 + rr, n, P.ldc, bias_n);
+        for (int half = 0; half < (int)(4 / sizeof(TC)); half++) {
+          float v[32], pre[32];
+#pragma unroll
+          for (int j = 0; j < 32; j++) v[j] = __uint_as_float(half == 0 ? r0[j] : r1[j]);
+          epi_math32_dispatch<TC>(P, dr, v, pre, m, nu + 32 * half, row_ok);
+          stage_row32(bufc, lane, half, v, (const TC*)nullptr);
+          if (has_pre) stage_row32(bufp, lane, half, pre, (const TC*)nullptr);
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+          if (P.reduce) tma_reduce_add_2d(&tmap_c, bufc, nu, m0 + q * 32);
+          else tma_store_2d(&tmap_c, bufc, nu, m0 + q * 32);
+          if (has_pre) tma_store_2d(&tmap_pre, bufp, nu, m0 + q * 32);
+          bulk_commit();
+        }
       }
-      __syncwarp();
     }
-    if (warp == 2) { DBG(4) }
+    if (lane == 0) bulk_wait_all();
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, BN);
-    DBG(5)
+    tmem_dealloc(tmem_base, 2 * BN);
   }
 }
 
@@ -402,10 +508,10 @@ EncodeTiledFn get_encode() {
 struct MapKey {
   const void* ptr;
   uint64_t inner, outer, stride;
-  uint32_t box_inner, box_outer;
+  uint32_t box_inner, box_outer, esz;
   bool operator==(const MapKey& o) const {
     return ptr == o.ptr && inner == o.inner && outer == o.outer && stride == o.stride && box_inner == o.box_inner &&
-           box_outer == o.box_outer;
+           box_outer == o.box_outer && esz == o.esz;
   }
 };
 struct MapHash {
@@ -414,19 +520,18 @@ struct MapHash {
     h = h * 1000003u ^ k.inner;
     h = h * 1000003u ^ k.outer;
     h = h * 1000003u ^ k.stride;
-    h = h * 1000003u ^ ((size_t)k.box_inner << 16 | k.box_outer);
+    h = h * 1000003u ^ ((size_t)k.box_inner << 20 | (size_t)k.box_outer << 4 | k.esz);
     return h;
   }
 };
 
-unsigned long long* g_dbg_buf = nullptr;
 std::mutex g_mu;
 std::unordered_map<MapKey, CUtensorMap, MapHash> g_maps;
 
-// 2-D bf16 tensor: `inner` contiguous elements, `outer` rows of `stride` elements
+// 2-D tensor of bf16 (esz 2) or fp32 (esz 4): `inner` contiguous elements, `outer` rows of `stride` elements
 int get_map(const void* ptr, uint64_t inner, uint64_t outer, uint64_t stride, uint32_t box_inner, uint32_t box_outer,
-            CUtensorMap* out) {
-  MapKey key{ptr, inner, outer, stride, box_inner, box_outer};
+            uint32_t esz, CUtensorMap* out) {
+  MapKey key{ptr, inner, outer, stride, box_inner, box_outer, esz};
   {
     std::lock_guard<std::mutex> lk(g_mu);
     auto it = g_maps.find(key);
@@ -441,16 +546,16 @@ int get_map(const void* ptr, uint64_t inner, uint64_t outer, uint64_t stride, ui
     return MAGIC_ERR_CUDA;
   }
   cuuint64_t dims[2] = {inner, outer};
-  cuuint64_t strides[1] = {stride * 2};
+  cuuint64_t strides[1] = {stride * esz};
   cuuint32_t box[2] = {box_inner, box_outer};
   cuuint32_t estr[2] = {1, 1};
   CUtensorMap m;
-  CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r = enc(&m, esz == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+                   const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
-    magic_set_error("magic_gemm(tc): cuTensorMapEncodeTiled failed (%d) inner=%llu outer=%llu stride=%llu", (int)r,
-                    (unsigned long long)inner, (unsigned long long)outer, (unsigned long long)stride);
+    magic_set_error("magic_gemm(tc): cuTensorMapEncodeTiled failed (%d) inner=%llu outer=%llu stride=%llu esz=%u", (int)r,
+                    (unsigned long long)inner, (unsigned long long)outer, (unsigned long long)stride, esz);
     return MAGIC_ERR_CUDA;
   }
   {
@@ -462,19 +567,29 @@ int get_map(const void* ptr, uint64_t inner, uint64_t outer, uint64_t stride, ui
   return MAGIC_OK;
 }
 
+constexpr size_t SMEM_MAX = 227 * 1024;
+constexpr size_t SMEM_FIXED = 1024 /*align slack*/ + NUM_EPI_WARPS * STG_BUFS * STG_BYTES + (2 * MAX_STAGES + 4) * 8 + 16;
+
 template <int BN, typename TC>
-int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, void* C, const TcParams& P, cudaStream_t st) {
-  constexpr size_t smem = 1024 + (size_t)STAGES * (BM * BK * 2 + BN * BK * 2) + (2 * STAGES + 1) * 8 + 16 +
-                          4 * 32 * 33 * sizeof(float);
-  static bool attr_set = false;
-  if (!attr_set) {
-    MAGIC_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, TC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const CUtensorMap& tp, TcParams& P,
+              cudaStream_t st) {
+  constexpr size_t stage_bytes = (size_t)BM * BK * 2 + (size_t)BN * BK * 2;
+  int stages = (int)((SMEM_MAX - SMEM_FIXED) / stage_bytes);
+  if (stages > MAX_STAGES) stages = MAX_STAGES;
+  // never more stages than k-blocks a CTA will ever load
+  const long work = (long)P.m_tiles * P.n_tiles * P.splits;
+  const int grid = (int)(work < magic_num_sms() ? work : magic_num_sms());
+  const long per_cta_kb = ((work + grid - 1) / grid) * (long)P.kb_per_split;
+  if (stages > per_cta_kb) stages = (int)(per_cta_kb < 2 ? 2 : per_cta_kb);
+  P.stages = stages;
+  const size_t smem = SMEM_FIXED + (size_t)stages * stage_bytes;
+  static size_t attr_smem = 0;
+  if (smem > attr_smem) {
+    MAGIC_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, TC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MAX),
                "magic_gemm(tc)");
-    attr_set = true;
+    attr_smem = SMEM_MAX;
   }
-  const int total_kb = (P.K + BK - 1) / BK;
-  dim3 grid((P.N + BN - 1) / BN, (P.M + BM - 1) / BM, (total_kb + P.kb_per_split - 1) / P.kb_per_split);
-  gemm_tc_kernel<BN, TC><<<grid, NTHREADS, smem, st>>>(ta, tb, (TC*)C, P);
+  gemm_tc_kernel<BN, TC><<<grid, NTHREADS, smem, st>>>(ta, tb, tc, tp, P);
   MAGIC_CHECK_LAUNCH("magic_gemm(tc)");
   return MAGIC_OK;
 }
@@ -488,9 +603,16 @@ bool tc_disabled() {
   return v == 1;
 }
 
-}  // namespace
+int force_bn() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("MAGIC_TC_BN");
+    v = e ? atoi(e) : 0;
+  }
+  return v;
+}
 
-extern "C" unsigned long long* magic_tc_debug_buffer(void) { return g_dbg_buf; }
+}  // namespace
 
 int gemm_tc_shape_ok(int M, int N, int K) { return (!tc_disabled() && M > 0 && N > 0 && K > 0) ? 1 : 0; }
 
@@ -501,57 +623,53 @@ int gemm_tc_dispatch(const void* A, const void* B, void* C, int c_dt, int M, int
   long lda, ldb;
   if (sak == 1) { a_mn = 0; lda = sam; } else if (sam == 1) { a_mn = 1; lda = sak; } else return MAGIC_ERR_UNSUPPORTED;
   if (sbk == 1) { b_mn = 0; ldb = sbn; } else if (sbn == 1) { b_mn = 1; ldb = sbk; } else return MAGIC_ERR_UNSUPPORTED;
-  // degenerate unit extents make both strides "1"-compatible; pick by the other stride being a valid ld
-  if (((uintptr_t)A & 15) || ((uintptr_t)B & 15) || (lda % 8) || (ldb % 8) || lda <= 0 || ldb <= 0)
-    return MAGIC_ERR_UNSUPPORTED;
+  auto al16 = [](const void* p) { return ((uintptr_t)p & 15) == 0; };
+  if (!al16(A) || !al16(B) || (lda % 8) || (ldb % 8) || lda <= 0 || ldb <= 0) return MAGIC_ERR_UNSUPPORTED;
   if (a_mn == 0 && lda < K) return MAGIC_ERR_UNSUPPORTED;
   if (a_mn == 1 && lda < M) return MAGIC_ERR_UNSUPPORTED;
   if (b_mn == 0 && ldb < K) return MAGIC_ERR_UNSUPPORTED;
   if (b_mn == 1 && ldb < N) return MAGIC_ERR_UNSUPPORTED;
-  const int BN = (N <= 64) ? 64 : 128;
-  CUtensorMap ta, tb;
-  int rc;
-  if (!a_mn) rc = get_map(A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, 64, BM, &ta);
-  else rc = get_map(A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, 64, 64, &ta);
-  if (rc) return rc;
-  if (!b_mn) rc = get_map(B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, 64, (uint32_t)BN, &tb);
-  else rc = get_map(B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, 64, 64, &tb);
-  if (rc) return rc;
-  TcParams P;
-  {
-    static unsigned long long* dbg_buf = nullptr;
-    static int dbg_on = -1;
-    if (dbg_on < 0) {
-      const char* e = getenv("MAGIC_TC_DEBUG");
-      dbg_on = (e && e[0] == '1') ? 1 : 0;
-      if (dbg_on) cudaMalloc(&dbg_buf, 8 * 8 * 65536);
-    }
-    P.dbg = dbg_on ? dbg_buf : nullptr;
-    if (dbg_on) g_dbg_buf = dbg_buf;
-  }
-  P.M = M; P.N = N; P.K = K; P.a_mn = a_mn; P.b_mn = b_mn; P.ldc = ldc; P.epi = epi;
-  {
-    const int cesz = c_dt == MAGIC_BF16 ? 2 : 4;
-    auto al16 = [](const void* p) { return ((uintptr_t)p & 15) == 0; };
-    bool ok = al16(C) && (ldc * cesz) % 16 == 0;
-    if (epi.bias) ok = ok && al16(epi.bias);
-    if (epi.pre_out) ok = ok && al16(epi.pre_out);
-    if (epi.residual) ok = ok && al16(epi.residual) && (epi.res_ld * cesz) % 16 == 0;
-    if (epi.dact_pre) ok = ok && al16(epi.dact_pre) && (epi.dact_ld * (epi.dact_dt == MAGIC_BF16 ? 2 : 4)) % 16 == 0;
-    P.fast_epi = ok ? 1 : 0;
-  }
-  // split-K for skinny outputs with a long reduction (weight gradients): fp32 C, purely linear epilogue
-  const int total_kb = (K + BK - 1) / BK;
-  P.kb_per_split = total_kb;
-  const long tiles = (long)((M + BM - 1) / BM) * ((N + BN - 1) / BN);
+  // epilogue operands must be legal for TMA stores / 128-bit loads
+  const int cesz = c_dt == MAGIC_BF16 ? 2 : 4;
+  if (!al16(C) || (ldc * cesz) % 16 != 0 || ldc < N) return MAGIC_ERR_UNSUPPORTED;
+  if (epi.bias && !al16(epi.bias)) return MAGIC_ERR_UNSUPPORTED;
+  if (epi.pre_out && !al16(epi.pre_out)) return MAGIC_ERR_UNSUPPORTED;
+  if (epi.residual && (!al16(epi.residual) || (epi.res_ld * cesz) % 16 != 0)) return MAGIC_ERR_UNSUPPORTED;
+  if (epi.dact_pre && (!al16(epi.dact_pre) || (epi.dact_ld * (epi.dact_dt == MAGIC_BF16 ? 2 : 4)) % 16 != 0))
+    return MAGIC_ERR_UNSUPPORTED;
   const bool linear_epi = c_dt == MAGIC_F32 && !epi.bias && epi.act == 0 && !epi.pre_out && !epi.dact_pre &&
-                          !epi.residual && epi.drop_p == 0.f && (epi.beta == 0.f || epi.beta == 1.f);
-  if (linear_epi && tiles * 2 <= magic_num_sms() && total_kb >= 8) {
-    int splits = (int)(magic_num_sms() / tiles);
-    if (splits > total_kb / 4) splits = total_kb / 4;
+                          !epi.residual && epi.drop_p == 0.f;
+  if (epi.beta != 0.f && !(epi.beta == 1.f && linear_epi)) return MAGIC_ERR_UNSUPPORTED;
+
+  TcParams P;
+  P.M = M; P.N = N; P.K = K; P.a_mn = a_mn; P.b_mn = b_mn; P.ldc = ldc; P.epi = epi;
+  P.epi.atomic = 0;
+  P.m_tiles = (M + BM - 1) / BM;
+  P.total_kb = (K + BK - 1) / BK;
+  // tile width: the widest tile that still gives every SM work (wider tiles re-read less of A)
+  const int sms = magic_num_sms();
+  int BN = 64;
+  if (N > 64) {
+    BN = 128;
+    const long t128 = (long)P.m_tiles * ((N + 127) / 128);
+    const long t256 = (long)P.m_tiles * ((N + 255) / 256);
+    if (N > 128 && t256 >= sms && P.total_kb >= 4) BN = 256;
+    else if (t128 < sms / 2) BN = 64;
+  }
+  if (force_bn() == 64 || force_bn() == 128 || force_bn() == 256) BN = force_bn();
+  P.n_tiles = (N + BN - 1) / BN;
+  // split-K for skinny outputs with a long reduction (weight gradients): fp32 C, purely linear epilogue
+  P.splits = 1;
+  P.kb_per_split = P.total_kb;
+  P.reduce = epi.beta == 1.f ? 1 : 0;
+  const long tiles = (long)P.m_tiles * P.n_tiles;
+  if (linear_epi && tiles * 2 <= sms && P.total_kb >= 8) {
+    int splits = (int)(sms / tiles);
+    if (splits > P.total_kb / 4) splits = P.total_kb / 4;
     if (splits > 1) {
-      P.kb_per_split = (total_kb + splits - 1) / splits;
-      P.epi.atomic = 1;
+      P.kb_per_split = (P.total_kb + splits - 1) / splits;
+      P.splits = (P.total_kb + P.kb_per_split - 1) / P.kb_per_split;
+      P.reduce = 1;
       if (epi.beta == 0.f) {
         if (ldc == N) {
           MAGIC_CUDA(cudaMemsetAsync(C, 0, (size_t)M * N * sizeof(float), st), "magic_gemm(tc) split-K memset");
@@ -562,11 +680,29 @@ int gemm_tc_dispatch(const void* A, const void* B, void* C, int c_dt, int M, int
       }
     }
   }
-  typedef __nv_bfloat16 bf;
-  if (BN == 64) {
-    if (c_dt == MAGIC_BF16) return launch_tc<64, bf>(ta, tb, C, P, st);
-    return launch_tc<64, float>(ta, tb, C, P, st);
+  CUtensorMap ta, tb, tc, tp;
+  int rc;
+  if (!a_mn) rc = get_map(A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, 64, BM, 2, &ta);
+  else rc = get_map(A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, 64, 64, 2, &ta);
+  if (rc) return rc;
+  if (!b_mn) rc = get_map(B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, 64, (uint32_t)BN, 2, &tb);
+  else rc = get_map(B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, 64, 64, 2, &tb);
+  if (rc) return rc;
+  const uint32_t unit_cols = 128 / cesz;
+  rc = get_map(C, (uint64_t)N, (uint64_t)M, (uint64_t)ldc, unit_cols, 32, cesz, &tc);
+  if (rc) return rc;
+  tp = tc;
+  if (epi.pre_out) {
+    rc = get_map(epi.pre_out, (uint64_t)N, (uint64_t)M, (uint64_t)ldc, unit_cols, 32, cesz, &tp);
+    if (rc) return rc;
   }
-  if (c_dt == MAGIC_BF16) return launch_tc<128, bf>(ta, tb, C, P, st);
-  return launch_tc<128, float>(ta, tb, C, P, st);
+  typedef __nv_bfloat16 bf;
+  if (c_dt == MAGIC_BF16) {
+    if (BN == 64) return launch_tc<64, bf>(ta, tb, tc, tp, P, st);
+    if (BN == 128) return launch_tc<128, bf>(ta, tb, tc, tp, P, st);
+    return launch_tc<256, bf>(ta, tb, tc, tp, P, st);
+  }
+  if (BN == 64) return launch_tc<64, float>(ta, tb, tc, tp, P, st);
+  if (BN == 128) return launch_tc<128, float>(ta, tb, tc, tp, P, st);
+  return launch_tc<256, float>(ta, tb, tc, tp, P, st);
 }
