@@ -80,18 +80,32 @@ def attn_cases(cases):
                     else:
                         ops.attention(qkv[i], kv[i], 0, 0, h, B, H, Lq, Lk, lens, None, None, None, pbar, 0.1, 3)
             timeit(f"attn fwd B{B} H{H} {Lq}x{Lk} bias{int(bias)} pbar{int(pbar)}", f, fl, by)
-        # backward through autograd once to get the saved state, then time the raw bwd call
-        q = qkv[0].clone().requires_grad_(True)
-        if Lq == Lk:
-            o, p = ops.attention(q, None, 0, h, 2 * h, B, H, Lq, Lk, lens, dist, sw, sb, True, 0.1, 3)
-        else:
-            k2 = kv[0].clone().requires_grad_(True)
-            o, p = ops.attention(q, k2, 0, 0, h, B, H, Lq, Lk, lens, None, None, None, True, 0.1, 3)
-        do = torch.randn_like(o)
-        dp = torch.randn_like(p) * 1e-3
+        # raw backward call (saved lse from a raw forward call), timed inside a graph like the rest
+        q = qkv[0]
+        kvt = q if Lq == Lk else kv[0]
+        q_off, k_off, v_off = (0, h, 2 * h) if Lq == Lk else (0, 0, h)
+        out = torch.empty(B * Lq, h, device=dev, dtype=torch.bfloat16)
+        lse = torch.empty(B, H, Lq, device=dev)
+        pb = torch.empty(B, Lq, Lk, device=dev)
+        seed = ops.seed_tensor(q.device)
+        P = lambda t: None if t is None else t.data_ptr()
+        _lib.call("magic_attn_fwd", q.data_ptr() + 2 * q_off, kvt.data_ptr() + 2 * k_off, kvt.data_ptr() + 2 * v_off,
+                  q.stride(0), kvt.stride(0), kvt.stride(0), out.data_ptr(), lse.data_ptr(), pb.data_ptr(), Lq * Lk, Lk,
+                  B, H, Lq, Lk, lens.data_ptr(), P(dist), P(sw), P(sb), 0.125, 1, 0.1, 3, seed.data_ptr(), _lib.stream())
+        do = torch.randn_like(out)
+        dp = torch.randn_like(pb) * 1e-3
+        delta = torch.empty_like(lse)
+        dq = torch.empty_like(q)
+        dkv = dq if Lq == Lk else torch.empty_like(kvt)
+        gs = torch.zeros(2, device=dev)
 
         def fb(i):
-            torch.autograd.grad((o, p), (q,), (do, dp), retain_graph=True)
+            _lib.call("magic_attn_bwd", q.data_ptr() + 2 * q_off, kvt.data_ptr() + 2 * k_off,
+                      kvt.data_ptr() + 2 * v_off, q.stride(0), kvt.stride(0), kvt.stride(0), do.data_ptr(),
+                      lse.data_ptr(), dp.data_ptr(), Lq * Lk, Lk, delta.data_ptr(), dq.data_ptr() + 2 * q_off,
+                      dkv.data_ptr() + 2 * k_off, dkv.data_ptr() + 2 * v_off, dq.stride(0), dkv.stride(0),
+                      dkv.stride(0), gs.data_ptr() if bias else None, B, H, Lq, Lk, lens.data_ptr(), P(dist), P(sw),
+                      P(sb), 0.125, 1, 0.1, 3, seed.data_ptr(), _lib.stream())
         timeit(f"attn bwd B{B} H{H} {Lq}x{Lk} bias{int(bias)} pbar1", fb, 2.5 * fl, 2 * by)
 
 

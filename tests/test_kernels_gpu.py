@@ -213,7 +213,10 @@ def _ref_attn(q, k, v, lens, dists, sw, sb, H):
 
 @pytest.mark.parametrize("dtype,tol", [(torch.float32, 3e-5), (torch.bfloat16, 2e-2)])
 @pytest.mark.parametrize("cfg", [dict(B=3, H=2, Lq=20, Lk=20, sprel=True), dict(B=4, H=2, Lq=37, Lk=80, sprel=False),
-                                 dict(B=2, H=12, Lq=80, Lk=80, sprel=False), dict(B=2, H=2, Lq=160, Lk=50, sprel=False)])
+                                 dict(B=2, H=12, Lq=80, Lk=80, sprel=False), dict(B=2, H=2, Lq=160, Lk=50, sprel=False),
+                                 dict(B=5, H=2, Lq=36, Lk=36, sprel=False), dict(B=2, H=2, Lq=50, Lk=50, sprel=True),
+                                 dict(B=2, H=2, Lq=160, Lk=160, sprel=False), dict(B=2, H=4, Lq=80, Lk=37, sprel=False),
+                                 dict(B=3, H=2, Lq=65, Lk=33, sprel=False), dict(B=1, H=2, Lq=200, Lk=200, sprel=False)])
 def test_attention(dtype, tol, cfg):
     torch.manual_seed(5)
     B, H, Lq, Lk = cfg["B"], cfg["H"], cfg["Lq"], cfg["Lk"]
@@ -377,6 +380,46 @@ def test_dropout_is_consistent_between_fwd_and_bwd():
     num = ((fa(qkv.detach() + eps * d) - fa(qkv.detach() - eps * d)) * go).sum() / (2 * eps)
     ana = (qkv.grad * d).sum()
     assert abs(num.item() - ana.item()) <= 2e-2 * abs(ana.item()) + 1e-3, (num.item(), ana.item())
+
+
+@pytest.mark.parametrize("cfg", [dict(B=3, H=2, Lq=80, Lk=80, sprel=False), dict(B=4, H=2, Lq=36, Lk=36, sprel=False),
+                                 dict(B=2, H=2, Lq=50, Lk=50, sprel=True), dict(B=2, H=2, Lq=37, Lk=160, sprel=False)])
+def test_attention_mma_matches_simt_with_dropout(cfg):
+    """bf16 tensor-core attention vs the fp32 SIMT kernels on the same (bf16-representable) inputs with attention
+    dropout on: both regenerate the same stateless mask, so outputs and gradients agree to bf16 precision."""
+    torch.manual_seed(12)
+    ops.set_seed(DEV, 4321)
+    B, H, Lq, Lk = cfg["B"], cfg["H"], cfg["Lq"], cfg["Lk"]
+    hd = H * 64
+    lens = torch.randint(max(1, Lk // 2), Lk + 1, (B,), device=DEV).int()
+    dists = torch.rand(B, Lq, Lk, device=DEV) * 30 if cfg["sprel"] else None
+    res = {}
+    base_q = torch.randn(B * Lq, 3 * hd if Lq == Lk else hd, device=DEV).bfloat16()
+    base_kv = torch.randn(B * Lk, 2 * hd, device=DEV).bfloat16()
+    go = torch.randn(B * Lq, hd, device=DEV).bfloat16()
+    gp = torch.randn(B, Lq, Lk, device=DEV) * 0.1
+    for dtype in (torch.float32, torch.bfloat16):
+        sw = torch.tensor([[-0.05]], device=DEV, requires_grad=True) if dists is not None else None
+        sb = torch.tensor([0.1], device=DEV, requires_grad=True) if dists is not None else None
+        q = base_q.to(dtype).requires_grad_()
+        if Lq == Lk:
+            o, pbar = ops.attention(q, None, 0, hd, 2 * hd, B, H, Lq, Lk, lens, dists, sw, sb, True, 0.2, 9)
+            kv = None
+        else:
+            kv = base_kv.to(dtype).requires_grad_()
+            o, pbar = ops.attention(q, kv, 0, 0, hd, B, H, Lq, Lk, lens, None, None, None, True, 0.2, 9)
+        ((o.float() * go.float()).sum() + (pbar * gp).sum()).backward()
+        res[dtype] = (o.float(), pbar, q.grad.float(), kv.grad.float() if kv is not None else None,
+                      sw.grad if sw is not None else None)
+    a, b_ = res[torch.float32], res[torch.bfloat16]
+    assert (a[0] == 0).float().mean() < 0.05  # dropout is on P, not on the output
+    close(b_[0], a[0], 2e-2, "mma attn out")
+    close(b_[1], a[1], 1e-2, "mma attn pbar")
+    close(b_[2], a[2], 4e-2, "mma attn dq(kv)")
+    if a[3] is not None:
+        close(b_[3], a[3], 4e-2, "mma attn dkv")
+    if a[4] is not None:
+        close(b_[4], a[4], 5e-2, "mma attn dsprel_w")
 
 
 def test_adamw_matches_reference_update_order():

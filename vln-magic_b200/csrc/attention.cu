@@ -10,6 +10,7 @@
 // Backward = two passes with the same structure (dQ by query rows, dK/dV by key rows); P is recomputed from
 // the saved log-sum-exp, the softmax row term delta is produced by pass 1.
 #include "common.cuh"
+#include "attention.cuh"
 #include "../../include/magic_b200.h"
 
 namespace {
@@ -22,29 +23,6 @@ constexpr int ROWS = NW * RPW;
 constexpr int MAXJ = 10;     // ceil(320 / 32)
 constexpr int MAXL = 32 * MAXJ;
 
-struct AttnParams {
-  const void *q, *k, *v;
-  long q_ld, k_ld, v_ld;        // elements between consecutive tokens
-  void* out;                    // [B*Lq, H*64]
-  float* lse;                   // [B, H, Lq]
-  float* pbar;                  // optional head-mean probs
-  long pbar_bs, pbar_rs;        // batch / row strides (elements)
-  const int* key_lens;          // [B] or null
-  const float* dists;           // [B, Lq, Lk] or null
-  const float *sprel_w, *sprel_b;
-  int B, H, Lq, Lk;
-  float scale;
-  float drop_p;
-  uint32_t salt;
-  const unsigned long long* seed_ptr;
-  // backward
-  const void* dout;
-  const float* dpbar;
-  float* delta;                 // [B, H, Lq]
-  void *dq, *dk, *dv;
-  long dq_ld, dk_ld, dv_ld;
-  float* dsprel;                // [2] : dw, db
-};
 
 __host__ __device__ inline int round4(int x) { return (x + 3) & ~3; }
 
@@ -489,6 +467,10 @@ int magic_attn_fwd(const void* q, const void* k, const void* v, long q_ld, long 
   AttnParams P = make_params(q, k, v, q_ld, k_ld, v_ld, B, H, Lq, Lk, key_lens, dists, sprel_w, sprel_b, scale, drop_p,
                              salt, seed_ptr);
   P.out = out; P.lse = lse; P.pbar = pbar; P.pbar_bs = pbar_bs; P.pbar_rs = pbar_rs;
+  if (dtype == MAGIC_BF16) {  // tensor-core path (attention_mma.cu) when the shape / alignment allows
+    const int rc = attn_mma_fwd(P, st);
+    if (rc != MAGIC_ERR_UNSUPPORTED) return rc;
+  }
   const size_t smem = ((size_t)2 * round4(Lk) * DP + NW * RPW * D + NW * RPW * MAXL) * sizeof(float);
   dim3 grid((Lq + ROWS - 1) / ROWS, B);
   if (dtype == MAGIC_F32) {
@@ -521,6 +503,10 @@ int magic_attn_bwd(const void* q, const void* k, const void* v, long q_ld, long 
   P.lse = const_cast<float*>(lse); P.dout = dout; P.dpbar = dpbar; P.pbar_bs = pbar_bs; P.pbar_rs = pbar_rs;
   P.delta = delta; P.dq = dq; P.dk = dk; P.dv = dv; P.dq_ld = dq_ld; P.dk_ld = dk_ld; P.dv_ld = dv_ld;
   P.dsprel = dsprel;
+  if (dtype == MAGIC_BF16) {
+    const int rc = attn_mma_bwd(P, st);
+    if (rc != MAGIC_ERR_UNSUPPORTED) return rc;
+  }
   const size_t smem1 = ((size_t)2 * round4(Lk) * DP + 2 * NW * RPW * D + NW * RPW * MAXL) * sizeof(float);
   const size_t smem2 =
       ((size_t)2 * round4(Lq) * DP + 2 * round4(Lq) + 2 * NW * RPW * D + 2 * NW * RPW * MAXL) * sizeof(float);

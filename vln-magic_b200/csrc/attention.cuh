@@ -1,0 +1,33 @@
+// Shared parameter block of the attention kernels (SIMT fp32/bf16 path in attention.cu, bf16 tensor-core
+// path in attention_mma.cu).
+#pragma once
+#include "common.cuh"
+
+struct AttnParams {
+  const void *q, *k, *v;
+  long q_ld, k_ld, v_ld;        // elements between consecutive tokens
+  void* out;                    // [B*Lq, H*64]
+  float* lse;                   // [B, H, Lq]
+  float* pbar;                  // optional head-mean probs
+  long pbar_bs, pbar_rs;        // batch / row strides (elements)
+  const int* key_lens;          // [B] or null
+  const float* dists;           // [B, Lq, Lk] or null
+  const float *sprel_w, *sprel_b;
+  int B, H, Lq, Lk;
+  float scale;
+  float drop_p;
+  uint32_t salt;
+  const unsigned long long* seed_ptr;
+  // backward
+  const void* dout;
+  const float* dpbar;
+  float* delta;                 // [B, H, Lq]
+  void *dq, *dk, *dv;
+  long dq_ld, dk_ld, dv_ld;
+  float* dsprel;                // [2] : dw, db
+};
+
+// bf16 mma.sync path (attention_mma.cu).  Return MAGIC_ERR_UNSUPPORTED when the shape / alignment is outside
+// what the tensor-core kernels cover; the caller then uses the SIMT kernels.
+int attn_mma_fwd(const AttnParams& P, cudaStream_t st);
+int attn_mma_bwd(const AttnParams& P, cudaStream_t st);

@@ -1,0 +1,589 @@
+// bf16 tensor-core attention for the MAGIC encoders (head_dim 64, Lq / Lk <= 160), forward and backward.
+//
+// The sequences are short (text 80/160 tokens, 36-view panoramas, 20/50-node graphs), so a whole key range fits
+// one register-resident score tile: one warp owns a 16-row slab of S = Q K^T (mma.sync m16n8k16, bf16 in, fp32
+// accumulate), adds the graph-distance bias w*dist+b and the key-padding mask INSIDE the tile, does the softmax
+// with quad shuffles, and feeds P straight back into the P V product as the A operand (no shared-memory round
+// trip).  K / V / Q tiles are staged by cp.async into 144-byte-pitch shared rows (conflict-free ldmatrix).
+//
+//   forward     grid (ceil(Lq/64), heads, B); with the KD attention map requested one CTA walks all heads of
+//               its rows and accumulates mean_heads(P) in shared memory (no atomics, deterministic)
+//   backward 1  (query-major) recomputes P from the saved log-sum-exp, dP = dO V^T, the softmax row term
+//               delta = sum_j P (dP*drop + dPbar/H), dS, dQ = dS K, and the sprel affine's gradients
+//   backward 2  (key-major) works on the transposed tile S^T = K Q^T so that P^T and dS^T are already the A
+//               operands of dV = P^T dO and dK = dS^T Q; no atomics, each dK/dV row is written exactly once
+//
+// Dropout uses the same stateless hash and element index as the SIMT kernels (attention.cu), so both paths
+// generate identical masks.  fp32 activations, longer sequences and unaligned views stay on the SIMT path.
+#include <stdlib.h>
+
+#include "attention.cuh"
+#include "../../include/magic_b200.h"
+
+namespace {
+
+typedef __nv_bfloat16 bf16;
+
+constexpr int D = 64;
+constexpr int PITCH = 72;   // bf16 elements per shared row (144 B: 16-byte aligned, ldmatrix conflict-free)
+constexpr int TILE = 64;    // rows (queries or keys) per CTA: 4 warps x 16
+constexpr int NTHREADS = 128;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void cp_async16(void* dst, const void* src, int src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(dst)), "l"(src), "r"(src_bytes)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+  asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+}
+
+__device__ __forceinline__ void ldsm_x4(const bf16* p, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
+               : "r"(smem_u32(p)));
+}
+__device__ __forceinline__ void ldsm_x4_t(const bf16* p, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
+               : "r"(smem_u32(p)));
+}
+__device__ __forceinline__ void mma16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, "
+      "{%0, %1, %2, %3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t pack2(float lo, float hi) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ float quad_sum(float v) {
+  v += __shfl_xor_sync(0xffffffffu, v, 1);
+  v += __shfl_xor_sync(0xffffffffu, v, 2);
+  return v;
+}
+__device__ __forceinline__ float quad_max(float v) {
+  v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 1));
+  v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 2));
+  return v;
+}
+
+// dst[rows_pad][PITCH] <- src[r * ld + 0..63] for r < rows_valid (>= 1); remaining rows are zero-filled
+__device__ __forceinline__ void load_rows(bf16* dst, const bf16* src, long ld, int rows_valid, int rows_pad) {
+  for (int e = threadIdx.x; e < rows_pad * 8; e += NTHREADS) {
+    const int r = e >> 3, c = e & 7;
+    const int rs = r < rows_valid ? r : rows_valid - 1;  // keep the address legal for the zero-fill form
+    cp_async16(dst + r * PITCH + c * 8, src + (size_t)rs * ld + c * 8, r < rows_valid ? 16 : 0);
+  }
+}
+
+// A fragments (16 rows x 64 k) of a row-major tile
+__device__ __forceinline__ void load_a_frags(const bf16* tile, int row0, int lane, uint32_t (&a)[4][4]) {
+#pragma unroll
+  for (int kk = 0; kk < 4; kk++)
+    ldsm_x4(tile + (row0 + (lane & 15)) * PITCH + kk * 16 + (lane >> 4) * 8, a[kk][0], a[kk][1], a[kk][2], a[kk][3]);
+}
+
+// acc[NT][4] (16 x NT*8) = A(16 x 64) * Y^T, Y = row-major [NT*8][64] tile ("B col-major": B[k][n] = Y[n][k])
+template <int NT>
+__device__ __forceinline__ void mma_a_yt(float (&acc)[NT][4], const uint32_t (&a)[4][4], const bf16* Y, int lane) {
+#pragma unroll
+  for (int j = 0; j < NT; j++) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
+  const bf16* base = Y + ((lane & 7) + ((lane >> 4) & 1) * 8) * PITCH + ((lane >> 3) & 1) * 8;
+#pragma unroll
+  for (int j = 0; j < NT; j += 2) {
+#pragma unroll
+    for (int kk = 0; kk < 4; kk++) {
+      uint32_t b0, b1, b2, b3;
+      ldsm_x4(base + j * 8 * PITCH + kk * 16, b0, b1, b2, b3);
+      mma16816(acc[j], a[kk], b0, b1);
+      mma16816(acc[j + 1], a[kk], b2, b3);
+    }
+  }
+}
+
+// o[8][4] (16 x 64) = C(16 x NT*8, fp32 fragments rounded to bf16) * Y, Y = row-major [NT*8][64] tile; k-steps
+// at or beyond `kmax` rows are skipped (their coefficients are exactly zero)
+template <int NT>
+__device__ __forceinline__ void mma_c_y(float (&o)[8][4], const float (&c)[NT][4], const bf16* Y, int lane, int kmax) {
+#pragma unroll
+  for (int dn = 0; dn < 8; dn++) o[dn][0] = o[dn][1] = o[dn][2] = o[dn][3] = 0.f;
+  const bf16* base = Y + ((lane & 7) + ((lane >> 3) & 1) * 8) * PITCH + ((lane >> 4) & 1) * 8;
+#pragma unroll
+  for (int k2 = 0; k2 < NT / 2; k2++) {
+    if (k2 * 16 < kmax) {
+      uint32_t a[4];
+      a[0] = pack2(c[2 * k2][0], c[2 * k2][1]);
+      a[1] = pack2(c[2 * k2][2], c[2 * k2][3]);
+      a[2] = pack2(c[2 * k2 + 1][0], c[2 * k2 + 1][1]);
+      a[3] = pack2(c[2 * k2 + 1][2], c[2 * k2 + 1][3]);
+#pragma unroll
+      for (int dn = 0; dn < 8; dn += 2) {
+        uint32_t b0, b1, b2, b3;
+        ldsm_x4_t(base + k2 * 16 * PITCH + dn * 8, b0, b1, b2, b3);
+        mma16816(o[dn], a, b0, b1);
+        mma16816(o[dn + 1], a, b2, b3);
+      }
+    }
+  }
+}
+
+// store a 16 x 64 fp32 fragment tile (scaled) as bf16 rows; row pointers may be null (row out of range)
+__device__ __forceinline__ void store_rows(bf16* ra, bf16* rb, const float (&o)[8][4], float mul, int t) {
+#pragma unroll
+  for (int dn = 0; dn < 8; dn++) {
+    if (ra) *reinterpret_cast<uint32_t*>(ra + dn * 8 + 2 * t) = pack2(o[dn][0] * mul, o[dn][1] * mul);
+    if (rb) *reinterpret_cast<uint32_t*>(rb + dn * 8 + 2 * t) = pack2(o[dn][2] * mul, o[dn][3] * mul);
+  }
+}
+
+// ===================================================================================================
+// forward
+// ===================================================================================================
+template <int NT>
+__global__ void __launch_bounds__(NTHREADS) attn_mma_fwd_kernel(AttnParams P, int hc) {
+  extern __shared__ __align__(16) uint8_t smraw[];
+  constexpr int LKP = NT * 8;
+  bf16* Ks = reinterpret_cast<bf16*>(smraw);
+  bf16* Vs = Ks + LKP * PITCH;
+  bf16* Qs = Vs + LKP * PITCH;
+  float* pb = reinterpret_cast<float*>(Qs + TILE * PITCH);  // [TILE][LKP], only when P.pbar
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
+  const int b = blockIdx.z, q0 = blockIdx.x * TILE, h_begin = blockIdx.y * hc;
+  const int Lq = P.Lq, Lk = P.Lk, H = P.H;
+  const int klen = P.key_lens ? min(Lk, P.key_lens[b]) : Lk;
+  const int rows_q = min(TILE, Lq - q0);
+  const bool wact = w * 16 < rows_q;
+  const float sw = P.dists ? P.sprel_w[0] : 0.f, sb = P.dists ? P.sprel_b[0] : 0.f;
+  const Dropout dr = make_dropout(P.drop_p, P.seed_ptr, P.salt);
+  const float invH = 1.f / (float)H;
+  const int ia = q0 + w * 16 + g, ib = ia + 8;
+  const bool va = ia < Lq, vb = ib < Lq;
+  if (P.pbar)
+    for (int e = threadIdx.x; e < TILE * LKP; e += NTHREADS) pb[e] = 0.f;
+
+  for (int hd = h_begin; hd < h_begin + hc; hd++) {
+    __syncthreads();
+    load_rows(Ks, (const bf16*)P.k + (size_t)b * Lk * P.k_ld + hd * D, P.k_ld, Lk, LKP);
+    load_rows(Vs, (const bf16*)P.v + (size_t)b * Lk * P.v_ld + hd * D, P.v_ld, Lk, LKP);
+    load_rows(Qs, (const bf16*)P.q + ((size_t)b * Lq + q0) * P.q_ld + hd * D, P.q_ld, rows_q, TILE);
+    cp_async_wait_all();
+    __syncthreads();
+    if (!wact) continue;  // warp-uniform; every warp reaches the barriers at the top of the next iteration
+
+    float s[NT][4];
+    {
+      uint32_t qa[4][4];
+      load_a_frags(Qs, w * 16, lane, qa);
+      mma_a_yt<NT>(s, qa, Ks, lane);
+    }
+    const size_t da = ((size_t)b * Lq + (va ? ia : 0)) * Lk, db = ((size_t)b * Lq + (vb ? ib : 0)) * Lk;
+    float mxa = -INFINITY, mxb = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < NT; j++) {
+#pragma unroll
+      for (int e = 0; e < 2; e++) {
+        const int c = j * 8 + 2 * t + e;
+        float x0 = s[j][e] * P.scale, x1 = s[j][2 + e] * P.scale;
+        if (c < klen) {
+          if (P.dists) {
+            x0 += sw * P.dists[da + c] + sb;
+            x1 += sw * P.dists[db + c] + sb;
+          }
+        } else {
+          x0 = x1 = -INFINITY;
+        }
+        s[j][e] = x0;
+        s[j][2 + e] = x1;
+        mxa = fmaxf(mxa, x0);
+        mxb = fmaxf(mxb, x1);
+      }
+    }
+    mxa = quad_max(mxa);
+    mxb = quad_max(mxb);
+    float suma = 0.f, sumb = 0.f;
+#pragma unroll
+    for (int j = 0; j < NT; j++) {
+#pragma unroll
+      for (int e = 0; e < 2; e++) {
+        const float e0 = (s[j][e] == -INFINITY) ? 0.f : __expf(s[j][e] - mxa);
+        const float e1 = (s[j][2 + e] == -INFINITY) ? 0.f : __expf(s[j][2 + e] - mxb);
+        s[j][e] = e0;
+        s[j][2 + e] = e1;
+        suma += e0;
+        sumb += e1;
+      }
+    }
+    suma = quad_sum(suma);
+    sumb = quad_sum(sumb);
+    const float inva = 1.f / suma, invb = 1.f / sumb;
+    if (t == 0) {
+      if (va) P.lse[((size_t)b * H + hd) * Lq + ia] = mxa + __logf(suma);
+      if (vb) P.lse[((size_t)b * H + hd) * Lq + ib] = mxb + __logf(sumb);
+    }
+    const size_t dia = (((size_t)b * H + hd) * Lq + ia) * Lk, dib = (((size_t)b * H + hd) * Lq + ib) * Lk;
+    float* pba = pb + (w * 16 + g) * LKP;
+    float* pbb = pba + 8 * LKP;
+#pragma unroll
+    for (int j = 0; j < NT; j++) {
+#pragma unroll
+      for (int e = 0; e < 2; e++) {
+        const int c = j * 8 + 2 * t + e;
+        const float pa = s[j][e] * inva, pc = s[j][2 + e] * invb;  // exactly 0 for masked / padded keys
+        if (P.pbar) {
+          pba[c] += pa * invH;
+          pbb[c] += pc * invH;
+        }
+        s[j][e] = pa * dr.scale(dia + c);
+        s[j][2 + e] = pc * dr.scale(dib + c);
+      }
+    }
+    float o[8][4];
+    mma_c_y<NT>(o, s, Vs, lane, klen);
+    bf16* ob = (bf16*)P.out + hd * D;
+    store_rows(va ? ob + ((size_t)b * Lq + ia) * (size_t)(H * D) : nullptr,
+               vb ? ob + ((size_t)b * Lq + ib) * (size_t)(H * D) : nullptr, o, 1.f, t);
+  }
+  if (P.pbar) {
+    __syncthreads();
+    for (int e = threadIdx.x; e < rows_q * Lk; e += NTHREADS) {
+      const int r = e / Lk, c = e - r * Lk;
+      P.pbar[(size_t)b * P.pbar_bs + (size_t)(q0 + r) * P.pbar_rs + c] = pb[r * LKP + c];
+    }
+  }
+}
+
+// ===================================================================================================
+// backward pass 1 (query-major): delta, dQ, d(sprel)
+// ===================================================================================================
+template <int NT>
+__global__ void __launch_bounds__(NTHREADS) attn_mma_bwd_q_kernel(AttnParams P) {
+  extern __shared__ __align__(16) uint8_t smraw[];
+  constexpr int LKP = NT * 8;
+  bf16* Ks = reinterpret_cast<bf16*>(smraw);
+  bf16* Vs = Ks + LKP * PITCH;
+  bf16* Qs = Vs + LKP * PITCH;
+  bf16* Gs = Qs + TILE * PITCH;
+  __shared__ float red[32];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
+  const int b = blockIdx.z, hd = blockIdx.y, q0 = blockIdx.x * TILE;
+  const int Lq = P.Lq, Lk = P.Lk, H = P.H;
+  const int klen = P.key_lens ? min(Lk, P.key_lens[b]) : Lk;
+  const int rows_q = min(TILE, Lq - q0);
+  const bool wact = w * 16 < rows_q;
+  const float sw = P.dists ? P.sprel_w[0] : 0.f, sb = P.dists ? P.sprel_b[0] : 0.f;
+  const Dropout dr = make_dropout(P.drop_p, P.seed_ptr, P.salt);
+  const float invH = 1.f / (float)H;
+  const int ia = q0 + w * 16 + g, ib = ia + 8;
+  const bool va = ia < Lq, vb = ib < Lq;
+
+  load_rows(Ks, (const bf16*)P.k + (size_t)b * Lk * P.k_ld + hd * D, P.k_ld, Lk, LKP);
+  load_rows(Vs, (const bf16*)P.v + (size_t)b * Lk * P.v_ld + hd * D, P.v_ld, Lk, LKP);
+  load_rows(Qs, (const bf16*)P.q + ((size_t)b * Lq + q0) * P.q_ld + hd * D, P.q_ld, rows_q, TILE);
+  load_rows(Gs, (const bf16*)P.dout + ((size_t)b * Lq + q0) * (size_t)(H * D) + hd * D, (long)H * D, rows_q, TILE);
+  cp_async_wait_all();
+  __syncthreads();
+
+  float acc_dw = 0.f, acc_db = 0.f;
+  if (wact) {
+    float p[NT][4], dp[NT][4];
+    {
+      uint32_t qa[4][4];
+      load_a_frags(Qs, w * 16, lane, qa);
+      mma_a_yt<NT>(p, qa, Ks, lane);
+    }
+    {
+      uint32_t ga[4][4];
+      load_a_frags(Gs, w * 16, lane, ga);
+      mma_a_yt<NT>(dp, ga, Vs, lane);
+    }
+    const float lsa = va ? P.lse[((size_t)b * H + hd) * Lq + ia] : 0.f;
+    const float lsb = vb ? P.lse[((size_t)b * H + hd) * Lq + ib] : 0.f;
+    const size_t da = ((size_t)b * Lq + (va ? ia : 0)) * Lk, db = ((size_t)b * Lq + (vb ? ib : 0)) * Lk;
+    const size_t dia = (((size_t)b * H + hd) * Lq + ia) * Lk, dib = (((size_t)b * H + hd) * Lq + ib) * Lk;
+    const float* dpa = P.dpbar ? P.dpbar + (size_t)b * P.pbar_bs + (size_t)(va ? ia : 0) * P.pbar_rs : nullptr;
+    const float* dpb = P.dpbar ? P.dpbar + (size_t)b * P.pbar_bs + (size_t)(vb ? ib : 0) * P.pbar_rs : nullptr;
+    float dla = 0.f, dlb = 0.f;
+#pragma unroll
+    for (int j = 0; j < NT; j++) {
+#pragma unroll
+      for (int e = 0; e < 2; e++) {
+        const int c = j * 8 + 2 * t + e;
+        float p0 = 0.f, p1 = 0.f, t0 = 0.f, t1 = 0.f;
+        if (c < klen) {
+          float x0 = p[j][e] * P.scale, x1 = p[j][2 + e] * P.scale;
+          if (P.dists) {
+            x0 += sw * P.dists[da + c] + sb;
+            x1 += sw * P.dists[db + c] + sb;
+          }
+          p0 = va ? __expf(x0 - lsa) : 0.f;
+          p1 = vb ? __expf(x1 - lsb) : 0.f;
+          t0 = dp[j][e] * dr.scale(dia + c);
+          t1 = dp[j][2 + e] * dr.scale(dib + c);
+          if (P.dpbar) {
+            t0 += dpa[c] * invH;
+            t1 += dpb[c] * invH;
+          }
+        }
+        p[j][e] = p0;
+        p[j][2 + e] = p1;
+        dp[j][e] = t0;
+        dp[j][2 + e] = t1;
+        dla = fmaf(p0, t0, dla);
+        dlb = fmaf(p1, t1, dlb);
+      }
+    }
+    dla = quad_sum(dla);
+    dlb = quad_sum(dlb);
+    if (t == 0) {
+      if (va) P.delta[((size_t)b * H + hd) * Lq + ia] = dla;
+      if (vb) P.delta[((size_t)b * H + hd) * Lq + ib] = dlb;
+    }
+#pragma unroll
+    for (int j = 0; j < NT; j++) {
+#pragma unroll
+      for (int e = 0; e < 2; e++) {
+        const int c = j * 8 + 2 * t + e;
+        const float ds0 = p[j][e] * (dp[j][e] - dla), ds1 = p[j][2 + e] * (dp[j][2 + e] - dlb);
+        p[j][e] = ds0;
+        p[j][2 + e] = ds1;
+        if (P.dists && c < klen) {
+          acc_dw = fmaf(ds0, P.dists[da + c], acc_dw);
+          acc_dw = fmaf(ds1, P.dists[db + c], acc_dw);
+          acc_db += ds0 + ds1;
+        }
+      }
+    }
+    float o[8][4];
+    mma_c_y<NT>(o, p, Ks, lane, klen);
+    bf16* qb = (bf16*)P.dq + hd * D;
+    store_rows(va ? qb + ((size_t)b * Lq + ia) * P.dq_ld : nullptr, vb ? qb + ((size_t)b * Lq + ib) * P.dq_ld : nullptr,
+               o, P.scale, t);
+  }
+  if (P.dists && P.dsprel) {
+    const float tw = block_sum(acc_dw, red);
+    const float tb = block_sum(acc_db, red);
+    if (threadIdx.x == 0) {
+      atomicAdd(P.dsprel, tw);
+      atomicAdd(P.dsprel + 1, tb);
+    }
+  }
+}
+
+// ===================================================================================================
+// backward pass 2 (key-major): dK, dV from the transposed tile
+// ===================================================================================================
+template <int NTQ>
+__global__ void __launch_bounds__(NTHREADS) attn_mma_bwd_kv_kernel(AttnParams P) {
+  extern __shared__ __align__(16) uint8_t smraw[];
+  constexpr int LQP = NTQ * 8;
+  bf16* Qs = reinterpret_cast<bf16*>(smraw);
+  bf16* Gs = Qs + LQP * PITCH;
+  bf16* Ks = Gs + LQP * PITCH;
+  bf16* Vs = Ks + TILE * PITCH;
+  float* ls = reinterpret_cast<float*>(Vs + TILE * PITCH);  // [LQP] lse
+  float* dl = ls + LQP;                                     // [LQP] delta
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
+  const int b = blockIdx.z, hd = blockIdx.y, k0 = blockIdx.x * TILE;
+  const int Lq = P.Lq, Lk = P.Lk, H = P.H;
+  const int klen = P.key_lens ? min(Lk, P.key_lens[b]) : Lk;
+  const int rows_k = min(TILE, Lk - k0);
+  const float sw = P.dists ? P.sprel_w[0] : 0.f, sb = P.dists ? P.sprel_b[0] : 0.f;
+  const Dropout dr = make_dropout(P.drop_p, P.seed_ptr, P.salt);
+  const float invH = 1.f / (float)H;
+
+  load_rows(Qs, (const bf16*)P.q + (size_t)b * Lq * P.q_ld + hd * D, P.q_ld, Lq, LQP);
+  load_rows(Gs, (const bf16*)P.dout + (size_t)b * Lq * (size_t)(H * D) + hd * D, (long)H * D, Lq, LQP);
+  load_rows(Ks, (const bf16*)P.k + ((size_t)b * Lk + k0) * P.k_ld + hd * D, P.k_ld, rows_k, TILE);
+  load_rows(Vs, (const bf16*)P.v + ((size_t)b * Lk + k0) * P.v_ld + hd * D, P.v_ld, rows_k, TILE);
+  for (int i = threadIdx.x; i < LQP; i += NTHREADS) {
+    ls[i] = i < Lq ? P.lse[((size_t)b * H + hd) * Lq + i] : 0.f;
+    dl[i] = i < Lq ? P.delta[((size_t)b * H + hd) * Lq + i] : 0.f;
+  }
+  cp_async_wait_all();
+  __syncthreads();
+  if (w * 16 >= rows_k) return;  // no barriers below
+
+  const int ja = k0 + w * 16 + g, jb = ja + 8;
+  const bool va = ja < Lk, vb = jb < Lk;
+  bf16* dka = va ? (bf16*)P.dk + ((size_t)b * Lk + ja) * P.dk_ld + hd * D : nullptr;
+  bf16* dkb = vb ? (bf16*)P.dk + ((size_t)b * Lk + jb) * P.dk_ld + hd * D : nullptr;
+  bf16* dva = va ? (bf16*)P.dv + ((size_t)b * Lk + ja) * P.dv_ld + hd * D : nullptr;
+  bf16* dvb = vb ? (bf16*)P.dv + ((size_t)b * Lk + jb) * P.dv_ld + hd * D : nullptr;
+  float o[8][4];
+  if (k0 + w * 16 >= klen) {  // every key of this slab is masked: exact zero gradients
+#pragma unroll
+    for (int dn = 0; dn < 8; dn++) o[dn][0] = o[dn][1] = o[dn][2] = o[dn][3] = 0.f;
+    store_rows(dka, dkb, o, 0.f, t);
+    store_rows(dva, dvb, o, 0.f, t);
+    return;
+  }
+  const bool ma = ja < klen, mb = jb < klen;
+  const size_t dbase = ((size_t)b * H + hd) * Lq;
+
+  float p[NTQ][4];
+  {
+    uint32_t ka[4][4];
+    load_a_frags(Ks, w * 16, lane, ka);
+    mma_a_yt<NTQ>(p, ka, Qs, lane);
+  }
+#pragma unroll
+  for (int n = 0; n < NTQ; n++) {
+#pragma unroll
+    for (int e = 0; e < 2; e++) {
+      const int c = n * 8 + 2 * t + e;  // query index
+      float p0 = 0.f, p1 = 0.f;
+      if (c < Lq) {
+        float x0 = p[n][e] * P.scale, x1 = p[n][2 + e] * P.scale;
+        if (P.dists) {
+          const size_t di = ((size_t)b * Lq + c) * Lk;
+          if (ma) x0 += sw * P.dists[di + ja] + sb;
+          if (mb) x1 += sw * P.dists[di + jb] + sb;
+        }
+        p0 = ma ? __expf(x0 - ls[c]) : 0.f;
+        p1 = mb ? __expf(x1 - ls[c]) : 0.f;
+      }
+      p[n][e] = p0;
+      p[n][2 + e] = p1;
+    }
+  }
+  // dV = (P^T o dropout) dO
+  {
+    float pd[NTQ][4];
+#pragma unroll
+    for (int n = 0; n < NTQ; n++) {
+#pragma unroll
+      for (int e = 0; e < 2; e++) {
+        const int c = n * 8 + 2 * t + e;
+        const size_t di = (dbase + c) * Lk;
+        pd[n][e] = p[n][e] * dr.scale(di + ja);
+        pd[n][2 + e] = p[n][2 + e] * dr.scale(di + jb);
+      }
+    }
+    mma_c_y<NTQ>(o, pd, Gs, lane, Lq);
+    store_rows(dva, dvb, o, 1.f, t);
+  }
+  // dS^T = P^T o (dP^T o dropout + dPbar^T / H - delta)
+  {
+    float dp[NTQ][4];
+    {
+      uint32_t vf[4][4];
+      load_a_frags(Vs, w * 16, lane, vf);
+      mma_a_yt<NTQ>(dp, vf, Gs, lane);
+    }
+#pragma unroll
+    for (int n = 0; n < NTQ; n++) {
+#pragma unroll
+      for (int e = 0; e < 2; e++) {
+        const int c = n * 8 + 2 * t + e;
+        const size_t di = (dbase + c) * Lk;
+        float t0 = dp[n][e] * dr.scale(di + ja), t1 = dp[n][2 + e] * dr.scale(di + jb);
+        if (P.dpbar && c < Lq) {
+          const float* dr_ = P.dpbar + (size_t)b * P.pbar_bs + (size_t)c * P.pbar_rs;
+          if (ma) t0 += dr_[ja] * invH;
+          if (mb) t1 += dr_[jb] * invH;
+        }
+        p[n][e] *= (t0 - dl[c]);
+        p[n][2 + e] *= (t1 - dl[c]);
+      }
+    }
+  }
+  mma_c_y<NTQ>(o, p, Qs, lane, Lq);
+  store_rows(dka, dkb, o, P.scale, t);
+}
+
+// ---- host side ----------------------------------------------------------------------------------------
+bool mma_disabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("MAGIC_ATTN_SIMT");
+    v = (e && e[0] == '1') ? 1 : 0;
+  }
+  return v == 1;
+}
+
+int pick_nt(int L) { return L <= 32 ? 4 : L <= 48 ? 6 : L <= 80 ? 10 : L <= 160 ? 20 : 0; }
+
+bool al16(const void* p) { return ((uintptr_t)p & 15) == 0; }
+bool ld_ok(long ld) { return ld >= D && (ld % 8) == 0; }
+
+template <typename K>
+int set_smem(K kernel, size_t bytes, const char* name) {
+  if (bytes > 48 * 1024)
+    MAGIC_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes), name);
+  return MAGIC_OK;
+}
+
+template <int NT>
+int launch_fwd(const AttnParams& P, cudaStream_t st) {
+  const size_t smem = (size_t)(2 * NT * 8 + TILE) * PITCH * 2 + (P.pbar ? (size_t)TILE * NT * 8 * 4 : 0);
+  int rc = set_smem(attn_mma_fwd_kernel<NT>, smem, "magic_attn_fwd");
+  if (rc) return rc;
+  const int hc = P.pbar ? P.H : 1;
+  dim3 grid((P.Lq + TILE - 1) / TILE, P.H / hc, P.B);
+  attn_mma_fwd_kernel<NT><<<grid, NTHREADS, smem, st>>>(P, hc);
+  MAGIC_CHECK_LAUNCH("magic_attn_fwd(mma)");
+  return MAGIC_OK;
+}
+
+template <int NT>
+int launch_bwd_q(const AttnParams& P, cudaStream_t st) {
+  const size_t smem = (size_t)(2 * NT * 8 + 2 * TILE) * PITCH * 2;
+  int rc = set_smem(attn_mma_bwd_q_kernel<NT>, smem, "magic_attn_bwd");
+  if (rc) return rc;
+  dim3 grid((P.Lq + TILE - 1) / TILE, P.H, P.B);
+  attn_mma_bwd_q_kernel<NT><<<grid, NTHREADS, smem, st>>>(P);
+  MAGIC_CHECK_LAUNCH("magic_attn_bwd(mma q)");
+  return MAGIC_OK;
+}
+
+template <int NTQ>
+int launch_bwd_kv(const AttnParams& P, cudaStream_t st) {
+  const size_t smem = (size_t)(2 * NTQ * 8 + 2 * TILE) * PITCH * 2 + (size_t)2 * NTQ * 8 * 4;
+  int rc = set_smem(attn_mma_bwd_kv_kernel<NTQ>, smem, "magic_attn_bwd");
+  if (rc) return rc;
+  dim3 grid((P.Lk + TILE - 1) / TILE, P.H, P.B);
+  attn_mma_bwd_kv_kernel<NTQ><<<grid, NTHREADS, smem, st>>>(P);
+  MAGIC_CHECK_LAUNCH("magic_attn_bwd(mma kv)");
+  return MAGIC_OK;
+}
+
+bool operands_ok(const AttnParams& P) {
+  return al16(P.q) && al16(P.k) && al16(P.v) && ld_ok(P.q_ld) && ld_ok(P.k_ld) && ld_ok(P.v_ld);
+}
+
+}  // namespace
+
+#define DISPATCH_NT(nt, fn, ...)                     \
+  switch (nt) {                                      \
+    case 4: return fn<4>(__VA_ARGS__);               \
+    case 6: return fn<6>(__VA_ARGS__);               \
+    case 10: return fn<10>(__VA_ARGS__);             \
+    default: return fn<20>(__VA_ARGS__);             \
+  }
+
+int attn_mma_fwd(const AttnParams& P, cudaStream_t st) {
+  const int nt = pick_nt(P.Lk);
+  if (mma_disabled() || nt == 0 || !operands_ok(P) || ((uintptr_t)P.out & 3)) return MAGIC_ERR_UNSUPPORTED;
+  DISPATCH_NT(nt, launch_fwd, P, st);
+}
+
+int attn_mma_bwd(const AttnParams& P, cudaStream_t st) {
+  const int nt = pick_nt(P.Lk), ntq = pick_nt(P.Lq);
+  if (mma_disabled() || nt == 0 || ntq == 0 || !operands_ok(P) || !al16(P.dout)) return MAGIC_ERR_UNSUPPORTED;
+  if (((uintptr_t)P.dq & 3) || ((uintptr_t)P.dk & 3) || ((uintptr_t)P.dv & 3) || (P.dq_ld & 1) || (P.dk_ld & 1) ||
+      (P.dv_ld & 1))
+    return MAGIC_ERR_UNSUPPORTED;
+  int rc;
+  switch (nt) {
+    case 4: rc = launch_bwd_q<4>(P, st); break;
+    case 6: rc = launch_bwd_q<6>(P, st); break;
+    case 10: rc = launch_bwd_q<10>(P, st); break;
+    default: rc = launch_bwd_q<20>(P, st); break;
+  }
+  if (rc) return rc;
+  DISPATCH_NT(ntq, launch_bwd_kv, P, st);
+}
