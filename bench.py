@@ -298,7 +298,8 @@ def run_ours(args):
     if cfg_t is not None:
         torch.manual_seed(0)
         teacher = magic_b200.GlocalTextPathCMTPreTraining(cfg_t).to(dev).eval().set_compute_dtype(dtype)
-    stepper = PretrainStepper(student, teacher, use_graphs=bool(args.graphs) and teacher is None)
+    stepper = PretrainStepper(student, teacher, use_graphs=bool(args.graphs) and teacher is None,
+                              side_stream=bool(args.side_stream), branch_streams=bool(args.branch_streams))
     ops.set_seed(dev, 1234 + rank)
 
     pool_n = args.pool
@@ -420,6 +421,8 @@ def main():
     ap.add_argument("--dropout", type=float, default=0.1)
     ap.add_argument("--graphs", type=int, default=1)
     ap.add_argument("--pool", type=int, default=8)
+    ap.add_argument("--side-stream", type=int, default=1)
+    ap.add_argument("--branch-streams", type=int, default=1)
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -1,5 +1,6 @@
 // Error channel, version and the GEMM dispatcher (tcgen05 path vs fp32 FFMA path).
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -13,6 +14,15 @@ void magic_set_error(const char* fmt, ...) {
   va_start(ap, fmt);
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
+}
+
+int magic_pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("MAGIC_PDL");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v;
 }
 
 int gemm_simt_dispatch(const void* A, int a_dt, const void* B, int b_dt, void* C, int c_dt, int M, int N, int K,

@@ -146,6 +146,8 @@ __device__ __forceinline__ void store_rows(bf16* ra, bf16* rb, const float (&o)[
 template <int NT>
 __global__ void __launch_bounds__(NTHREADS) attn_mma_fwd_kernel(AttnParams P, int hc) {
   extern __shared__ __align__(16) uint8_t smraw[];
+  pdl_trigger();
+  pdl_wait();
   constexpr int LKP = NT * 8;
   bf16* Ks = reinterpret_cast<bf16*>(smraw);
   bf16* Vs = Ks + LKP * PITCH;
@@ -262,6 +264,8 @@ __global__ void __launch_bounds__(NTHREADS) attn_mma_fwd_kernel(AttnParams P, in
 template <int NT>
 __global__ void __launch_bounds__(NTHREADS) attn_mma_bwd_q_kernel(AttnParams P) {
   extern __shared__ __align__(16) uint8_t smraw[];
+  pdl_trigger();
+  pdl_wait();
   constexpr int LKP = NT * 8;
   bf16* Ks = reinterpret_cast<bf16*>(smraw);
   bf16* Vs = Ks + LKP * PITCH;
@@ -379,6 +383,8 @@ __global__ void __launch_bounds__(NTHREADS) attn_mma_bwd_q_kernel(AttnParams P) 
 template <int NTQ>
 __global__ void __launch_bounds__(NTHREADS) attn_mma_bwd_kv_kernel(AttnParams P) {
   extern __shared__ __align__(16) uint8_t smraw[];
+  pdl_trigger();
+  pdl_wait();
   constexpr int LQP = NTQ * 8;
   bf16* Qs = reinterpret_cast<bf16*>(smraw);
   bf16* Gs = Qs + LQP * PITCH;
@@ -524,8 +530,7 @@ int launch_fwd(const AttnParams& P, cudaStream_t st) {
   if (rc) return rc;
   const int hc = P.pbar ? P.H : 1;
   dim3 grid((P.Lq + TILE - 1) / TILE, P.H / hc, P.B);
-  attn_mma_fwd_kernel<NT><<<grid, NTHREADS, smem, st>>>(P, hc);
-  MAGIC_CHECK_LAUNCH("magic_attn_fwd(mma)");
+  MAGIC_CUDA(magic_launch(attn_mma_fwd_kernel<NT>, grid, dim3(NTHREADS), smem, st, P, hc), "magic_attn_fwd(mma)");
   return MAGIC_OK;
 }
 
@@ -535,8 +540,7 @@ int launch_bwd_q(const AttnParams& P, cudaStream_t st) {
   int rc = set_smem(attn_mma_bwd_q_kernel<NT>, smem, "magic_attn_bwd");
   if (rc) return rc;
   dim3 grid((P.Lq + TILE - 1) / TILE, P.H, P.B);
-  attn_mma_bwd_q_kernel<NT><<<grid, NTHREADS, smem, st>>>(P);
-  MAGIC_CHECK_LAUNCH("magic_attn_bwd(mma q)");
+  MAGIC_CUDA(magic_launch(attn_mma_bwd_q_kernel<NT>, grid, dim3(NTHREADS), smem, st, P), "magic_attn_bwd(mma q)");
   return MAGIC_OK;
 }
 
@@ -546,8 +550,7 @@ int launch_bwd_kv(const AttnParams& P, cudaStream_t st) {
   int rc = set_smem(attn_mma_bwd_kv_kernel<NTQ>, smem, "magic_attn_bwd");
   if (rc) return rc;
   dim3 grid((P.Lk + TILE - 1) / TILE, P.H, P.B);
-  attn_mma_bwd_kv_kernel<NTQ><<<grid, NTHREADS, smem, st>>>(P);
-  MAGIC_CHECK_LAUNCH("magic_attn_bwd(mma kv)");
+  MAGIC_CUDA(magic_launch(attn_mma_bwd_kv_kernel<NTQ>, grid, dim3(NTHREADS), smem, st, P), "magic_attn_bwd(mma kv)");
   return MAGIC_OK;
 }
 

@@ -54,6 +54,35 @@ static inline int magic_num_sms() {
 }
 
 // ---------------------------------------------------------------------------------------------
+// Programmatic dependent launch (PDL).  A kernel launched through magic_launch() may be scheduled while its
+// predecessor in the stream is still draining: it calls pdl_trigger() first (so ITS successor can be staged as
+// early as possible) and pdl_wait() before its first access to global memory, which blocks until the
+// predecessor grid has completed and its writes are visible.  Everything before pdl_wait() (barrier init, TMEM
+// allocation, tensor-map prefetch, index math) overlaps the predecessor's tail.  The step is a chain of
+// several hundred small dependent kernels, so the launch gap is a first-order cost.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+int magic_pdl_enabled();  // api.cu: env MAGIC_PDL (default on)
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t magic_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                       Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = magic_pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
+// ---------------------------------------------------------------------------------------------
 // element access: activations are f32 or bf16; math is always fp32
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ float ldf(const float* p, size_t i) { return p[i]; }

@@ -316,6 +316,7 @@ __global__ void __launch_bounds__(NTHREADS, 1)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int total_work = P.m_tiles * P.n_tiles * P.splits;
+  pdl_trigger();
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmap_a);
@@ -337,6 +338,7 @@ __global__ void __launch_bounds__(NTHREADS, 1)
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  pdl_wait();  // everything above overlapped the previous kernel's tail; global memory is touched only below
 
   if (warp == 0) {
     if (lane == 0) {
@@ -476,7 +478,7 @@ __global__ void __launch_bounds__(NTHREADS, 1)
         }
       }
     }
-    if (lane == 0) bulk_wait_all();
+    if (lane == 0) bulk_wait_read<0>();  // smem must outlive the stores' reads; the writes land before grid completion
   }
   tc_fence_before();
   __syncthreads();
@@ -589,8 +591,8 @@ int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& t
                "magic_gemm(tc)");
     attr_smem = SMEM_MAX;
   }
-  gemm_tc_kernel<BN, TC><<<grid, NTHREADS, smem, st>>>(ta, tb, tc, tp, P);
-  MAGIC_CHECK_LAUNCH("magic_gemm(tc)");
+  MAGIC_CUDA(magic_launch(gemm_tc_kernel<BN, TC>, dim3(grid), dim3(NTHREADS), smem, st, ta, tb, tc, tp, P),
+             "magic_gemm(tc)");
   return MAGIC_OK;
 }
 

@@ -126,21 +126,89 @@ __global__ void __launch_bounds__(64)
 }
 
 // ---- cross-entropy, one CTA per row ---------------------------------------------------------------
+// 16-byte vector access for the vocabulary-sized rows (bf16: 8 elements, fp32: 4 elements)
+template <typename T>
+struct RowVec;
+template <>
+struct RowVec<float> {
+  static constexpr int N = 4;
+  static __device__ __forceinline__ void load(const float* p, float (&v)[4]) {
+    const float4 t = *reinterpret_cast<const float4*>(p);
+    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+  }
+  static __device__ __forceinline__ void store(float* p, const float (&v)[4]) {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  }
+};
+template <>
+struct RowVec<__nv_bfloat16> {
+  static constexpr int N = 8;
+  static __device__ __forceinline__ void load(const __nv_bfloat16* p, float (&v)[8]) {
+    const uint4 t = *reinterpret_cast<const uint4*>(p);
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&t);
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      const float2 f = __bfloat1622float2(h[i]);
+      v[2 * i] = f.x; v[2 * i + 1] = f.y;
+    }
+  }
+  static __device__ __forceinline__ void store(__nv_bfloat16* p, const float (&v)[8]) {
+    uint4 t;
+    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&t);
+#pragma unroll
+    for (int i = 0; i < 4; i++) h[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+    *reinterpret_cast<uint4*>(p) = t;
+  }
+};
+
+// online log-sum-exp update of (m, s) with value x
+__device__ __forceinline__ void lse_push(float& m, float& s, float x) {
+  if (x > m) {
+    s = s * expf(m - x) + 1.f;  // m = -inf: s is 0 and expf(-inf) = 0
+    m = x;
+  } else if (x > -INFINITY) {
+    s += expf(x - m);
+  }
+}
+__device__ __forceinline__ void lse_merge(float& m, float& s, float m2, float s2) {
+  const float mm = fmaxf(m, m2);
+  if (mm == -INFINITY) return;
+  s = s * expf(m - mm) + s2 * expf(m2 - mm);
+  m = mm;
+}
+
+// one CTA per row; a single pass over the logits (online softmax), 16-byte loads when `vec` (aligned rows)
 template <typename T>
 __global__ void __launch_bounds__(256)
     ce_fwd_kernel(const T* __restrict__ logits, const long long* __restrict__ labels, float* __restrict__ loss,
-                  float* __restrict__ lse_out, int C, long ld, long long ignore_index) {
-  __shared__ float red[32];
+                  float* __restrict__ lse_out, int C, long ld, long long ignore_index, int vec) {
+  __shared__ float red_m[8], red_s[8];
   const int r = blockIdx.x;
   const T* row = logits + (size_t)r * ld;
-  float mx = -INFINITY;
-  for (int c = threadIdx.x; c < C; c += blockDim.x) mx = fmaxf(mx, ldf(row, c));
-  mx = block_max(mx, red);
-  float s = 0.f;
-  for (int c = threadIdx.x; c < C; c += blockDim.x) s += expf(ldf(row, c) - mx);
-  s = block_sum(s, red);
+  float m = -INFINITY, s = 0.f;
+  constexpr int VN = RowVec<T>::N;
+  const int cv = vec ? (C / VN) * VN : 0;
+  for (int c = threadIdx.x * VN; c < cv; c += blockDim.x * VN) {
+    float v[VN];
+    RowVec<T>::load(row + c, v);
+#pragma unroll
+    for (int i = 0; i < VN; i++) lse_push(m, s, v[i]);
+  }
+  for (int c = cv + threadIdx.x; c < C; c += blockDim.x) lse_push(m, s, ldf(row, c));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float m2 = __shfl_xor_sync(0xffffffffu, m, o), s2 = __shfl_xor_sync(0xffffffffu, s, o);
+    lse_merge(m, s, m2, s2);
+  }
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  if (lane == 0) {
+    red_m[w] = m;
+    red_s[w] = s;
+  }
+  __syncthreads();
   if (threadIdx.x == 0) {
-    const float lse = mx + logf(s);
+    for (int i = 1; i < 8; i++) lse_merge(m, s, red_m[i], red_s[i]);
+    const float lse = m + logf(s);
     lse_out[r] = lse;
     const long long y = labels[r];
     loss[r] = (y == ignore_index) ? 0.f : lse - ldf(row, (size_t)y);
@@ -150,14 +218,24 @@ __global__ void __launch_bounds__(256)
 template <typename T>
 __global__ void __launch_bounds__(256)
     ce_bwd_kernel(const T* __restrict__ logits, const long long* __restrict__ labels, const float* __restrict__ lse,
-                  const float* __restrict__ dloss, T* __restrict__ dlogits, int C, long ld, long long ignore_index) {
+                  const float* __restrict__ dloss, T* __restrict__ dlogits, int C, long ld, long long ignore_index,
+                  int vec) {
   const int r = blockIdx.x;
   const long long y = labels[r];
   const float g = (y == ignore_index) ? 0.f : dloss[r];
   const float l = lse[r];
   const T* row = logits + (size_t)r * ld;
   T* drow = dlogits + (size_t)r * ld;
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+  constexpr int VN = RowVec<T>::N;
+  const int cv = vec ? (C / VN) * VN : 0;
+  for (int c = threadIdx.x * VN; c < cv; c += blockDim.x * VN) {
+    float v[VN];
+    RowVec<T>::load(row + c, v);
+#pragma unroll
+    for (int i = 0; i < VN; i++) v[i] = g * (expf(v[i] - l) - ((long long)(c + i) == y ? 1.f : 0.f));
+    RowVec<T>::store(drow + c, v);
+  }
+  for (int c = cv + threadIdx.x; c < C; c += blockDim.x) {
     const float p = expf(ldf(row, c) - l);
     stf(drow, c, g * (p - ((long long)c == y ? 1.f : 0.f)));
   }
@@ -234,11 +312,13 @@ int magic_sap_fuse_bwd(const float* dgl, const float* dll, const float* dfl, con
 int magic_ce_fwd(const void* logits, const long long* labels, float* loss, float* lse, int R, int C, long ld,
                  long long ignore_index, int dtype, cudaStream_t st) {
   if (R <= 0) return MAGIC_OK;
+  const int esz = dtype == MAGIC_BF16 ? 2 : 4;
+  const int vec = (((uintptr_t)logits & 15) == 0 && (ld * esz) % 16 == 0) ? 1 : 0;
   if (dtype == MAGIC_F32)
-    ce_fwd_kernel<float><<<R, 256, 0, st>>>((const float*)logits, labels, loss, lse, C, ld, ignore_index);
+    ce_fwd_kernel<float><<<R, 256, 0, st>>>((const float*)logits, labels, loss, lse, C, ld, ignore_index, vec);
   else if (dtype == MAGIC_BF16)
     ce_fwd_kernel<__nv_bfloat16><<<R, 256, 0, st>>>((const __nv_bfloat16*)logits, labels, loss, lse, C, ld,
-                                                   ignore_index);
+                                                   ignore_index, vec);
   else {
     magic_set_error("magic_ce_fwd: bad dtype");
     return MAGIC_ERR_ARG;
@@ -250,12 +330,14 @@ int magic_ce_fwd(const void* logits, const long long* labels, float* loss, float
 int magic_ce_bwd(const void* logits, const long long* labels, const float* lse, const float* dloss, void* dlogits,
                  int R, int C, long ld, long long ignore_index, int dtype, cudaStream_t st) {
   if (R <= 0) return MAGIC_OK;
+  const int esz = dtype == MAGIC_BF16 ? 2 : 4;
+  const int vec = (((uintptr_t)logits & 15) == 0 && ((uintptr_t)dlogits & 15) == 0 && (ld * esz) % 16 == 0) ? 1 : 0;
   if (dtype == MAGIC_F32)
     ce_bwd_kernel<float><<<R, 256, 0, st>>>((const float*)logits, labels, lse, dloss, (float*)dlogits, C, ld,
-                                            ignore_index);
+                                            ignore_index, vec);
   else if (dtype == MAGIC_BF16)
     ce_bwd_kernel<__nv_bfloat16><<<R, 256, 0, st>>>((const __nv_bfloat16*)logits, labels, lse, dloss,
-                                                   (__nv_bfloat16*)dlogits, C, ld, ignore_index);
+                                                   (__nv_bfloat16*)dlogits, C, ld, ignore_index, vec);
   else {
     magic_set_error("magic_ce_bwd: bad dtype");
     return MAGIC_ERR_ARG;

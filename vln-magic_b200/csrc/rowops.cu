@@ -71,6 +71,8 @@ __global__ void __launch_bounds__(ROW_WARPS * 32)
                   const float* __restrict__ beta, T* __restrict__ y, float* __restrict__ stats, int M, int h,
                   float eps, float p_in, uint32_t salt_in, float p_out, uint32_t salt_out,
                   const unsigned long long* seed_ptr) {
+  pdl_trigger();
+  pdl_wait();
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const Dropout din = make_dropout(p_in, seed_ptr, salt_in), dout = make_dropout(p_out, seed_ptr, salt_out);
   for (int r = blockIdx.x * ROW_WARPS + w; r < M; r += gridDim.x * ROW_WARPS) {
@@ -107,6 +109,8 @@ __global__ void __launch_bounds__(ROW_WARPS * 32)
                   T* __restrict__ dres, float* __restrict__ dgamma, float* __restrict__ dbeta, int M, int h,
                   float p_in, uint32_t salt_in, float p_out, uint32_t salt_out,
                   const unsigned long long* seed_ptr) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ float sm[];  // [2*h] : dgamma | dbeta partials
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   for (int c = threadIdx.x; c < 2 * h; c += blockDim.x) sm[c] = 0.f;
@@ -168,6 +172,8 @@ __global__ void __launch_bounds__(ROW_WARPS * 32)
                         const float* __restrict__ gamma, const float* __restrict__ beta, T* __restrict__ y,
                         float* __restrict__ stats, int M, int L, int h, float eps, float p_out, uint32_t salt_out,
                         const unsigned long long* seed_ptr) {
+  pdl_trigger();
+  pdl_wait();
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const Dropout dout = make_dropout(p_out, seed_ptr, salt_out);
   for (int r = blockIdx.x * ROW_WARPS + w; r < M; r += gridDim.x * ROW_WARPS) {
@@ -201,6 +207,8 @@ __global__ void __launch_bounds__(ROW_WARPS * 32)
                         float* __restrict__ dpos, float* __restrict__ dtype0, float* __restrict__ dgamma,
                         float* __restrict__ dbeta, int M, int L, int h, float p_out, uint32_t salt_out,
                         const unsigned long long* seed_ptr) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ float sm[];  // [3*h] : dgamma | dbeta | dtype0
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   for (int c = threadIdx.x; c < 3 * h; c += blockDim.x) sm[c] = 0.f;
@@ -389,6 +397,8 @@ __global__ void __launch_bounds__(ROW_WARPS * 32)
 template <typename T>
 __global__ void gather_rows_kernel(const T* __restrict__ src, const long long* __restrict__ idx, T* __restrict__ out,
                                    int R, int h) {
+  pdl_trigger();
+  pdl_wait();
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   for (int r = blockIdx.x * ROW_WARPS + w; r < R; r += gridDim.x * ROW_WARPS) {
     const long long s = idx[r];
@@ -398,6 +408,8 @@ __global__ void gather_rows_kernel(const T* __restrict__ src, const long long* _
 template <typename T>
 __global__ void scatter_rows_kernel(const T* __restrict__ dout, const long long* __restrict__ idx,
                                     T* __restrict__ dsrc, int R, int h) {
+  pdl_trigger();
+  pdl_wait();
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   for (int r = blockIdx.x * ROW_WARPS + w; r < R; r += gridDim.x * ROW_WARPS) {
     const long long s = idx[r];
@@ -571,6 +583,8 @@ __global__ void __launch_bounds__(ROW_WARPS * 32)
 template <typename T>
 __global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ x, float* __restrict__ out, int M, int N,
                                                      long ld, int rows_per_cta) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float sm[8][33];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int n = blockIdx.x * 32 + tx;
@@ -598,6 +612,8 @@ __global__ void cast_kernel(const TI* __restrict__ in, TO* __restrict__ out, siz
 template <typename T>
 __global__ void act_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ pre, T* __restrict__ dz, size_t n,
                                int act, float p, uint32_t salt, const unsigned long long* seed_ptr) {
+  pdl_trigger();
+  pdl_wait();
   const Dropout dr = make_dropout(p, seed_ptr, salt);
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
     const float z = ldf(pre, i);
@@ -611,6 +627,8 @@ __global__ void act_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ p
 template <typename T>
 __global__ void add_kernel(const T* __restrict__ a, const T* __restrict__ b, const T* __restrict__ c,
                            T* __restrict__ out, size_t n) {
+  pdl_trigger();
+  pdl_wait();
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
     float v = ldf(a, i) + ldf(b, i);
     if (c) v += ldf(c, i);
@@ -708,7 +726,7 @@ int magic_ln_fwd(const void* x, const void* res, const float* gamma, const float
                  const unsigned long long* seed_ptr, cudaStream_t st) {
   MAGIC_CHECK_ARG(h > 0 && h <= MAXE * 32, "magic_ln_fwd: hidden size %d unsupported (max %d)", h, MAXE * 32);
   if (M <= 0) return MAGIC_OK;
-  DISPATCH_T(dtype, DISPATCH_NE(h, (ln_fwd_kernel<T, NE><<<row_grid(M), ROW_WARPS * 32, 0, st>>>(
+  DISPATCH_T(dtype, DISPATCH_NE(h, (magic_launch(ln_fwd_kernel<T, NE>, dim3(row_grid(M)), dim3(ROW_WARPS * 32), 0, st, 
                         (const T*)x, (const T*)res, gamma, beta, (T*)y, stats, M, h, eps, p_in, salt_in, p_out,
                         salt_out, seed_ptr))));
   MAGIC_CHECK_LAUNCH("magic_ln_fwd");
@@ -721,7 +739,7 @@ int magic_ln_bwd(const void* dy, const void* x, const void* res, const float* ga
   MAGIC_CHECK_ARG(h > 0 && h <= MAXE * 32, "magic_ln_bwd: hidden size %d unsupported", h);
   if (M <= 0) return MAGIC_OK;
   const size_t smem = 2 * (size_t)h * sizeof(float);
-  DISPATCH_T(dtype, DISPATCH_NE(h, (ln_bwd_kernel<T, NE><<<row_grid(M), ROW_WARPS * 32, smem, st>>>(
+  DISPATCH_T(dtype, DISPATCH_NE(h, (magic_launch(ln_bwd_kernel<T, NE>, dim3(row_grid(M)), dim3(ROW_WARPS * 32), smem, st, 
                         (const T*)dy, (const T*)x, (const T*)res, gamma, stats, (T*)dx, (T*)dres, dgamma, dbeta, M, h,
                         p_in, salt_in, p_out, salt_out, seed_ptr))));
   MAGIC_CHECK_LAUNCH("magic_ln_bwd");
@@ -734,7 +752,7 @@ int magic_embed_ln_fwd(const long long* ids, const float* word, const float* pos
                        cudaStream_t st) {
   MAGIC_CHECK_ARG(h > 0 && h <= MAXE * 32, "magic_embed_ln_fwd: hidden size %d unsupported", h);
   if (M <= 0) return MAGIC_OK;
-  DISPATCH_T(dtype, DISPATCH_NE(h, (embed_ln_fwd_kernel<T, NE><<<row_grid(M), ROW_WARPS * 32, 0, st>>>(
+  DISPATCH_T(dtype, DISPATCH_NE(h, (magic_launch(embed_ln_fwd_kernel<T, NE>, dim3(row_grid(M)), dim3(ROW_WARPS * 32), 0, st, 
                         ids, word, pos, type0, gamma, beta, (T*)y, stats, M, L, h, eps, p_out, salt_out, seed_ptr))));
   MAGIC_CHECK_LAUNCH("magic_embed_ln_fwd");
   return MAGIC_OK;
@@ -747,7 +765,7 @@ int magic_embed_ln_bwd(const void* dy, const long long* ids, const float* word, 
   MAGIC_CHECK_ARG(h > 0 && h <= MAXE * 32, "magic_embed_ln_bwd: hidden size %d unsupported", h);
   if (M <= 0) return MAGIC_OK;
   const size_t smem = 3 * (size_t)h * sizeof(float);
-  DISPATCH_T(dtype, DISPATCH_NE(h, (embed_ln_bwd_kernel<T, NE><<<row_grid(M), ROW_WARPS * 32, smem, st>>>(
+  DISPATCH_T(dtype, DISPATCH_NE(h, (magic_launch(embed_ln_bwd_kernel<T, NE>, dim3(row_grid(M)), dim3(ROW_WARPS * 32), smem, st, 
                         (const T*)dy, ids, word, pos, type0, gamma, stats, dword, dpos, dtype0, dgamma, dbeta, M, L, h,
                         p_out, salt_out, seed_ptr))));
   MAGIC_CHECK_LAUNCH("magic_embed_ln_bwd");
@@ -783,7 +801,7 @@ int magic_posfuse_bwd(const void* dy, const long long* idx, const float* f, cons
 
 int magic_gather_rows(const void* src, const long long* idx, void* out, int R, int h, int dtype, cudaStream_t st) {
   if (R <= 0) return MAGIC_OK;
-  DISPATCH_T(dtype, (gather_rows_kernel<T><<<row_grid(R), ROW_WARPS * 32, 0, st>>>((const T*)src, idx, (T*)out, R, h)));
+  DISPATCH_T(dtype, (magic_launch(gather_rows_kernel<T>, dim3(row_grid(R)), dim3(ROW_WARPS * 32), 0, st, (const T*)src, idx, (T*)out, R, h)));
   MAGIC_CHECK_LAUNCH("magic_gather_rows");
   return MAGIC_OK;
 }
@@ -794,7 +812,7 @@ int magic_scatter_rows(const void* dout, const long long* idx, void* dsrc, int R
   MAGIC_CUDA(cudaMemsetAsync(dsrc, 0, (size_t)n_src_rows * h * esz, st), "magic_scatter_rows(memset)");
   if (R <= 0) return MAGIC_OK;
   DISPATCH_T(dtype,
-             (scatter_rows_kernel<T><<<row_grid(R), ROW_WARPS * 32, 0, st>>>((const T*)dout, idx, (T*)dsrc, R, h)));
+             (magic_launch(scatter_rows_kernel<T>, dim3(row_grid(R)), dim3(ROW_WARPS * 32), 0, st, (const T*)dout, idx, (T*)dsrc, R, h)));
   MAGIC_CHECK_LAUNCH("magic_scatter_rows");
   return MAGIC_OK;
 }
@@ -844,7 +862,7 @@ int magic_colsum(const void* x, float* out, int M, int N, long ld, int dtype, cu
   if (chunks > max_chunks) chunks = max_chunks;
   const int rows_per_cta = (M + chunks - 1) / chunks;
   dim3 grid((N + 31) / 32, (M + rows_per_cta - 1) / rows_per_cta);
-  DISPATCH_T(dtype, (colsum_kernel<T><<<grid, 256, 0, st>>>((const T*)x, out, M, N, ld, rows_per_cta)));
+  DISPATCH_T(dtype, (magic_launch(colsum_kernel<T>, dim3(grid), dim3(256), 0, st, (const T*)x, out, M, N, ld, rows_per_cta)));
   MAGIC_CHECK_LAUNCH("magic_colsum");
   return MAGIC_OK;
 }
@@ -855,7 +873,7 @@ int magic_act_bwd(const void* dy, const void* pre, void* dz, long long n, int ac
   long long blocks = (n + 1023) / 1024;
   const long long cap = 8LL * magic_num_sms();
   if (blocks > cap) blocks = cap;
-  DISPATCH_T(dtype, (act_bwd_kernel<T><<<(int)blocks, 256, 0, st>>>((const T*)dy, (const T*)pre, (T*)dz, (size_t)n, act,
+  DISPATCH_T(dtype, (magic_launch(act_bwd_kernel<T>, dim3((int)blocks), dim3(256), 0, st, (const T*)dy, (const T*)pre, (T*)dz, (size_t)n, act,
                                                                     drop_p, salt, seed_ptr)));
   MAGIC_CHECK_LAUNCH("magic_act_bwd");
   return MAGIC_OK;
@@ -866,7 +884,7 @@ int magic_add(const void* a, const void* b, const void* c, void* out, long long 
   long long blocks = (n + 1023) / 1024;
   const long long cap = 8LL * magic_num_sms();
   if (blocks > cap) blocks = cap;
-  DISPATCH_T(dtype, (add_kernel<T><<<(int)blocks, 256, 0, st>>>((const T*)a, (const T*)b, (const T*)c, (T*)out,
+  DISPATCH_T(dtype, (magic_launch(add_kernel<T>, dim3((int)blocks), dim3(256), 0, st, (const T*)a, (const T*)b, (const T*)c, (T*)out,
                                                                 (size_t)n)));
   MAGIC_CHECK_LAUNCH("magic_add");
   return MAGIC_OK;

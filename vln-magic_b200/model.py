@@ -337,24 +337,34 @@ class GlocalTextPathCMT(nn.Module):
                            pe[1].weight, pe[1].bias, pe[1].eps, fc.dtype)
 
     def forward(self, batch, mode, fc, ix, img_fts=None):
+        """The text and panorama encoders are independent, and so are the global and local cross-modal encoders:
+        each pair runs as two concurrent stream branches (every kernel here fills only a fraction of the 148 SMs,
+        so the step is bound by the length of the dependent-kernel chain, not by throughput).  Autograd replays
+        each branch's backward on the stream its forward ran on; under CUDA-graph capture the branches become
+        parallel paths of the graph."""
         B, Lt = batch["txt_ids"].shape
         G = batch["gmap_step_ids"].shape[1]
         Vp = batch["vp_pos_fts"].shape[1]
         h = self.config.hidden_size
-        txt, txt_attns = self.forward_text(batch, ix, fc)
-        pano, fused, img_attns = self.forward_pano(batch, ix, fc, img_fts)
-        g_in = self.gmap_input(pano, fused, batch, ix, fc)
-        v_in = self.vp_input(pano, batch, ix, fc)
         ge, le = self.global_encoder, self.local_encoder
+
+        def visual():
+            pano, fused, img_attns = self.forward_pano(batch, ix, fc, img_fts)
+            return pano, fused, img_attns, self.gmap_input(pano, fused, batch, ix, fc), self.vp_input(pano, batch, ix, fc)
+
+        (pano, fused, img_attns, g_in, v_in), (txt, txt_attns) = ops.run_branches(
+            visual, lambda: self.forward_text(batch, ix, fc))
         if mode == "nav":
-            g, g_attn = _cross_encoder(ge.encoder, g_in, txt, B, G, Lt, ix["key_lens_gmap"], ix["key_lens_txt"], fc,
-                                       batch["gmap_pair_dists"] if ge.sprel_linear is not None else None,
-                                       ge.sprel_linear)
-            v, v_attn = _cross_encoder(le.encoder, v_in, txt, B, Vp, Lt, ix["key_lens_vp"], ix["key_lens_txt"], fc)
+            dists = batch["gmap_pair_dists"] if ge.sprel_linear is not None else None
+            (v, v_attn), (g, g_attn) = ops.run_branches(
+                lambda: _cross_encoder(le.encoder, v_in, txt, B, Vp, Lt, ix["key_lens_vp"], ix["key_lens_txt"], fc),
+                lambda: _cross_encoder(ge.encoder, g_in, txt, B, G, Lt, ix["key_lens_gmap"], ix["key_lens_txt"], fc,
+                                       dists, ge.sprel_linear))
             g, v = g.view(B, G, h), v.view(B, Vp, h)
         else:
-            g, g_attn = _cross_encoder(ge.encoder, txt, g_in, B, Lt, G, ix["key_lens_txt"], ix["key_lens_gmap"], fc)
-            v, v_attn = _cross_encoder(le.encoder, txt, v_in, B, Lt, Vp, ix["key_lens_txt"], ix["key_lens_vp"], fc)
+            (v, v_attn), (g, g_attn) = ops.run_branches(
+                lambda: _cross_encoder(le.encoder, txt, v_in, B, Lt, Vp, ix["key_lens_txt"], ix["key_lens_vp"], fc),
+                lambda: _cross_encoder(ge.encoder, txt, g_in, B, Lt, G, ix["key_lens_txt"], ix["key_lens_gmap"], fc))
             g, v = g.view(B, Lt, h), v.view(B, Lt, h)
         return dict(txt_embeds=txt.view(B, Lt, h), txt_attn_list=txt_attns, pano_embeds=pano,
                     pano_fused_embeds=fused, img_attn_list=img_attns, gmap_embeds=g, gmap_attn_list=g_attn,

@@ -91,10 +91,89 @@ def _lin_dgrad(dy2, w, dx, act=0, dact_pre=None, drop_p=0.0, salt=0, seed=None):
          seed=seed)
 
 
+# ---------------------------------------------------------------------------------------------------
+# weight-gradient side stream: dW / db are only needed by the optimizer, so when every parameter
+# accumulates straight into the gradient arena the wgrad GEMMs and bias column-sums are issued on a second
+# stream and overlap the dgrad chain (under CUDA-graph capture they become a parallel branch of the graph).
+# Operands are kept alive until `join_side_stream()` so the caching allocator cannot recycle them early.
+# ---------------------------------------------------------------------------------------------------
+_SIDE = {"on": False, "stream": None, "hold": [], "used": False}
+
+
+def enable_side_stream(flag=True):
+    _SIDE["on"] = bool(flag)
+
+
+def _side_stream(*sinks):
+    """-> the side stream (already ordered after the current stream) or None."""
+    if not _SIDE["on"] or any(getattr(p, "_magic_grad", None) is None for p in sinks if p is not None):
+        return None
+    if _SIDE["stream"] is None:
+        _SIDE["stream"] = torch.cuda.Stream()
+    _SIDE["stream"].wait_stream(torch.cuda.current_stream())
+    _SIDE["used"] = True
+    return _SIDE["stream"]
+
+
+def join_side_stream():
+    """Order the current stream after all side-stream work issued so far (call before the optimizer)."""
+    if _SIDE["used"]:
+        torch.cuda.current_stream().wait_stream(_SIDE["stream"])
+        _SIDE["used"] = False
+    _SIDE["hold"].clear()
+
+
+# ---------------------------------------------------------------------------------------------------
+# independent sub-networks as concurrent stream branches
+# ---------------------------------------------------------------------------------------------------
+_BRANCH = {"on": True, "stream": None}
+
+
+def enable_branch_streams(flag=True):
+    _BRANCH["on"] = bool(flag)
+
+
+def _record(obj, stream):
+    """Tell the caching allocator that tensors produced on the branch stream are consumed on `stream`."""
+    if torch.is_tensor(obj):
+        obj.record_stream(stream)
+    elif isinstance(obj, (tuple, list)):
+        for o in obj:
+            _record(o, stream)
+
+
+def run_branches(side_fn, main_fn):
+    """Run two independent closures concurrently: `side_fn` on a second stream, `main_fn` on the current one,
+    then join.  Returns (side_result, main_result).  The call order (side first) is fixed, so stateful host-side
+    counters (dropout salts) do not depend on whether branching is enabled."""
+    if not _BRANCH["on"]:
+        a = side_fn()
+        return a, main_fn()
+    main = torch.cuda.current_stream()
+    if _BRANCH["stream"] is None:
+        _BRANCH["stream"] = torch.cuda.Stream()
+    side = _BRANCH["stream"]
+    side.wait_stream(main)
+    with torch.cuda.stream(side):
+        a = side_fn()
+    b = main_fn()
+    main.wait_stream(side)
+    _record(a, main)
+    return a, b
+
+
 def _lin_wgrad(dy2, x2, w, bias):
     """dW[N,K] (+)= dy^T x ; db (+)= colsum(dy).  Returns the autograd values."""
     M, N = dy2.shape
     K = x2.shape[1]
+    side = _side_stream(w, bias)
+    if side is not None:
+        _SIDE["hold"].extend((dy2, x2))
+        with torch.cuda.stream(side):
+            gemm(dy2, 1, dy2.stride(0), x2, K, 1, w._magic_grad, N, K, M, beta=1.0)
+            if bias is not None:
+                call("magic_colsum", ptr(dy2), ptr(bias._magic_grad), M, N, dy2.stride(0), dt(dy2), stream())
+        return None, None
     gw, rw, beta = _sink(w)
     gemm(dy2, 1, dy2.stride(0), x2, K, 1, gw, N, K, M, beta=beta)
     rb = None
@@ -139,8 +218,14 @@ class LinearFn(torch.autograd.Function):
             dz = dy2
         dx = None
         if ctx.needs_input_grad[0]:
-            dx = torch.empty_like(x2)
-            _lin_dgrad(dz, w, dx)
+            if dz.shape[1] >= 4096 and x2.dtype != torch.float32:
+                # vocabulary-sized reduction with a tiny output (MLM decoder dgrad): fp32 C so the GEMM may split K
+                dx32 = torch.empty(x2.shape, dtype=torch.float32, device=x2.device)
+                _lin_dgrad(dz, w, dx32)
+                dx = dx32.to(x2.dtype)
+            else:
+                dx = torch.empty_like(x2)
+                _lin_dgrad(dz, w, dx)
             dx = dx.view(xshape)
         rw, rb = _lin_wgrad(dz, x2, w, bias)
         return dx, rw, rb, None, dres, None, None, None
@@ -209,8 +294,12 @@ class PackedLinearFn(torch.autograd.Function):
         gbs = [getattr(b, "_magic_grad", None) for b in bs]
         rws, rbs = [None] * n, [None] * n
         if _adjacent(gws) and _adjacent(gbs):
-            gemm(dy2, 1, Nt, x2, K, 1, gws[0], Nt, K, M, beta=1.0, ldc=K)
-            call("magic_colsum", ptr(dy2), ptr(gbs[0]), M, Nt, Nt, dt(dy2), stream())
+            side = _side_stream()
+            if side is not None:
+                _SIDE["hold"].extend((dy2, x2))
+            with torch.cuda.stream(side if side is not None else torch.cuda.current_stream()):
+                gemm(dy2, 1, Nt, x2, K, 1, gws[0], Nt, K, M, beta=1.0, ldc=K)
+                call("magic_colsum", ptr(dy2), ptr(gbs[0]), M, Nt, Nt, dt(dy2), stream())
         else:
             off = 0
             for i, (w, b, Ni) in enumerate(zip(ws, bs, Ns)):

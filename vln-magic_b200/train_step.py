@@ -17,7 +17,8 @@ from .parallel import FlatAllReduce, broadcast_flat
 
 class PretrainStepper:
     def __init__(self, student, teacher=None, kdl=None, lr=5e-5, betas=(0.9, 0.98), weight_decay=0.01,
-                 max_grad_norm=5.0, use_graphs=False, rw_generator=None):
+                 max_grad_norm=5.0, use_graphs=False, rw_generator=None, side_stream=True,
+                 branch_streams=True):
         self.student, self.teacher = student, teacher
         self.kdl = makd.kdl_config(kdl)
         lowp = student.compute_dtype == torch.bfloat16
@@ -28,6 +29,8 @@ class PretrainStepper:
                 p.requires_grad_(False)
         self.opt = FusedAdamW(self.arena, lr=lr, betas=betas, weight_decay=weight_decay, max_grad_norm=max_grad_norm)
         self.use_graphs = use_graphs
+        ops.enable_side_stream(side_stream)
+        ops.enable_branch_streams(branch_streams)
         self.graphs = {}
         self.rw_generator = rw_generator
         self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
@@ -53,6 +56,7 @@ class PretrainStepper:
             s_out = self.student(batch, task, True)
             mix = ops.loss_mix(None, None, s_out["loss"], 0.0, s_out.get("loss_inv_n"))
         mix[0].backward()
+        ops.join_side_stream()
         if finish:
             self._finish()
         return mix
