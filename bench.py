@@ -298,7 +298,7 @@ def run_ours(args):
     if cfg_t is not None:
         torch.manual_seed(0)
         teacher = magic_b200.GlocalTextPathCMTPreTraining(cfg_t).to(dev).eval().set_compute_dtype(dtype)
-    stepper = PretrainStepper(student, teacher, use_graphs=bool(args.graphs) and teacher is None,
+    stepper = PretrainStepper(student, teacher, use_graphs=bool(args.graphs),
                               side_stream=bool(args.side_stream), branch_streams=bool(args.branch_streams))
     ops.set_seed(dev, 1234 + rank)
 
@@ -313,25 +313,47 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    host_loss = [torch.zeros(1).pin_memory() for _ in range(2)]
+    loss_ev = [torch.cuda.Event() for _ in range(2)]
+
+    def pick(i):
+        return ("mlm" if i % 2 == 0 else "sap"), (i // 2) % pool_n
+
     def run_steps(n, first, from_host, delay_cycles=0):
         out = None
+        nxt = None
+        if from_host:
+            task, j = pick(first)
+            nxt = stepper.prefetch(task, pin_pools[task][j])
         for i in range(first, first + n):
             if delay_cycles:
                 # keep the GPU busy while the host queues this step's launches, so per-call CUDA events bracket
                 # back-to-back device execution rather than host launch latency
                 _lib.COUNTERS["launches"] -= 1
                 _lib.call("magic_delay", int(delay_cycles), _lib.stream())
-            task = "mlm" if i % 2 == 0 else "sap"
-            j = (i // 2) % pool_n
-            if from_host and stepper.use_graphs:
-                b = pin_pools[task][j]  # pinned host buffers are copied straight into the graph's static inputs
-            elif from_host:
-                b = batch_to_device(pin_pools[task][j], dev, non_blocking=True)
+            task, j = pick(i)
+            if from_host:
+                # end to end: every step's inputs start in pinned host memory; the copy of step i+1 is issued on the
+                # copy stream before step i's loss is read back, as the reference's PrefetchLoader does
+                b = nxt
+                if i + 1 < first + n:
+                    t2, j2 = pick(i + 1)
+                    nxt = stepper.prefetch(t2, pin_pools[t2][j2])
             else:
                 b = dev_pools[task][j]
             out = stepper.step(task, b)
             if from_host:
-                _ = out[0].item()  # device -> host read of the step's loss
+                # device -> host read of EVERY step's loss, one step late (async copy into pinned memory + event),
+                # so the host queues step i+1 while step i runs instead of draining the GPU each step
+                k = i % 2
+                host_loss[k].copy_(out[0:1], non_blocking=True)
+                loss_ev[k].record()
+                if i > first:
+                    loss_ev[1 - k].synchronize()
+                    _ = host_loss[1 - k].item()
+        if from_host:
+            loss_ev[(first + n - 1) % 2].synchronize()
+            _ = host_loss[(first + n - 1) % 2].item()
         return out
 
     # warm-up (also builds the CUDA graphs, one per task/shape)

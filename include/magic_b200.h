@@ -154,6 +154,8 @@ typedef struct MagicMseSeg {
   const void* t;      /* teacher */
   void* ds;           /* backward: gradient wrt s, same layout as s (may be NULL in forward) */
   const float* w;     /* per-row MKTD weights (kd_loss.py:11-13) or NULL */
+  const float* scale_dev; /* optional DEVICE scalar multiplied into `scale` (device-resident MKRW weight, so a
+                             captured CUDA graph sees the weights drawn for the current step) or NULL */
   long long rows, inner, s_rs, t_rs; /* rows x inner elements, row strides in elements */
   float scale;        /* MKRW weight / (rows*inner)  (mean reduction, kd_loss.py:8,14) */
   int s_dt, t_dt;
@@ -171,12 +173,13 @@ int magic_loss_mix_bwd(const float* g, int n, float alpha, const float* inv_n, f
                        float* d_sup, cudaStream_t st);
 /* measurement aid: keeps the stream busy for ~cycles SM clocks so the host can queue launches ahead of the GPU */
 int magic_delay(long long cycles, cudaStream_t st);
+/* scale_dev: optional device scalar multiplied into `scale` (see MagicMseSeg.scale_dev) */
 int magic_makd_kl_fwd(const void* s, const void* t, int R, int C, long ld, float temperature, const float* w,
-                      float scale, float* stats /* [R,2] */, float* loss /* [1], zeroed here */, int dtype,
-                      cudaStream_t st);
+                      float scale, const float* scale_dev, float* stats /* [R,2] */,
+                      float* loss /* [1], zeroed here */, int dtype, cudaStream_t st);
 int magic_makd_kl_bwd(const void* s, const void* t, void* ds, int R, int C, long ld, float temperature,
-                      const float* w, float scale, const float* stats, const float* gout, int dtype,
-                      cudaStream_t st);
+                      const float* w, float scale, const float* scale_dev, const float* stats, const float* gout,
+                      int dtype, cudaStream_t st);
 
 /* ---- optimizer (pretrain_src/optim/adamw.py:53-112, clip grad_norm r2r_magic_pretrain.json:22) ----- */
 int magic_sumsq(const float* g, long long n, float* out, int zero_first, cudaStream_t st);

@@ -37,7 +37,8 @@ both = [None, None]
 dist.all_gather_object(both, idx)
 assert len(both[0]) == len(both[1]) == 51 and set(both[0]) | set(both[1]) == set(range(101))
 dist.barrier()
-print("rank", rank, "ok")
+sys.stdout.write("rank " + str(rank) + " ok\n")
+sys.stdout.flush()
 ''' % ROOT
 
 
@@ -49,7 +50,7 @@ def test_gloo_world2(tmp_path):
                         "--master-addr", "127.0.0.1", "--master-port", "29731", str(script)],
                        capture_output=True, text=True, timeout=240, env=env)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
-    assert "rank 0 ok" in r.stdout and "rank 1 ok" in r.stdout
+    assert r.stdout.count("ok") == 2 and "rank 0" in r.stdout and "rank 1" in r.stdout, r.stdout
 
 
 def test_reference_arm_runs_on_rank0_only():

@@ -1,0 +1,101 @@
+"""GPU tests of the training step driver (train_step.PretrainStepper): CUDA-graph replay, concurrent stream
+branches, the weight-gradient side stream and the host->device prefetch must all reproduce the plain eager,
+single-stream step on the same inputs (fp32 mode, dropout off; fp32 atomics reorder sums, hence 2e-5)."""
+import copy
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+import magic_b200  # noqa: E402
+from magic_b200 import synth  # noqa: E402
+from magic_b200.config import make_config  # noqa: E402
+from magic_b200.graph_index import prepare_batch, batch_to_device, pad_batch  # noqa: E402
+from magic_b200.train_step import PretrainStepper  # noqa: E402
+
+DEV = "cuda"
+
+
+def rel(a, b):
+    a, b = a.float(), b.float()
+    return ((a - b).norm() / (b.norm() + 1e-20)).item()
+
+
+def models(teacher, dtype=torch.float32):
+    cfg_s = make_config(128, role="student", teacher_hidden_size=256 if teacher else None, hidden_dropout_prob=0.0,
+                        attention_probs_dropout_prob=0.0)
+    torch.manual_seed(1)
+    s = magic_b200.GlocalTextPathCMTPreTraining(cfg_s).to(DEV).train().set_compute_dtype(dtype)
+    t = None
+    if teacher:
+        cfg_t = make_config(256, role="teacher", hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0)
+        torch.manual_seed(0)
+        t = magic_b200.GlocalTextPathCMTPreTraining(cfg_t).to(DEV).eval().set_compute_dtype(dtype)
+    return s, t
+
+
+def host_pool(n=3, B=4):
+    pools = {}
+    for task in ("mlm", "sap"):
+        bs = [prepare_batch(synth.make_batch(task, B, seed=50 + i + (0 if task == "mlm" else 100))) for i in range(n)]
+        K = magic_b200.INDEX_KEY
+        rcap = (max(b["traj_view_img_fts"].shape[0] for b in bs) + 7) // 8 * 8
+        mcap = (max(b[K]["mlm_rows"].numel() for b in bs) + 63) // 64 * 64 if task == "mlm" else None
+        ecap = (max(b[K]["entries"].numel() for b in bs) + 255) // 256 * 256
+        scap = (max(b[K]["src_ids"].numel() for b in bs) + 255) // 256 * 256
+        pools[task] = [pad_batch(b, rcap, mcap, ecap, scap) for b in bs]
+    return pools
+
+
+def run(teacher, n_steps=4, prefetch=False, **kw):
+    s, t = models(teacher)
+    g = torch.Generator().manual_seed(7)
+    st = PretrainStepper(s, t, lr=1e-3, rw_generator=g, **kw)
+    pools = host_pool()
+    losses = []
+    for i in range(n_steps):
+        task = "mlm" if i % 2 == 0 else "sap"
+        hb = pools[task][(i // 2) % len(pools[task])]
+        if prefetch:
+            pinned = {k: (v.pin_memory() if torch.is_tensor(v) else
+                          ({kk: (vv.pin_memory() if torch.is_tensor(vv) else vv) for kk, vv in v.items()}
+                           if k == magic_b200.INDEX_KEY else v)) for k, v in hb.items()}
+            b = st.prefetch(task, pinned)
+        else:
+            b = batch_to_device(hb, DEV)
+        losses.append(st.step(task, b).clone())
+    torch.cuda.synchronize()
+    return torch.stack(losses).cpu(), st.arena.flat_p.clone().cpu()
+
+
+@pytest.mark.parametrize("teacher", [False, True])
+def test_graph_streams_prefetch_match_plain_eager(teacher):
+    base_l, base_p = run(teacher, use_graphs=False, side_stream=False, branch_streams=False)
+    assert torch.isfinite(base_l).all()
+    if teacher:
+        assert (base_l[:, 2] > 0).all()  # the KD term is live
+    for kw in (dict(use_graphs=False, side_stream=True, branch_streams=True),
+               dict(use_graphs=True, side_stream=True, branch_streams=True),
+               dict(use_graphs=True, side_stream=True, branch_streams=True, prefetch=True),
+               dict(use_graphs=False, side_stream=False, branch_streams=False, prefetch=True)):
+        l, p = run(teacher, **kw)
+        assert rel(l, base_l) < 2e-5, (kw, l, base_l)
+        assert rel(p, base_p) < 2e-5, kw
+
+
+def test_graph_replay_follows_per_step_mkrw_draw():
+    """The MKRW weights live in device memory read by the captured kernels: two replays of the same graph on the
+    same batch with different draws must give different KD totals, equal to the eager values for those draws."""
+    s, t = models(True)
+    pools = host_pool(n=1)
+    b = batch_to_device(pools["sap"][0], DEV)
+    outs = {}
+    for graphs in (False, True):
+        s2, t2 = copy.deepcopy(s), copy.deepcopy(t)
+        st = PretrainStepper(s2, t2, lr=0.0, weight_decay=0.0, rw_generator=torch.Generator().manual_seed(3),
+                             use_graphs=graphs)
+        outs[graphs] = torch.stack([st.step("sap", b).clone() for _ in range(3)]).cpu()
+    assert rel(outs[True], outs[False]) < 2e-5
+    kd = outs[True][:, 2]
+    assert (kd[0] - kd[1]).abs() > 1e-4 * kd[0].abs() and (kd[1] - kd[2]).abs() > 1e-4 * kd[1].abs()

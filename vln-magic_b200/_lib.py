@@ -26,7 +26,7 @@ _CT = {
 
 class MagicMseSeg(ctypes.Structure):
     _fields_ = [("s", ctypes.c_void_p), ("t", ctypes.c_void_p), ("ds", ctypes.c_void_p), ("w", ctypes.c_void_p),
-                ("rows", ctypes.c_longlong), ("inner", ctypes.c_longlong), ("s_rs", ctypes.c_longlong),
+                ("scale_dev", ctypes.c_void_p), ("rows", ctypes.c_longlong), ("inner", ctypes.c_longlong), ("s_rs", ctypes.c_longlong),
                 ("t_rs", ctypes.c_longlong), ("scale", ctypes.c_float), ("s_dt", ctypes.c_int),
                 ("t_dt", ctypes.c_int), ("vec_ok", ctypes.c_int)]
 

@@ -64,7 +64,7 @@ static inline int magic_num_sms() {
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
-int magic_pdl_enabled();  // api.cu: env MAGIC_PDL (default on)
+int magic_pdl_enabled();  // api.cu: env MAGIC_PDL=1 (default off)
 
 template <typename... KArgs, typename... Args>
 static inline cudaError_t magic_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
@@ -166,3 +166,55 @@ __device__ __forceinline__ float gelu_grad_f(float x) {
   const float pdf = 0.3989422804014327f * expf(-0.5f * x * x);
   return cdf + x * pdf;
 }
+
+// 16-byte vector access for the vocabulary-sized rows (bf16: 8 elements, fp32: 4 elements)
+template <typename T>
+struct RowVec;
+template <>
+struct RowVec<float> {
+  static constexpr int N = 4;
+  static __device__ __forceinline__ void load(const float* p, float (&v)[4]) {
+    const float4 t = *reinterpret_cast<const float4*>(p);
+    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+  }
+  static __device__ __forceinline__ void store(float* p, const float (&v)[4]) {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  }
+};
+template <>
+struct RowVec<__nv_bfloat16> {
+  static constexpr int N = 8;
+  static __device__ __forceinline__ void load(const __nv_bfloat16* p, float (&v)[8]) {
+    const uint4 t = *reinterpret_cast<const uint4*>(p);
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&t);
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      const float2 f = __bfloat1622float2(h[i]);
+      v[2 * i] = f.x; v[2 * i + 1] = f.y;
+    }
+  }
+  static __device__ __forceinline__ void store(__nv_bfloat16* p, const float (&v)[8]) {
+    uint4 t;
+    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&t);
+#pragma unroll
+    for (int i = 0; i < 4; i++) h[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+    *reinterpret_cast<uint4*>(p) = t;
+  }
+};
+
+// online log-sum-exp update of (m, s) with value x
+__device__ __forceinline__ void lse_push(float& m, float& s, float x) {
+  if (x > m) {
+    s = s * expf(m - x) + 1.f;  // m = -inf: s is 0 and expf(-inf) = 0
+    m = x;
+  } else if (x > -INFINITY) {
+    s += expf(x - m);
+  }
+}
+__device__ __forceinline__ void lse_merge(float& m, float& s, float m2, float s2) {
+  const float mm = fmaxf(m, m2);
+  if (mm == -INFINITY) return;
+  s = s * expf(m - mm) + s2 * expf(m2 - mm);
+  m = mm;
+}
+

@@ -46,7 +46,7 @@ __global__ void __launch_bounds__(NT) makd_mse_kernel(const __grid_constant__ Ar
     const long long row = local / cpr;
     const long long c0 = (local % cpr) * CH;
     const long long c1 = min(S.inner, c0 + CH);
-    const float wr = S.w ? S.w[row] : 1.f;
+    const float wr = (S.w ? S.w[row] : 1.f) * (S.scale_dev ? S.scale_dev[0] : 1.f);
     const size_t sb = (size_t)row * S.s_rs, tb = (size_t)row * S.t_rs;
     const float coef = BWD ? 2.f * S.scale * wr * ((gseg ? gseg[si] : 0.f) + (gtot ? gtot[0] : 0.f)) : 0.f;
     float acc = 0.f;
@@ -112,32 +112,64 @@ __global__ void __launch_bounds__(NT) makd_mse_kernel(const __grid_constant__ Ar
 // ---- KL on logits: one CTA per row -----------------------------------------------------------------
 __device__ __forceinline__ float fix_inf(float v, float invT) { return (v == -INFINITY ? -1e6f : v) * invT; }
 
+// pass 1: online (max, sum) of both rows together; pass 2: KL.  16-byte loads on aligned rows.
 template <typename T>
 __global__ void __launch_bounds__(NT)
     makd_kl_fwd_kernel(const T* __restrict__ s, const T* __restrict__ t, int C, long ld, float invT,
-                       const float* __restrict__ w, float scale, float* __restrict__ stats,
-                       float* __restrict__ loss) {
+                       const float* __restrict__ w, float scale, const float* __restrict__ scale_dev,
+                       float* __restrict__ stats, float* __restrict__ loss, int vec) {
   __shared__ float red[32];
+  __shared__ float rm[2][8], rs[2][8];
   const int r = blockIdx.x;
   const T* sr = s + (size_t)r * ld;
   const T* tr = t + (size_t)r * ld;
-  float ms = -INFINITY, mt = -INFINITY;
-  for (int c = threadIdx.x; c < C; c += NT) {
-    ms = fmaxf(ms, fix_inf(ldf(sr, c), invT));
-    mt = fmaxf(mt, fix_inf(ldf(tr, c), invT));
+  constexpr int VN = RowVec<T>::N;
+  const int cv = vec ? (C / VN) * VN : 0;
+  float ms = -INFINITY, zs = 0.f, mt = -INFINITY, zt = 0.f;
+  for (int c = threadIdx.x * VN; c < cv; c += NT * VN) {
+    float a[VN], b[VN];
+    RowVec<T>::load(sr + c, a);
+    RowVec<T>::load(tr + c, b);
+#pragma unroll
+    for (int i = 0; i < VN; i++) {
+      lse_push(ms, zs, fix_inf(a[i], invT));
+      lse_push(mt, zt, fix_inf(b[i], invT));
+    }
   }
-  ms = block_max(ms, red);
-  mt = block_max(mt, red);
-  float zs = 0.f, zt = 0.f;
-  for (int c = threadIdx.x; c < C; c += NT) {
-    zs += expf(fix_inf(ldf(sr, c), invT) - ms);
-    zt += expf(fix_inf(ldf(tr, c), invT) - mt);
+  for (int c = cv + threadIdx.x; c < C; c += NT) {
+    lse_push(ms, zs, fix_inf(ldf(sr, c), invT));
+    lse_push(mt, zt, fix_inf(ldf(tr, c), invT));
   }
-  zs = block_sum(zs, red);
-  zt = block_sum(zt, red);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    lse_merge(ms, zs, __shfl_xor_sync(0xffffffffu, ms, o), __shfl_xor_sync(0xffffffffu, zs, o));
+    lse_merge(mt, zt, __shfl_xor_sync(0xffffffffu, mt, o), __shfl_xor_sync(0xffffffffu, zt, o));
+  }
+  const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
+  if (lane == 0) {
+    rm[0][wp] = ms; rs[0][wp] = zs; rm[1][wp] = mt; rs[1][wp] = zt;
+  }
+  __syncthreads();
+  ms = rm[0][0]; zs = rs[0][0]; mt = rm[1][0]; zt = rs[1][0];
+#pragma unroll
+  for (int i = 1; i < NT / 32; i++) {
+    lse_merge(ms, zs, rm[0][i], rs[0][i]);
+    lse_merge(mt, zt, rm[1][i], rs[1][i]);
+  }
   const float lse_s = ms + logf(zs), lse_t = mt + logf(zt);
   float kl = 0.f;
-  for (int c = threadIdx.x; c < C; c += NT) {
+  for (int c = threadIdx.x * VN; c < cv; c += NT * VN) {
+    float a[VN], b[VN];
+    RowVec<T>::load(sr + c, a);
+    RowVec<T>::load(tr + c, b);
+#pragma unroll
+    for (int i = 0; i < VN; i++) {
+      const float la = fix_inf(a[i], invT) - lse_s, lb = fix_inf(b[i], invT) - lse_t;
+      const float p = expf(lb);
+      if (p > 0.f) kl += p * (lb - la);
+    }
+  }
+  for (int c = cv + threadIdx.x; c < C; c += NT) {
     const float a = fix_inf(ldf(sr, c), invT) - lse_s, b = fix_inf(ldf(tr, c), invT) - lse_t;
     const float p = expf(b);
     if (p > 0.f) kl += p * (b - a);  // xlogy(p,p) - p*logq ; p == 0 contributes exactly 0
@@ -146,22 +178,33 @@ __global__ void __launch_bounds__(NT)
   if (threadIdx.x == 0) {
     stats[2 * r] = lse_s;
     stats[2 * r + 1] = lse_t;
-    atomicAdd(loss, kl * (w ? w[r] : 1.f) * scale);
+    atomicAdd(loss, kl * (w ? w[r] : 1.f) * scale * (scale_dev ? scale_dev[0] : 1.f));
   }
 }
 
 template <typename T>
 __global__ void __launch_bounds__(NT)
     makd_kl_bwd_kernel(const T* __restrict__ s, const T* __restrict__ t, T* __restrict__ ds, int C, long ld,
-                       float invT, const float* __restrict__ w, float scale, const float* __restrict__ stats,
-                       const float* __restrict__ gout) {
+                       float invT, const float* __restrict__ w, float scale, const float* __restrict__ scale_dev,
+                       const float* __restrict__ stats, const float* __restrict__ gout, int vec) {
   const int r = blockIdx.x;
   const T* sr = s + (size_t)r * ld;
   const T* tr = t + (size_t)r * ld;
   T* dr = ds + (size_t)r * ld;
   const float lse_s = stats[2 * r], lse_t = stats[2 * r + 1];
-  const float coef = gout[0] * scale * (w ? w[r] : 1.f) * invT;
-  for (int c = threadIdx.x; c < C; c += NT) {
+  const float coef = gout[0] * scale * (scale_dev ? scale_dev[0] : 1.f) * (w ? w[r] : 1.f) * invT;
+  constexpr int VN = RowVec<T>::N;
+  const int cv = vec ? (C / VN) * VN : 0;
+  for (int c = threadIdx.x * VN; c < cv; c += NT * VN) {
+    float a[VN], b[VN];
+    RowVec<T>::load(sr + c, a);
+    RowVec<T>::load(tr + c, b);
+#pragma unroll
+    for (int i = 0; i < VN; i++)
+      a[i] = a[i] != -INFINITY ? coef * (expf(a[i] * invT - lse_s) - expf(fix_inf(b[i], invT) - lse_t)) : 0.f;
+    RowVec<T>::store(dr + c, a);
+  }
+  for (int c = cv + threadIdx.x; c < C; c += NT) {
     const float sv = ldf(sr, c);
     float g = 0.f;
     if (sv != -INFINITY) g = coef * (expf(sv * invT - lse_s) - expf(fix_inf(ldf(tr, c), invT) - lse_t));
@@ -262,15 +305,18 @@ int magic_loss_mix_bwd(const float* g, int n, float alpha, const float* inv_n, f
 }
 
 int magic_makd_kl_fwd(const void* s, const void* t, int R, int C, long ld, float temperature, const float* w,
-                      float scale, float* stats, float* loss, int dtype, cudaStream_t st) {
+                      float scale, const float* scale_dev, float* stats, float* loss, int dtype, cudaStream_t st) {
   MAGIC_CUDA(cudaMemsetAsync(loss, 0, sizeof(float), st), "magic_makd_kl_fwd");
   if (R <= 0) return MAGIC_OK;
   const float invT = 1.f / temperature;
+  const int esz = dtype == MAGIC_BF16 ? 2 : 4;
+  const int vec = (((uintptr_t)s & 15) == 0 && ((uintptr_t)t & 15) == 0 && (ld * esz) % 16 == 0) ? 1 : 0;
   if (dtype == MAGIC_F32)
-    makd_kl_fwd_kernel<float><<<R, NT, 0, st>>>((const float*)s, (const float*)t, C, ld, invT, w, scale, stats, loss);
+    makd_kl_fwd_kernel<float><<<R, NT, 0, st>>>((const float*)s, (const float*)t, C, ld, invT, w, scale, scale_dev,
+                                                stats, loss, vec);
   else if (dtype == MAGIC_BF16)
     makd_kl_fwd_kernel<__nv_bfloat16><<<R, NT, 0, st>>>((const __nv_bfloat16*)s, (const __nv_bfloat16*)t, C, ld, invT,
-                                                       w, scale, stats, loss);
+                                                       w, scale, scale_dev, stats, loss, vec);
   else {
     magic_set_error("magic_makd_kl_fwd: bad dtype");
     return MAGIC_ERR_ARG;
@@ -280,16 +326,20 @@ int magic_makd_kl_fwd(const void* s, const void* t, int R, int C, long ld, float
 }
 
 int magic_makd_kl_bwd(const void* s, const void* t, void* ds, int R, int C, long ld, float temperature,
-                      const float* w, float scale, const float* stats, const float* gout, int dtype,
-                      cudaStream_t st) {
+                      const float* w, float scale, const float* scale_dev, const float* stats, const float* gout,
+                      int dtype, cudaStream_t st) {
   if (R <= 0) return MAGIC_OK;
   const float invT = 1.f / temperature;
+  const int esz = dtype == MAGIC_BF16 ? 2 : 4;
+  const int vec = (((uintptr_t)s & 15) == 0 && ((uintptr_t)t & 15) == 0 && ((uintptr_t)ds & 15) == 0 &&
+                   (ld * esz) % 16 == 0) ? 1 : 0;
   if (dtype == MAGIC_F32)
     makd_kl_bwd_kernel<float><<<R, NT, 0, st>>>((const float*)s, (const float*)t, (float*)ds, C, ld, invT, w, scale,
-                                                stats, gout);
+                                                scale_dev, stats, gout, vec);
   else if (dtype == MAGIC_BF16)
     makd_kl_bwd_kernel<__nv_bfloat16><<<R, NT, 0, st>>>((const __nv_bfloat16*)s, (const __nv_bfloat16*)t,
-                                                       (__nv_bfloat16*)ds, C, ld, invT, w, scale, stats, gout);
+                                                       (__nv_bfloat16*)ds, C, ld, invT, w, scale, scale_dev, stats,
+                                                       gout, vec);
   else {
     magic_set_error("magic_makd_kl_bwd: bad dtype");
     return MAGIC_ERR_ARG;

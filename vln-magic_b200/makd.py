@@ -23,11 +23,19 @@ def kdl_config(kdl=None):
     return k
 
 
-def mkrw_weights(rw_temp=4.0, device="cuda", generator=None):
-    """softmax(randn(5)/rw_temp)*5, order [txt, img, global, local, predict] (agent.py:866-869).
-    Returned as python floats (they scale kernel arguments; drawn per step per rank like the reference)."""
+def mkrw_weights(rw_temp=4.0, device="cuda", generator=None, out=None, ring=None):
+    """softmax(randn(5)/rw_temp)*5, order [txt, img, global, local, predict] (agent.py:866-869); drawn per step
+    per rank like the reference.  Without `out`: python floats (they scale kernel arguments).  With `out` (a
+    device tensor [5]): drawn on the host generator, written into `out` in place and `out` is returned, so
+    kernels captured in a CUDA graph read the current step's weights."""
     r = torch.randn(5, generator=generator)
-    return (torch.softmax(r / rw_temp, 0) * 5).tolist()
+    w = torch.softmax(r / rw_temp, 0) * 5
+    if out is None:
+        return w.tolist()
+    if ring is not None:
+        return ring.upload(w, out)  # pinned ring: no host sync, safe when the host runs ahead of the GPU
+    out.copy_(w)
+    return out
 
 
 def mktd_weights(t_sample_loss, decay=0.7):
@@ -39,22 +47,32 @@ def _w_for(x, w):
 
 
 def compute_kd_losses(student, s_out, t_out, task, rw, t_w, kdl=None):
-    """-> (named dict of per-ability scalars as a [10] tensor view, mse_total scalar, kl scalar or None)."""
+    """-> (named dict of per-ability scalars as a [10] tensor view, mse_total scalar, kl scalar or None).
+    `rw`: the 5 MKRW ability weights, either python floats (baked into the kernel arguments) or a DEVICE tensor
+    [5] (read by the kernels at run time, so a captured CUDA graph follows the per-step draw)."""
     k = kdl_config(kdl)
+    rw_dev = rw if torch.is_tensor(rw) else None
+    if rw_dev is not None:
+        rw_dev = rw_dev.float().contiguous()
+        rw = [1.0] * 5
+
+    def sdev(i):
+        return rw_dev[i:i + 1] if rw_dev is not None else None
+
     bert = student.bert
     emb, att = "emb" in k["kdl_task_types"], "attn" in k["kdl_task_types"]
     tasks = k["kdl_tasks"]
     pairs, owner = [], []
 
-    def add_emb(name, proj, s, t, rwi):
+    def add_emb(name, proj, s, t, ri):
         if not emb:
             return
         ps = ops.linear(s, proj.weight, proj.bias)
         t = t.detach()
-        pairs.append((ps, t, _w_for(ps, t_w), rwi / ps.numel()))
+        pairs.append((ps, t, _w_for(ps, t_w), rw[ri] / ps.numel(), sdev(ri)))
         owner.append(name)
 
-    def add_attn(name, s_list, t_list, rwi, n_layers):
+    def add_attn(name, s_list, t_list, ri, n_layers):
         if not att or not s_list:
             return
         items = []
@@ -65,29 +83,29 @@ def compute_kd_losses(student, s_out, t_out, task, rw, t_w, kdl=None):
                 items.append((sl, tl))
         numel = sum(a.numel() for a, _ in items)
         for a, b in items:
-            pairs.append((a, b.detach(), _w_for(a, t_w), rwi / numel))
+            pairs.append((a, b.detach(), _w_for(a, t_w), rw[ri] / numel, sdev(ri)))
             owner.append(name)
 
     # agent.py:560 -- the attention maps are compared on their first min(layers) layers
     min_len = min(len(s_out["txt_attn_list"]), len(t_out["txt_attn_list"])) if att else 0
     if "txt" in tasks:
-        add_emb("txt_emb_loss", bert.txt_emb_w, s_out["txt_embeds"], t_out["txt_embeds"], rw[0])
-        add_attn("txt_attn_loss", s_out["txt_attn_list"], t_out["txt_attn_list"], rw[0], min_len)
+        add_emb("txt_emb_loss", bert.txt_emb_w, s_out["txt_embeds"], t_out["txt_embeds"], 0)
+        add_attn("txt_attn_loss", s_out["txt_attn_list"], t_out["txt_attn_list"], 0, min_len)
     if "img" in tasks:
-        add_emb("img_emb_loss", bert.kdl_img_w, s_out["pano_embeds"], t_out["pano_embeds"], rw[1])
-        add_emb("avg_img_emb_loss", bert.kdl_avg_img_w, s_out["pano_fused_embeds"], t_out["pano_fused_embeds"], rw[1])
+        add_emb("img_emb_loss", bert.kdl_img_w, s_out["pano_embeds"], t_out["pano_embeds"], 1)
+        add_emb("avg_img_emb_loss", bert.kdl_avg_img_w, s_out["pano_fused_embeds"], t_out["pano_fused_embeds"], 1)
         if att and len(s_out["img_attn_list"]) != len(t_out["img_attn_list"]):
             raise ValueError("img_attns of teacher and student must have the same shape (agent.py:628)")
-        add_attn("img_attn_loss", s_out["img_attn_list"], t_out["img_attn_list"], rw[1], len(s_out["img_attn_list"]))
+        add_attn("img_attn_loss", s_out["img_attn_list"], t_out["img_attn_list"], 1, len(s_out["img_attn_list"]))
     mlm = task.startswith("mlm")
     gw, lw = (bert.gmap_txt_w, bert.vp_txt_w) if mlm else (bert.global_cross_w, bert.local_cross_w)
     nx = min(len(s_out["gmap_attn_list"]), len(t_out["gmap_attn_list"]), max(min_len, 0)) if att else 0
     if "global" in tasks:
-        add_emb("global_emb_loss", gw, s_out["gmap_embeds"], t_out["gmap_embeds"], rw[2])
-        add_attn("global_attn_loss", s_out["gmap_attn_list"], t_out["gmap_attn_list"], rw[2], nx)
+        add_emb("global_emb_loss", gw, s_out["gmap_embeds"], t_out["gmap_embeds"], 2)
+        add_attn("global_attn_loss", s_out["gmap_attn_list"], t_out["gmap_attn_list"], 2, nx)
     if "local" in tasks:
-        add_emb("local_emb_loss", lw, s_out["vp_embeds"], t_out["vp_embeds"], rw[3])
-        add_attn("local_attn_loss", s_out["vp_attn_list"], t_out["vp_attn_list"], rw[3], nx)
+        add_emb("local_emb_loss", lw, s_out["vp_embeds"], t_out["vp_embeds"], 3)
+        add_attn("local_attn_loss", s_out["vp_attn_list"], t_out["vp_attn_list"], 3, nx)
     per_seg, mse_total = ops.makd_mse(pairs) if pairs else (None, None)
     kl = None
     if "predict" in tasks:
@@ -98,7 +116,7 @@ def compute_kd_losses(student, s_out, t_out, task, rw, t_w, kdl=None):
         R, C = s_log.shape
         T = float(k["kd_temperature"])
         scale = (T * T / R if w is not None else T * T / (R * C)) * rw[4]
-        kl = ops.makd_kl(s_log, t_log, T, w, scale)
+        kl = ops.makd_kl(s_log, t_log, T, w, scale, sdev(4))
     return dict(per_seg=per_seg, owner=owner, mse_total=mse_total, kl=kl)
 
 

@@ -33,6 +33,30 @@ def bump_seed(device):
     seed_tensor(device).add_(0x9E3779B97F4A7C15 & 0x7FFFFFFFFFFFFFFF)
 
 
+class PinnedRing:
+    """Host -> device upload of a few per-step scalars without a host sync and without the overwrite race of a
+    single pinned buffer: the host may run several steps ahead of the GPU, so each upload uses the next of `n`
+    pinned slots and a slot is only rewritten after the copy that last read it has completed."""
+
+    def __init__(self, numel, dtype=torch.float32, n=8):
+        self.bufs = [torch.zeros(numel, dtype=dtype).pin_memory() for _ in range(n)]
+        self.events = [None] * n
+        self.i = 0
+
+    def upload(self, values, dst):
+        k = self.i % len(self.bufs)
+        self.i += 1
+        if self.events[k] is not None:
+            self.events[k].synchronize()
+        buf = self.bufs[k]
+        buf.copy_(torch.as_tensor(values, dtype=buf.dtype).reshape(-1))
+        dst.copy_(buf, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        self.events[k] = ev
+        return dst
+
+
 _salt = [0]
 
 
@@ -754,6 +778,7 @@ def _mk_segs(pairs, with_ds):
         arr[i].s, arr[i].t = s.data_ptr(), t.data_ptr()
         arr[i].ds = p["ds"].data_ptr() if with_ds else None
         arr[i].w = p["w"].data_ptr() if p["w"] is not None else None
+        arr[i].scale_dev = p["sdev"].data_ptr() if p.get("sdev") is not None else None
         arr[i].rows, arr[i].inner = p["rows"], p["inner"]
         arr[i].s_rs, arr[i].t_rs = p["s_rs"], p["t_rs"]
         arr[i].scale = p["scale"]
@@ -776,7 +801,8 @@ class MakdMseFn(torch.autograd.Function):
             w = ws[i]
             if w is not None:
                 w = w.contiguous().float()
-            pairs.append(dict(s=s, t=t, w=w, rows=rows, inner=inner, s_rs=inner, t_rs=inner, scale=meta[i]["scale"]))
+            pairs.append(dict(s=s, t=t, w=w, rows=rows, inner=inner, s_rs=inner, t_rs=inner, scale=meta[i]["scale"],
+                              sdev=meta[i].get("sdev")))
         loss = torch.empty(L.MAKD_MAX_SEGS + 1, dtype=torch.float32, device=ss[0].device)
         segs = _mk_segs(pairs, False)
         call("magic_makd_mse_fwd", segs, n, ptr(loss), stream())
@@ -800,8 +826,9 @@ class MakdMseFn(torch.autograd.Function):
 
 
 def makd_mse(pairs):
-    """pairs: list of (s, t, w_or_None, scale). Returns (per-segment losses [n], their sum)."""
-    meta = [dict(scale=float(p[3])) for p in pairs]
+    """pairs: list of (s, t, w_or_None, scale[, scale_dev]). `scale_dev` is an optional 1-element DEVICE tensor
+    multiplied into the host `scale` (device-resident MKRW weight).  Returns (per-segment losses [n], their sum)."""
+    meta = [dict(scale=float(p[3]), sdev=(p[4] if len(p) > 4 else None)) for p in pairs]
     return MakdMseFn.apply(meta, *[p[0] for p in pairs], *[p[1] for p in pairs], *[p[2] for p in pairs])
 
 
@@ -835,7 +862,7 @@ def loss_mix(mse_total, kl, sup, alpha, inv_n=None):
 
 class MakdKlFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, s, t, temperature, w, scale):
+    def forward(ctx, s, t, temperature, w, scale, sdev):
         R, C = s.shape
         s, t = _rows2d(s), _rows2d(t)
         if t.dtype != s.dtype:
@@ -846,26 +873,26 @@ class MakdKlFn(torch.autograd.Function):
             w = w.contiguous().float()
         stats = torch.empty(R, 2, dtype=torch.float32, device=s.device)
         loss = torch.empty(1, dtype=torch.float32, device=s.device)
-        call("magic_makd_kl_fwd", ptr(s), ptr(t), R, C, s.stride(0), temperature, ptr(w), scale, ptr(stats), ptr(loss),
-             dt(s), stream())
-        ctx.save_for_backward(s, t, w, stats)
+        call("magic_makd_kl_fwd", ptr(s), ptr(t), R, C, s.stride(0), temperature, ptr(w), scale, ptr(sdev), ptr(stats),
+             ptr(loss), dt(s), stream())
+        ctx.save_for_backward(s, t, w, stats, sdev)
         ctx.meta = (temperature, scale)
         return loss.view(())
 
     @staticmethod
     def backward(ctx, dloss):
-        s, t, w, stats = ctx.saved_tensors
+        s, t, w, stats, sdev = ctx.saved_tensors
         temperature, scale = ctx.meta
         R, C = s.shape
         g = dloss.reshape(1).contiguous().float()
         ds = torch.empty_strided(s.shape, s.stride(), dtype=s.dtype, device=s.device)
-        call("magic_makd_kl_bwd", ptr(s), ptr(t), ptr(ds), R, C, s.stride(0), temperature, ptr(w), scale, ptr(stats),
-             ptr(g), dt(s), stream())
-        return ds, None, None, None, None
+        call("magic_makd_kl_bwd", ptr(s), ptr(t), ptr(ds), R, C, s.stride(0), temperature, ptr(w), scale, ptr(sdev),
+             ptr(stats), ptr(g), dt(s), stream())
+        return ds, None, None, None, None, None
 
 
-def makd_kl(s, t, temperature, w, scale):
-    return MakdKlFn.apply(s, t, float(temperature), w, float(scale))
+def makd_kl(s, t, temperature, w, scale, scale_dev=None):
+    return MakdKlFn.apply(s, t, float(temperature), w, float(scale), scale_dev)
 
 
 # ---------------------------------------------------------------------------------------------------

@@ -9,6 +9,7 @@ import torch
 
 from ._lib import call, ptr, stream
 from .arena import ParamArena
+from .ops import PinnedRing
 
 
 def warmup_linear(step, warmup_step, tot_step):
@@ -31,7 +32,7 @@ class FusedAdamW:
         self.m = torch.zeros(arena.total, dtype=torch.float32, device=dev)
         self.v = torch.zeros(arena.total, dtype=torch.float32, device=dev)
         self.hyper = torch.zeros(8, dtype=torch.float32, device=dev)
-        self.hyper_host = torch.zeros(8, dtype=torch.float32).pin_memory()
+        self.hyper_ring = PinnedRing(8)
         self.sumsq = torch.zeros(1, dtype=torch.float32, device=dev)
         self.step_count = 0
         self.param_groups = [dict(lr=lr)]  # so `for g in optimizer.param_groups: g['lr'] = ...` keeps working
@@ -42,10 +43,8 @@ class FusedAdamW:
         lr = self.param_groups[0]["lr"] if lr is None else lr
         b1, b2 = self.betas
         bc1, bc2 = 1.0 - b1 ** self.step_count, 1.0 - b2 ** self.step_count
-        h = self.hyper_host
-        h[0], h[1], h[2], h[3], h[4], h[5] = lr, lr * math.sqrt(bc2) / bc1, b1, b2, self.eps, \
-            (self.max_grad_norm if self.max_grad_norm else 0.0)
-        self.hyper.copy_(h, non_blocking=True)
+        self.hyper_ring.upload([lr, lr * math.sqrt(bc2) / bc1, b1, b2, self.eps,
+                                (self.max_grad_norm if self.max_grad_norm else 0.0), 0.0, 0.0], self.hyper)
 
     def apply(self):
         """Device work of one step (graph-capturable): grad-norm, AdamW on both groups, bf16 shadow."""

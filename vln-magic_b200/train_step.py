@@ -15,6 +15,13 @@ from .arena import ParamArena
 from .parallel import FlatAllReduce, broadcast_flat
 
 
+class _Prefetched:
+    """A batch whose host->device copy is in flight on the copy stream (PretrainStepper.prefetch)."""
+
+    def __init__(self, task, batch, ready, slot, index):
+        self.task, self.batch, self.ready, self.slot, self.index = task, batch, ready, slot, index
+
+
 class PretrainStepper:
     def __init__(self, student, teacher=None, kdl=None, lr=5e-5, betas=(0.9, 0.98), weight_decay=0.01,
                  max_grad_norm=5.0, use_graphs=False, rw_generator=None, side_stream=True,
@@ -40,6 +47,8 @@ class PretrainStepper:
             broadcast_flat(self.arena.flat_p, 0)  # DDP's wrap-time parameter broadcast (utils/misc.py:63-66)
             self.arena.refresh_lowp()
         self.launches_per_step = None
+        self._copy_stream, self._staging = None, {}
+        self._rw_dev = None
 
     # -- the device side of one step -------------------------------------------------------------
     def _finish(self):
@@ -61,10 +70,65 @@ class PretrainStepper:
             self._finish()
         return mix
 
+    # -- host -> device prefetch (the reference's PrefetchLoader, data/loader.py:78-124) -----------------
+    def prefetch(self, task, host_batch):
+        """Start copying a pinned host batch (graph_index.prepare_batch output) to the device on a dedicated
+        copy stream and return a handle that `step()` accepts in place of a device batch.  Two staging sets per
+        batch signature are used alternately, so the copy of batch i+1 overlaps the compute of batch i."""
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream()
+        sig = self._signature(task, host_batch)
+        slot = self._staging.get(sig)
+        if slot is None:
+            def dev_like(v):
+                return torch.empty(v.shape, dtype=v.dtype, device=self.device)
+            sets = []
+            for _ in range(2):
+                sets.append({k: (dev_like(v) if torch.is_tensor(v) else
+                                 ({kk: (dev_like(vv) if torch.is_tensor(vv) else vv) for kk, vv in v.items()}
+                                  if k == INDEX_KEY else v)) for k, v in host_batch.items()})
+            slot = self._staging[sig] = dict(sets=sets, free=[None, None], n=0)
+            # the fresh buffers may recycle memory that kernels already queued on this stream still use
+            self._copy_stream.wait_stream(torch.cuda.current_stream())
+        i = slot["n"] % 2
+        slot["n"] += 1
+        dst = slot["sets"][i]
+        with torch.cuda.stream(self._copy_stream):
+            if slot["free"][i] is not None:
+                self._copy_stream.wait_event(slot["free"][i])  # the previous consumer of this set has finished
+            self._copy_into(dst, host_batch)
+            for k, v in host_batch.items():  # python-side members (vp-id lists, static ints) travel by reference
+                if not torch.is_tensor(v) and k != INDEX_KEY:
+                    dst[k] = v
+            ready = torch.cuda.Event()
+            ready.record(self._copy_stream)
+        return _Prefetched(task, dst, ready, slot, i)
+
     def step(self, task, batch, lr=None):
-        """batch: device batch with index tables (graph_index.prepare_batch + batch_to_device).
-        Returns the device tensor [total, supervised_mean, kd_total] (no host sync)."""
-        rw = makd.mkrw_weights(self.kdl["rw_temp"], generator=self.rw_generator) if self.teacher is not None else None
+        """batch: device batch with index tables (graph_index.prepare_batch + batch_to_device), or the handle
+        returned by `prefetch()`.  Returns the device tensor [total, supervised_mean, kd_total] (no host sync)."""
+        handle = None
+        if isinstance(batch, _Prefetched):
+            handle, batch = batch, batch.batch
+            torch.cuda.current_stream().wait_event(handle.ready)
+        out = self._step(task, batch, lr)
+        if handle is not None:
+            done = torch.cuda.Event()
+            done.record(torch.cuda.current_stream())
+            handle.slot["free"][handle.index] = done
+        return out
+
+    def _step(self, task, batch, lr=None):
+        rw = None
+        if self.teacher is not None:
+            if self.use_graphs:  # device-resident weights: the captured kernels read this step's draw
+                if self._rw_dev is None:
+                    self._rw_dev = torch.ones(5, dtype=torch.float32, device=self.device)
+                    self._rw_ring = ops.PinnedRing(5)
+                rw = makd.mkrw_weights(self.kdl["rw_temp"], generator=self.rw_generator, out=self._rw_dev,
+                                       ring=self._rw_ring)
+            else:
+                rw = makd.mkrw_weights(self.kdl["rw_temp"], generator=self.rw_generator)
         self.opt.set_hyper(lr)
         ops.bump_seed(self.device)
         if not self.use_graphs:
@@ -94,8 +158,6 @@ class PretrainStepper:
                         dst[k][kk].copy_(vv, non_blocking=True)
 
     def _graph_step(self, task, batch, rw):
-        if self.teacher is not None:
-            raise NotImplementedError("graph replay with MAKD needs device-resident MKRW weights (round 2)")
         sig = self._signature(task, batch)
         entry = self.graphs.get(sig)
         if entry is None:
