@@ -159,6 +159,25 @@ def family_cost(name, a):
     if name in ("magic_ln_fwd", "magic_ln_bwd"):
         M, h, dtc = (a[6], a[7], a[9]) if name == "magic_ln_fwd" else (a[9], a[10], a[11])
         return 0.0, M * h * esz(dtc) * (3 if name == "magic_ln_fwd" else 5)
+    if name in ("magic_makd_mse_fwd", "magic_makd_mse_bwd"):
+        by = 0.0
+        for i in range(a[1]):
+            sg = a[0][i]
+            n = sg.rows * sg.inner
+            by += n * (esz(sg.s_dt) + esz(sg.t_dt)) + (n * esz(sg.s_dt) if name.endswith("bwd") else 0)
+        return 0.0, by
+    if name in ("magic_makd_kl_fwd", "magic_makd_kl_bwd"):
+        R, C = a[2], a[3] if name.endswith("fwd") else a[4]
+        if name.endswith("bwd"):
+            R, C, dtc = a[3], a[4], a[-2]
+            return 0.0, R * C * esz(dtc) * 3
+        dtc = a[-2]
+        return 0.0, R * C * esz(dtc) * 2 * 2   # two passes over student + teacher rows
+    if name in ("magic_ce_fwd", "magic_ce_bwd"):
+        R, C, dtc = (a[4], a[5], a[8]) if name.endswith("fwd") else (a[5], a[6], a[9])
+        return 0.0, R * C * esz(dtc) * (1 if name.endswith("fwd") else 2)
+    if name == "magic_colsum":
+        return 0.0, a[2] * a[3] * esz(a[5])
     if name == "magic_adamw":
         return 0.0, a[5] * (28 + (2 if a[4] else 0))
     if name == "magic_sumsq":
@@ -393,16 +412,21 @@ def run_ours(args):
     roof, fams = None, None
     if rank == 0:
         # instrumented pass (eager, per-call CUDA events on the launch stream) for the roofline numbers
+        # (single stream, eager; a delay kernel every 32 calls keeps the host ahead of the GPU -- see _lib.profile_start)
         g = stepper.use_graphs
         stepper.use_graphs = False
+        ops.enable_side_stream(False)
+        ops.enable_branch_streams(False)
         run_steps(2, 0, False)
         torch.cuda.synchronize()
-        _lib.profile_start()
+        _lib.profile_start(delay_every=32, delay_cycles=2e6)
         nprof = 4
-        run_steps(nprof, 100, False, delay_cycles=60e6)
+        run_steps(nprof, 100, False)
         torch.cuda.synchronize()
         roof, fams = summarise_profile(_lib.profile_stop(), nprof, pk)
         stepper.use_graphs = g
+        ops.enable_side_stream(bool(args.side_stream))
+        ops.enable_branch_streams(bool(args.branch_streams))
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         v, n, tstep = cpu_step_rate(w, 12.0, 8, args.dropout)

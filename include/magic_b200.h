@@ -114,7 +114,8 @@ int magic_rowdot_bwd(const float* dy, const void* x, const float* w, void* dx, f
 int magic_colsum(const void* x, float* out, int M, int N, long ld, int dtype, cudaStream_t st); /* out += */
 int magic_cast(const void* in, int in_dt, void* out, int out_dt, long long n, cudaStream_t st);
 /* glue: out = a + b (+ c); strided 2-D copy; segment sums (per-sample means of masked-token losses) */
-int magic_add(const void* a, const void* b, const void* c, void* out, long long n, int dtype, cudaStream_t st);
+int magic_add(const void* a, const void* b, const void* c, void* out, long long n, float scale, int dtype,
+              cudaStream_t st); /* out = scale * (a + b (+ c)) */
 int magic_copy2d(const void* src, long src_ld, void* dst, long dst_ld, int rows, int cols, int dtype,
                  cudaStream_t st);
 int magic_segsum(const float* vals, const long long* seg, const float* seg_scale, float* out, int R, int n_seg,
@@ -147,6 +148,20 @@ int magic_ce_fwd(const void* logits, const long long* labels, float* loss, float
                  long long ignore_index, int dtype, cudaStream_t st);
 int magic_ce_bwd(const void* logits, const long long* labels, const float* lse, const float* dloss, void* dlogits,
                  int R, int C, long ld, long long ignore_index, int dtype, cudaStream_t st);
+
+/* ---- MRC / CFP task heads (outputs pinned at pretrain_src/train_r2r_magic.py:483-488 and :545-560) ----
+ * zero_rows: x[rows[i], :] = 0 in place (masked last-step views, data/tasks.py:178-181; rows[i] < 0 skipped).
+ * soft_ce: loss[r] = KL(targets[r] || softmax(logits[r])) summed over C classes (F.kl_div 'none' .sum(1));
+ *          stats[r] = (logsumexp, sum of targets) saved for backward.
+ * l2norm:  y = x / max(||x||_2, eps) per row (F.normalize); inv_norm[r] saved for backward. */
+int magic_zero_rows(void* x, const long long* rows, int n, int h, int dtype, cudaStream_t st);
+int magic_soft_ce_fwd(const void* logits, const float* targets, float* loss, float* stats /* [R,2] */, int R, int C,
+                      long ld, long tld, int dtype, cudaStream_t st);
+int magic_soft_ce_bwd(const void* logits, const float* targets, const float* stats, const float* dloss,
+                      void* dlogits, int R, int C, long ld, long tld, int dtype, cudaStream_t st);
+int magic_l2norm_fwd(const void* x, void* y, float* inv_norm, int R, int h, float eps, int dtype, cudaStream_t st);
+int magic_l2norm_bwd(const void* dy, const void* y, const float* inv_norm, void* dx, int R, int h, int dtype,
+                     cudaStream_t st);
 
 /* ---- MAKD losses (pretrain_src/optim/kd_loss.py:5-41; aggregation map_nav_src/r2r/agent.py:546-719) */
 typedef struct MagicMseSeg {

@@ -179,3 +179,75 @@ def test_ignore_labels_and_no_cpu_fallback():
     cpu_b = synth.make_batch("sap", 2)
     with pytest.raises(Exception):
         prod(cpu_b, "sap", True)
+
+
+ALL_TASKS = ("mlm", "sap", "mrc", "cfp")
+
+
+@pytest.mark.parametrize("dtype,tol,gtol", [(torch.float32, 1e-4, 2e-3), (torch.bfloat16, 2e-2, None)])
+def test_mrc_head(dtype, tol, gtol):
+    """MRC (a9): 4-tuple contract of train_r2r_magic.py:483, masked-view gather order, KL against soft labels."""
+    oracle, prod = build_pair(128, seed=9, pretrain_tasks=ALL_TASKS)
+    prod.set_compute_dtype(dtype)
+    b = get_batch("mrc", B=6, seed=21)
+    with torch.no_grad():
+        rl, rt, r3, r4 = oracle(oracle_batch(b), "mrc", False)
+        pl, pt, p3, p4 = prod(b, "mrc", False)
+    assert r3 is None and r4 is None and p3 is None and p4 is None
+    assert pl.shape == rl.shape == (int(b["vp_view_mrc_masks"].sum()), 1000)
+    assert torch.equal(pt, rt)                       # gathered soft labels: bit-exact (index work)
+    assert rel(pl, rl) < tol
+    if dtype == torch.float32:
+        assert torch.equal(pl.argmax(-1), rl.argmax(-1))
+    oracle.train()
+    prod.train()
+    ro, po = oracle(oracle_batch(b), "mrc", True), prod(b, "mrc", True)
+    assert rel(po["loss"], ro["loss"]) < tol
+    if gtol is not None:
+        ro["loss"].mean().backward()
+        po["loss"].mean().backward()
+        go = dict(oracle.named_parameters())
+        bad = [(n, rel(p.grad, go[n].grad)) for n, p in prod.named_parameters()
+               if go[n].grad is not None and go[n].grad.norm() > 1e-7 and rel(p.grad, go[n].grad) > gtol]
+        assert not bad, bad[:10]
+        assert prod.image_classifier.net[3].weight.grad.abs().max() > 0
+
+
+@pytest.mark.parametrize("dtype,tol,gtol", [(torch.float32, 1e-4, 2e-3), (torch.bfloat16, 2e-2, None)])
+def test_cfp_head(dtype, tol, gtol):
+    """CFP (a9): 4-tuple of [B, D] features (train_r2r_magic.py:545-546) and the symmetric InfoNCE of
+    validate_cfp (:550-562) as the training loss."""
+    oracle, prod = build_pair(128, seed=10, pretrain_tasks=ALL_TASKS, cfp_temperature=0.5)
+    prod.set_compute_dtype(dtype)
+    b = get_batch("cfp", B=6, seed=22)
+    with torch.no_grad():
+        r = oracle(oracle_batch(b), "cfp", False)
+        p = prod(b, "cfp", False)
+    assert len(p) == 4
+    for x, y in zip(p, r):
+        assert x.shape == y.shape == (6, 128)
+        assert rel(x, y) < tol
+    if dtype == torch.float32:
+        tgt = torch.arange(6, device=DEV)
+        for i in range(3):  # retrieval decisions of validate_cfp: bit-exact argmax
+            assert torch.equal((p[i] @ p[3].T).argmax(1), (r[i] @ r[3].T).argmax(1))
+    oracle.train()
+    prod.train()
+    ro, po = oracle(oracle_batch(b), "cfp", True), prod(b, "cfp", True)
+    assert po["loss"].shape == ro["loss"].shape
+    assert rel(po["loss"], ro["loss"]) < tol
+    if gtol is not None:
+        ro["loss"].mean().backward()
+        po["loss"].mean().backward()
+        go = dict(oracle.named_parameters())
+        bad = [(n, rel(p_.grad, go[n].grad)) for n, p_ in prod.named_parameters()
+               if go[n].grad is not None and go[n].grad.norm() > 1e-7 and rel(p_.grad, go[n].grad) > gtol]
+        assert not bad, bad[:10]
+        assert prod.cfp_txt_proj.weight.grad.abs().max() > 0
+
+
+def test_unknown_task_raises_like_reference():
+    _, prod = build_pair(128, seed=11)
+    b = get_batch("sap", B=2, seed=5)
+    with pytest.raises(ValueError):
+        prod(b, "itm", True)

@@ -34,12 +34,17 @@ def _ref_tasks():
 
 
 @pytest.mark.skipif(not os.path.exists(REF), reason="reference not mounted")
-@pytest.mark.parametrize("task", ["mlm", "sap"])
+@pytest.mark.parametrize("task", ["mlm", "sap", "mrc", "cfp"])
 def test_collate_matches_reference(task):
     tasks = _ref_tasks()
     samples = synth.make_samples(task, 6, seed=5)
     ours = synth.collate([dict(s) for s in samples])
-    ref = (tasks.mlm_collate if task == "mlm" else tasks.sap_collate)([dict(s) for s in samples])
+    ref_samples = [dict(s) for s in samples]
+    if task == "cfp":  # CfpDataset adds a per-sample config echo (data/tasks.py:606); not a model input
+        for s_ in ref_samples:
+            s_["extra_heads"] = False
+    ref = getattr(tasks, task + "_collate")(ref_samples)
+    ref.pop("extra_heads", None)
     assert set(ours.keys()) == set(ref.keys()), set(ours.keys()) ^ set(ref.keys())
     for k, v in ref.items():
         if torch.is_tensor(v):

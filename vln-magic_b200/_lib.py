@@ -81,11 +81,18 @@ class MagicError(RuntimeError):
 _LAUNCHES = {"magic_attn_bwd": 2, "magic_scatter_rows": 1, "magic_gmap_aggregate_bwd": 1}
 COUNTERS = {"calls": 0, "launches": 0}
 _PROFILE = None  # {name: [(start_event, end_event, args)]} when bench.py profiles kernel families
+_PROFILE_EVERY = 0  # > 0: keep the stream busy with a delay kernel every N calls so the host stays ahead of the GPU
+_PROFILE_N = 0
 
 
-def profile_start():
-    global _PROFILE
+def profile_start(delay_every=0, delay_cycles=3e6):
+    """Per-call CUDA-event timing of every C-ABI call (bench.py's roofline pass).  In eager mode the host issues
+    launches more slowly than the GPU retires these small kernels; a short `magic_delay` kernel every
+    `delay_every` calls (outside the event brackets) lets the host queue the next calls while the stream is
+    busy, so each bracket measures back-to-back device execution and not host launch latency."""
+    global _PROFILE, _PROFILE_EVERY, _PROFILE_N, _PROFILE_CYCLES
     _PROFILE = {}
+    _PROFILE_EVERY, _PROFILE_N, _PROFILE_CYCLES = int(delay_every), 0, int(delay_cycles)
 
 
 def profile_stop():
@@ -99,6 +106,11 @@ def call(name, *args):
     COUNTERS["calls"] += 1
     COUNTERS["launches"] += _LAUNCHES.get(name, 1)
     if _PROFILE is not None:
+        global _PROFILE_N
+        if _PROFILE_EVERY > 0 and name != "magic_delay":
+            if _PROFILE_N % _PROFILE_EVERY == 0:
+                lib.magic_delay(_PROFILE_CYCLES, stream())
+            _PROFILE_N += 1
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         rc = getattr(lib, name)(*args)

@@ -626,13 +626,13 @@ __global__ void act_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ p
 
 template <typename T>
 __global__ void add_kernel(const T* __restrict__ a, const T* __restrict__ b, const T* __restrict__ c,
-                           T* __restrict__ out, size_t n) {
+                           T* __restrict__ out, size_t n, float scale) {
   pdl_trigger();
   pdl_wait();
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
     float v = ldf(a, i) + ldf(b, i);
     if (c) v += ldf(c, i);
-    stf(out, i, v);
+    stf(out, i, v * scale);
   }
 }
 
@@ -879,13 +879,14 @@ int magic_act_bwd(const void* dy, const void* pre, void* dz, long long n, int ac
   return MAGIC_OK;
 }
 
-int magic_add(const void* a, const void* b, const void* c, void* out, long long n, int dtype, cudaStream_t st) {
+int magic_add(const void* a, const void* b, const void* c, void* out, long long n, float scale, int dtype,
+              cudaStream_t st) {
   if (n <= 0) return MAGIC_OK;
   long long blocks = (n + 1023) / 1024;
   const long long cap = 8LL * magic_num_sms();
   if (blocks > cap) blocks = cap;
   DISPATCH_T(dtype, (magic_launch(add_kernel<T>, dim3((int)blocks), dim3(256), 0, st, (const T*)a, (const T*)b, (const T*)c, (T*)out,
-                                                                (size_t)n)));
+                                                                (size_t)n, scale)));
   MAGIC_CHECK_LAUNCH("magic_add");
   return MAGIC_OK;
 }

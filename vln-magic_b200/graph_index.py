@@ -114,6 +114,19 @@ def build_index(batch):
         key_lens_vp=vp_lens_t.to(torch.int32), key_lens_pano=_cpu(batch["traj_vp_view_lens"]).to(torch.int32),
         n_nodes=B * G, n_src=int(len(src_ids)),
     )
+    Lt = batch["txt_ids"].shape[1]
+    idx["cls_rows_txt"] = torch.arange(B, dtype=torch.int64) * Lt
+    idx["arange_b"] = torch.arange(B, dtype=torch.int64)
+    if "vp_view_mrc_masks" in batch:
+        # MRC: masked views of the last-step panorama, row-major (b, view) order = boolean-mask order of
+        # `vp_view_probs[mask]` (train_r2r_magic.py:483; data/tasks.py:183-187)
+        m = _cpu(batch["vp_view_mrc_masks"]).bool()
+        V = batch["traj_view_img_fts"].shape[1]
+        bb, jj = m.nonzero(as_tuple=True)
+        last = torch.from_numpy(np.asarray(last_rows, dtype=np.int64))
+        idx["mrc_rows"] = (bb * Vp + 1 + jj).to(torch.int64)          # rows of vp_embeds [B*Vp, h]
+        idx["mrc_tgt_rows"] = (bb * m.shape[1] + jj).to(torch.int64)  # rows of vp_view_probs [B*V, C]
+        idx["mrc_fts_rows"] = (last[bb] * V + jj).to(torch.int64)     # rows of traj_view_img_fts [R*V, F]
     if "txt_labels" in batch:
         lab = _cpu(batch["txt_labels"])
         sel = (lab != -1)

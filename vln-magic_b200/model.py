@@ -551,8 +551,50 @@ class GlocalTextPathCMTPreTraining(nn.Module):
         return o
 
     def forward_mrc(self, batch, compute_loss=True):
-        raise NotImplementedError("mrc head: R2R/RxR pretraining uses [mlm, sap, cfp] "
-                                  "(r2r_magic_pretrain.json:49-53); scheduled after the mlm/sap/cfp path")
+        """Masked region classification (outputs pinned at train_r2r_magic.py:483-488): the masked views of the
+        last-step panorama are zeroed, the local branch's tokens at those views are classified over
+        `image_prob_size` classes against the soft labels `vp_view_probs[mask]` with KL."""
+        ix = self._index(batch)
+        fc = self._fc(False)
+        fts = batch["traj_view_img_fts"]
+        R, V, Fd = fts.shape
+        fts2 = ops.zero_rows_(fts.reshape(R * V, Fd).clone(), ix["mrc_fts_rows"]).view(R, V, Fd)
+        o = self.bert(batch, "nav", fc, ix, img_fts=fts2)
+        B, Vp, h = o["vp_embeds"].shape
+        x = ops.gather_rows(o["vp_embeds"].reshape(B * Vp, h), ix["mrc_rows"])
+        logits = self._cls(self.image_classifier, x)
+        probs = batch["vp_view_probs"]
+        with torch.no_grad():
+            targets = ops.gather_rows(probs.reshape(-1, probs.shape[-1]).float(), ix["mrc_tgt_rows"])
+        if not compute_loss:
+            return (logits.float() if logits.dtype != torch.float32 else logits), targets, None, None
+        o.update(loss=ops.soft_cross_entropy(logits, targets), logits=logits, view_targets=targets)
+        return o
 
     def forward_cfp(self, batch, compute_loss=True):
-        raise NotImplementedError("cfp head is scheduled after the mlm/sap path (DESIGN.md, scope table)")
+        """Cross-modal feature pooling (outputs pinned at train_r2r_magic.py:545-546): L2-normalised projections of
+        the global / local [stop] tokens, their fusion and the text [CLS] token; loss = symmetric InfoNCE of each
+        visual feature against the text feature at `cfp_temperature` (validate_cfp, :550-562)."""
+        ix = self._index(batch)
+        fc = self._fc(False)
+        o = self.bert(batch, "nav", fc, ix)
+        g3, v3, t3 = o["gmap_embeds"], o["vp_embeds"], o["txt_embeds"]
+        B, G, h = g3.shape
+        g0 = ops.gather_rows(g3.reshape(B * G, h), ix["stop_rows_g"])
+        v0 = ops.gather_rows(v3.reshape(B * v3.shape[1], h), ix["stop_rows_v"])
+        t0 = ops.gather_rows(t3.reshape(B * t3.shape[1], h), ix["cls_rows_txt"])
+        g = ops.l2norm(ops.linear(g0, self.cfp_gmap_proj.weight, self.cfp_gmap_proj.bias))
+        v = ops.l2norm(ops.linear(v0, self.cfp_vp_proj.weight, self.cfp_vp_proj.bias))
+        f = ops.l2norm(ops.add(g, v))
+        t = ops.l2norm(ops.linear(t0, self.cfp_txt_proj.weight, self.cfp_txt_proj.bias))
+        if not compute_loss:
+            return tuple(x.float() if x.dtype != torch.float32 else x for x in (g, v, f, t))
+        inv_tem = 1.0 / float(self.config.cfp_temperature)
+        tgt = ix["arange_b"]
+
+        def nce(a):
+            return ops.add(ops.cross_entropy(ops.matmul_nt(a, t, inv_tem), tgt, -100),
+                           ops.cross_entropy(ops.matmul_nt(t, a, inv_tem), tgt, -100))
+
+        o.update(loss=ops.add(nce(g), nce(v), nce(f), scale=1.0 / 6.0), cfp_outputs=(g, v, f, t))
+        return o

@@ -899,24 +899,121 @@ def makd_kl(s, t, temperature, w, scale, scale_dev=None):
 # glue
 # ---------------------------------------------------------------------------------------------------
 class AddFn(torch.autograd.Function):
-    """out = a + b (+ c), elementwise, same shape/dtype."""
+    """out = scale * (a + b (+ c)), elementwise, same shape/dtype."""
 
     @staticmethod
-    def forward(ctx, a, b, c):
+    def forward(ctx, a, b, c, scale):
         a, b = a.contiguous(), b.contiguous()
         c = c.contiguous() if c is not None else None
         out = torch.empty_like(a)
-        call("magic_add", ptr(a), ptr(b), ptr(c), ptr(out), a.numel(), dt(a), stream())
-        ctx.has_c = c is not None
+        call("magic_add", ptr(a), ptr(b), ptr(c), ptr(out), a.numel(), scale, dt(a), stream())
+        ctx.has_c, ctx.scale = c is not None, scale
         return out
 
     @staticmethod
     def backward(ctx, d):
-        return d, d, (d if ctx.has_c else None)
+        if ctx.scale != 1.0:
+            d = d * ctx.scale
+        return d, d, (d if ctx.has_c else None), None
 
 
-def add(a, b, c=None):
-    return AddFn.apply(a, b, c)
+def add(a, b, c=None, scale=1.0):
+    return AddFn.apply(a, b, c, float(scale))
+
+
+class MatmulNTFn(torch.autograd.Function):
+    """C[M,N] = alpha * A[M,K] B[N,K]^T for two ACTIVATIONS (contrastive similarity matrices)."""
+
+    @staticmethod
+    def forward(ctx, a, b, alpha):
+        a, b = a.contiguous(), b.contiguous()
+        M, K = a.shape
+        N = b.shape[0]
+        ldc = (N + 7) // 8 * 8  # 16-byte rows so the gradient is a legal tensor-core operand
+        out = torch.empty(M, ldc, dtype=a.dtype, device=a.device)[:, :N]
+        gemm(a, K, 1, b, 1, K, out, M, N, K, alpha=alpha)
+        ctx.save_for_backward(a, b)
+        ctx.alpha = alpha
+        return out
+
+    @staticmethod
+    def backward(ctx, dc):
+        a, b = ctx.saved_tensors
+        M, K = a.shape
+        N = b.shape[0]
+        dc = _rows2d(dc)
+        da = torch.empty_like(a)
+        db = torch.empty_like(b)
+        gemm(dc, dc.stride(0), 1, b, K, 1, da, M, K, N, alpha=ctx.alpha)
+        gemm(dc, 1, dc.stride(0), a, K, 1, db, N, K, M, alpha=ctx.alpha)
+        return da, db, None
+
+
+def matmul_nt(a, b, alpha=1.0):
+    return MatmulNTFn.apply(a, b, float(alpha))
+
+
+class L2NormFn(torch.autograd.Function):
+    """y = x / max(||x||_2, eps) per row (F.normalize)."""
+
+    @staticmethod
+    def forward(ctx, x, eps):
+        x = x.contiguous()
+        R, h = x.shape
+        y = torch.empty_like(x)
+        inv = torch.empty(R, dtype=torch.float32, device=x.device)
+        call("magic_l2norm_fwd", ptr(x), ptr(y), ptr(inv), R, h, eps, dt(x), stream())
+        ctx.save_for_backward(y, inv)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        y, inv = ctx.saved_tensors
+        dy = dy.contiguous()
+        dx = torch.empty_like(y)
+        call("magic_l2norm_bwd", ptr(dy), ptr(y), ptr(inv), ptr(dx), y.shape[0], y.shape[1], dt(y), stream())
+        return dx, None
+
+
+def l2norm(x, eps=1e-12):
+    return L2NormFn.apply(x, float(eps))
+
+
+class SoftCrossEntropyFn(torch.autograd.Function):
+    """loss[r] = KL(targets[r] || softmax(logits[r])), targets fp32 soft labels (MRC)."""
+
+    @staticmethod
+    def forward(ctx, logits, targets):
+        logits = _rows2d(logits)
+        targets = targets.contiguous().float()
+        R, C = logits.shape
+        loss = torch.empty(R, dtype=torch.float32, device=logits.device)
+        stats = torch.empty(R, 2, dtype=torch.float32, device=logits.device)
+        call("magic_soft_ce_fwd", ptr(logits), ptr(targets), ptr(loss), ptr(stats), R, C, logits.stride(0),
+             targets.stride(0), dt(logits), stream())
+        ctx.save_for_backward(logits, targets, stats)
+        return loss
+
+    @staticmethod
+    def backward(ctx, dloss):
+        logits, targets, stats = ctx.saved_tensors
+        R, C = logits.shape
+        dloss = dloss.contiguous().float()
+        dlogits = torch.empty_strided(logits.shape, logits.stride(), dtype=logits.dtype, device=logits.device)
+        call("magic_soft_ce_bwd", ptr(logits), ptr(targets), ptr(stats), ptr(dloss), ptr(dlogits), R, C,
+             logits.stride(0), targets.stride(0), dt(logits), stream())
+        return dlogits, None
+
+
+def soft_cross_entropy(logits, targets):
+    return SoftCrossEntropyFn.apply(logits, targets)
+
+
+def zero_rows_(x2d, rows):
+    """In place: x2d[rows[i], :] = 0 (rows < 0 are skipped).  No autograd (network inputs)."""
+    if rows.numel():
+        call("magic_zero_rows", ptr(x2d), ptr(rows), rows.numel(), x2d.shape[1], dt(x2d), stream())
+    return x2d
 
 
 class Cat2Fn(torch.autograd.Function):

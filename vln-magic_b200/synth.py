@@ -128,6 +128,17 @@ def make_samples(task, B, L=80, T_max=5, G_max=20, seed=1234, with_labels=None):
             ang = _angle_fts(rs.uniform(-math.pi, math.pi, N_VIEWS), rs.uniform(-math.pi / 6, math.pi / 6, N_VIEWS))
             loc.append(torch.from_numpy(np.concatenate([ang, np.ones((N_VIEWS, 3), np.float32)], 1)))
             nav.append(torch.LongTensor([1] * len(cands[t]) + [0] * (N_VIEWS - len(cands[t]))))
+        if task == "mrc":
+            # MrcDataset.__getitem__ (data/tasks.py:220-223): mask >= 1 view of the last panorama, zero its feature,
+            # soft labels over image_prob_size classes for every view (no [stop])
+            m = rs.rand(N_VIEWS) < 0.15
+            if not m.any():
+                m[int(rs.randint(0, N_VIEWS))] = True
+            mt = torch.from_numpy(m)
+            out["traj_view_img_fts"][-1] = out["traj_view_img_fts"][-1].masked_fill(mt[:, None], 0)
+            out["vp_view_mrc_masks"] = mt
+            pr = torch.softmax(torch.from_numpy(rs.randn(N_VIEWS, 1000).astype(np.float32)) * 2, -1)
+            out["vp_view_probs"] = pr
         out["traj_loc_fts"] = loc
         out["traj_nav_types"] = nav
         out["traj_cand_vpids"] = cands
@@ -209,6 +220,9 @@ def collate(samples):
     # local length from traj_vp_view_lens (see graph_index.build_index)
     batch["vp_lens"] = torch.LongTensor([len(x[-1]) for x in batch["vp_pos_fts"]])
     batch["vp_pos_fts"] = pad_tensors(batch["vp_pos_fts"])
+    if "vp_view_mrc_masks" in batch:  # mrc_collate, data/tasks.py:296-298
+        batch["vp_view_mrc_masks"] = _pad_1d(batch["vp_view_mrc_masks"], False)
+        batch["vp_view_probs"] = pad_tensors(batch["vp_view_probs"])
     if "global_act_labels" in batch:
         batch["local_act_labels"] = torch.LongTensor(batch["local_act_labels"])
         batch["global_act_labels"] = torch.LongTensor(batch["global_act_labels"])
