@@ -49,6 +49,14 @@ int magic_gemm(const void* A, int a_dt, long sam, long sak, const void* B, int b
                float beta, float drop_p, unsigned salt, const unsigned long long* seed_ptr, int allow_tc,
                cudaStream_t st);
 
+/* Weight and bias gradient of y = x W^T + b in one launch (the backward of every nn.Linear named at
+ * train_r2r_magic.py:189-208; replaces autograd's addmm-backward + sum kernels):
+ *   dw[n*dw_ld + k] = beta*dw + sum_m dy[m*dy_ld + n] * x[m*x_ld + k]    (fp32)
+ *   dbias[n]       += sum_m dy[m*dy_ld + n]                               (fp32, may be NULL)
+ * M = tokens (the reduction), N = out features, K = in features. */
+int magic_gemm_wgrad(const void* dy, int dy_dt, long dy_ld, const void* x, int x_dt, long x_ld, float* dw, long dw_ld,
+                     float* dbias, int M, int N, int K, float beta, int allow_tc, cudaStream_t st);
+
 /* ---- fused attention with graph-distance bias (GlobalMapEncoder: sprel_linear(gmap_pair_dists)) ----
  * q/k/v: rows are tokens, head hd occupies columns [hd*64, hd*64+64) of a row; *_ld = row stride.
  * out [B*Lq, H*64]; lse [B,H,Lq]; pbar (optional) = head-mean probabilities at

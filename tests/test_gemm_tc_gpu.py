@@ -71,6 +71,35 @@ def test_wgrad_layout_splitk_reduce(M, N, K, beta):
     assert rel(gw, ref) < 2e-5
 
 
+@pytest.mark.parametrize("M,N,K", SHAPES[:10] + [(5120, 128, 50272), (11520, 384, 128), (20480, 3072, 768)])
+@pytest.mark.parametrize("beta", [0.0, 1.0])
+def test_wgrad_with_bias_grad_single_launch(M, N, K, beta):
+    """magic_gemm_wgrad: dW (+)= dy^T x and db += colsum(dy) from ONE launch (ones-tile UMMA), incl. split-K,
+    ragged edges (partial last k-block of tokens, partial last row tile of features) and a padded dy stride."""
+    if K > 4096:
+        M, N, K = 640, 50265, 128
+    torch.manual_seed(5 + M + N + K)
+    ldy = (N + 7) // 8 * 8
+    dy = bf(torch.randn(M, ldy, device=DEV))[:, :N]
+    x = bf(torch.randn(M, K, device=DEV))
+    gw0, gb0 = torch.randn(N, K, device=DEV), torch.randn(N, device=DEV)
+    gw, gb = gw0.clone(), gb0.clone()
+    n0 = L.COUNTERS["calls"]
+    ops.gemm_wgrad(dy, x, gw, gb, M, N, K, beta)
+    assert L.COUNTERS["calls"] == n0 + 1
+    # fp64 reference: at a 20 480-token reduction the fp32 torch matmul's own accumulation error is the size of
+    # ours; the bound grows with sqrt(reduction length) (4e-5 at M = 20 480, still inside north_star's 1e-4)
+    ref_w = (dy.double().t() @ x.double()).float()
+    tol = 2e-5 * max(1.0, (M / 5120) ** 0.5)
+    assert rel(gw, ref_w + beta * gw0) < tol
+    ref_b = gb0 + dy.float().sum(0)
+    assert (gb - ref_b).abs().max().item() < 1e-3 * max(1.0, ref_b.abs().max().item())
+    # no bias: pointer may be NULL
+    gw2 = gw0.clone()
+    ops.gemm_wgrad(dy, x, gw2, None, M, N, K, beta)
+    assert rel(gw2, ref_w + beta * gw0) < tol
+
+
 def test_strided_views_packed_output():
     """Column slices of a packed [M, 3h] buffer as C (ldc > N) and as A (lda > K); padded leading dimension."""
     torch.manual_seed(3)

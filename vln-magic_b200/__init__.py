@@ -7,4 +7,4 @@ Public surface (mirrors the reference's module API for this path):
   optim.FusedAdamW / build_optimizer / get_lr_sched                          pretrain_src/optim/*
 """
 from .model import GlocalTextPathCMTPreTraining, GlocalTextPathCMT, stack_attns  # noqa: F401
-from .graph_index import prepare_batch, batch_to_device, INDEX_KEY  # noqa: F401
+from .graph_index import prepare_batch, batch_to_device, flatten_batch, INDEX_KEY, FLAT_KEY  # noqa: F401

@@ -60,11 +60,34 @@ int magic_gemm(const void* A, int a_dt, long sam, long sak, const void* B, int b
   epi.drop_p = drop_p;
   epi.seed_ptr = seed_ptr;
   epi.salt = salt;
+  epi.rowsum = nullptr;
   if (allow_tc && a_dt == MAGIC_BF16 && b_dt == MAGIC_BF16) {
     const int rc = gemm_tc_dispatch(A, B, C, c_dt, M, N, K, sam, sak, sbk, sbn, ldc, epi, st);
     if (rc != MAGIC_ERR_UNSUPPORTED) return rc;
   }
   return gemm_simt_dispatch(A, a_dt, B, b_dt, C, c_dt, M, N, K, sam, sak, sbk, sbn, ldc, epi, st);
+}
+
+/* weight + bias gradient of y = x W^T + b in ONE launch on the tensor-core path: the bias gradient is an extra
+ * 16-column UMMA against a tile of ones (see gemm_tc.cu), so no separate column-sum kernel runs. */
+int magic_gemm_wgrad(const void* dy, int dy_dt, long dy_ld, const void* x, int x_dt, long x_ld, float* dw, long dw_ld,
+                     float* dbias, int M, int N, int K, float beta, int allow_tc, cudaStream_t st) {
+  MAGIC_CHECK_ARG(M >= 0 && N >= 0 && K >= 0, "magic_gemm_wgrad: negative shape");
+  if (N == 0 || K == 0 || M == 0) return MAGIC_OK;
+  GemmEpi epi;
+  memset(&epi, 0, sizeof(epi));
+  epi.alpha = 1.f;
+  epi.beta = beta;
+  epi.rowsum = dbias;
+  if (allow_tc && dy_dt == MAGIC_BF16 && x_dt == MAGIC_BF16) {
+    // A(m=n_out, k=token) = dy[token*dy_ld + n_out]; B(k=token, n=k_in) = x[token*x_ld + k_in]
+    const int rc = gemm_tc_dispatch(dy, x, dw, MAGIC_F32, N, K, M, 1, dy_ld, x_ld, 1, dw_ld, epi, st);
+    if (rc != MAGIC_ERR_UNSUPPORTED) return rc;
+  }
+  epi.rowsum = nullptr;
+  const int rc = gemm_simt_dispatch(dy, dy_dt, x, x_dt, dw, MAGIC_F32, N, K, M, 1, dy_ld, x_ld, 1, dw_ld, epi, st);
+  if (rc != MAGIC_OK || dbias == nullptr) return rc;
+  return magic_colsum(dy, dbias, M, N, dy_ld, dy_dt, st);
 }
 
 }  // extern "C"

@@ -20,6 +20,7 @@ struct GemmEpi {
   float drop_p;                        // dropout applied to the activation OUTPUT (forward) / its gradient (backward)
   const unsigned long long* seed_ptr;  // device pointer
   uint32_t salt;
+  float* rowsum;                       // optional [M] fp32: rowsum[m] += alpha * sum_k A(m,k)  (bias gradient of a wgrad GEMM)
 };
 
 __device__ __forceinline__ float act_fwd(int act, float v) {

@@ -39,6 +39,8 @@ constexpr int NTHREADS = 64 + NUM_EPI_WARPS * 32;  // 10 warps
 constexpr int STG_BYTES = 4096;                    // one staging buffer: 32 rows x 128 B
 constexpr int STG_BUFS = 2;                        // per epilogue warp
 constexpr int MAX_STAGES = 8;
+constexpr int RS_COLS = 16;                        // accumulator columns of the row-sum (bias gradient) UMMA
+constexpr int ONES_BYTES = RS_COLS * 128;          // 16 rows x 64 bf16 ones, K-major SWIZZLE_128B tile
 
 // ---- PTX wrappers -------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -133,6 +135,12 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
         "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
         "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
       : "r"(taddr));
+}
+// 32 lanes x 1 column -> one register per thread
+__device__ __forceinline__ uint32_t tmem_ld1(uint32_t taddr) {
+  uint32_t r;
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r) : "r"(taddr));
+  return r;
 }
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
@@ -308,7 +316,8 @@ __global__ void __launch_bounds__(NTHREADS, 1)
   uint8_t* sA = smem;
   uint8_t* sB = sA + stages * A_BYTES;
   uint8_t* sStage = sB + stages * B_BYTES;  // [NUM_EPI_WARPS][STG_BUFS][4096], 1024-aligned
-  uint64_t* full = (uint64_t*)(sStage + NUM_EPI_WARPS * STG_BUFS * STG_BYTES);
+  uint8_t* sOnes = sStage + NUM_EPI_WARPS * STG_BUFS * STG_BYTES;  // 1024-aligned (all staging sizes are)
+  uint64_t* full = (uint64_t*)(sOnes + ONES_BYTES);
   uint64_t* empty = full + MAX_STAGES;
   uint64_t* tmem_full = empty + MAX_STAGES;  // [2]
   uint64_t* tmem_empty = tmem_full + 2;      // [2]
@@ -333,7 +342,13 @@ __global__ void __launch_bounds__(NTHREADS, 1)
     }
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(tmem_ptr, 2 * BN);
+  const bool rowsum = P.epi.rowsum != nullptr;  // host guarantees BN <= 128 then
+  const uint32_t tmem_cols = rowsum ? 4 * BN : 2 * BN;
+  if (rowsum) {
+    for (int i = threadIdx.x; i < ONES_BYTES / 4; i += NTHREADS) reinterpret_cast<uint32_t*>(sOnes)[i] = 0x3F803F80u;
+    fence_proxy_async();  // the tensor core reads this tile through the async proxy
+  }
+  if (warp == 1) tmem_alloc(tmem_ptr, tmem_cols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -384,6 +399,11 @@ __global__ void __launch_bounds__(NTHREADS, 1)
         const int kb0 = ks * P.kb_per_split, kb1 = min(P.total_kb, kb0 + P.kb_per_split);
         const int as = it & 1;
         const uint32_t aph = (it >> 1) & 1;
+        // bias gradient: the CTAs of the first tile column also multiply A by a tile of ones
+        const bool rs_tile = rowsum && (work % (P.m_tiles * P.n_tiles)) % P.n_tiles == 0;
+        const uint32_t rs_idesc = make_idesc(BM, RS_COLS, P.a_mn, 0);
+        const uint32_t tmem_rs = tmem_base + (uint32_t)(2 * BN + as * RS_COLS);
+        const uint64_t ones_desc = make_desc(smem_u32(sOnes), 16, 1024);
         mbar_wait(&tmem_empty[as], aph ^ 1);  // epilogue has drained this accumulator buffer
         tc_fence_after();
         const uint32_t tmem_c = tmem_base + (uint32_t)(as * BN);
@@ -399,6 +419,7 @@ __global__ void __launch_bounds__(NTHREADS, 1)
             const uint64_t bdesc =
                 P.b_mn ? make_desc(b_base + k * 2048, 8192, 1024) : make_desc(b_base + k * 32, 16, 1024);
             umma_bf16(tmem_c, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            if (rs_tile) umma_bf16(tmem_rs, adesc, ones_desc, rs_idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           }
           umma_commit(&empty[s]);  // frees this smem stage once the MMAs above have read it
           if (++s == stages) { s = 0; ph ^= 1; }
@@ -425,6 +446,11 @@ __global__ void __launch_bounds__(NTHREADS, 1)
       const int m = m0 + q * 32 + lane;
       const bool row_ok = m < P.M;
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN);
+      if (rowsum && hf == 0 && n0 == 0) {  // column 0 of the ones product = sum_k A(m, k)
+        const uint32_t r = tmem_ld1(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(2 * BN + as * RS_COLS));
+        tmem_wait_ld();
+        if (row_ok) atomicAdd(P.epi.rowsum + m, P.epi.alpha * __uint_as_float(r));
+      }
       bool released = false;
       if (UNITS <= hf) {  // nothing to drain for this warp (BN = 64 with bf16 output): just release
         tc_fence_before();
@@ -484,7 +510,7 @@ __global__ void __launch_bounds__(NTHREADS, 1)
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 2 * BN);
+    tmem_dealloc(tmem_base, tmem_cols);
   }
 }
 
@@ -570,7 +596,8 @@ int get_map(const void* ptr, uint64_t inner, uint64_t outer, uint64_t stride, ui
 }
 
 constexpr size_t SMEM_MAX = 227 * 1024;
-constexpr size_t SMEM_FIXED = 1024 /*align slack*/ + NUM_EPI_WARPS * STG_BUFS * STG_BYTES + (2 * MAX_STAGES + 4) * 8 + 16;
+constexpr size_t SMEM_FIXED = 1024 /*align slack*/ + NUM_EPI_WARPS * STG_BUFS * STG_BYTES + ONES_BYTES +
+                              (2 * MAX_STAGES + 4) * 8 + 16;
 
 template <int BN, typename TC>
 int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const CUtensorMap& tp, TcParams& P,
@@ -659,6 +686,7 @@ int gemm_tc_dispatch(const void* A, const void* B, void* C, int c_dt, int M, int
     else if (t128 < sms / 2) BN = 64;
   }
   if (force_bn() == 64 || force_bn() == 128 || force_bn() == 256) BN = force_bn();
+  if (epi.rowsum && BN > 128) BN = 128;  // the row-sum accumulators need TMEM columns beyond the two tile buffers
   P.n_tiles = (N + BN - 1) / BN;
   // split-K for skinny outputs with a long reduction (weight gradients): fp32 C, purely linear epilogue
   P.splits = 1;

@@ -212,3 +212,90 @@ def batch_to_device(batch, device, non_blocking=False):
         else:
             out[k] = v
     return out
+
+
+# ---------------------------------------------------------------------------------------------------
+# flat batches: every tensor of a batch (and of its index tables) as a view into ONE byte buffer, so a batch moves
+# host -> device (or into a CUDA graph's static inputs) with a single copy instead of ~35 small ones
+# ---------------------------------------------------------------------------------------------------
+FLAT_KEY = "_magic_flat"
+_ALIGN = 256
+
+
+def _tensor_items(batch):
+    for k in sorted(batch.keys()):
+        v = batch[k]
+        if k == FLAT_KEY:
+            continue
+        if k == INDEX_KEY:
+            for kk in sorted(v.keys()):
+                if torch.is_tensor(v[kk]):
+                    yield (k, kk), v[kk]
+        elif torch.is_tensor(v):
+            yield (k, None), v
+
+
+def flat_layout(batch):
+    """-> ([(key, subkey, offset, shape, dtype)], total bytes); deterministic in the batch's shape signature."""
+    lay, off = [], 0
+    for (k, kk), t in _tensor_items(batch):
+        lay.append((k, kk, off, tuple(t.shape), t.dtype))
+        off += (t.numel() * t.element_size() + _ALIGN - 1) // _ALIGN * _ALIGN
+    return lay, max(off, _ALIGN)
+
+
+def _views(batch, flat, lay):
+    out = {k: v for k, v in batch.items() if not torch.is_tensor(v) and k != INDEX_KEY}
+    if INDEX_KEY in batch:
+        out[INDEX_KEY] = {kk: vv for kk, vv in batch[INDEX_KEY].items() if not torch.is_tensor(vv)}
+    for k, kk, off, shape, dtype in lay:
+        n = 1
+        for s in shape:
+            n *= s
+        nb = n * torch.empty(0, dtype=dtype).element_size()
+        t = flat[off:off + nb].view(dtype).view(shape)
+        if kk is None:
+            out[k] = t
+        else:
+            out[k][kk] = t
+    out[FLAT_KEY] = flat
+    return out
+
+
+def flatten_batch(batch, device=None, pin=False):
+    """Repack a batch so that all its tensors are views into one uint8 buffer (`batch[FLAT_KEY]`), on the host
+    (optionally pinned) or on `device`.  A batch that is already flat moves with one copy."""
+    lay, total = flat_layout(batch)
+    src_flat = batch.get(FLAT_KEY)
+    if src_flat is None or src_flat.numel() != total:
+        src_flat = torch.empty(total, dtype=torch.uint8)
+        host = _views(batch, src_flat, lay)
+        for (k, kk), t in _tensor_items(batch):
+            dst = host[k] if kk is None else host[k][kk]
+            dst.copy_(t)
+    else:
+        host = batch
+    if device is None:
+        if pin and not src_flat.is_pinned():
+            return _views(host, src_flat.pin_memory(), lay)
+        return host
+    return _views(host, src_flat.to(device, non_blocking=True), lay)
+
+
+def copy_batch_(dst, src):
+    """dst <- src for two batches of the same signature; one copy when both are flat."""
+    fd, fs = dst.get(FLAT_KEY), src.get(FLAT_KEY)
+    if fd is not None and fs is not None and fd.numel() == fs.numel():
+        fd.copy_(fs, non_blocking=True)
+        return 1
+    n = 0
+    for (k, kk), t in _tensor_items(src):
+        (dst[k] if kk is None else dst[k][kk]).copy_(t, non_blocking=True)
+        n += 1
+    return n
+
+
+def alloc_like(batch, device):
+    """An uninitialised flat device batch with the layout of `batch` (python-side members shared by reference)."""
+    lay, total = flat_layout(batch)
+    return _views(batch, torch.empty(total, dtype=torch.uint8, device=device), lay)

@@ -186,6 +186,12 @@ def run_branches(side_fn, main_fn):
     return a, b
 
 
+def gemm_wgrad(dy2, x2, gw, gb, M, N, K, beta, dw_ld=None):
+    """gw[N,K] = beta*gw + dy^T x ; gb[N] += colsum(dy) -- one launch (bias gradient rides the wgrad GEMM)."""
+    call("magic_gemm_wgrad", ptr(dy2), dt(dy2), dy2.stride(0), ptr(x2), dt(x2), x2.stride(0), ptr(gw),
+         K if dw_ld is None else dw_ld, ptr(gb), M, N, K, beta, 1, stream())
+
+
 def _lin_wgrad(dy2, x2, w, bias):
     """dW[N,K] (+)= dy^T x ; db (+)= colsum(dy).  Returns the autograd values."""
     M, N = dy2.shape
@@ -194,16 +200,13 @@ def _lin_wgrad(dy2, x2, w, bias):
     if side is not None:
         _SIDE["hold"].extend((dy2, x2))
         with torch.cuda.stream(side):
-            gemm(dy2, 1, dy2.stride(0), x2, K, 1, w._magic_grad, N, K, M, beta=1.0)
-            if bias is not None:
-                call("magic_colsum", ptr(dy2), ptr(bias._magic_grad), M, N, dy2.stride(0), dt(dy2), stream())
+            gemm_wgrad(dy2, x2, w._magic_grad, bias._magic_grad if bias is not None else None, M, N, K, 1.0)
         return None, None
     gw, rw, beta = _sink(w)
-    gemm(dy2, 1, dy2.stride(0), x2, K, 1, gw, N, K, M, beta=beta)
-    rb = None
+    gb, rb = None, None
     if bias is not None:
         gb, rb, _ = _sink(bias)
-        call("magic_colsum", ptr(dy2), ptr(gb), M, N, dy2.stride(0), dt(dy2), stream())
+    gemm_wgrad(dy2, x2, gw, gb, M, N, K, beta)
     return rw, rb
 
 
@@ -322,16 +325,14 @@ class PackedLinearFn(torch.autograd.Function):
             if side is not None:
                 _SIDE["hold"].extend((dy2, x2))
             with torch.cuda.stream(side if side is not None else torch.cuda.current_stream()):
-                gemm(dy2, 1, Nt, x2, K, 1, gws[0], Nt, K, M, beta=1.0, ldc=K)
-                call("magic_colsum", ptr(dy2), ptr(gbs[0]), M, Nt, Nt, dt(dy2), stream())
+                gemm_wgrad(dy2, x2, gws[0], gbs[0], M, Nt, K, 1.0)
         else:
             off = 0
             for i, (w, b, Ni) in enumerate(zip(ws, bs, Ns)):
                 gw, rws[i], beta = _sink(w)
                 dv = dy2[:, off:off + Ni]
-                gemm(dv, 1, Nt, x2, K, 1, gw, Ni, K, M, beta=beta, ldc=K)
                 gb, rbs[i], _ = _sink(b)
-                call("magic_colsum", ptr(dv), ptr(gb), M, Ni, Nt, dt(dy2), stream())
+                gemm_wgrad(dv, x2, gw, gb, M, Ni, K, beta)
                 off += Ni
         return (dx, None, *rws, *rbs)
 

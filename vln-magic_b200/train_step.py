@@ -9,7 +9,7 @@ import torch
 import torch.distributed as dist
 
 from . import _lib, makd, ops
-from .graph_index import INDEX_KEY
+from .graph_index import FLAT_KEY, INDEX_KEY, alloc_like, copy_batch_
 from .optim import FusedAdamW
 from .arena import ParamArena
 from .parallel import FlatAllReduce, broadcast_flat
@@ -80,14 +80,8 @@ class PretrainStepper:
         sig = self._signature(task, host_batch)
         slot = self._staging.get(sig)
         if slot is None:
-            def dev_like(v):
-                return torch.empty(v.shape, dtype=v.dtype, device=self.device)
-            sets = []
-            for _ in range(2):
-                sets.append({k: (dev_like(v) if torch.is_tensor(v) else
-                                 ({kk: (dev_like(vv) if torch.is_tensor(vv) else vv) for kk, vv in v.items()}
-                                  if k == INDEX_KEY else v)) for k, v in host_batch.items()})
-            slot = self._staging[sig] = dict(sets=sets, free=[None, None], n=0)
+            slot = self._staging[sig] = dict(sets=[alloc_like(host_batch, self.device) for _ in range(2)],
+                                             free=[None, None], n=0)
             # the fresh buffers may recycle memory that kernels already queued on this stream still use
             self._copy_stream.wait_stream(torch.cuda.current_stream())
         i = slot["n"] % 2
@@ -96,7 +90,7 @@ class PretrainStepper:
         with torch.cuda.stream(self._copy_stream):
             if slot["free"][i] is not None:
                 self._copy_stream.wait_event(slot["free"][i])  # the previous consumer of this set has finished
-            self._copy_into(dst, host_batch)
+            copy_batch_(dst, host_batch)  # ONE copy when the host batch is flat (graph_index.flatten_batch)
             for k, v in host_batch.items():  # python-side members (vp-id lists, static ints) travel by reference
                 if not torch.is_tensor(v) and k != INDEX_KEY:
                     dst[k] = v
@@ -141,30 +135,21 @@ class PretrainStepper:
         sig = [task]
         for k in sorted(batch.keys()):
             v = batch[k]
+            if k == FLAT_KEY:
+                continue
             if torch.is_tensor(v):
                 sig.append((k, tuple(v.shape)))
             elif k == INDEX_KEY:
                 sig.append(tuple((kk, tuple(vv.shape) if torch.is_tensor(vv) else vv) for kk, vv in sorted(v.items())))
         return tuple(sig)
 
-    @staticmethod
-    def _copy_into(dst, src):
-        for k, v in src.items():
-            if torch.is_tensor(v):
-                dst[k].copy_(v, non_blocking=True)
-            elif k == INDEX_KEY:
-                for kk, vv in v.items():
-                    if torch.is_tensor(vv):
-                        dst[k][kk].copy_(vv, non_blocking=True)
-
     def _graph_step(self, task, batch, rw):
         sig = self._signature(task, batch)
         entry = self.graphs.get(sig)
         if entry is None:
             dev = self.device
-            static = {k: (v.to(dev, copy=True) if torch.is_tensor(v) else
-                          ({kk: (vv.to(dev, copy=True) if torch.is_tensor(vv) else vv) for kk, vv in v.items()}
-                           if k == INDEX_KEY else v)) for k, v in batch.items()}
+            static = alloc_like(batch, dev)
+            copy_batch_(static, batch)
             s = torch.cuda.Stream()
             s.wait_stream(torch.cuda.current_stream())
             # warm-up on a side stream (allocator, cudaFuncSetAttribute, lazy init) WITHOUT changing the
@@ -187,7 +172,7 @@ class PretrainStepper:
             entry = (g, static, out, _lib.COUNTERS["launches"] - n0)
             self.graphs[sig] = entry
         g, static, out, n_launch = entry
-        self._copy_into(static, batch)
+        copy_batch_(static, batch)
         g.replay()
         _lib.COUNTERS["launches"] += n_launch  # kernels replayed inside the graph
         if self.world > 1:
