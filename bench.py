@@ -27,8 +27,27 @@ WORKLOADS = {
     # BASELINE.json configs[2]: teacher h=768 (9/2/4) -> MAGIC-S distillation step, batch 64
     "magic_s_distill_t768_b64": dict(hidden=128, n_l=6, n_x=3, n_p=2, B=64, L=80, T_max=5, G_max=20,
                                      teacher=dict(hidden=768, n_l=9, n_x=4, n_p=2)),
+    # MAGIC-L (h=768, 6/2/3) pretraining step without a teacher: the tensor-core-bound shape of the same path
+    "magic_l_pretrain_b32": dict(hidden=768, n_l=6, n_x=3, n_p=2, B=32, L=80, T_max=5, G_max=20, teacher=None),
+    # BASELINE.json configs[3] per GPU: MAGIC-L with ICoD teacher/student co-update (both models train), batch 32
+    "magic_l_icod_b32": dict(hidden=768, n_l=6, n_x=3, n_p=2, B=32, L=80, T_max=5, G_max=20, co_update=True,
+                             teacher=dict(hidden=768, n_l=9, n_x=4, n_p=2)),
+    # BASELINE.json configs[4] per GPU: RxR-shape stress (160-token instr, 50-node graph, 12 steps), batch 128,
+    # teacher h=768 -> MAGIC-S
+    "rxr_stress_distill_b128": dict(hidden=128, n_l=6, n_x=3, n_p=2, B=128, L=160, T_max=12, G_max=50,
+                                    teacher=dict(hidden=768, n_l=9, n_x=4, n_p=2)),
 }
-FWD_GFLOP_PER_SAMPLE = {128: 0.669, 768: 22.08}
+# forward GFLOP per sample, keyed (hidden, n_l, L): student / teacher shapes of the workloads above
+FWD_GFLOP = {(128, 6, 80): 0.669, (768, 6, 80): 17.29, (768, 9, 80): 22.08, (128, 6, 160): 1.42, (768, 9, 160): 44.9}
+
+
+def train_gflop_per_sample(w):
+    """3 x forward for every model that trains + 1 x forward for a frozen teacher."""
+    g = 3.0 * FWD_GFLOP.get((w["hidden"], w["n_l"], w["L"]), 0.0)
+    t = w.get("teacher")
+    if t:
+        g += (3.0 if w.get("co_update") else 1.0) * FWD_GFLOP.get((t["hidden"], t["n_l"], w["L"]), 0.0)
+    return g
 
 
 def peaks():
@@ -325,8 +344,9 @@ def run_ours(args):
     teacher = None
     if cfg_t is not None:
         torch.manual_seed(0)
-        teacher = magic_b200.GlocalTextPathCMTPreTraining(cfg_t).to(dev).eval().set_compute_dtype(dtype)
-    stepper = PretrainStepper(student, teacher, use_graphs=bool(args.graphs),
+        teacher = magic_b200.GlocalTextPathCMTPreTraining(cfg_t).to(dev).set_compute_dtype(dtype)
+        teacher = teacher.train() if w.get("co_update") else teacher.eval()
+    stepper = PretrainStepper(student, teacher, use_graphs=bool(args.graphs), co_update=bool(w.get("co_update")),
                               side_stream=bool(args.side_stream), branch_streams=bool(args.branch_streams))
     ops.set_seed(dev, 1234 + rank)
 
@@ -444,14 +464,19 @@ def run_ours(args):
                    sample=f"fp32 PyTorch oracle port, student step fwd+bwd+clip+AdamW at batch 8 (bounded sample of the "
                           f"batch-{B} workload), MLM/SAP 1:1, {n} steps, median {tstep * 1e3:.0f} ms/step")
     if rank == 0:
-        train_gflop = 3 * FWD_GFLOP_PER_SAMPLE.get(w["hidden"], 0.0)
+        train_gflop = train_gflop_per_sample(w)
+        kind = "MLM+SAP step" if w["teacher"] is None else ("MLM+SAP+distill step, ICoD co-update" if w.get("co_update")
+                                                            else "MLM+SAP+distill step")
         line = dict(
-            metric="pretrain samples/s (MLM+SAP step)", value=value, unit="samples/s", n_gpus=world, steps=args.steps,
+            metric=f"pretrain samples/s ({kind})", value=value, unit="samples/s", n_gpus=world, steps=args.steps,
             warmup=max(args.warmup, 3), ms_per_step=ms / args.steps, higher_is_better=True, scaling="weak",
             vs_baseline=None, dtype=args.dtype, data="synthetic",
             config=dict(workload=args.workload, hidden=w["hidden"], layers=f"{w['n_l']}/{w['n_p']}/{w['n_x']}",
                         batch_per_gpu=B, global_batch=B * world, seq_len=w["L"], views=36, graph_nodes=w["G_max"],
                         traj_steps_max=w["T_max"], tasks="mlm:sap 1:1", dropout=args.dropout,
+                        teacher=("h%d %d/%d/%d%s" % (w["teacher"]["hidden"], w["teacher"]["n_l"], w["teacher"]["n_p"],
+                                                     w["teacher"]["n_x"], " (trained, ICoD)" if w.get("co_update")
+                                                     else " (frozen)")) if w["teacher"] else None,
                         optimizer="fused AdamW + clip 5.0", cuda_graphs=bool(stepper.use_graphs),
                         parallelism=f"dp{world}",
                         l2="inputs cycle through a pool of %d batches/task (~%.0f MB) > 126 MB L2" % (

@@ -650,8 +650,14 @@ def mktd_weights(t_sample_loss, decay=0.7):
     return KD.exponential_decay(t_sample_loss.detach(), decay_rate=decay)
 
 
-def makd_losses(student, s_out, t_out, task, rw, t_w, kdl=None):
-    """agent.py:546-719 (role 't2s') with the pretrain reductions of optim/kd_loss.py.
+def makd_losses(student, s_out, t_out, task, rw, t_w, kdl=None, role="t2s"):
+    """agent.py:546-719 with the pretrain reductions of optim/kd_loss.py.  `student` is always the SMALL model: it
+    owns the up-projections (txt_emb_w, kdl_img_w, kdl_avg_img_w, global_cross_w, local_cross_w).
+      role 't2s' (agent.py:550-552): learner = small model; prediction = proj(s_out), target = t_out.detach().
+      role 's2t' (agent.py:553-556, ICoD): learner = LARGE model; the caller passes (s_out, t_out) =
+        (large model's outputs, small model's outputs) exactly like agent.py:1022; prediction = s_out as is,
+        target = proj(t_out).detach() (agent.py:571,605-606,647,665); `t_w` are then the SMALL model's MKTD
+        weights (agent.py:1009-1011 stored under the same 'sample_weights' key).
     Returns dict of the 10 named scalars (agent.py:824-835 names)."""
     k = dict(KDL_DEFAULT)
     if kdl:
@@ -666,20 +672,29 @@ def makd_losses(student, s_out, t_out, task, rw, t_w, kdl=None):
     # [DECISION] x-layer maps are additionally clipped to their own common depth (the reference expression
     # `[:, :min_len]` would raise on teacher/student pairs with different num_x_layers, e.g. 4 vs 3)
     nx = min(min_len, s_out["gmap_attns"].shape[1], t_out["gmap_attns"].shape[1])
+
+    def pair(proj, key):
+        if role == "t2s":
+            return proj(s_out[key]), t_out[key].detach()
+        return s_out[key], proj(t_out[key]).detach()
+
+    def e(proj, key, ri):
+        return KD.mse_loss(*pair(proj, key), t_w) * rw[ri] if emb else z
+
     if "txt" in k["kdl_tasks"]:
-        L["txt_emb_loss"] = KD.mse_loss(bert.txt_emb_w(s_out["txt_embeds"]), t_out["txt_embeds"].detach(), t_w) * rw[0] if emb else z
+        L["txt_emb_loss"] = e(bert.txt_emb_w, "txt_embeds", 0)
         L["txt_attn_loss"] = KD.mse_loss(s_out["txt_attns"][:, :min_len], t_out["txt_attns"][:, :min_len].detach(), t_w) * rw[0] if att else z
     if "img" in k["kdl_tasks"]:
         # agent.py:620-622: under RW the two image emb losses are NOT halved
-        L["img_emb_loss"] = KD.mse_loss(bert.kdl_img_w(s_out["pano_embeds"]), t_out["pano_embeds"].detach(), t_w) * rw[1] if emb else z
-        L["avg_img_emb_loss"] = KD.mse_loss(bert.kdl_avg_img_w(s_out["pano_fused_embeds"]), t_out["pano_fused_embeds"].detach(), t_w) * rw[1] if emb else z
+        L["img_emb_loss"] = e(bert.kdl_img_w, "pano_embeds", 1)
+        L["avg_img_emb_loss"] = e(bert.kdl_avg_img_w, "pano_fused_embeds", 1)
         L["img_attn_loss"] = KD.mse_loss(s_out["img_attns"], t_out["img_attns"].detach(), t_w) * rw[1] if att else z  # agent.py:628 unsliced
     gw, lw = (bert.gmap_txt_w, bert.vp_txt_w) if task.startswith("mlm") else (bert.global_cross_w, bert.local_cross_w)
     if "global" in k["kdl_tasks"]:
-        L["global_emb_loss"] = KD.mse_loss(gw(s_out["gmap_embeds"]), t_out["gmap_embeds"].detach(), t_w) * rw[2] if emb else z
+        L["global_emb_loss"] = e(gw, "gmap_embeds", 2)
         L["global_attn_loss"] = KD.mse_loss(s_out["gmap_attns"][:, :nx], t_out["gmap_attns"][:, :nx].detach(), t_w) * rw[2] if att else z
     if "local" in k["kdl_tasks"]:
-        L["local_emb_loss"] = KD.mse_loss(lw(s_out["vp_embeds"]), t_out["vp_embeds"].detach(), t_w) * rw[3] if emb else z
+        L["local_emb_loss"] = e(lw, "vp_embeds", 3)
         L["local_attn_loss"] = KD.mse_loss(s_out["vp_attns"][:, :nx], t_out["vp_attns"][:, :nx].detach(), t_w) * rw[3] if att else z
     if "predict" in k["kdl_tasks"]:
         w = t_w
@@ -703,3 +718,28 @@ def distill_step_loss(student, teacher, batch, task, rw, kdl=None):
     kd_total = sum(L.values())
     total = k["kd_alpha"] * kd_total + (1 - k["kd_alpha"]) * sup  # agent.py:1119
     return total, sup, kd_total, L, s_out, t_out
+
+
+def icod_step_loss(student, teacher, batch, task, rw, t_rw, kdl=None):
+    """ICoD co-update (`--train_kdl_teacher`, agent.py:1019-1022, 1136-1149; agent_base.py:260-279): one step
+    yields TWO losses.  The small model learns from the large one exactly as in `distill_step_loss` (role t2s); the
+    large model, whose forward now runs WITH grad, learns from the small one (role s2t: targets are the small
+    model's outputs pushed through the small model's projections, detached) mixed with its own supervised loss
+    by t_kdl_alpha (parser.py:184: 0.5).  Under RW the large model's ability weights are the small model's draw
+    of the step (agent.py:869-871: t_softmax_weights = s_softmax_weights); `t_rw` is kept separate for the 'grad' mode.
+    [DECISION] the s2t KD sum enters like the t2s one (mean-reduced terms, no extra batch factor): the fine-tune
+    rollout's `* train_ml` (agent.py:1143) is a sum-over-steps convention that pretraining's mean losses lack.
+    Returns (total_s, total_t, dict_s, dict_t, s_out, t_out)."""
+    k = dict(KDL_DEFAULT)
+    k.setdefault("t_kd_alpha", 0.5)
+    if kdl:
+        k.update(kdl)
+    t_out = teacher(batch, task, True)
+    s_out = student(batch, task, True)
+    t_w = mktd_weights(t_out["sample_loss"], k["t_sample_preprocess_exp_decay"]) if k["teacher_sample_hard_mining"] else None
+    s_w = mktd_weights(s_out["sample_loss"], k["t_sample_preprocess_exp_decay"]) if k["teacher_sample_hard_mining"] else None
+    Ls = makd_losses(student, s_out, t_out, task, rw, t_w, k, role="t2s")
+    Lt = makd_losses(student, t_out, s_out, task, t_rw, s_w, k, role="s2t")
+    total_s = k["kd_alpha"] * sum(Ls.values()) + (1 - k["kd_alpha"]) * s_out["loss"].mean()
+    total_t = k["t_kd_alpha"] * sum(Lt.values()) + (1 - k["t_kd_alpha"]) * t_out["loss"].mean()  # agent.py:1145
+    return total_s, total_t, Ls, Lt, s_out, t_out

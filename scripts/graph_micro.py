@@ -120,14 +120,19 @@ def ln_cases(cases):
             with torch.no_grad():
                 ops.layer_norm(xs[i], g, b, 1e-12, res=rs[i], p_in=0.1, salt_in=5)
         timeit(f"ln fwd {M}x{h} res+drop", f, 0, 3 * M * h * 2)
-        x = xs[0].clone().requires_grad_(True)
-        r = rs[0].clone().requires_grad_(True)
-        gg = g.clone().requires_grad_(True)
-        b2 = b.clone().requires_grad_(True)
-        y = ops.layer_norm(x, gg, b2, 1e-12, res=r, p_in=0.1, salt_in=5)
-        dy = torch.randn_like(y)
-        timeit(f"ln bwd {M}x{h} res+drop", lambda i: torch.autograd.grad(y, (x, r, gg, b2), dy, retain_graph=True), 0,
-               5 * M * h * 2)
+        st = torch.empty(M, 2, device=dev)
+        ys = [torch.empty_like(xs[0]) for _ in range(NSET)]
+        seed = ops.seed_tensor(torch.device(dev))
+        _lib.call("magic_ln_fwd", xs[0].data_ptr(), rs[0].data_ptr(), g.data_ptr(), b.data_ptr(), ys[0].data_ptr(),
+                  st.data_ptr(), M, h, 1e-12, 1, 0.1, 5, 0.0, 0, seed.data_ptr(), _lib.stream())
+        dys = [torch.randn(M, h, device=dev).bfloat16() for _ in range(NSET)]
+        dxs = [torch.empty_like(xs[0]) for _ in range(NSET)]
+        drs = [torch.empty_like(xs[0]) for _ in range(NSET)]
+        dg, db = torch.zeros(h, device=dev), torch.zeros(h, device=dev)
+        timeit(f"ln bwd {M}x{h} res+drop",
+               lambda i: _lib.call("magic_ln_bwd", dys[i].data_ptr(), xs[0].data_ptr(), rs[0].data_ptr(), g.data_ptr(),
+                                   st.data_ptr(), dxs[i].data_ptr(), drs[i].data_ptr(), dg.data_ptr(), db.data_ptr(),
+                                   M, h, 1, 0.1, 5, 0.0, 0, seed.data_ptr(), _lib.stream()), 0, 5 * M * h * 2)
 
 
 which = sys.argv[1] if len(sys.argv) > 1 else "all"
@@ -139,4 +144,4 @@ if which in ("all", "attn"):
     attn_cases([(64, 2, 80, 80, False), (224, 2, 36, 36, False), (64, 2, 20, 20, True), (64, 2, 20, 80, False),
                 (64, 2, 37, 80, False), (64, 2, 80, 37, False), (64, 12, 80, 80, False)])
 if which in ("all", "ln"):
-    ln_cases([(5120, 128), (8064, 128), (5120, 768)])
+    ln_cases([(5120, 128), (8064, 128), (5120, 768), (11520, 768)])

@@ -92,7 +92,7 @@ def test_ffn_and_packed(dtype, tol):
 
 
 @pytest.mark.parametrize("dtype,tol", [(torch.float32, 2e-5), (torch.bfloat16, 2e-2)])
-@pytest.mark.parametrize("h", [128, 256, 768])
+@pytest.mark.parametrize("h", [128, 200, 256, 384, 768])  # 200: scalar kernel; the others: vectorised kernel
 def test_layer_norm(dtype, tol, h):
     torch.manual_seed(2)
     M = 333
@@ -216,7 +216,8 @@ def _ref_attn(q, k, v, lens, dists, sw, sb, H):
                                  dict(B=2, H=12, Lq=80, Lk=80, sprel=False), dict(B=2, H=2, Lq=160, Lk=50, sprel=False),
                                  dict(B=5, H=2, Lq=36, Lk=36, sprel=False), dict(B=2, H=2, Lq=50, Lk=50, sprel=True),
                                  dict(B=2, H=2, Lq=160, Lk=160, sprel=False), dict(B=2, H=4, Lq=80, Lk=37, sprel=False),
-                                 dict(B=3, H=2, Lq=65, Lk=33, sprel=False), dict(B=1, H=2, Lq=200, Lk=200, sprel=False)])
+                                 dict(B=3, H=2, Lq=65, Lk=33, sprel=False), dict(B=1, H=2, Lq=200, Lk=200, sprel=False),
+                                 dict(B=2, H=3, Lq=40, Lk=40, sprel=True), dict(B=3, H=6, Lq=37, Lk=80, sprel=False)])
 def test_attention(dtype, tol, cfg):
     torch.manual_seed(5)
     B, H, Lq, Lk = cfg["B"], cfg["H"], cfg["Lq"], cfg["Lk"]

@@ -117,6 +117,44 @@ def test_distill_step_loss_and_grads_fp32(task):
 
 
 @pytest.mark.parametrize("task", ["sap", "mlm"])
+def test_icod_co_update_losses_and_grads_fp32(task):
+    """ICoD (`--train_kdl_teacher`): the s2t role of compute_kd_losses (agent.py:553-556, 571, 605-606, 647, 665)
+    and the two-loss step vs the oracle -- both totals, the 10 named s2t scalars, and the gradients of BOTH models
+    (one backward over the sum of the two disjoint graphs == the reference's two backward calls)."""
+    t_oracle, t_prod = build_pair(256, role="teacher", seed=3)
+    s_oracle, s_prod = build_pair(128, ht=256, seed=4)
+    for m in (s_oracle, s_prod, t_oracle, t_prod):
+        m.train()
+    b = get_batch(task, seed=78)
+    rw = [1.3, 0.6, 1.1, 0.9, 1.1]
+    rwt = torch.tensor(rw, device=DEV)
+    tot_s, tot_t, Ls, Lt, _, _ = O.icod_step_loss(s_oracle, t_oracle, oracle_batch(b), task, rwt, rwt)
+    tot_s.backward(retain_graph=True)  # the reference's order (agent_base.py:260-268)
+    tot_t.backward()
+    mix_s, mix_t, res_s, res_t, _, _ = makd.icod_step_loss(s_prod, t_prod, b, task, rw, rw)
+    (mix_s[0] + mix_t[0]).backward()
+    assert abs(mix_s[0].item() - tot_s.item()) <= 1e-4 * abs(tot_s.item()), (mix_s[0].item(), tot_s.item())
+    assert abs(mix_t[0].item() - tot_t.item()) <= 1e-4 * abs(tot_t.item()), (mix_t[0].item(), tot_t.item())
+    for res, Lo in ((res_s, Ls), (res_t, Lt)):
+        named = makd.named_losses(res)
+        for k, v in Lo.items():
+            assert abs(named[k] - v.item()) <= 1e-4 * abs(v.item()) + 1e-7, (k, named[k], v.item())
+    for oracle, prod in ((s_oracle, s_prod), (t_oracle, t_prod)):
+        go = dict(oracle.named_parameters())
+        bad = []
+        for n, p in prod.named_parameters():
+            ref = go[n].grad
+            if ref is None:
+                assert p.grad is None or p.grad.abs().max() == 0, n
+                continue
+            assert p.grad is not None, n
+            r = rel(p.grad, ref)
+            if r > 2e-3 and ref.norm() > 1e-7:
+                bad.append((n, r, ref.norm().item()))
+        assert not bad, bad[:10]
+
+
+@pytest.mark.parametrize("task", ["sap", "mlm"])
 def test_bf16_mode(task):
     oracle, prod = build_pair(128, ht=256, seed=5)
     prod.set_compute_dtype(torch.bfloat16)

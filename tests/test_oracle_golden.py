@@ -61,3 +61,33 @@ def test_cuda_path_matches_golden(task):
     else:
         assert torch.equal(s_out["logits"].argmax(1).cpu(), gold["logits_argmax"])
         assert _close(s_out["logits"][:, :64], gold["logits_head"], 1e-4)
+
+
+def test_oracle_icod_graphs_are_disjoint_and_s2t_vanishes_on_matched_models():
+    """ICoD restatement (oracle.icod_step_loss; agent.py:553-556, 1019-1022, 1136-1149), CPU:
+    (i) every cross-model target is detached, so the small model's loss gives no gradient to the large model and
+        vice versa (which is why one backward over the sum equals the reference's two backward calls);
+    (ii) with kd_alpha = t_kd_alpha = 1 and the predict ability only, both directions compare the same two logit
+        sets with swapped roles: KL(t||s) and KL(s||t) are both >= 0 and vanish together when the logits agree."""
+    from oracle import magic_oracle as O
+    from magic_b200 import synth
+    _, _, teacher, student = G.build()
+    teacher.train()
+    b = synth.make_batch("sap", 4, seed=2027)
+    rw = torch.tensor(G.RW)
+    tot_s, tot_t, Ls, Lt, s_out, t_out = O.icod_step_loss(student, teacher, b, "sap", rw, rw)
+    assert set(Ls) == set(Lt) and all(float(v) >= 0 for v in list(Ls.values()) + list(Lt.values()))
+    tot_t.backward(retain_graph=True)
+    assert all(p.grad is None or float(p.grad.abs().max()) == 0 for p in student.parameters())
+    assert any(p.grad is not None and float(p.grad.abs().max()) > 0 for p in teacher.parameters())
+    for p in teacher.parameters():
+        p.grad = None
+    tot_s.backward()
+    assert all(p.grad is None or float(p.grad.abs().max()) == 0 for p in teacher.parameters())
+    assert any(p.grad is not None and float(p.grad.abs().max()) > 0 for p in student.parameters())
+    # (ii) identical logits -> the predict KL is exactly 0 in both roles
+    same = dict(s_out)
+    k = dict(kdl_tasks=("predict",))
+    z1 = O.makd_losses(student, s_out, same, "sap", rw, None, k, role="t2s")["predict_loss"]
+    z2 = O.makd_losses(student, same, s_out, "sap", rw, None, k, role="s2t")["predict_loss"]
+    assert abs(float(z1)) < 1e-7 and abs(float(z2)) < 1e-7

@@ -99,3 +99,29 @@ def test_graph_replay_follows_per_step_mkrw_draw():
     assert rel(outs[True], outs[False]) < 2e-5
     kd = outs[True][:, 2]
     assert (kd[0] - kd[1]).abs() > 1e-4 * kd[0].abs() and (kd[1] - kd[2]).abs() > 1e-4 * kd[1].abs()
+
+
+def test_icod_co_update_steps_both_models_and_graph_replay_matches_eager():
+    """ICoD (co_update=True): one step moves the parameters of BOTH models; the CUDA-graph replay of the two-model
+    step (teacher forward with grad, two optimizers) reproduces the eager step."""
+    res = {}
+    for graphs in (False, True):
+        s, t = models(True)
+        t.train()
+        p0_s, p0_t = None, None
+        st = PretrainStepper(s, t, lr=1e-3, rw_generator=torch.Generator().manual_seed(11), use_graphs=graphs,
+                             side_stream=graphs, branch_streams=graphs, co_update=True)
+        p0_s, p0_t = st.arena.flat_p.clone(), st.t_arena.flat_p.clone()
+        pools = host_pool(n=2)
+        outs = []
+        for i in range(4):
+            task = "mlm" if i % 2 == 0 else "sap"
+            outs.append(st.step(task, batch_to_device(pools[task][(i // 2) % 2], DEV)).clone())
+        torch.cuda.synchronize()
+        outs = torch.stack(outs).cpu()
+        assert outs.shape == (4, 6) and torch.isfinite(outs).all()
+        assert (outs[:, 2] > 0).all() and (outs[:, 5] > 0).all()  # both KD directions are live
+        assert (st.arena.flat_p - p0_s).abs().max() > 0 and (st.t_arena.flat_p - p0_t).abs().max() > 0
+        res[graphs] = (outs, st.arena.flat_p.clone().cpu(), st.t_arena.flat_p.clone().cpu())
+    for a, b in zip(res[True], res[False]):
+        assert rel(a, b) < 2e-5

@@ -6,8 +6,11 @@
 // with quad shuffles, and feeds P straight back into the P V product as the A operand (no shared-memory round
 // trip).  K / V / Q tiles are staged by cp.async into 144-byte-pitch shared rows (conflict-free ldmatrix).
 //
-//   forward     grid (ceil(Lq/64), heads, B); with the KD attention map requested one CTA walks all heads of
-//               its rows and accumulates mean_heads(P) in shared memory (no atomics, deterministic)
+//   forward     grid (ceil(Lq/64), heads, B); with the KD attention map requested the heads of one query tile are
+//               split over a thread-block CLUSTER (2 or 4 CTAs along grid.y, each walking H/cluster heads and
+//               accumulating its partial mean_heads(P) in shared memory); after a cluster barrier every CTA sums
+//               its slice of the tile over the peers' partials through distributed shared memory in rank order
+//               (no atomics, no zero-fill, deterministic) and writes the map once
 //   backward 1  (query-major) recomputes P from the saved log-sum-exp, dP = dO V^T, the softmax row term
 //               delta = sum_j P (dP*drop + dPbar/H), dS, dQ = dS K, and the sprel affine's gradients
 //   backward 2  (key-major) works on the transposed tile S^T = K Q^T so that P^T and dS^T are already the A
@@ -16,6 +19,8 @@
 // Dropout uses the same stateless hash and element index as the SIMT kernels (attention.cu), so both paths
 // generate identical masks.  fp32 activations, longer sequences and unaligned views stay on the SIMT path.
 #include <stdlib.h>
+
+#include <cooperative_groups.h>
 
 #include "attention.cuh"
 #include "../../include/magic_b200.h"
@@ -144,7 +149,7 @@ __device__ __forceinline__ void store_rows(bf16* ra, bf16* rb, const float (&o)[
 // forward
 // ===================================================================================================
 template <int NT>
-__global__ void __launch_bounds__(NTHREADS) attn_mma_fwd_kernel(AttnParams P, int hc) {
+__global__ void __launch_bounds__(NTHREADS) attn_mma_fwd_kernel(AttnParams P, int hc, int csize) {
   extern __shared__ __align__(16) uint8_t smraw[];
   pdl_trigger();
   pdl_wait();
@@ -152,7 +157,7 @@ __global__ void __launch_bounds__(NTHREADS) attn_mma_fwd_kernel(AttnParams P, in
   bf16* Ks = reinterpret_cast<bf16*>(smraw);
   bf16* Vs = Ks + LKP * PITCH;
   bf16* Qs = Vs + LKP * PITCH;
-  float* pb = reinterpret_cast<float*>(Qs + TILE * PITCH);  // [TILE][LKP], only when P.pbar
+  float* pb = reinterpret_cast<float*>(Qs + TILE * PITCH);  // [TILE][LKP + 8], only when P.pbar
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
   const int b = blockIdx.z, q0 = blockIdx.x * TILE, h_begin = blockIdx.y * hc;
   const int Lq = P.Lq, Lk = P.Lk, H = P.H;
@@ -164,8 +169,12 @@ __global__ void __launch_bounds__(NTHREADS) attn_mma_fwd_kernel(AttnParams P, in
   const float invH = 1.f / (float)H;
   const int ia = q0 + w * 16 + g, ib = ia + 8;
   const bool va = ia < Lq, vb = ib < Lq;
-  if (P.pbar)
-    for (int e = threadIdx.x; e < TILE * LKP; e += NTHREADS) pb[e] = 0.f;
+  // head-mean of P over this CTA's heads: a thread owns the same (row, column) cells of the score tile for every
+  // head, so it accumulates them in its own shared-memory cells (8-byte accesses, pitch LKP + 8 floats: no bank
+  // conflicts, no synchronisation, and the first head stores instead of adding so nothing is zero-filled)
+  constexpr int PBP = LKP + 8;
+  float* pba = pb + (w * 16 + g) * PBP + 2 * t;
+  float* pbb = pba + 8 * PBP;
 
   for (int hd = h_begin; hd < h_begin + hc; hd++) {
     __syncthreads();
@@ -227,18 +236,40 @@ __global__ void __launch_bounds__(NTHREADS) attn_mma_fwd_kernel(AttnParams P, in
       if (vb) P.lse[((size_t)b * H + hd) * Lq + ib] = mxb + __logf(sumb);
     }
     const size_t dia = (((size_t)b * H + hd) * Lq + ia) * Lk, dib = (((size_t)b * H + hd) * Lq + ib) * Lk;
-    float* pba = pb + (w * 16 + g) * LKP;
-    float* pbb = pba + 8 * LKP;
 #pragma unroll
     for (int j = 0; j < NT; j++) {
 #pragma unroll
       for (int e = 0; e < 2; e++) {
         const int c = j * 8 + 2 * t + e;
         const float pa = s[j][e] * inva, pc = s[j][2 + e] * invb;  // exactly 0 for masked / padded keys
-        if (P.pbar) {
-          pba[c] += pa * invH;
-          pbb[c] += pc * invH;
+        s[j][e] = pa;  // normalised probabilities (the head-mean below reads them before dropout scales them)
+        s[j][2 + e] = pc;
+      }
+    }
+    if (P.pbar) {
+      if (hd == h_begin) {
+#pragma unroll
+        for (int j = 0; j < NT; j++) {
+          *reinterpret_cast<float2*>(pba + j * 8) = make_float2(s[j][0] * invH, s[j][1] * invH);
+          *reinterpret_cast<float2*>(pbb + j * 8) = make_float2(s[j][2] * invH, s[j][3] * invH);
         }
+      } else {
+#pragma unroll
+        for (int j = 0; j < NT; j++) {
+          float2 a = *reinterpret_cast<float2*>(pba + j * 8), c2 = *reinterpret_cast<float2*>(pbb + j * 8);
+          a.x += s[j][0] * invH; a.y += s[j][1] * invH;
+          c2.x += s[j][2] * invH; c2.y += s[j][3] * invH;
+          *reinterpret_cast<float2*>(pba + j * 8) = a;
+          *reinterpret_cast<float2*>(pbb + j * 8) = c2;
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < NT; j++) {
+#pragma unroll
+      for (int e = 0; e < 2; e++) {
+        const int c = j * 8 + 2 * t + e;
+        const float pa = s[j][e], pc = s[j][2 + e];
         s[j][e] = pa * dr.scale(dia + c);
         s[j][2 + e] = pc * dr.scale(dib + c);
       }
@@ -250,10 +281,28 @@ __global__ void __launch_bounds__(NTHREADS) attn_mma_fwd_kernel(AttnParams P, in
                vb ? ob + ((size_t)b * Lq + ib) * (size_t)(H * D) : nullptr, o, 1.f, t);
   }
   if (P.pbar) {
-    __syncthreads();
-    for (int e = threadIdx.x; e < rows_q * Lk; e += NTHREADS) {
-      const int r = e / Lk, c = e - r * Lk;
-      P.pbar[(size_t)b * P.pbar_bs + (size_t)(q0 + r) * P.pbar_rs + c] = pb[r * LKP + c];
+    if (csize == 1) {
+      __syncthreads();
+      for (int e = threadIdx.x; e < rows_q * Lk; e += NTHREADS) {
+        const int r = e / Lk, c = e - r * Lk;
+        P.pbar[(size_t)b * P.pbar_bs + (size_t)(q0 + r) * P.pbar_rs + c] = pb[r * PBP + c];
+      }
+    } else {
+      namespace cg = cooperative_groups;
+      cg::cluster_group cluster = cg::this_cluster();
+      cluster.sync();  // every peer's partial head-mean is complete and visible cluster-wide
+      const int rank = (int)cluster.block_rank();
+      const float* peer[4];
+      for (int r = 0; r < csize; r++) peer[r] = cluster.map_shared_rank(pb, r);
+      const int total = rows_q * Lk, per = (total + csize - 1) / csize;
+      const int e0 = rank * per, e1 = min(total, e0 + per);
+      for (int e = e0 + threadIdx.x; e < e1; e += NTHREADS) {
+        const int r = e / Lk, c = e - r * Lk;
+        float acc = 0.f;
+        for (int k = 0; k < csize; k++) acc += peer[k][r * PBP + c];  // fixed rank order: deterministic
+        P.pbar[(size_t)b * P.pbar_bs + (size_t)(q0 + r) * P.pbar_rs + c] = acc;
+      }
+      cluster.sync();  // keep this CTA's shared memory alive until the peers have read it
     }
   }
 }
@@ -525,12 +574,22 @@ int set_smem(K kernel, size_t bytes, const char* name) {
 
 template <int NT>
 int launch_fwd(const AttnParams& P, cudaStream_t st) {
-  const size_t smem = (size_t)(2 * NT * 8 + TILE) * PITCH * 2 + (P.pbar ? (size_t)TILE * NT * 8 * 4 : 0);
+  // KD attention map: the heads of a query tile are shared out over a cluster of 4 / 2 CTAs when each still gets
+  // >= 2 heads (below that the cluster barrier costs more than the serial head walk it replaces: measured)
+  int csize = 1;
+  if (P.pbar && P.H >= 4) csize = (P.H % 4 == 0 && P.H >= 8) ? 4 : (P.H % 2 == 0) ? 2 : 1;
+  const size_t smem = (size_t)(2 * NT * 8 + TILE) * PITCH * 2 + (P.pbar ? (size_t)TILE * (NT * 8 + 8) * 4 : 0);
   int rc = set_smem(attn_mma_fwd_kernel<NT>, smem, "magic_attn_fwd");
   if (rc) return rc;
-  const int hc = P.pbar ? P.H : 1;
+  const int hc = P.pbar ? P.H / csize : 1;
   dim3 grid((P.Lq + TILE - 1) / TILE, P.H / hc, P.B);
-  MAGIC_CUDA(magic_launch(attn_mma_fwd_kernel<NT>, grid, dim3(NTHREADS), smem, st, P, hc), "magic_attn_fwd(mma)");
+  if (csize > 1) {
+    MAGIC_CUDA(magic_launch_cluster(attn_mma_fwd_kernel<NT>, grid, dim3(NTHREADS), smem, st, dim3(1, csize, 1), P, hc,
+                                    csize),
+               "magic_attn_fwd(mma, cluster)");
+  } else {
+    MAGIC_CUDA(magic_launch(attn_mma_fwd_kernel<NT>, grid, dim3(NTHREADS), smem, st, P, hc, 1), "magic_attn_fwd(mma)");
+  }
   return MAGIC_OK;
 }
 

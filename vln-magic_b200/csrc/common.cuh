@@ -82,6 +82,27 @@ static inline cudaError_t magic_launch(void (*kernel)(KArgs...), dim3 grid, dim3
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
+// same, with a thread-block cluster of `cluster` CTAs (distributed shared memory between them)
+template <typename... KArgs, typename... Args>
+static inline cudaError_t magic_launch_cluster(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                                               cudaStream_t st, dim3 cluster, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = cluster.x;
+  attr[0].val.clusterDim.y = cluster.y;
+  attr[0].val.clusterDim.z = cluster.z;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = magic_pdl_enabled() ? 2 : 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // ---------------------------------------------------------------------------------------------
 // element access: activations are f32 or bf16; math is always fp32
 // ---------------------------------------------------------------------------------------------

@@ -163,6 +163,192 @@ __global__ void __launch_bounds__(ROW_WARPS * 32)
 }
 
 // =================================================================================================
+// LayerNorm, vectorised variant for h % 128 == 0 (every model width of the reference: 128/256/384/768):
+// a lane owns 4 CONSECUTIVE columns of each 128-column chunk, so a warp moves one contiguous 256 B (bf16) or
+// 512 B (fp32) segment per instruction instead of 32 two-byte elements, and gamma/beta sit in registers for the
+// whole row loop.  Same math, same dropout indices (mask = hash(seed, salt, row*h + col)) as the scalar kernels.
+// =================================================================================================
+template <typename T>
+struct Vec4;
+template <>
+struct Vec4<float> {
+  static __device__ __forceinline__ void load(const float* p, float (&v)[4]) {
+    const float4 t = *reinterpret_cast<const float4*>(p);
+    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+  }
+  static __device__ __forceinline__ void store(float* p, const float (&v)[4]) {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  }
+};
+template <>
+struct Vec4<__nv_bfloat16> {
+  static __device__ __forceinline__ void load(const __nv_bfloat16* p, float (&v)[4]) {
+    const uint2 t = *reinterpret_cast<const uint2*>(p);
+    const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&t.x));
+    const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&t.y));
+    v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+  }
+  static __device__ __forceinline__ void store(__nv_bfloat16* p, const float (&v)[4]) {
+    uint2 t;
+    *reinterpret_cast<__nv_bfloat162*>(&t.x) = __floats2bfloat162_rn(v[0], v[1]);
+    *reinterpret_cast<__nv_bfloat162*>(&t.y) = __floats2bfloat162_rn(v[2], v[3]);
+    *reinterpret_cast<uint2*>(p) = t;
+  }
+};
+
+template <typename T, int NCH>
+__global__ void __launch_bounds__(ROW_WARPS * 32)
+    ln_fwd_vec_kernel(const T* __restrict__ x, const T* __restrict__ res, const float* __restrict__ gamma,
+                      const float* __restrict__ beta, T* __restrict__ y, float* __restrict__ stats, int M, float eps,
+                      float p_in, uint32_t salt_in, float p_out, uint32_t salt_out,
+                      const unsigned long long* seed_ptr) {
+  pdl_trigger();
+  pdl_wait();
+  constexpr int h = NCH * 128;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const Dropout din = make_dropout(p_in, seed_ptr, salt_in), dout = make_dropout(p_out, seed_ptr, salt_out);
+  float g[NCH][4], bt[NCH][4];
+#pragma unroll
+  for (int c = 0; c < NCH; c++) {
+    Vec4<float>::load(gamma + c * 128 + lane * 4, g[c]);
+    Vec4<float>::load(beta + c * 128 + lane * 4, bt[c]);
+  }
+  for (int r = blockIdx.x * ROW_WARPS + w; r < M; r += gridDim.x * ROW_WARPS) {
+    const size_t base = (size_t)r * h + lane * 4;
+    float v[NCH][4];
+#pragma unroll
+    for (int c = 0; c < NCH; c++) Vec4<T>::load(x + base + c * 128, v[c]);
+    if (p_in > 0.f) {
+#pragma unroll
+      for (int c = 0; c < NCH; c++)
+#pragma unroll
+        for (int e = 0; e < 4; e++) v[c][e] *= din.scale(base + c * 128 + e);
+    }
+    if (res) {
+#pragma unroll
+      for (int c = 0; c < NCH; c++) {
+        float t[4];
+        Vec4<T>::load(res + base + c * 128, t);
+#pragma unroll
+        for (int e = 0; e < 4; e++) v[c][e] += t[e];
+      }
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int c = 0; c < NCH; c++) s += (v[c][0] + v[c][1]) + (v[c][2] + v[c][3]);
+    const float mean = warp_sum(s) * (1.f / (float)h);
+    float q = 0.f;
+#pragma unroll
+    for (int c = 0; c < NCH; c++)
+#pragma unroll
+      for (int e = 0; e < 4; e++) {
+        const float d = v[c][e] - mean;
+        q += d * d;
+      }
+    const float rstd = rsqrtf(warp_sum(q) * (1.f / (float)h) + eps);
+#pragma unroll
+    for (int c = 0; c < NCH; c++) {
+      float o[4];
+#pragma unroll
+      for (int e = 0; e < 4; e++) o[e] = (v[c][e] - mean) * rstd * g[c][e] + bt[c][e];
+      if (p_out > 0.f) {
+#pragma unroll
+        for (int e = 0; e < 4; e++) o[e] *= dout.scale(base + c * 128 + e);
+      }
+      Vec4<T>::store(y + base + c * 128, o);
+    }
+    if (lane == 0 && stats) {
+      stats[2 * r] = mean;
+      stats[2 * r + 1] = rstd;
+    }
+  }
+}
+
+template <typename T, int NCH>
+__global__ void __launch_bounds__(ROW_WARPS * 32)
+    ln_bwd_vec_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T* __restrict__ res,
+                      const float* __restrict__ gamma, const float* __restrict__ stats, T* __restrict__ dx,
+                      T* __restrict__ dres, float* __restrict__ dgamma, float* __restrict__ dbeta, int M, float p_in,
+                      uint32_t salt_in, float p_out, uint32_t salt_out, const unsigned long long* seed_ptr) {
+  pdl_trigger();
+  pdl_wait();
+  constexpr int h = NCH * 128;
+  extern __shared__ float sm[];  // [2*h] : dgamma | dbeta partials
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  for (int c = threadIdx.x; c < 2 * h; c += blockDim.x) sm[c] = 0.f;
+  __syncthreads();
+  const Dropout din = make_dropout(p_in, seed_ptr, salt_in), dout = make_dropout(p_out, seed_ptr, salt_out);
+  float g[NCH][4], pg[NCH][4], pb[NCH][4];
+#pragma unroll
+  for (int c = 0; c < NCH; c++) {
+    Vec4<float>::load(gamma + c * 128 + lane * 4, g[c]);
+#pragma unroll
+    for (int e = 0; e < 4; e++) pg[c][e] = pb[c][e] = 0.f;
+  }
+  for (int r = blockIdx.x * ROW_WARPS + w; r < M; r += gridDim.x * ROW_WARPS) {
+    const size_t base = (size_t)r * h + lane * 4;
+    const float mean = stats[2 * r], rstd = stats[2 * r + 1];
+    float xh[NCH][4], d[NCH][4];
+    float c1 = 0.f, c2 = 0.f;
+#pragma unroll
+    for (int c = 0; c < NCH; c++) {
+      float t[4], gy[4];
+      Vec4<T>::load(x + base + c * 128, t);
+      Vec4<T>::load(dy + base + c * 128, gy);
+      if (p_in > 0.f) {
+#pragma unroll
+        for (int e = 0; e < 4; e++) t[e] *= din.scale(base + c * 128 + e);
+      }
+      if (res) {
+        float rr[4];
+        Vec4<T>::load(res + base + c * 128, rr);
+#pragma unroll
+        for (int e = 0; e < 4; e++) t[e] += rr[e];
+      }
+      if (p_out > 0.f) {
+#pragma unroll
+        for (int e = 0; e < 4; e++) gy[e] *= dout.scale(base + c * 128 + e);
+      }
+#pragma unroll
+      for (int e = 0; e < 4; e++) {
+        xh[c][e] = (t[e] - mean) * rstd;
+        pg[c][e] += gy[e] * xh[c][e];
+        pb[c][e] += gy[e];
+        d[c][e] = gy[e] * g[c][e];
+        c1 += d[c][e];
+        c2 += d[c][e] * xh[c][e];
+      }
+    }
+    c1 = warp_sum(c1) * (1.f / (float)h);
+    c2 = warp_sum(c2) * (1.f / (float)h);
+#pragma unroll
+    for (int c = 0; c < NCH; c++) {
+      float o[4];
+#pragma unroll
+      for (int e = 0; e < 4; e++) o[e] = rstd * (d[c][e] - c1 - xh[c][e] * c2);
+      if (dres) Vec4<T>::store(dres + base + c * 128, o);
+      if (p_in > 0.f) {
+#pragma unroll
+        for (int e = 0; e < 4; e++) o[e] *= din.scale(base + c * 128 + e);
+      }
+      Vec4<T>::store(dx + base + c * 128, o);
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < NCH; c++)
+#pragma unroll
+    for (int e = 0; e < 4; e++) {
+      atomicAdd(&sm[c * 128 + lane * 4 + e], pg[c][e]);
+      atomicAdd(&sm[h + c * 128 + lane * 4 + e], pb[c][e]);
+    }
+  flush_cols(sm, dgamma, h);
+  for (int c = threadIdx.x; c < h; c += blockDim.x) {
+    const float v = sm[h + c];
+    if (v != 0.f) atomicAdd(dbeta + c, v);
+  }
+}
+
+// =================================================================================================
 // text embedding + LayerNorm:  y[r] = drop_out( LN(word[ids[r]] + pos[r % L] + type0) )
 // =================================================================================================
 template <typename T, int NE>
@@ -689,6 +875,33 @@ __global__ void __launch_bounds__(256) invert_norm_kernel(const float* __restric
     return MAGIC_ERR_ARG;                                      \
   }
 
+#define DISPATCH_NCH(h, ...)           \
+  if ((h) == 128) {                    \
+    constexpr int NCH = 1;             \
+    __VA_ARGS__;                       \
+  } else if ((h) == 256) {             \
+    constexpr int NCH = 2;             \
+    __VA_ARGS__;                       \
+  } else if ((h) == 384) {             \
+    constexpr int NCH = 3;             \
+    __VA_ARGS__;                       \
+  } else if ((h) == 512) {             \
+    constexpr int NCH = 4;             \
+    __VA_ARGS__;                       \
+  } else if ((h) == 768) {             \
+    constexpr int NCH = 6;             \
+    __VA_ARGS__;                       \
+  } else {                             \
+    magic_set_error("layer norm: vector path has no instance for h=%d", (int)(h)); \
+    return MAGIC_ERR_ARG;              \
+  }
+
+// every pointer of a vectorised row kernel must be 16-byte aligned (NULL = absent operand)
+static inline bool vec_ok(const void* a, const void* b, const void* c, const void* d, const void* e) {
+  return ((((uintptr_t)a) | ((uintptr_t)b) | ((uintptr_t)c) | ((uintptr_t)d) | ((uintptr_t)e)) & 15) == 0;
+}
+static inline bool vec_h(int h) { return h == 128 || h == 256 || h == 384 || h == 512 || h == 768; }
+
 #define DISPATCH_NE(h, ...)            \
   if ((h) <= 64) {                     \
     constexpr int NE = 2;              \
@@ -726,6 +939,13 @@ int magic_ln_fwd(const void* x, const void* res, const float* gamma, const float
                  const unsigned long long* seed_ptr, cudaStream_t st) {
   MAGIC_CHECK_ARG(h > 0 && h <= MAXE * 32, "magic_ln_fwd: hidden size %d unsupported (max %d)", h, MAXE * 32);
   if (M <= 0) return MAGIC_OK;
+  if (vec_h(h) && vec_ok(x, res, y, gamma, beta)) {
+    DISPATCH_T(dtype, DISPATCH_NCH(h, (magic_launch(ln_fwd_vec_kernel<T, NCH>, dim3(row_grid(M)), dim3(ROW_WARPS * 32),
+                          0, st, (const T*)x, (const T*)res, gamma, beta, (T*)y, stats, M, eps, p_in, salt_in, p_out,
+                          salt_out, seed_ptr))));
+    MAGIC_CHECK_LAUNCH("magic_ln_fwd");
+    return MAGIC_OK;
+  }
   DISPATCH_T(dtype, DISPATCH_NE(h, (magic_launch(ln_fwd_kernel<T, NE>, dim3(row_grid(M)), dim3(ROW_WARPS * 32), 0, st, 
                         (const T*)x, (const T*)res, gamma, beta, (T*)y, stats, M, h, eps, p_in, salt_in, p_out,
                         salt_out, seed_ptr))));
@@ -739,6 +959,13 @@ int magic_ln_bwd(const void* dy, const void* x, const void* res, const float* ga
   MAGIC_CHECK_ARG(h > 0 && h <= MAXE * 32, "magic_ln_bwd: hidden size %d unsupported", h);
   if (M <= 0) return MAGIC_OK;
   const size_t smem = 2 * (size_t)h * sizeof(float);
+  if (vec_h(h) && vec_ok(dy, x, res, dx, dres) && vec_ok(gamma, nullptr, nullptr, nullptr, nullptr)) {
+    DISPATCH_T(dtype, DISPATCH_NCH(h, (magic_launch(ln_bwd_vec_kernel<T, NCH>, dim3(row_grid(M)), dim3(ROW_WARPS * 32),
+                          smem, st, (const T*)dy, (const T*)x, (const T*)res, gamma, stats, (T*)dx, (T*)dres, dgamma,
+                          dbeta, M, p_in, salt_in, p_out, salt_out, seed_ptr))));
+    MAGIC_CHECK_LAUNCH("magic_ln_bwd");
+    return MAGIC_OK;
+  }
   DISPATCH_T(dtype, DISPATCH_NE(h, (magic_launch(ln_bwd_kernel<T, NE>, dim3(row_grid(M)), dim3(ROW_WARPS * 32), smem, st, 
                         (const T*)dy, (const T*)x, (const T*)res, gamma, stats, (T*)dx, (T*)dres, dgamma, dbeta, M, h,
                         p_in, salt_in, p_out, salt_out, seed_ptr))));

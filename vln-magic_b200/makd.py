@@ -8,7 +8,7 @@ import torch
 from . import ops
 from .kd_loss import exponential_decay
 
-KDL_DEFAULT = dict(kd_alpha=0.5, kd_temperature=2.0, rw_temp=4.0, t_sample_preprocess_exp_decay=0.7,
+KDL_DEFAULT = dict(kd_alpha=0.5, t_kd_alpha=0.5, kd_temperature=2.0, rw_temp=4.0, t_sample_preprocess_exp_decay=0.7,
                    teacher_sample_hard_mining=True, kdl_tasks=("txt", "img", "local", "global", "predict"),
                    kdl_task_types=("emb", "attn"))
 
@@ -46,10 +46,15 @@ def _w_for(x, w):
     return w if (w is not None and x.shape[0] == w.shape[0]) else None
 
 
-def compute_kd_losses(student, s_out, t_out, task, rw, t_w, kdl=None):
+def compute_kd_losses(student, s_out, t_out, task, rw, t_w, kdl=None, role="t2s"):
     """-> (named dict of per-ability scalars as a [10] tensor view, mse_total scalar, kl scalar or None).
     `rw`: the 5 MKRW ability weights, either python floats (baked into the kernel arguments) or a DEVICE tensor
-    [5] (read by the kernels at run time, so a captured CUDA graph follows the per-step draw)."""
+    [5] (read by the kernels at run time, so a captured CUDA graph follows the per-step draw).
+    `student` is always the SMALL model (it owns the up-projections).  role 't2s' (agent.py:550-552): the small
+    model learns, prediction = proj(s_out), target = t_out.detach().  role 's2t' (agent.py:553-556, ICoD): the
+    LARGE model learns; pass (s_out, t_out) = (large model's outputs, small model's outputs) as agent.py:1022
+    does; prediction = s_out, target = proj(t_out).detach() (agent.py:571,605-606,647,665) and `t_w` are the small
+    model's MKTD weights."""
     k = kdl_config(kdl)
     rw_dev = rw if torch.is_tensor(rw) else None
     if rw_dev is not None:
@@ -67,8 +72,12 @@ def compute_kd_losses(student, s_out, t_out, task, rw, t_w, kdl=None):
     def add_emb(name, proj, s, t, ri):
         if not emb:
             return
-        ps = ops.linear(s, proj.weight, proj.bias)
-        t = t.detach()
+        if role == "t2s":
+            ps = ops.linear(s, proj.weight, proj.bias)
+            t = t.detach()
+        else:
+            with torch.no_grad():
+                ps, t = s, ops.linear(t.detach(), proj.weight, proj.bias)
         pairs.append((ps, t, _w_for(ps, t_w), rw[ri] / ps.numel(), sdev(ri)))
         owner.append(name)
 
@@ -144,3 +153,21 @@ def distill_step_loss(student, teacher, batch, task, rw, kdl=None):
     res = compute_kd_losses(student, s_out, t_out, task, rw, t_w, k)
     mix = ops.loss_mix(res["mse_total"], res["kl"], s_out["loss"], k["kd_alpha"], s_out.get("loss_inv_n"))
     return mix, res, s_out, t_out
+
+
+def icod_step_loss(student, teacher, batch, task, rw, t_rw, kdl=None):
+    """ICoD co-update (`--train_kdl_teacher`; agent.py:1019-1022, 1136-1149, agent_base.py:260-279): the large
+    model's forward runs WITH grad and one step produces two losses, one per model, from two disjoint autograd
+    graphs (every cross-model target is detached).  Returns (mix_s, mix_t, res_s, res_t, s_out, t_out); each mix is
+    the device vector [total, supervised_mean, kd_total] of `ops.loss_mix`."""
+    k = kdl_config(kdl)
+    t_out = teacher(batch, task, True, output_kd=True)
+    s_out = student(batch, task, True, output_kd=True)
+    hard = k["teacher_sample_hard_mining"]
+    t_w = mktd_weights(t_out["sample_loss"], k["t_sample_preprocess_exp_decay"]) if hard else None
+    s_w = mktd_weights(s_out["sample_loss"], k["t_sample_preprocess_exp_decay"]) if hard else None
+    res_s = compute_kd_losses(student, s_out, t_out, task, rw, t_w, k, role="t2s")
+    res_t = compute_kd_losses(student, t_out, s_out, task, t_rw, s_w, k, role="s2t")
+    mix_s = ops.loss_mix(res_s["mse_total"], res_s["kl"], s_out["loss"], k["kd_alpha"], s_out.get("loss_inv_n"))
+    mix_t = ops.loss_mix(res_t["mse_total"], res_t["kl"], t_out["loss"], k["t_kd_alpha"], t_out.get("loss_inv_n"))
+    return mix_s, mix_t, res_s, res_t, s_out, t_out

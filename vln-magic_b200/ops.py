@@ -102,9 +102,16 @@ def _lin_fwd(x2, w, bias, out, act=0, pre_out=None, residual=None, drop_p=0.0, s
 
 def _rows2d(t):
     """2-D view usable as a GEMM operand without a copy when the rows are unit-stride (padded ld allowed)."""
-    if t.dim() == 2 and t.stride(1) == 1 and t.stride(0) >= t.shape[1]:
-        return t
-    return t.reshape(-1, t.shape[-1]).contiguous()
+    if not (t.dim() == 2 and t.stride(1) == 1 and t.stride(0) >= t.shape[1]):
+        t = t.reshape(-1, t.shape[-1]).contiguous()
+    if t.dtype == torch.bfloat16 and t.shape[1] >= 4096 and t.stride(0) % 8 != 0:
+        # a vocabulary-wide gradient that autograd re-materialised densely (CE + KD both feed the MLM logits, the
+        # engine sums them into a fresh [rows, 50265] tensor): re-pad the rows to 16 B so the tcgen05 path takes it
+        # (the FFMA fallback costs 4.4 ms per GEMM at the teacher-distillation sizes, the copy 40 us)
+        pad = torch.empty(t.shape[0], (t.shape[1] + 7) // 8 * 8, dtype=t.dtype, device=t.device)[:, :t.shape[1]]
+        pad.copy_(t)
+        t = pad
+    return t
 
 
 def _lin_dgrad(dy2, w, dx, act=0, dact_pre=None, drop_p=0.0, salt=0, seed=None):

@@ -25,13 +25,22 @@ class _Prefetched:
 class PretrainStepper:
     def __init__(self, student, teacher=None, kdl=None, lr=5e-5, betas=(0.9, 0.98), weight_decay=0.01,
                  max_grad_norm=5.0, use_graphs=False, rw_generator=None, side_stream=True,
-                 branch_streams=True):
+                 branch_streams=True, co_update=False, t_lr=None):
+        """co_update=True is ICoD (`--train_kdl_teacher`, agent_base.py:260-279): the teacher is trained too, from
+        the s2t losses, with its own arena / AdamW state / clip, and both models step once per batch."""
         self.student, self.teacher = student, teacher
         self.kdl = makd.kdl_config(kdl)
+        self.co_update = bool(co_update and teacher is not None)
         lowp = student.compute_dtype == torch.bfloat16
         self.arena = ParamArena(student, lowp=lowp)
-        if teacher is not None and lowp:
-            self.t_arena = ParamArena(teacher, lowp=True, requires_grad_only=False, with_grads=False)
+        self.t_arena = self.t_opt = None
+        if self.co_update:
+            self.t_arena = ParamArena(teacher, lowp=teacher.compute_dtype == torch.bfloat16)
+            self.t_opt = FusedAdamW(self.t_arena, lr=lr if t_lr is None else t_lr, betas=betas,
+                                    weight_decay=weight_decay, max_grad_norm=max_grad_norm)
+        elif teacher is not None:
+            if lowp:
+                self.t_arena = ParamArena(teacher, lowp=True, requires_grad_only=False, with_grads=False)
             for p in teacher.parameters():
                 p.requires_grad_(False)
         self.opt = FusedAdamW(self.arena, lr=lr, betas=betas, weight_decay=weight_decay, max_grad_norm=max_grad_norm)
@@ -43,9 +52,13 @@ class PretrainStepper:
         self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
         self.device = self.arena.device
         self.allreduce = FlatAllReduce(self.arena.flat_g) if self.world > 1 else None
+        self.t_allreduce = FlatAllReduce(self.t_arena.flat_g) if (self.world > 1 and self.co_update) else None
         if self.world > 1:
             broadcast_flat(self.arena.flat_p, 0)  # DDP's wrap-time parameter broadcast (utils/misc.py:63-66)
             self.arena.refresh_lowp()
+            if self.co_update:
+                broadcast_flat(self.t_arena.flat_p, 0)
+                self.t_arena.refresh_lowp()
         self.launches_per_step = None
         self._copy_stream, self._staging = None, {}
         self._rw_dev = None
@@ -56,9 +69,25 @@ class PretrainStepper:
         if self.allreduce is not None:
             self.allreduce()
         self.opt.apply()
+        if self.co_update:  # agent_base.py:271-274: clip + step the student, then clip + step the teacher
+            if self.t_allreduce is not None:
+                self.t_allreduce()
+            self.t_opt.apply()
 
     def _device_step(self, task, batch, rw, finish=True):
         self.arena.zero_grad()
+        if self.co_update:
+            self.t_arena.zero_grad()
+            # agent.py:869-871: under RW the teacher's ability weights ARE the student's draw of this step
+            mix, mix_t, _, _, _, _ = makd.icod_step_loss(self.student, self.teacher, batch, task, rw, rw, self.kdl)
+            # the reference calls loss.backward(retain_graph=True) then t_loss.backward() (agent_base.py:260-268);
+            # every cross-model target is detached, so the two graphs are disjoint and one pass over their sum
+            # produces exactly those gradients
+            (mix[0] + mix_t[0]).backward()
+            ops.join_side_stream()
+            if finish:
+                self._finish()
+            return torch.cat([mix, mix_t])
         if self.teacher is not None:
             mix, res, s_out, t_out = makd.distill_step_loss(self.student, self.teacher, batch, task, rw, self.kdl)
         else:
@@ -124,6 +153,8 @@ class PretrainStepper:
             else:
                 rw = makd.mkrw_weights(self.kdl["rw_temp"], generator=self.rw_generator)
         self.opt.set_hyper(lr)
+        if self.co_update:
+            self.t_opt.set_hyper(None)
         ops.bump_seed(self.device)
         if not self.use_graphs:
             return self._device_step(task, batch, rw)
@@ -154,16 +185,19 @@ class PretrainStepper:
             s.wait_stream(torch.cuda.current_stream())
             # warm-up on a side stream (allocator, cudaFuncSetAttribute, lazy init) WITHOUT changing the
             # training state: parameters and moments are restored afterwards
-            snap = (self.arena.flat_p.clone(), self.opt.m.clone(), self.opt.v.clone())
+            pairs = [(self.arena, self.opt)] + ([(self.t_arena, self.t_opt)] if self.co_update else [])
+            snap = [(a.flat_p.clone(), o.m.clone(), o.v.clone()) for a, o in pairs]
             with torch.cuda.stream(s):
                 for _ in range(2):
                     self._device_step(task, static, rw, finish=self.world == 1)
                     if self.world > 1:
-                        self.opt.apply()
-                self.arena.flat_p.copy_(snap[0])
-                self.opt.m.copy_(snap[1])
-                self.opt.v.copy_(snap[2])
-                self.arena.refresh_lowp()
+                        for _, o in pairs:
+                            o.apply()
+                for (a, o), (p0, m0, v0) in zip(pairs, snap):
+                    a.flat_p.copy_(p0)
+                    o.m.copy_(m0)
+                    o.v.copy_(v0)
+                    a.refresh_lowp()
             torch.cuda.current_stream().wait_stream(s)
             g = torch.cuda.CUDAGraph()
             n0 = _lib.COUNTERS["launches"]
