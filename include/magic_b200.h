@@ -194,6 +194,9 @@ int magic_loss_mix_fwd(const float* mse_total, const float* kl, const float* sup
                        const float* inv_n, float* out, cudaStream_t st);
 int magic_loss_mix_bwd(const float* g, int n, float alpha, const float* inv_n, float* d_mse, float* d_kl,
                        float* d_sup, cudaStream_t st);
+/* measurement aid: when dev_buf (32 x u64, device) is non-NULL, CTA 0 of every tensor-core GEMM launched afterwards
+ * stamps clock64() at its phase boundaries into it (scripts/gemm_trace.py); NULL switches tracing off */
+int magic_gemm_set_trace(unsigned long long* dev_buf);
 /* measurement aid: keeps the stream busy for ~cycles SM clocks so the host can queue launches ahead of the GPU */
 int magic_delay(long long cycles, cudaStream_t st);
 /* scale_dev: optional device scalar multiplied into `scale` (see MagicMseSeg.scale_dev) */

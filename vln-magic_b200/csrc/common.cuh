@@ -198,6 +198,11 @@ struct RowVec<float> {
     const float4 t = *reinterpret_cast<const float4*>(p);
     v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
   }
+  // streaming (evict-first) variant for data that is read exactly once
+  static __device__ __forceinline__ void load_cs(const float* p, float (&v)[4]) {
+    const float4 t = __ldcs(reinterpret_cast<const float4*>(p));
+    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+  }
   static __device__ __forceinline__ void store(float* p, const float (&v)[4]) {
     *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
   }
@@ -207,6 +212,15 @@ struct RowVec<__nv_bfloat16> {
   static constexpr int N = 8;
   static __device__ __forceinline__ void load(const __nv_bfloat16* p, float (&v)[8]) {
     const uint4 t = *reinterpret_cast<const uint4*>(p);
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&t);
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      const float2 f = __bfloat1622float2(h[i]);
+      v[2 * i] = f.x; v[2 * i + 1] = f.y;
+    }
+  }
+  static __device__ __forceinline__ void load_cs(const __nv_bfloat16* p, float (&v)[8]) {
+    const uint4 t = __ldcs(reinterpret_cast<const uint4*>(p));
     const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&t);
 #pragma unroll
     for (int i = 0; i < 4; i++) {

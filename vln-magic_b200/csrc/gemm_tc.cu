@@ -228,8 +228,20 @@ struct TcParams {
   int a_mn, b_mn;  // 1 = MN-major operand
   long ldc;
   int reduce;      // 1: accumulate into C with TMA reduce-add (fp32 C; beta = 1 and/or split-K)
+  unsigned long long* trace;  // measurement aid (magic_gemm_set_trace): CTA 0 stamps clock64() at phase boundaries
   GemmEpi epi;
 };
+
+__device__ __forceinline__ void stamp(const TcParams& P, int i) {
+  if (P.trace != nullptr && blockIdx.x == 0) {
+    P.trace[i] = (unsigned long long)clock64();
+    if (i == 0 || i == 10) {
+      unsigned long long g;
+      asm volatile("mov.u64 %0, %globaltimer;" : "=l"(g));
+      P.trace[16 + i] = g;
+    }
+  }
+}
 
 // fused epilogue math on 32 columns [nb, nb+32) of row m.  `v` in: raw accumulators; out: final values.
 // If epi.pre_out is set, `pre` receives the pre-activation values (already in storage precision).
@@ -326,6 +338,7 @@ __global__ void __launch_bounds__(NTHREADS, 1)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int total_work = P.m_tiles * P.n_tiles * P.splits;
   pdl_trigger();
+  if (threadIdx.x == 0) stamp(P, 0);
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmap_a);
@@ -354,6 +367,7 @@ __global__ void __launch_bounds__(NTHREADS, 1)
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
   pdl_wait();  // everything above overlapped the previous kernel's tail; global memory is touched only below
+  if (threadIdx.x == 0) stamp(P, 1);
 
   if (warp == 0) {
     if (lane == 0) {
@@ -384,6 +398,7 @@ __global__ void __launch_bounds__(NTHREADS, 1)
               tma_load_2d(&tmap_b, &full[s], b_dst + j * 64 * BK * 2, n0 + 64 * j, k0);
           }
           if (++s == stages) { s = 0; ph ^= 1; }
+          if (work == 0 && kb == kb0) stamp(P, 2);
         }
       }
     }
@@ -410,6 +425,7 @@ __global__ void __launch_bounds__(NTHREADS, 1)
         for (int kb = kb0; kb < kb1; kb++) {
           mbar_wait(&full[s], ph);
           tc_fence_after();
+          if (work == 0 && kb == kb0) stamp(P, 3);
           const uint32_t a_base = smem_u32(sA + s * A_BYTES), b_base = smem_u32(sB + s * B_BYTES);
 #pragma unroll
           for (int k = 0; k < BK / 16; k++) {
@@ -425,6 +441,7 @@ __global__ void __launch_bounds__(NTHREADS, 1)
           if (++s == stages) { s = 0; ph ^= 1; }
         }
         umma_commit(&tmem_full[as]);  // accumulator complete
+        if (work == 0) stamp(P, 4);
       }
     }
   } else {
@@ -443,6 +460,8 @@ __global__ void __launch_bounds__(NTHREADS, 1)
       const uint32_t aph = (it >> 1) & 1;
       mbar_wait(&tmem_full[as], aph);
       tc_fence_after();
+      const bool tr = work == 0 && warp == 2 && lane == 0;
+      if (tr) stamp(P, 5);
       const int m = m0 + q * 32 + lane;
       const bool row_ok = m < P.M;
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN);
@@ -465,6 +484,7 @@ __global__ void __launch_bounds__(NTHREADS, 1)
         tmem_ld32(t_row + (uint32_t)(u * UNIT_COLS), r0);
         if (sizeof(TC) == 2) tmem_ld32(t_row + (uint32_t)(u * UNIT_COLS + 32), r1);
         tmem_wait_ld();
+        if (tr && u == hf) stamp(P, 6);
         if (u + 2 >= UNITS && !released) {  // last TMEM read of this warp for this tile: hand the buffer back
           tc_fence_before();
           __syncwarp();
@@ -494,6 +514,7 @@ __global__ void __launch_bounds__(NTHREADS, 1)
           stage_row32(bufc, lane, half, v, (const TC*)nullptr);
           if (has_pre) stage_row32(bufp, lane, half, pre, (const TC*)nullptr);
         }
+        if (tr && u == hf) stamp(P, 7);
         fence_proxy_async();
         __syncwarp();
         if (lane == 0) {
@@ -502,15 +523,19 @@ __global__ void __launch_bounds__(NTHREADS, 1)
           if (has_pre) tma_store_2d(&tmap_pre, bufp, nu, m0 + q * 32);
           bulk_commit();
         }
+        if (tr && u == hf) stamp(P, 8);
       }
     }
     if (lane == 0) bulk_wait_read<0>();  // smem must outlive the stores' reads; the writes land before grid completion
   }
+  if (warp == 2 && lane == 0) stamp(P, 9);
   tc_fence_before();
   __syncthreads();
+  if (threadIdx.x == 0) stamp(P, 10);
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, tmem_cols);
+    if (lane == 0) stamp(P, 11);
   }
 }
 
@@ -632,6 +657,8 @@ bool tc_disabled() {
   return v == 1;
 }
 
+unsigned long long* g_trace = nullptr;
+
 int force_bn() {
   static int v = -1;
   if (v < 0) {
@@ -642,6 +669,11 @@ int force_bn() {
 }
 
 }  // namespace
+
+extern "C" int magic_gemm_set_trace(unsigned long long* dev_buf) {
+  g_trace = dev_buf;
+  return MAGIC_OK;
+}
 
 int gemm_tc_shape_ok(int M, int N, int K) { return (!tc_disabled() && M > 0 && N > 0 && K > 0) ? 1 : 0; }
 
@@ -673,6 +705,7 @@ int gemm_tc_dispatch(const void* A, const void* B, void* C, int c_dt, int M, int
   TcParams P;
   P.M = M; P.N = N; P.K = K; P.a_mn = a_mn; P.b_mn = b_mn; P.ldc = ldc; P.epi = epi;
   P.epi.atomic = 0;
+  P.trace = g_trace;
   P.m_tiles = (M + BM - 1) / BM;
   P.total_kb = (K + BK - 1) / BK;
   // tile width: the widest tile that still gives every SM work (wider tiles re-read less of A)

@@ -31,80 +31,108 @@ __device__ __forceinline__ void st_any(void* p, int dt, size_t i, float v) {
   else ((float*)p)[i] = v;
 }
 
+// One CTA owns a CONTIGUOUS range of chunks (balanced over the grid), so a thread carries its partial sum across
+// chunks and the block reduction + 2 atomics happen once per (CTA, segment) instead of once per chunk.  Row tails
+// stay on the 128-bit path whenever `inner` is a multiple of the vector width.
+template <typename T, bool BWD>
+__device__ __forceinline__ float mse_chunk(const MagicMseSeg& S, size_t sb, size_t tb, long long c0, long long c1,
+                                           float coef) {
+  constexpr int VN = RowVec<T>::N;
+  constexpr int UN = CH / (NT * VN);  // 4 (fp32) / 2 (bf16) independent 16-byte loads per tensor per thread
+  const T* sp = (const T*)S.s + sb;
+  const T* tp = (const T*)S.t + tb;
+  T* dp = BWD ? (T*)S.ds + sb : nullptr;
+  float acc = 0.f;
+  const long long base = c0 + (long long)threadIdx.x * VN;
+  if (c1 - c0 == CH) {
+    float a[UN][VN], b[UN][VN];
+#pragma unroll
+    for (int k = 0; k < UN; k++) {
+      RowVec<T>::load_cs(sp + base + (long long)k * NT * VN, a[k]);
+      RowVec<T>::load_cs(tp + base + (long long)k * NT * VN, b[k]);
+    }
+#pragma unroll
+    for (int k = 0; k < UN; k++) {
+#pragma unroll
+      for (int i = 0; i < VN; i++) {
+        const float d = a[k][i] - b[k][i];
+        if (BWD) a[k][i] = coef * d;
+        else acc = fmaf(d, d, acc);
+      }
+      if (BWD) RowVec<T>::store(dp + base + (long long)k * NT * VN, a[k]);
+    }
+  } else {
+    const long long cv = c0 + (c1 - c0) / VN * VN;  // c0 is a multiple of CH, so [c0, cv) stays 16-byte aligned
+    for (long long c = base; c < cv; c += NT * VN) {
+      float a[VN], b[VN];
+      RowVec<T>::load_cs(sp + c, a);
+      RowVec<T>::load_cs(tp + c, b);
+#pragma unroll
+      for (int i = 0; i < VN; i++) {
+        const float d = a[i] - b[i];
+        if (BWD) a[i] = coef * d;
+        else acc = fmaf(d, d, acc);
+      }
+      if (BWD) RowVec<T>::store(dp + c, a);
+    }
+    for (long long c = cv + threadIdx.x; c < c1; c += NT) {  // < VN leftover elements of a ragged row
+      const float d = ldf(sp, c) - ldf(tp, c);
+      if (BWD) stf(dp, c, coef * d);
+      else acc = fmaf(d, d, acc);
+    }
+  }
+  return acc;
+}
+
 template <bool BWD>
 __global__ void __launch_bounds__(NT) makd_mse_kernel(const __grid_constant__ Args A, float* __restrict__ loss,
                                                       const float* __restrict__ gseg,
                                                       const float* __restrict__ gtot) {
   __shared__ float red[32];
   const long long total = A.chunk0[A.nseg];
-  for (long long ch = blockIdx.x; ch < total; ch += gridDim.x) {
-    int si = 0;
-    while (si + 1 < A.nseg && ch >= A.chunk0[si + 1]) si++;
+  const long long ch_beg = total * blockIdx.x / gridDim.x, ch_end = total * (blockIdx.x + 1) / gridDim.x;
+  int si = 0;
+  float seg_acc = 0.f;  // this thread's share of segment si, already multiplied by row weight * scale
+  for (long long ch = ch_beg; ch < ch_end; ch++) {
+    if (ch >= A.chunk0[si + 1]) {
+      if (!BWD) {
+        const float tot = block_sum(seg_acc, red);
+        if (threadIdx.x == 0 && tot != 0.f) {
+          atomicAdd(loss + si, tot);
+          atomicAdd(loss + MAGIC_MAKD_MAX_SEGS, tot);  // running total of all segments
+        }
+        seg_acc = 0.f;
+      }
+      while (ch >= A.chunk0[si + 1]) si++;
+    }
     const MagicMseSeg& S = A.seg[si];
     const long long cpr = (S.inner + CH - 1) / CH;
     const long long local = ch - A.chunk0[si];
     const long long row = local / cpr;
     const long long c0 = (local % cpr) * CH;
     const long long c1 = min(S.inner, c0 + CH);
-    const float wr = (S.w ? S.w[row] : 1.f) * (S.scale_dev ? S.scale_dev[0] : 1.f);
+    const float wr = (S.w ? S.w[row] : 1.f) * (S.scale_dev ? S.scale_dev[0] : 1.f) * S.scale;
     const size_t sb = (size_t)row * S.s_rs, tb = (size_t)row * S.t_rs;
-    const float coef = BWD ? 2.f * S.scale * wr * ((gseg ? gseg[si] : 0.f) + (gtot ? gtot[0] : 0.f)) : 0.f;
+    const float coef = BWD ? 2.f * wr * ((gseg ? gseg[si] : 0.f) + (gtot ? gtot[0] : 0.f)) : 0.f;
     float acc = 0.f;
-    const bool vec = S.vec_ok && (c1 - c0) == CH;
-    if (vec && S.s_dt == MAGIC_F32) {
-      const float4* s4 = reinterpret_cast<const float4*>((const float*)S.s + sb + c0);
-      const float4* t4 = reinterpret_cast<const float4*>((const float*)S.t + tb + c0);
-      float4* d4 = BWD ? reinterpret_cast<float4*>((float*)S.ds + sb + c0) : nullptr;
-      float4 a[4], b[4];
-#pragma unroll
-      for (int k = 0; k < 4; k++) {
-        a[k] = __ldcs(s4 + threadIdx.x + k * NT);
-        b[k] = __ldcs(t4 + threadIdx.x + k * NT);
-      }
-#pragma unroll
-      for (int k = 0; k < 4; k++) {
-        const float dx = a[k].x - b[k].x, dy = a[k].y - b[k].y, dz = a[k].z - b[k].z, dw = a[k].w - b[k].w;
-        if (BWD) d4[threadIdx.x + k * NT] = make_float4(coef * dx, coef * dy, coef * dz, coef * dw);
-        else acc += dx * dx + dy * dy + dz * dz + dw * dw;
-      }
-    } else if (vec && S.s_dt == MAGIC_BF16) {
-      const uint4* s4 = reinterpret_cast<const uint4*>((const __nv_bfloat16*)S.s + sb + c0);
-      const uint4* t4 = reinterpret_cast<const uint4*>((const __nv_bfloat16*)S.t + tb + c0);
-      uint4* d4 = BWD ? reinterpret_cast<uint4*>((__nv_bfloat16*)S.ds + sb + c0) : nullptr;
-      uint4 a[2], b[2];
-#pragma unroll
-      for (int k = 0; k < 2; k++) {
-        a[k] = __ldcs(s4 + threadIdx.x + k * NT);
-        b[k] = __ldcs(t4 + threadIdx.x + k * NT);
-      }
-#pragma unroll
-      for (int k = 0; k < 2; k++) {
-        const __nv_bfloat162* ah = reinterpret_cast<const __nv_bfloat162*>(&a[k]);
-        const __nv_bfloat162* bh = reinterpret_cast<const __nv_bfloat162*>(&b[k]);
-        uint4 o;
-        __nv_bfloat162* oh = reinterpret_cast<__nv_bfloat162*>(&o);
-#pragma unroll
-        for (int e = 0; e < 4; e++) {
-          const float2 fa = __bfloat1622float2(ah[e]), fb = __bfloat1622float2(bh[e]);
-          const float dx = fa.x - fb.x, dy = fa.y - fb.y;
-          if (BWD) oh[e] = __floats2bfloat162_rn(coef * dx, coef * dy);
-          else acc += dx * dx + dy * dy;
-        }
-        if (BWD) d4[threadIdx.x + k * NT] = o;
-      }
+    if (S.vec_ok && S.s_dt == MAGIC_F32) {
+      acc = mse_chunk<float, BWD>(S, sb, tb, c0, c1, coef);
+    } else if (S.vec_ok && S.s_dt == MAGIC_BF16) {
+      acc = mse_chunk<__nv_bfloat16, BWD>(S, sb, tb, c0, c1, coef);
     } else {
       for (long long c = c0 + threadIdx.x; c < c1; c += NT) {
         const float d = ld_any(S.s, S.s_dt, sb + c) - ld_any(S.t, S.t_dt, tb + c);
         if (BWD) st_any(S.ds, S.s_dt, sb + c, coef * d);
-        else acc += d * d;
+        else acc = fmaf(d, d, acc);
       }
     }
-    if (!BWD) {
-      acc = block_sum(acc, red);
-      if (threadIdx.x == 0) {
-        atomicAdd(loss + si, acc * wr * S.scale);
-        atomicAdd(loss + MAGIC_MAKD_MAX_SEGS, acc * wr * S.scale);  // running total of all segments
-      }
+    if (!BWD) seg_acc = fmaf(acc, wr, seg_acc);
+  }
+  if (!BWD && ch_end > ch_beg) {
+    const float tot = block_sum(seg_acc, red);
+    if (threadIdx.x == 0 && tot != 0.f) {
+      atomicAdd(loss + si, tot);
+      atomicAdd(loss + MAGIC_MAKD_MAX_SEGS, tot);
     }
   }
 }
@@ -112,72 +140,111 @@ __global__ void __launch_bounds__(NT) makd_mse_kernel(const __grid_constant__ Ar
 // ---- KL on logits: one CTA per row -----------------------------------------------------------------
 __device__ __forceinline__ float fix_inf(float v, float invT) { return (v == -INFINITY ? -1e6f : v) * invT; }
 
-// pass 1: online (max, sum) of both rows together; pass 2: KL.  16-byte loads on aligned rows.
+// ONE pass over both rows: per thread an online triple for the teacher (max m_t, z_t = sum e^{x_t - m_t},
+// a = sum e^{x_t - m_t} (x_t - x_s)) and an online pair for the student (m_s, z_s); then
+//   KL(row) = a / z_t - (m_t - m_s) - log(z_t / z_s)          [= sum_c p_t (log p_t - log p_s)]
+// so each logit is read from HBM exactly once (the two-pass form re-read both rows).  The running maxima are
+// updated once per 16-byte vector (vector max first), which removes the per-element branches.
+struct KlAcc {
+  float ms, zs, mt, zt, a;
+};
+__device__ __forceinline__ void kl_merge(KlAcc& x, const KlAcc& y) {
+  const float ms = fmaxf(x.ms, y.ms), mt = fmaxf(x.mt, y.mt);
+  if (ms > -INFINITY) x.zs = x.zs * __expf(x.ms - ms) + y.zs * __expf(y.ms - ms);
+  if (mt > -INFINITY) {
+    const float fx = __expf(x.mt - mt), fy = __expf(y.mt - mt);
+    x.zt = x.zt * fx + y.zt * fy;
+    x.a = x.a * fx + y.a * fy;
+  }
+  x.ms = ms;
+  x.mt = mt;
+}
+template <int VN>
+__device__ __forceinline__ void kl_push(KlAcc& k, const float (&xs)[VN], const float (&xt)[VN]) {
+  float vs = xs[0], vt = xt[0];
+#pragma unroll
+  for (int i = 1; i < VN; i++) {
+    vs = fmaxf(vs, xs[i]);
+    vt = fmaxf(vt, xt[i]);
+  }
+  if (vs > k.ms) {
+    k.zs *= __expf(k.ms - vs);  // m = -inf: z is 0 and exp(-inf) = 0
+    k.ms = vs;
+  }
+  if (vt > k.mt) {
+    const float f = __expf(k.mt - vt);
+    k.zt *= f;
+    k.a *= f;
+    k.mt = vt;
+  }
+#pragma unroll
+  for (int i = 0; i < VN; i++) {
+    k.zs += __expf(xs[i] - k.ms);
+    const float e = __expf(xt[i] - k.mt);
+    k.zt += e;
+    k.a = fmaf(e, xt[i] - xs[i], k.a);  // e == 0 (masked / far below the max) contributes exactly 0
+  }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(NT)
     makd_kl_fwd_kernel(const T* __restrict__ s, const T* __restrict__ t, int C, long ld, float invT,
                        const float* __restrict__ w, float scale, const float* __restrict__ scale_dev,
                        float* __restrict__ stats, float* __restrict__ loss, int vec) {
-  __shared__ float red[32];
-  __shared__ float rm[2][8], rs[2][8];
+  __shared__ KlAcc part[NT / 32];
   const int r = blockIdx.x;
   const T* sr = s + (size_t)r * ld;
   const T* tr = t + (size_t)r * ld;
   constexpr int VN = RowVec<T>::N;
   const int cv = vec ? (C / VN) * VN : 0;
-  float ms = -INFINITY, zs = 0.f, mt = -INFINITY, zt = 0.f;
-  for (int c = threadIdx.x * VN; c < cv; c += NT * VN) {
-    float a[VN], b[VN];
-    RowVec<T>::load(sr + c, a);
-    RowVec<T>::load(tr + c, b);
+  KlAcc k{-INFINITY, 0.f, -INFINITY, 0.f, 0.f};
+  int c = threadIdx.x * VN;
+  for (; c + NT * VN < cv; c += 2 * NT * VN) {  // two independent 16-byte loads per row in flight
+    float a0[VN], b0[VN], a1[VN], b1[VN];
+    RowVec<T>::load_cs(sr + c, a0);
+    RowVec<T>::load_cs(tr + c, b0);
+    RowVec<T>::load_cs(sr + c + NT * VN, a1);
+    RowVec<T>::load_cs(tr + c + NT * VN, b1);
 #pragma unroll
     for (int i = 0; i < VN; i++) {
-      lse_push(ms, zs, fix_inf(a[i], invT));
-      lse_push(mt, zt, fix_inf(b[i], invT));
+      a0[i] = fix_inf(a0[i], invT); b0[i] = fix_inf(b0[i], invT);
+      a1[i] = fix_inf(a1[i], invT); b1[i] = fix_inf(b1[i], invT);
     }
+    kl_push<VN>(k, a0, b0);
+    kl_push<VN>(k, a1, b1);
   }
-  for (int c = cv + threadIdx.x; c < C; c += NT) {
-    lse_push(ms, zs, fix_inf(ldf(sr, c), invT));
-    lse_push(mt, zt, fix_inf(ldf(tr, c), invT));
+  for (; c < cv; c += NT * VN) {
+    float a0[VN], b0[VN];
+    RowVec<T>::load_cs(sr + c, a0);
+    RowVec<T>::load_cs(tr + c, b0);
+#pragma unroll
+    for (int i = 0; i < VN; i++) {
+      a0[i] = fix_inf(a0[i], invT); b0[i] = fix_inf(b0[i], invT);
+    }
+    kl_push<VN>(k, a0, b0);
+  }
+  for (int c2 = cv + threadIdx.x; c2 < C; c2 += NT) {
+    const float xs[1] = {fix_inf(ldf(sr, c2), invT)}, xt[1] = {fix_inf(ldf(tr, c2), invT)};
+    kl_push<1>(k, xs, xt);
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
-    lse_merge(ms, zs, __shfl_xor_sync(0xffffffffu, ms, o), __shfl_xor_sync(0xffffffffu, zs, o));
-    lse_merge(mt, zt, __shfl_xor_sync(0xffffffffu, mt, o), __shfl_xor_sync(0xffffffffu, zt, o));
+    KlAcc y;
+    y.ms = __shfl_xor_sync(0xffffffffu, k.ms, o);
+    y.zs = __shfl_xor_sync(0xffffffffu, k.zs, o);
+    y.mt = __shfl_xor_sync(0xffffffffu, k.mt, o);
+    y.zt = __shfl_xor_sync(0xffffffffu, k.zt, o);
+    y.a = __shfl_xor_sync(0xffffffffu, k.a, o);
+    kl_merge(k, y);
   }
   const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
-  if (lane == 0) {
-    rm[0][wp] = ms; rs[0][wp] = zs; rm[1][wp] = mt; rs[1][wp] = zt;
-  }
+  if (lane == 0) part[wp] = k;
   __syncthreads();
-  ms = rm[0][0]; zs = rs[0][0]; mt = rm[1][0]; zt = rs[1][0];
-#pragma unroll
-  for (int i = 1; i < NT / 32; i++) {
-    lse_merge(ms, zs, rm[0][i], rs[0][i]);
-    lse_merge(mt, zt, rm[1][i], rs[1][i]);
-  }
-  const float lse_s = ms + logf(zs), lse_t = mt + logf(zt);
-  float kl = 0.f;
-  for (int c = threadIdx.x * VN; c < cv; c += NT * VN) {
-    float a[VN], b[VN];
-    RowVec<T>::load(sr + c, a);
-    RowVec<T>::load(tr + c, b);
-#pragma unroll
-    for (int i = 0; i < VN; i++) {
-      const float la = fix_inf(a[i], invT) - lse_s, lb = fix_inf(b[i], invT) - lse_t;
-      const float p = expf(lb);
-      if (p > 0.f) kl += p * (lb - la);
-    }
-  }
-  for (int c = cv + threadIdx.x; c < C; c += NT) {
-    const float a = fix_inf(ldf(sr, c), invT) - lse_s, b = fix_inf(ldf(tr, c), invT) - lse_t;
-    const float p = expf(b);
-    if (p > 0.f) kl += p * (b - a);  // xlogy(p,p) - p*logq ; p == 0 contributes exactly 0
-  }
-  kl = block_sum(kl, red);
   if (threadIdx.x == 0) {
-    stats[2 * r] = lse_s;
-    stats[2 * r + 1] = lse_t;
+    for (int i = 1; i < NT / 32; i++) kl_merge(k, part[i]);
+    const float kl = k.a / k.zt - (k.mt - k.ms) - logf(k.zt / k.zs);
+    stats[2 * r] = k.ms + logf(k.zs);
+    stats[2 * r + 1] = k.mt + logf(k.zt);
     atomicAdd(loss, kl * (w ? w[r] : 1.f) * scale * (scale_dev ? scale_dev[0] : 1.f));
   }
 }
