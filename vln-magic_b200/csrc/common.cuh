@@ -152,33 +152,65 @@ __device__ __forceinline__ float block_max(float v, float* red) {
 // stateless dropout RNG: keep(idx) is a pure function of (seed, salt, idx) so backward regenerates
 // the forward mask instead of storing it.
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t magic_hash(uint64_t seed, uint32_t salt, uint64_t idx) {
-  uint64_t z = seed + 0x9E3779B97F4A7C15ull * (uint64_t)(salt + 1) + idx * 0xD1342543DE82EF95ull;
-  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
-  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
-  z = z ^ (z >> 31);
-  return (uint32_t)(z >> 32);
+// 32-bit avalanche mix ("lowbias32"): 2 multiplies + 3 xor-shifts.  The per-element cost matters: the hash runs inside
+// GEMM / LayerNorm / attention epilogues (one call per element), where a 64-bit splitmix was ~3x the instructions.
+__device__ __forceinline__ uint32_t magic_mix32(uint32_t x) {
+  x ^= x >> 16;
+  x *= 0x7feb352du;
+  x ^= x >> 15;
+  x *= 0x846ca68bu;
+  x ^= x >> 16;
+  return x;
 }
+// (seed, salt) -> 32-bit stream key, once per thread
+__device__ __forceinline__ uint32_t magic_key(uint64_t seed, uint32_t salt) {
+  return magic_mix32((uint32_t)seed ^ magic_mix32((uint32_t)(seed >> 32) + 0x9E3779B9u * (salt + 1u)));
+}
+// element index is taken modulo 2^32 (every tensor on this path has < 2^32 elements)
+__device__ __forceinline__ uint32_t magic_hash(uint32_t key, uint64_t idx) { return magic_mix32((uint32_t)idx ^ key); }
 struct Dropout {
   float p;           // drop probability (0 = disabled)
   float inv_keep;    // 1 / (1 - p)
   uint32_t thresh;   // drop iff hash < thresh
-  uint32_t salt;
-  uint64_t seed;
+  uint32_t key;      // magic_key(seed, salt)
   __device__ __forceinline__ float scale(uint64_t idx) const {
     if (p <= 0.f) return 1.f;
-    return magic_hash(seed, salt, idx) < thresh ? 0.f : inv_keep;
+    return magic_hash(key, idx) < thresh ? 0.f : inv_keep;
   }
 };
-// host+device constructor; seed_ptr is DEVICE memory (so a captured CUDA graph sees fresh seeds)
+// seed_ptr is DEVICE memory (so a captured CUDA graph sees fresh seeds)
 __device__ __forceinline__ Dropout make_dropout(float p, const unsigned long long* seed_ptr, uint32_t salt) {
   Dropout d;
   d.p = p;
   d.inv_keep = p > 0.f ? 1.f / (1.f - p) : 1.f;
   d.thresh = p > 0.f ? (uint32_t)fminf(4294967295.f, p * 4294967296.f) : 0u;
-  d.salt = salt;
-  d.seed = (p > 0.f && seed_ptr) ? *seed_ptr : 0ull;
+  d.key = magic_key((p > 0.f && seed_ptr) ? *seed_ptr : 0ull, salt);
   return d;
+}
+
+// erf by Abramowitz-Stegun 7.1.26 (|abs err| < 1.5e-7): one reciprocal + one exp2 on the MUFU pipe and 7 FMA-pipe
+// ops, branch-free.  Used where the value is stored in bf16 (rounding 4e-3 relative); fp32 storage keeps erff.
+// `e` returns exp(-x*x) (the Gaussian factor the GELU derivative needs as well).
+__device__ __forceinline__ float erf_fast(float x, float& e) {
+  const float ax = fabsf(x);
+  float t;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, ax, 1.f)));
+  float q = fmaf(t, 1.061405429f, -1.453152027f);
+  q = fmaf(q, t, 1.421413741f);
+  q = fmaf(q, t, -0.284496736f);
+  q = fmaf(q, t, 0.254829592f);
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-1.4426950408889634f * ax * ax));
+  const float y = fmaf(-q * t, e, 1.f);
+  return copysignf(y, x);
+}
+__device__ __forceinline__ float gelu_fast_f(float x) {
+  float e;
+  return 0.5f * x * (1.f + erf_fast(x * 0.70710678118654752f, e));
+}
+__device__ __forceinline__ float gelu_grad_fast_f(float x) {
+  float e;  // exp(-x^2 / 2)
+  const float cdf = 0.5f * (1.f + erf_fast(x * 0.70710678118654752f, e));
+  return fmaf(x * 0.3989422804014327f, e, cdf);
 }
 
 __device__ __forceinline__ float gelu_f(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752f)); }

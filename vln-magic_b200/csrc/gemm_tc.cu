@@ -41,6 +41,7 @@ constexpr int STG_BUFS = 2;                        // per epilogue warp
 constexpr int MAX_STAGES = 8;
 constexpr int RS_COLS = 16;                        // accumulator columns of the row-sum (bias gradient) UMMA
 constexpr int ONES_BYTES = RS_COLS * 128;          // 16 rows x 64 bf16 ones, K-major SWIZZLE_128B tile
+constexpr int BIAS_BYTES = 2 * 256 * 4;            // bias of the current / next tile (BN <= 256 fp32 each)
 
 // ---- PTX wrappers -------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -243,20 +244,90 @@ __device__ __forceinline__ void stamp(const TcParams& P, int i) {
   }
 }
 
+// activation on the tensor-core path: bf16 storage takes the branch-free MUFU forms (common.cuh erf_fast)
+template <typename TC, int ACT>
+__device__ __forceinline__ float tc_act_fwd(float v) {
+  if (ACT == MAGIC_ACT_GELU) return sizeof(TC) == 2 ? gelu_fast_f(v) : gelu_f(v);
+  if (ACT == MAGIC_ACT_RELU) return fmaxf(v, 0.f);
+  return v;
+}
+template <typename TC, int ACT>
+__device__ __forceinline__ float tc_act_bwd(float z) {
+  if (ACT == MAGIC_ACT_GELU) return sizeof(TC) == 2 ? gelu_grad_fast_f(z) : gelu_grad_f(z);
+  if (ACT == MAGIC_ACT_RELU) return z > 0.f ? 1.f : 0.f;
+  return 1.f;
+}
+
+// One epilogue "unit" = UNIT_COLS columns of one accumulator row (128 bytes of C).  The side operand of the unit
+// (residual in the forward pass, pre-activation in the backward pass; storage type of C) is fetched into registers
+// BEFORE the thread waits for the accumulator, so its global-memory latency hides behind the MMA main loop.
+template <typename TC>
+struct SideRegs {
+  uint4 r[8];  // 128 bytes: 64 bf16 or 32 fp32
+};
+// -> true when `sr` holds the unit (full-width unit, or a row beyond M whose values are never stored); false on
+// the N edge, where epi_math32 falls back to guarded element loads
+template <typename TC>
+__device__ __forceinline__ bool side_load(SideRegs<TC>& sr, const TC* p, bool row_ok, int ncols) {
+  constexpr int UC = 128 / (int)sizeof(TC);
+  if (row_ok && ncols >= UC) {
+    const uint4* q = reinterpret_cast<const uint4*>(p);
+#pragma unroll
+    for (int i = 0; i < 8; i++) sr.r[i] = __ldg(q + i);
+    return true;
+  }
+#pragma unroll
+  for (int i = 0; i < 8; i++) sr.r[i] = make_uint4(0u, 0u, 0u, 0u);
+  return !row_ok;
+}
+// columns [32*half, 32*half+32) of the unit as floats
+// (`half` selects between two statically indexed copies so the registers never become a local-memory array)
+template <int HALF>
+__device__ __forceinline__ void side_get32_s(const SideRegs<__nv_bfloat16>& sr, float (&v)[32]) {
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    const uint4 t = sr.r[HALF * 4 + i];
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&t);
+#pragma unroll
+    for (int e = 0; e < 4; e++) {
+      const float2 f = __bfloat1622float2(h[e]);
+      v[8 * i + 2 * e] = f.x; v[8 * i + 2 * e + 1] = f.y;
+    }
+  }
+}
+__device__ __forceinline__ void side_get32(const SideRegs<__nv_bfloat16>& sr, int half, float (&v)[32]) {
+  if (half == 0) side_get32_s<0>(sr, v);
+  else side_get32_s<1>(sr, v);
+}
+__device__ __forceinline__ void side_get32(const SideRegs<float>& sr, int, float (&v)[32]) {
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    v[4 * i] = __uint_as_float(sr.r[i].x); v[4 * i + 1] = __uint_as_float(sr.r[i].y);
+    v[4 * i + 2] = __uint_as_float(sr.r[i].z); v[4 * i + 3] = __uint_as_float(sr.r[i].w);
+  }
+}
+
 // fused epilogue math on 32 columns [nb, nb+32) of row m.  `v` in: raw accumulators; out: final values.
 // If epi.pre_out is set, `pre` receives the pre-activation values (already in storage precision).
-template <typename TC, int ACT>
+// `sbias`: this tile's bias staged in shared memory (zero beyond N), indexed from the tile's first column.
+// `side`: prefetched residual (forward) or pre-activation (backward, when `side_is_dact`), else unused.
+template <typename TC, int ACT, bool DACT>
 __device__ __forceinline__ void epi_math32(const TcParams& P, const Dropout& dr, float (&v)[32], float (&pre)[32],
-                                           int m, int nb, bool row_ok) {
+                                           int m, int nb, bool row_ok, const float* sbias, const SideRegs<TC>& side,
+                                           int half, bool side_ok) {
   const GemmEpi& epi = P.epi;
   const int ncols = P.N - nb;  // may be < 32 on the N edge (or <= 0: whole chunk clipped by the store)
   const bool full = ncols >= 32;
+  if (epi.alpha != 1.f) {
 #pragma unroll
-  for (int j = 0; j < 32; j++) v[j] *= epi.alpha;
-  if (epi.dact_pre != nullptr) {
+    for (int j = 0; j < 32; j++) v[j] *= epi.alpha;
+  }
+  if constexpr (DACT) {
     float z[32];
     const size_t poff = (size_t)m * epi.dact_ld + nb;
-    if (!row_ok || ncols <= 0) {
+    if (side_ok) {
+      side_get32(side, half, z);
+    } else if (!row_ok || ncols <= 0) {
 #pragma unroll
       for (int j = 0; j < 32; j++) z[j] = 0.f;
     } else if (epi.dact_dt == MAGIC_BF16) {
@@ -267,19 +338,19 @@ __device__ __forceinline__ void epi_math32(const TcParams& P, const Dropout& dr,
       else ld_row32_edge((const float*)epi.dact_pre + poff, z, ncols);
     }
 #pragma unroll
-    for (int j = 0; j < 32; j++) v[j] *= act_bwd(ACT, z[j]);
+    for (int j = 0; j < 32; j++) v[j] *= tc_act_bwd<TC, ACT>(z[j]);
     if (dr.p > 0.f) {
 #pragma unroll
       for (int j = 0; j < 32; j++) v[j] *= dr.scale(poff + j);
     }
     return;
   }
-  if (epi.bias && ncols > 0) {
-    float b[32];
-    if (full) ld_row32(epi.bias + nb, b);
-    else ld_row32_edge(epi.bias + nb, b, ncols);
+  if (epi.bias) {
 #pragma unroll
-    for (int j = 0; j < 32; j++) v[j] += b[j];
+    for (int j = 0; j < 32; j += 4) {
+      const float4 b = *reinterpret_cast<const float4*>(sbias + j);  // warp-uniform address: broadcast
+      v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+    }
   }
   if (epi.pre_out) {
 #pragma unroll
@@ -288,32 +359,34 @@ __device__ __forceinline__ void epi_math32(const TcParams& P, const Dropout& dr,
   }
   if (ACT != 0) {
 #pragma unroll
-    for (int j = 0; j < 32; j++) v[j] = act_fwd(ACT, v[j]);
+    for (int j = 0; j < 32; j++) v[j] = tc_act_fwd<TC, ACT>(v[j]);
   }
   if (dr.p > 0.f) {
     const size_t off = (size_t)m * P.ldc + nb;
 #pragma unroll
     for (int j = 0; j < 32; j++) v[j] *= dr.scale(off + j);
   }
-  if (epi.residual && row_ok && ncols > 0) {
+  if (epi.residual) {
     float rs[32];
-    const TC* rp = (const TC*)epi.residual + (size_t)m * epi.res_ld + nb;
-    if (full) ld_row32(rp, rs);
-    else ld_row32_edge(rp, rs, ncols);
+    if (side_ok) {
+      side_get32(side, half, rs);
+    } else if (row_ok && ncols > 0) {
+      const TC* rp = (const TC*)epi.residual + (size_t)m * epi.res_ld + nb;
+      if (full) ld_row32(rp, rs);
+      else ld_row32_edge(rp, rs, ncols);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; j++) rs[j] = 0.f;
+    }
 #pragma unroll
     for (int j = 0; j < 32; j++) v[j] += rs[j];
   }
 }
 
-template <typename TC>
-__device__ __forceinline__ void epi_math32_dispatch(const TcParams& P, const Dropout& dr, float (&v)[32],
-                                                    float (&pre)[32], int m, int nb, bool row_ok) {
-  if (P.epi.act == MAGIC_ACT_GELU) epi_math32<TC, MAGIC_ACT_GELU>(P, dr, v, pre, m, nb, row_ok);
-  else if (P.epi.act == MAGIC_ACT_RELU) epi_math32<TC, MAGIC_ACT_RELU>(P, dr, v, pre, m, nb, row_ok);
-  else epi_math32<TC, MAGIC_ACT_NONE>(P, dr, v, pre, m, nb, row_ok);
-}
-
-template <int BN, typename TC>
+// One kernel instantiation per (tile width, C type, activation, forward / backward-derivative epilogue): each carries
+// only its own epilogue code.  These launches execute every instruction once or twice, so instruction fetch of a
+// do-everything epilogue (3 activations x 2 directions, unrolled) was a first-order cost of the small GEMMs.
+template <int BN, typename TC, int ACT, bool DACT>
 __global__ void __launch_bounds__(NTHREADS, 1)
     gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                    const __grid_constant__ CUtensorMap tmap_c, const __grid_constant__ CUtensorMap tmap_pre,
@@ -329,7 +402,8 @@ __global__ void __launch_bounds__(NTHREADS, 1)
   uint8_t* sB = sA + stages * A_BYTES;
   uint8_t* sStage = sB + stages * B_BYTES;  // [NUM_EPI_WARPS][STG_BUFS][4096], 1024-aligned
   uint8_t* sOnes = sStage + NUM_EPI_WARPS * STG_BUFS * STG_BYTES;  // 1024-aligned (all staging sizes are)
-  uint64_t* full = (uint64_t*)(sOnes + ONES_BYTES);
+  float* sBias = (float*)(sOnes + ONES_BYTES);  // [2][256]: this tile's bias (double-buffered over tiles)
+  uint64_t* full = (uint64_t*)(sOnes + ONES_BYTES + BIAS_BYTES);
   uint64_t* empty = full + MAX_STAGES;
   uint64_t* tmem_full = empty + MAX_STAGES;  // [2]
   uint64_t* tmem_empty = tmem_full + 2;      // [2]
@@ -448,9 +522,17 @@ __global__ void __launch_bounds__(NTHREADS, 1)
     // ===== epilogue: warps 2..9; TMEM lane quarter = warp % 4, column half = (warp - 2) / 4 =====
     const int q = warp & 3;
     const int hf = (warp - 2) >> 2;
+    const int et = (int)threadIdx.x - 64;  // 0..255 within the epilogue warps
     uint8_t* stg = sStage + (warp - 2) * (STG_BUFS * STG_BYTES);
     const Dropout dr = make_dropout(P.epi.drop_p, P.epi.seed_ptr, P.epi.salt);
     const bool has_pre = P.epi.pre_out != nullptr;
+    const bool use_bias = !DACT && P.epi.bias != nullptr;
+    // side operand prefetched into registers: pre-activation (backward) or residual (forward), storage type of C
+    const bool side_dact = DACT && P.epi.dact_dt == (sizeof(TC) == 2 ? MAGIC_BF16 : MAGIC_F32);
+    const bool side_res = !DACT && P.epi.residual != nullptr;
+    const bool has_side = side_dact || side_res;
+    const TC* side_base = side_dact ? (const TC*)P.epi.dact_pre : (const TC*)P.epi.residual;
+    const long side_ld = side_dact ? P.epi.dact_ld : P.epi.res_ld;
     int nstore = 0;  // staging buffers used so far by this warp (buffer = nstore & 1)
     int it = 0;
     for (int work = blockIdx.x; work < total_work; work += gridDim.x, it++) {
@@ -458,12 +540,26 @@ __global__ void __launch_bounds__(NTHREADS, 1)
       const int m0 = (tile / P.n_tiles) * BM, n0 = (tile % P.n_tiles) * BN;
       const int as = it & 1;
       const uint32_t aph = (it >> 1) & 1;
+      const int m = m0 + q * 32 + lane;
+      const bool row_ok = m < P.M;
+      // everything that does not depend on the accumulator happens BEFORE the wait: the tile's bias goes to shared
+      // memory (one global load per thread instead of 64 on the critical path) and the first unit's side operand
+      // to registers; both latencies hide behind the TMA / MMA main loop
+      float* sb = sBias + (it & 1) * 256;
+      if (use_bias) {
+        if (et < BN) sb[et] = (n0 + et < P.N) ? __ldg(P.epi.bias + n0 + et) : 0.f;
+        asm volatile("bar.sync 1, 256;" ::: "memory");  // the 8 epilogue warps only
+      }
+      SideRegs<TC> side;
+      bool side_ok = false;
+      if (has_side && hf < UNITS) {
+        const int nu = n0 + hf * UNIT_COLS;
+        side_ok = side_load(side, side_base + (size_t)m * side_ld + nu, row_ok, P.N - nu);
+      }
       mbar_wait(&tmem_full[as], aph);
       tc_fence_after();
       const bool tr = work == 0 && warp == 2 && lane == 0;
       if (tr) stamp(P, 5);
-      const int m = m0 + q * 32 + lane;
-      const bool row_ok = m < P.M;
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN);
       if (rowsum && hf == 0 && n0 == 0) {  // column 0 of the ones product = sum_k A(m, k)
         const uint32_t r = tmem_ld1(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(2 * BN + as * RS_COLS));
@@ -480,18 +576,17 @@ __global__ void __launch_bounds__(NTHREADS, 1)
 #pragma unroll 1
       for (int u = hf; u < UNITS; u += 2) {
         const int nu = n0 + u * UNIT_COLS;
-        uint32_t r0[32], r1[32];
-        tmem_ld32(t_row + (uint32_t)(u * UNIT_COLS), r0);
-        if (sizeof(TC) == 2) tmem_ld32(t_row + (uint32_t)(u * UNIT_COLS + 32), r1);
-        tmem_wait_ld();
-        if (tr && u == hf) stamp(P, 6);
-        if (u + 2 >= UNITS && !released) {  // last TMEM read of this warp for this tile: hand the buffer back
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&tmem_empty[as]);
-          released = true;
+        if (has_side && u != hf)  // later units: issued before the TMEM read so the two latencies overlap
+          side_ok = side_load(side, side_base + (size_t)m * side_ld + nu, row_ok, P.N - nu);
+        if (nu >= P.N) {  // unit entirely beyond the N edge (warp-uniform): nothing to read or store
+          if (u + 2 >= UNITS && !released) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty[as]);
+            released = true;
+          }
+          continue;
         }
-        if (nu >= P.N) continue;  // unit entirely beyond the N edge (warp-uniform)
         // staging buffers: at most one store group may still be reading (the other buffer)
         if (lane == 0) {
           if (has_pre) bulk_wait_read<0>();
@@ -505,12 +600,24 @@ __global__ void __launch_bounds__(NTHREADS, 1)
           bufp = stg + (nstore & 1) * STG_BYTES;
           nstore++;
         }
-#pragma unroll
-        for (int half = 0; half < (int)(4 / sizeof(TC)); half++) {
+        constexpr int HALVES = 4 / (int)sizeof(TC);  // 32-column TMEM reads per unit: 2 (bf16 C) / 1 (fp32 C)
+#pragma unroll 1
+        for (int half = 0; half < HALVES; half++) {
+          uint32_t r[32];
+          tmem_ld32(t_row + (uint32_t)(u * UNIT_COLS + 32 * half), r);
+          tmem_wait_ld();
+          if (tr && u == hf && half == 0) stamp(P, 6);
+          if (half == HALVES - 1 && u + 2 >= UNITS && !released) {  // last TMEM read of this warp for this tile
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty[as]);
+            released = true;
+          }
           float v[32], pre[32];
 #pragma unroll
-          for (int j = 0; j < 32; j++) v[j] = __uint_as_float(half == 0 ? r0[j] : r1[j]);
-          epi_math32_dispatch<TC>(P, dr, v, pre, m, nu + 32 * half, row_ok);
+          for (int j = 0; j < 32; j++) v[j] = __uint_as_float(r[j]);
+          epi_math32<TC, ACT, DACT>(P, dr, v, pre, m, nu + 32 * half, row_ok, sb + (nu - n0) + 32 * half, side, half,
+                                    side_ok);
           stage_row32(bufc, lane, half, v, (const TC*)nullptr);
           if (has_pre) stage_row32(bufp, lane, half, pre, (const TC*)nullptr);
         }
@@ -621,11 +728,11 @@ int get_map(const void* ptr, uint64_t inner, uint64_t outer, uint64_t stride, ui
 }
 
 constexpr size_t SMEM_MAX = 227 * 1024;
-constexpr size_t SMEM_FIXED = 1024 /*align slack*/ + NUM_EPI_WARPS * STG_BUFS * STG_BYTES + ONES_BYTES +
+constexpr size_t SMEM_FIXED = 1024 /*align slack*/ + NUM_EPI_WARPS * STG_BUFS * STG_BYTES + ONES_BYTES + BIAS_BYTES +
                               (2 * MAX_STAGES + 4) * 8 + 16;
 
-template <int BN, typename TC>
-int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const CUtensorMap& tp, TcParams& P,
+template <int BN, typename TC, int ACT, bool DACT>
+int launch_tc_k(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const CUtensorMap& tp, TcParams& P,
               cudaStream_t st) {
   constexpr size_t stage_bytes = (size_t)BM * BK * 2 + (size_t)BN * BK * 2;
   int stages = (int)((SMEM_MAX - SMEM_FIXED) / stage_bytes);
@@ -639,13 +746,32 @@ int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& t
   const size_t smem = SMEM_FIXED + (size_t)stages * stage_bytes;
   static size_t attr_smem = 0;
   if (smem > attr_smem) {
-    MAGIC_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, TC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MAX),
+    MAGIC_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, TC, ACT, DACT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)SMEM_MAX),
                "magic_gemm(tc)");
     attr_smem = SMEM_MAX;
   }
-  MAGIC_CUDA(magic_launch(gemm_tc_kernel<BN, TC>, dim3(grid), dim3(NTHREADS), smem, st, ta, tb, tc, tp, P),
+  MAGIC_CUDA(magic_launch(gemm_tc_kernel<BN, TC, ACT, DACT>, dim3(grid), dim3(NTHREADS), smem, st, ta, tb, tc, tp, P),
              "magic_gemm(tc)");
   return MAGIC_OK;
+}
+
+// epilogue variant from the call: fp32 C (weight gradients, fp32 heads) only ever takes the linear epilogue
+template <int BN, typename TC>
+int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const CUtensorMap& tp, TcParams& P,
+              cudaStream_t st) {
+  const bool dact = P.epi.dact_pre != nullptr;
+  const int act = P.epi.act;
+  if (!dact && act == MAGIC_ACT_NONE) return launch_tc_k<BN, TC, MAGIC_ACT_NONE, false>(ta, tb, tc, tp, P, st);
+  if (sizeof(TC) == 2) {
+    typedef __nv_bfloat16 bf;
+    if (!dact && act == MAGIC_ACT_GELU) return launch_tc_k<BN, bf, MAGIC_ACT_GELU, false>(ta, tb, tc, tp, P, st);
+    if (!dact && act == MAGIC_ACT_RELU) return launch_tc_k<BN, bf, MAGIC_ACT_RELU, false>(ta, tb, tc, tp, P, st);
+    if (dact && act == MAGIC_ACT_GELU) return launch_tc_k<BN, bf, MAGIC_ACT_GELU, true>(ta, tb, tc, tp, P, st);
+    if (dact && act == MAGIC_ACT_RELU) return launch_tc_k<BN, bf, MAGIC_ACT_RELU, true>(ta, tb, tc, tp, P, st);
+    if (dact) return launch_tc_k<BN, bf, MAGIC_ACT_NONE, true>(ta, tb, tc, tp, P, st);
+  }
+  return MAGIC_ERR_UNSUPPORTED;  // fp32 C with an activation epilogue: the caller falls back to the FFMA kernel
 }
 
 bool tc_disabled() {
