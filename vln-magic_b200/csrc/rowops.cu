@@ -273,10 +273,8 @@ __global__ void __launch_bounds__(ROW_WARPS * 32)
   pdl_trigger();
   pdl_wait();
   constexpr int h = NCH * 128;
-  extern __shared__ float sm[];  // [2*h] : dgamma | dbeta partials
+  extern __shared__ float sm[];  // [ROW_WARPS][2*h] : per-warp dgamma | dbeta partials
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  for (int c = threadIdx.x; c < 2 * h; c += blockDim.x) sm[c] = 0.f;
-  __syncthreads();
   const Dropout din = make_dropout(p_in, seed_ptr, salt_in), dout = make_dropout(p_out, seed_ptr, salt_out);
   float g[NCH][4], pg[NCH][4], pb[NCH][4];
 #pragma unroll
@@ -334,17 +332,21 @@ __global__ void __launch_bounds__(ROW_WARPS * 32)
       Vec4<T>::store(dx + base + c * 128, o);
     }
   }
+  // column sums: every warp parks its register partials in its own smem row (128-bit stores, no atomics: shared
+  // fp32 atomics are CAS loops and 8 warps hitting the same 2h words made this tail the longest part of the
+  // kernel), then each thread adds the ROW_WARPS rows of its columns and issues ONE global reduction per column
+  float* mine = sm + (size_t)w * 2 * h;
 #pragma unroll
-  for (int c = 0; c < NCH; c++)
+  for (int c = 0; c < NCH; c++) {
+    *reinterpret_cast<float4*>(mine + c * 128 + lane * 4) = make_float4(pg[c][0], pg[c][1], pg[c][2], pg[c][3]);
+    *reinterpret_cast<float4*>(mine + h + c * 128 + lane * 4) = make_float4(pb[c][0], pb[c][1], pb[c][2], pb[c][3]);
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < 2 * h; c += blockDim.x) {
+    float v = 0.f;
 #pragma unroll
-    for (int e = 0; e < 4; e++) {
-      atomicAdd(&sm[c * 128 + lane * 4 + e], pg[c][e]);
-      atomicAdd(&sm[h + c * 128 + lane * 4 + e], pb[c][e]);
-    }
-  flush_cols(sm, dgamma, h);
-  for (int c = threadIdx.x; c < h; c += blockDim.x) {
-    const float v = sm[h + c];
-    if (v != 0.f) atomicAdd(dbeta + c, v);
+    for (int ww = 0; ww < ROW_WARPS; ww++) v += sm[(size_t)ww * 2 * h + c];
+    if (v != 0.f) atomicAdd(c < h ? dgamma + c : dbeta + (c - h), v);
   }
 }
 
@@ -518,8 +520,18 @@ __global__ void __launch_bounds__(ROW_WARPS * 32)
   __syncthreads();
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   float pg[NE], pbt[NE], pdb[NE];
+  // dW partials live in registers across the row loop when they fit (h <= 128): one shared-memory atomic per
+  // (warp, weight) at the end instead of one per (row, weight)
+  constexpr bool REG_DW = NE * MAXK <= 64;
+  float pw[REG_DW ? NE : 1][REG_DW ? MAXK : 1];
 #pragma unroll
   for (int i = 0; i < NE; i++) pg[i] = pbt[i] = pdb[i] = 0.f;
+  if (REG_DW) {
+#pragma unroll
+    for (int i = 0; i < (REG_DW ? NE : 1); i++)
+#pragma unroll
+      for (int k = 0; k < (REG_DW ? MAXK : 1); k++) pw[i][k] = 0.f;
+  }
   for (int r = blockIdx.x * ROW_WARPS + w; r < M; r += gridDim.x * ROW_WARPS) {
     const size_t base = (size_t)r * h;
     float fr[MAXK];
@@ -551,9 +563,25 @@ __global__ void __launch_bounds__(ROW_WARPS * 32)
       const int c = lane + 32 * i;
       if (c < h) {
         pdb[i] += d[i];
+        if (REG_DW) {
 #pragma unroll
-        for (int k = 0; k < MAXK; k++)
-          if (k < K) atomicAdd(&s_dW[(size_t)c * K + k], d[i] * fr[k]);
+          for (int k = 0; k < MAXK; k++) pw[REG_DW ? i : 0][REG_DW ? k : 0] = fmaf(d[i], fr[k], pw[REG_DW ? i : 0][REG_DW ? k : 0]);
+        } else {
+#pragma unroll
+          for (int k = 0; k < MAXK; k++)
+            if (k < K) atomicAdd(&s_dW[(size_t)c * K + k], d[i] * fr[k]);
+        }
+      }
+    }
+  }
+  if (REG_DW) {
+#pragma unroll
+    for (int i = 0; i < (REG_DW ? NE : 1); i++) {
+      const int c = lane + 32 * i;
+      if (c < h) {
+#pragma unroll
+        for (int k = 0; k < (REG_DW ? MAXK : 1); k++)
+          if (k < K) atomicAdd(&s_dW[(size_t)c * K + k], pw[i][k]);
       }
     }
   }
@@ -960,8 +988,14 @@ int magic_ln_bwd(const void* dy, const void* x, const void* res, const float* ga
   if (M <= 0) return MAGIC_OK;
   const size_t smem = 2 * (size_t)h * sizeof(float);
   if (vec_h(h) && vec_ok(dy, x, res, dx, dres) && vec_ok(gamma, nullptr, nullptr, nullptr, nullptr)) {
-    DISPATCH_T(dtype, DISPATCH_NCH(h, (magic_launch(ln_bwd_vec_kernel<T, NCH>, dim3(row_grid(M)), dim3(ROW_WARPS * 32),
-                          smem, st, (const T*)dy, (const T*)x, (const T*)res, gamma, stats, (T*)dx, (T*)dres, dgamma,
+    // several rows per warp at the narrow widths: fewer CTAs -> fewer column reductions into dgamma / dbeta
+    const int rpw = h <= 128 ? 4 : h <= 256 ? 2 : 1;
+    int grid = (M + ROW_WARPS * rpw - 1) / (ROW_WARPS * rpw);
+    const int cap = magic_num_sms() * 4;
+    grid = grid < 1 ? 1 : (grid > cap ? cap : grid);
+    const size_t smem_v = (size_t)ROW_WARPS * 2 * h * sizeof(float);  // <= 48 KB at h = 768
+    DISPATCH_T(dtype, DISPATCH_NCH(h, (magic_launch(ln_bwd_vec_kernel<T, NCH>, dim3(grid), dim3(ROW_WARPS * 32),
+                          smem_v, st, (const T*)dy, (const T*)x, (const T*)res, gamma, stats, (T*)dx, (T*)dres, dgamma,
                           dbeta, M, p_in, salt_in, p_out, salt_out, seed_ptr))));
     MAGIC_CHECK_LAUNCH("magic_ln_bwd");
     return MAGIC_OK;
