@@ -214,7 +214,12 @@ def summarise_profile(prof, n_steps, pk):
     for name, recs in prof.items():
         if name == "magic_delay":
             continue
-        ms = sum(e0.elapsed_time(e1) for e0, e1, _ in recs)
+        per_call = [e0.elapsed_time(e1) for e0, e1, _ in recs]
+        ms = sum(per_call)
+        if os.environ.get("BENCH_DEBUG_PROFILE"):
+            srt = sorted(per_call)
+            sys.stderr.write(f"[profile] {name}: n={len(srt)} sum={ms:.3f} ms median={srt[len(srt) // 2] * 1e3:.1f} us "
+                             f"max={srt[-1] * 1e3:.1f} us top5={[round(x * 1e3, 1) for x in srt[-5:]]}\n")
         fl = by = 0.0
         for _, _, a in recs:
             f, b = family_cost(name, a)
@@ -311,7 +316,7 @@ def run_reference(args):
     v = sample_B * len(times) / tot
     sample = f"fp32 PyTorch oracle port (reference model files absent upstream), student step fwd+bwd+clip+AdamW, " \
              f"batch {sample_B} per step (bounded sample of the batch-{w['B']} workload), MLM/SAP 1:1"
-    print(json.dumps(dict(
+    emit(OUT_FD, (dict(
         impl="reference", metric="pretrain samples/s (MLM+SAP step)", value=v, unit="samples/s", n_gpus=args.gpus,
         steps=args.steps, warmup=args.warmup, ms_per_step=1e3 * tot / len(times), higher_is_better=True,
         scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
@@ -445,6 +450,8 @@ def run_ours(args):
         # (single stream, eager; a delay kernel every 32 calls keeps the host ahead of the GPU -- see _lib.profile_start)
         g = stepper.use_graphs
         stepper.use_graphs = False
+        # rank 0 runs this pass ALONE: it must not issue the gradient all-reduce (the other ranks are not in it)
+        stepper.allreduce = stepper.t_allreduce = None
         ops.enable_side_stream(False)
         ops.enable_branch_streams(False)
         run_steps(2, 0, False)
@@ -486,12 +493,31 @@ def run_ours(args):
             e2e=dict(value=e2e_v, unit="samples/s", h2d_bytes_per_step=int(in_bytes), d2h_bytes_per_step=4,
                      ms_per_step=ms_e2e / args.steps),
             gpu_launches=int(launches), clocks=clocks)
-        print(json.dumps(line))
+        emit(OUT_FD, line)
     if world > 1:
         dist.destroy_process_group()
 
 
+def claim_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version banner to fd 1
+    when NCCL_DEBUG is set), so fd 1 is pointed at stderr for the whole run and the result line goes to the saved
+    descriptor."""
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    return saved
+
+
+def emit(saved_fd, obj):
+    os.write(saved_fd, (json.dumps(obj) + "\n").encode())
+
+
+OUT_FD = None
+
+
 def main():
+    global OUT_FD
+    OUT_FD = claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
