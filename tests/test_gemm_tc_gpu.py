@@ -178,3 +178,44 @@ def test_unaligned_shapes_take_the_fp32_kernel():
     out = torch.empty(M, N, device=DEV, dtype=torch.bfloat16)
     ops.gemm(x, K, 1, w, 1, K, out, M, N, K)
     assert rel(out, x.float() @ w.float().t()) < 4e-3
+
+
+# ---- CTA-pair kernels (cta_group::2, 256 x 256 tiles): shapes the heuristic sends there (>= 37 pair tiles) ---------
+PAIR_SHAPES = [(5120, 768, 768), (5120, 3072, 768), (5120, 768, 3072), (11520, 768, 256), (5000, 712, 520),
+               (20480, 2304, 768)]
+
+
+@pytest.mark.parametrize("M,N,K", PAIR_SHAPES)
+def test_pair_fwd_bias_gelu_residual(M, N, K):
+    torch.manual_seed(7 + M + N + K)
+    x, w = bf(torch.randn(M, K, device=DEV)), bf(torch.randn(N, K, device=DEV) * 0.05)
+    b = torch.randn(N, device=DEV)
+    out = torch.full((M, N), float("nan"), device=DEV, dtype=torch.bfloat16)
+    ops.gemm(x, K, 1, w, 1, K, out, M, N, K, bias=b)
+    ref = F.linear(x.float(), w.float(), b)
+    assert torch.isfinite(out.float()).all()
+    assert rel(out, ref) < 4e-3
+    # GELU + pre-activation copy-out, then residual epilogue
+    pre = torch.empty_like(out)
+    ops.gemm(x, K, 1, w, 1, K, out, M, N, K, bias=b, act=1, pre_out=pre)
+    assert rel(pre, ref) < 4e-3
+    assert rel(out, F.gelu(bf(ref).float())) < 6e-3
+    res = bf(torch.randn(M, N, device=DEV))
+    ops.gemm(x, K, 1, w, 1, K, out, M, N, K, bias=b, residual=res)
+    assert rel(out, ref + res.float()) < 4e-3
+
+
+@pytest.mark.parametrize("M,N,K", PAIR_SHAPES[:5])
+def test_pair_dgrad_mn_major_b_and_dact(M, N, K):
+    """dx[M,K] = (dy[M,N] W[N,K]) * gelu'(pre): A K-major, B MN-major, backward-activation epilogue."""
+    torch.manual_seed(8 + M + N + K)
+    dy, w = bf(torch.randn(M, N, device=DEV)), bf(torch.randn(N, K, device=DEV) * 0.05)
+    dx = torch.full((M, K), float("nan"), device=DEV, dtype=torch.bfloat16)
+    ops.gemm(dy, N, 1, w, K, 1, dx, M, K, N)
+    ref = dy.float() @ w.float()
+    assert rel(dx, ref) < 4e-3
+    pre = bf(torch.randn(M, K, device=DEV))
+    ops.gemm(dy, N, 1, w, K, 1, dx, M, K, N, act=1, dact_pre=pre)
+    z = pre.float()
+    g = 0.5 * (1 + torch.erf(z * 0.70710678)) + z * torch.exp(-0.5 * z * z) * 0.3989422804
+    assert rel(dx, ref * g) < 6e-3

@@ -98,6 +98,72 @@ __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
 
+// ---- CTA pair (cta_group::2): two CTAs of a cluster on one TPC share the operands of a 256 x BN tile -----------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// TMA load issued by EITHER CTA of the pair; the transaction bytes are credited to the LEADER's (rank 0) mbarrier:
+// clearing bit 24 of the shared::cluster address selects the even CTA's copy of the barrier
+__device__ __forceinline__ void tma_load_2d_pair(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], "
+      "[%2];" ::"r"(smem_u32(dst)),
+      "l"(map), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void umma_bf16_pair(uint32_t tmem_c, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                               uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_c),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrives on the barrier at this smem offset in BOTH CTAs once the MMAs issued so far have completed
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+          smem_u32(bar)),
+      "h"((unsigned short)3)
+      : "memory");
+}
+// arrive on the LEADER's copy of a barrier from either CTA
+__device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
+  uint32_t raddr;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(raddr) : "r"(smem_u32(bar)), "r"(0));
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(raddr) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "WAIT_LOOP_C:\n"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE_C;\n"
+      "bra WAIT_LOOP_C;\n"
+      "DONE_C:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t* dst_smem, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(cols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+
 __device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t cols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(cols)
                : "memory");
@@ -386,14 +452,20 @@ __device__ __forceinline__ void epi_math32(const TcParams& P, const Dropout& dr,
 // One kernel instantiation per (tile width, C type, activation, forward / backward-derivative epilogue): each carries
 // only its own epilogue code.  These launches execute every instruction once or twice, so instruction fetch of a
 // do-everything epilogue (3 activations x 2 directions, unrolled) was a first-order cost of the small GEMMs.
-template <int BN, typename TC, int ACT, bool DACT>
+// CTAS = 2: a cluster of two CTAs owns a 256 x BN tile.  Each CTA loads ITS 128 rows of A and HALF of the B tile
+// (BN/2 rows), the leader (cluster rank 0) issues tcgen05.mma.cta_group::2 (UMMA 256 x BN x 16) that reads both
+// CTAs' shared memory and writes each CTA's 128 accumulator rows into its own TMEM, and both CTAs drain their
+// rows.  Per SM and k-block the operand traffic drops from 16 KB + BN*128 B to 16 KB + BN*64 B for the same
+// number of MMA cycles, which is what the L2 -> SM path (the bound of the 128 x BN single-CTA main loop) needs.
+template <int BN, typename TC, int ACT, bool DACT, int CTAS>
 __global__ void __launch_bounds__(NTHREADS, 1)
     gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                    const __grid_constant__ CUtensorMap tmap_c, const __grid_constant__ CUtensorMap tmap_pre,
                    const TcParams P) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   constexpr int A_BYTES = BM * BK * 2;
-  constexpr int B_BYTES = BN * BK * 2;
+  constexpr int B_ROWS = BN / CTAS;  // rows of the B tile this CTA stages
+  constexpr int B_BYTES = B_ROWS * BK * 2;
   constexpr int UNIT_COLS = 128 / (int)sizeof(TC);  // columns of one 128-byte staging row: 64 (bf16) / 32 (fp32)
   constexpr int UNITS = BN / UNIT_COLS;             // store units per lane quarter per tile
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -410,7 +482,10 @@ __global__ void __launch_bounds__(NTHREADS, 1)
   uint32_t* tmem_ptr = (uint32_t*)(tmem_empty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int total_work = P.m_tiles * P.n_tiles * P.splits;
+  const int total_work = P.m_tiles * P.n_tiles * P.splits;  // CTAS = 2: m_tiles counts 256-row pair tiles
+  const int crank = CTAS == 2 ? (int)cluster_ctarank() : 0;
+  const int wfirst = (int)blockIdx.x / CTAS, wstride = (int)gridDim.x / CTAS;  // work walk of this CTA (pair)
+  const bool leader = crank == 0;
   pdl_trigger();
   if (threadIdx.x == 0) stamp(P, 0);
 
@@ -425,7 +500,7 @@ __global__ void __launch_bounds__(NTHREADS, 1)
     }
     for (int s = 0; s < 2; s++) {
       mbar_init(&tmem_full[s], 1);
-      mbar_init(&tmem_empty[s], NUM_EPI_WARPS);
+      mbar_init(&tmem_empty[s], NUM_EPI_WARPS * CTAS);  // pair: both CTAs' epilogue warps release the leader's copy
     }
     fence_barrier_init();
   }
@@ -435,9 +510,13 @@ __global__ void __launch_bounds__(NTHREADS, 1)
     for (int i = threadIdx.x; i < ONES_BYTES / 4; i += NTHREADS) reinterpret_cast<uint32_t*>(sOnes)[i] = 0x3F803F80u;
     fence_proxy_async();  // the tensor core reads this tile through the async proxy
   }
-  if (warp == 1) tmem_alloc(tmem_ptr, tmem_cols);
+  if (warp == 1) {
+    if (CTAS == 2) tmem_alloc_pair(tmem_ptr, tmem_cols);
+    else tmem_alloc(tmem_ptr, tmem_cols);
+  }
   tc_fence_before();
-  __syncthreads();
+  if (CTAS == 2) cluster_sync_all();  // the peer's barriers must be initialised before anything signals them
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
   pdl_wait();  // everything above overlapped the previous kernel's tail; global memory is touched only below
@@ -448,16 +527,35 @@ __global__ void __launch_bounds__(NTHREADS, 1)
       // ===== TMA producer =====
       int s = 0;
       uint32_t ph = 0;
-      for (int work = blockIdx.x; work < total_work; work += gridDim.x) {
+      for (int work = wfirst; work < total_work; work += wstride) {
         const int tile = work % (P.m_tiles * P.n_tiles), ks = work / (P.m_tiles * P.n_tiles);
-        const int m0 = (tile / P.n_tiles) * BM, n0 = (tile % P.n_tiles) * BN;
+        const int m0 = (tile / P.n_tiles) * (BM * CTAS) + crank * BM, n0 = (tile % P.n_tiles) * BN + crank * B_ROWS;
         const int kb0 = ks * P.kb_per_split, kb1 = min(P.total_kb, kb0 + P.kb_per_split);
         for (int kb = kb0; kb < kb1; kb++) {
           mbar_wait(&empty[s], ph ^ 1);
-          mbar_expect_tx(&full[s], A_BYTES + B_BYTES);
           uint8_t* a_dst = sA + s * A_BYTES;
           uint8_t* b_dst = sB + s * B_BYTES;
           const int k0 = kb * BK;
+          if (CTAS == 2) {
+            // both CTAs' bytes land on the leader's barrier; only the leader posts the expected count
+            if (leader) mbar_expect_tx(&full[s], 2 * (A_BYTES + B_BYTES));
+            if (!P.a_mn) {
+              tma_load_2d_pair(&tmap_a, &full[s], a_dst, k0, m0);
+            } else {
+              tma_load_2d_pair(&tmap_a, &full[s], a_dst, m0, k0);
+              tma_load_2d_pair(&tmap_a, &full[s], a_dst + 64 * BK * 2, m0 + 64, k0);
+            }
+            if (!P.b_mn) {
+              tma_load_2d_pair(&tmap_b, &full[s], b_dst, k0, n0);  // box {64 k, BN/2 rows}
+            } else {
+#pragma unroll
+              for (int j = 0; j < B_ROWS / 64; j++)
+                tma_load_2d_pair(&tmap_b, &full[s], b_dst + j * 64 * BK * 2, n0 + 64 * j, k0);
+            }
+            if (++s == stages) { s = 0; ph ^= 1; }
+            continue;
+          }
+          mbar_expect_tx(&full[s], A_BYTES + B_BYTES);
           if (!P.a_mn) {
             tma_load_2d(&tmap_a, &full[s], a_dst, k0, m0);  // box {64 k, 128 rows}
           } else {
@@ -477,13 +575,13 @@ __global__ void __launch_bounds__(NTHREADS, 1)
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ===== MMA issuer =====
-      const uint32_t idesc = make_idesc(BM, BN, P.a_mn, P.b_mn);
+    if (lane == 0 && leader) {
+      // ===== MMA issuer (pair: the leader CTA only) =====
+      const uint32_t idesc = make_idesc(BM * CTAS, BN, P.a_mn, P.b_mn);
       int s = 0;
       uint32_t ph = 0;
       int it = 0;
-      for (int work = blockIdx.x; work < total_work; work += gridDim.x, it++) {
+      for (int work = wfirst; work < total_work; work += wstride, it++) {
         const int ks = work / (P.m_tiles * P.n_tiles);
         const int kb0 = ks * P.kb_per_split, kb1 = min(P.total_kb, kb0 + P.kb_per_split);
         const int as = it & 1;
@@ -493,7 +591,8 @@ __global__ void __launch_bounds__(NTHREADS, 1)
         const uint32_t rs_idesc = make_idesc(BM, RS_COLS, P.a_mn, 0);
         const uint32_t tmem_rs = tmem_base + (uint32_t)(2 * BN + as * RS_COLS);
         const uint64_t ones_desc = make_desc(smem_u32(sOnes), 16, 1024);
-        mbar_wait(&tmem_empty[as], aph ^ 1);  // epilogue has drained this accumulator buffer
+        if (CTAS == 2) mbar_wait_cluster(&tmem_empty[as], aph ^ 1);  // both CTAs have drained this buffer
+        else mbar_wait(&tmem_empty[as], aph ^ 1);                   // epilogue has drained this accumulator buffer
         tc_fence_after();
         const uint32_t tmem_c = tmem_base + (uint32_t)(as * BN);
         for (int kb = kb0; kb < kb1; kb++) {
@@ -508,13 +607,20 @@ __global__ void __launch_bounds__(NTHREADS, 1)
                 P.a_mn ? make_desc(a_base + k * 2048, 8192, 1024) : make_desc(a_base + k * 32, 16, 1024);
             const uint64_t bdesc =
                 P.b_mn ? make_desc(b_base + k * 2048, 8192, 1024) : make_desc(b_base + k * 32, 16, 1024);
-            umma_bf16(tmem_c, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
-            if (rs_tile) umma_bf16(tmem_rs, adesc, ones_desc, rs_idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            if (CTAS == 2) {
+              umma_bf16_pair(tmem_c, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            } else {
+              umma_bf16(tmem_c, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+              if (rs_tile) umma_bf16(tmem_rs, adesc, ones_desc, rs_idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            }
           }
-          umma_commit(&empty[s]);  // frees this smem stage once the MMAs above have read it
+          // frees this smem stage (in both CTAs of a pair) once the MMAs above have read it
+          if (CTAS == 2) umma_commit_pair(&empty[s]);
+          else umma_commit(&empty[s]);
           if (++s == stages) { s = 0; ph ^= 1; }
         }
-        umma_commit(&tmem_full[as]);  // accumulator complete
+        if (CTAS == 2) umma_commit_pair(&tmem_full[as]);  // accumulator complete (both CTAs' epilogues wake)
+        else umma_commit(&tmem_full[as]);
         if (work == 0) stamp(P, 4);
       }
     }
@@ -535,9 +641,9 @@ __global__ void __launch_bounds__(NTHREADS, 1)
     const long side_ld = side_dact ? P.epi.dact_ld : P.epi.res_ld;
     int nstore = 0;  // staging buffers used so far by this warp (buffer = nstore & 1)
     int it = 0;
-    for (int work = blockIdx.x; work < total_work; work += gridDim.x, it++) {
+    for (int work = wfirst; work < total_work; work += wstride, it++) {
       const int tile = work % (P.m_tiles * P.n_tiles);
-      const int m0 = (tile / P.n_tiles) * BM, n0 = (tile % P.n_tiles) * BN;
+      const int m0 = (tile / P.n_tiles) * (BM * CTAS) + crank * BM, n0 = (tile % P.n_tiles) * BN;
       const int as = it & 1;
       const uint32_t aph = (it >> 1) & 1;
       const int m = m0 + q * 32 + lane;
@@ -570,7 +676,7 @@ __global__ void __launch_bounds__(NTHREADS, 1)
       if (UNITS <= hf) {  // nothing to drain for this warp (BN = 64 with bf16 output): just release
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&tmem_empty[as]);
+        if (lane == 0) { if (CTAS == 2) mbar_arrive_leader(&tmem_empty[as]); else mbar_arrive(&tmem_empty[as]); }
         released = true;
       }
 #pragma unroll 1
@@ -582,7 +688,7 @@ __global__ void __launch_bounds__(NTHREADS, 1)
           if (u + 2 >= UNITS && !released) {
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tmem_empty[as]);
+            if (lane == 0) { if (CTAS == 2) mbar_arrive_leader(&tmem_empty[as]); else mbar_arrive(&tmem_empty[as]); }
             released = true;
           }
           continue;
@@ -610,7 +716,7 @@ __global__ void __launch_bounds__(NTHREADS, 1)
           if (half == HALVES - 1 && u + 2 >= UNITS && !released) {  // last TMEM read of this warp for this tile
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tmem_empty[as]);
+            if (lane == 0) { if (CTAS == 2) mbar_arrive_leader(&tmem_empty[as]); else mbar_arrive(&tmem_empty[as]); }
             released = true;
           }
           float v[32], pre[32];
@@ -637,11 +743,13 @@ __global__ void __launch_bounds__(NTHREADS, 1)
   }
   if (warp == 2 && lane == 0) stamp(P, 9);
   tc_fence_before();
-  __syncthreads();
+  if (CTAS == 2) cluster_sync_all();  // the leader's MMAs read the peer's shared memory: leave together
+  else __syncthreads();
   if (threadIdx.x == 0) stamp(P, 10);
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, tmem_cols);
+    if (CTAS == 2) tmem_dealloc_pair(tmem_base, tmem_cols);
+    else tmem_dealloc(tmem_base, tmem_cols);
     if (lane == 0) stamp(P, 11);
   }
 }
@@ -731,45 +839,53 @@ constexpr size_t SMEM_MAX = 227 * 1024;
 constexpr size_t SMEM_FIXED = 1024 /*align slack*/ + NUM_EPI_WARPS * STG_BUFS * STG_BYTES + ONES_BYTES + BIAS_BYTES +
                               (2 * MAX_STAGES + 4) * 8 + 16;
 
-template <int BN, typename TC, int ACT, bool DACT>
+template <int BN, typename TC, int ACT, bool DACT, int CTAS>
 int launch_tc_k(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const CUtensorMap& tp, TcParams& P,
-              cudaStream_t st) {
-  constexpr size_t stage_bytes = (size_t)BM * BK * 2 + (size_t)BN * BK * 2;
+                cudaStream_t st) {
+  constexpr size_t stage_bytes = (size_t)BM * BK * 2 + (size_t)(BN / CTAS) * BK * 2;
   int stages = (int)((SMEM_MAX - SMEM_FIXED) / stage_bytes);
   if (stages > MAX_STAGES) stages = MAX_STAGES;
   // never more stages than k-blocks a CTA will ever load
   const long work = (long)P.m_tiles * P.n_tiles * P.splits;
-  const int grid = (int)(work < magic_num_sms() ? work : magic_num_sms());
-  const long per_cta_kb = ((work + grid - 1) / grid) * (long)P.kb_per_split;
+  const int slots = magic_num_sms() / CTAS;  // CTAs (CTAS = 1) or CTA pairs (CTAS = 2) that run at once
+  const int groups = (int)(work < slots ? work : slots);
+  const long per_cta_kb = ((work + groups - 1) / groups) * (long)P.kb_per_split;
   if (stages > per_cta_kb) stages = (int)(per_cta_kb < 2 ? 2 : per_cta_kb);
   P.stages = stages;
   const size_t smem = SMEM_FIXED + (size_t)stages * stage_bytes;
   static size_t attr_smem = 0;
   if (smem > attr_smem) {
-    MAGIC_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, TC, ACT, DACT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    (int)SMEM_MAX),
+    MAGIC_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, TC, ACT, DACT, CTAS>,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MAX),
                "magic_gemm(tc)");
     attr_smem = SMEM_MAX;
   }
-  MAGIC_CUDA(magic_launch(gemm_tc_kernel<BN, TC, ACT, DACT>, dim3(grid), dim3(NTHREADS), smem, st, ta, tb, tc, tp, P),
-             "magic_gemm(tc)");
+  if (CTAS == 2) {
+    MAGIC_CUDA(magic_launch_cluster(gemm_tc_kernel<BN, TC, ACT, DACT, CTAS>, dim3(groups * 2), dim3(NTHREADS), smem, st,
+                                    dim3(2, 1, 1), ta, tb, tc, tp, P),
+               "magic_gemm(tc, cta pair)");
+  } else {
+    MAGIC_CUDA(magic_launch(gemm_tc_kernel<BN, TC, ACT, DACT, CTAS>, dim3(groups), dim3(NTHREADS), smem, st, ta, tb, tc,
+                            tp, P),
+               "magic_gemm(tc)");
+  }
   return MAGIC_OK;
 }
 
 // epilogue variant from the call: fp32 C (weight gradients, fp32 heads) only ever takes the linear epilogue
-template <int BN, typename TC>
+template <int BN, typename TC, int CTAS>
 int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const CUtensorMap& tp, TcParams& P,
               cudaStream_t st) {
   const bool dact = P.epi.dact_pre != nullptr;
   const int act = P.epi.act;
-  if (!dact && act == MAGIC_ACT_NONE) return launch_tc_k<BN, TC, MAGIC_ACT_NONE, false>(ta, tb, tc, tp, P, st);
+  if (!dact && act == MAGIC_ACT_NONE) return launch_tc_k<BN, TC, MAGIC_ACT_NONE, false, CTAS>(ta, tb, tc, tp, P, st);
   if (sizeof(TC) == 2) {
     typedef __nv_bfloat16 bf;
-    if (!dact && act == MAGIC_ACT_GELU) return launch_tc_k<BN, bf, MAGIC_ACT_GELU, false>(ta, tb, tc, tp, P, st);
-    if (!dact && act == MAGIC_ACT_RELU) return launch_tc_k<BN, bf, MAGIC_ACT_RELU, false>(ta, tb, tc, tp, P, st);
-    if (dact && act == MAGIC_ACT_GELU) return launch_tc_k<BN, bf, MAGIC_ACT_GELU, true>(ta, tb, tc, tp, P, st);
-    if (dact && act == MAGIC_ACT_RELU) return launch_tc_k<BN, bf, MAGIC_ACT_RELU, true>(ta, tb, tc, tp, P, st);
-    if (dact) return launch_tc_k<BN, bf, MAGIC_ACT_NONE, true>(ta, tb, tc, tp, P, st);
+    if (!dact && act == MAGIC_ACT_GELU) return launch_tc_k<BN, bf, MAGIC_ACT_GELU, false, CTAS>(ta, tb, tc, tp, P, st);
+    if (!dact && act == MAGIC_ACT_RELU) return launch_tc_k<BN, bf, MAGIC_ACT_RELU, false, CTAS>(ta, tb, tc, tp, P, st);
+    if (dact && act == MAGIC_ACT_GELU) return launch_tc_k<BN, bf, MAGIC_ACT_GELU, true, CTAS>(ta, tb, tc, tp, P, st);
+    if (dact && act == MAGIC_ACT_RELU) return launch_tc_k<BN, bf, MAGIC_ACT_RELU, true, CTAS>(ta, tb, tc, tp, P, st);
+    if (dact) return launch_tc_k<BN, bf, MAGIC_ACT_NONE, true, CTAS>(ta, tb, tc, tp, P, st);
   }
   return MAGIC_ERR_UNSUPPORTED;  // fp32 C with an activation epilogue: the caller falls back to the FFMA kernel
 }
@@ -784,6 +900,16 @@ bool tc_disabled() {
 }
 
 unsigned long long* g_trace = nullptr;
+
+// MAGIC_TC_PAIR: 0 = never use CTA pairs, 1 (default) = by the heuristic, 2 = whenever the shape allows
+int pair_mode() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("MAGIC_TC_PAIR");
+    v = e ? atoi(e) : 1;
+  }
+  return v;
+}
 
 int force_bn() {
   static int v = -1;
@@ -846,13 +972,24 @@ int gemm_tc_dispatch(const void* A, const void* B, void* C, int c_dt, int M, int
   }
   if (force_bn() == 64 || force_bn() == 128 || force_bn() == 256) BN = force_bn();
   if (epi.rowsum && BN > 128) BN = 128;  // the row-sum accumulators need TMEM columns beyond the two tile buffers
+  // CTA pairs (256 x 256 tiles, cta_group::2) for the wide GEMMs with a real reduction depth: bf16 C, no bias-gradient
+  // rider, and enough pair tiles to occupy at least half of the 74 pairs
+  bool pair = false;
+  if (pair_mode() != 0 && c_dt == MAGIC_BF16 && !epi.rowsum && epi.beta == 0.f && N >= 256 && M >= 512 && P.total_kb >= 4) {
+    const long pt = (long)((M + 255) / 256) * ((N + 255) / 256);
+    pair = pt * 4 >= sms || pair_mode() == 2;
+  }
+  if (pair) {
+    BN = 256;
+    P.m_tiles = (M + 2 * BM - 1) / (2 * BM);
+  }
   P.n_tiles = (N + BN - 1) / BN;
   // split-K for skinny outputs with a long reduction (weight gradients): fp32 C, purely linear epilogue
   P.splits = 1;
   P.kb_per_split = P.total_kb;
   P.reduce = epi.beta == 1.f ? 1 : 0;
   const long tiles = (long)P.m_tiles * P.n_tiles;
-  if (linear_epi && tiles * 2 <= sms && P.total_kb >= 8) {
+  if (!pair && linear_epi && tiles * 2 <= sms && P.total_kb >= 8) {
     int splits = (int)(sms / tiles);
     if (splits > P.total_kb / 4) splits = P.total_kb / 4;
     if (splits > 1) {
@@ -874,7 +1011,7 @@ int gemm_tc_dispatch(const void* A, const void* B, void* C, int c_dt, int M, int
   if (!a_mn) rc = get_map(A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, 64, BM, 2, &ta);
   else rc = get_map(A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, 64, 64, 2, &ta);
   if (rc) return rc;
-  if (!b_mn) rc = get_map(B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, 64, (uint32_t)BN, 2, &tb);
+  if (!b_mn) rc = get_map(B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, 64, (uint32_t)(pair ? BN / 2 : BN), 2, &tb);
   else rc = get_map(B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, 64, 64, 2, &tb);
   if (rc) return rc;
   const uint32_t unit_cols = 128 / cesz;
@@ -886,12 +1023,13 @@ int gemm_tc_dispatch(const void* A, const void* B, void* C, int c_dt, int M, int
     if (rc) return rc;
   }
   typedef __nv_bfloat16 bf;
+  if (pair) return launch_tc<256, bf, 2>(ta, tb, tc, tp, P, st);
   if (c_dt == MAGIC_BF16) {
-    if (BN == 64) return launch_tc<64, bf>(ta, tb, tc, tp, P, st);
-    if (BN == 128) return launch_tc<128, bf>(ta, tb, tc, tp, P, st);
-    return launch_tc<256, bf>(ta, tb, tc, tp, P, st);
+    if (BN == 64) return launch_tc<64, bf, 1>(ta, tb, tc, tp, P, st);
+    if (BN == 128) return launch_tc<128, bf, 1>(ta, tb, tc, tp, P, st);
+    return launch_tc<256, bf, 1>(ta, tb, tc, tp, P, st);
   }
-  if (BN == 64) return launch_tc<64, float>(ta, tb, tc, tp, P, st);
-  if (BN == 128) return launch_tc<128, float>(ta, tb, tc, tp, P, st);
-  return launch_tc<256, float>(ta, tb, tc, tp, P, st);
+  if (BN == 64) return launch_tc<64, float, 1>(ta, tb, tc, tp, P, st);
+  if (BN == 128) return launch_tc<128, float, 1>(ta, tb, tc, tp, P, st);
+  return launch_tc<256, float, 1>(ta, tb, tc, tp, P, st);
 }
