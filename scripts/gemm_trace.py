@@ -14,7 +14,8 @@ from magic_b200 import ops, _lib
 dev = "cuda"
 NREP, NSET = 40, 4
 NAMES = ["entry", "setup done", "first TMA issued", "first stage landed", "last MMA committed", "accum ready (epi)",
-         "tmem ld done", "epi math+staged", "TMA store issued", "stores read smem", "final sync", "dealloc"]
+         "tmem ld done", "epi math+staged", "TMA store issued", "stores read smem", "final sync", "dealloc",
+         "  (first k-block MMAs issued)", "  (second stage landed)", "  (producer: first empty wait passed)"]
 
 
 def chain(fn, reps=5):

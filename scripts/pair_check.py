@@ -7,8 +7,14 @@ import magic_b200
 from magic_b200 import ops
 
 dev = "cuda"
-for (M, N, K) in [(512, 256, 256), (5120, 768, 768), (5120, 768, 3072), (5120, 3072, 768), (5120, 2304, 768),
-                  (11520, 768, 768), (8192, 8192, 8192)]:
+SHAPES = [(512, 256, 256), (5120, 768, 768), (5120, 768, 3072), (5120, 3072, 768), (5120, 2304, 768),
+          (11520, 768, 768), (8192, 8192, 8192)]
+if len(sys.argv) > 1 and sys.argv[1] == "small":
+    SHAPES = [(640, 768, 768), (1184, 768, 768), (1280, 768, 768), (2368, 768, 768), (2560, 768, 768), (2560, 2304, 768),
+              (2560, 3072, 768), (2560, 768, 3072), (1184, 3072, 768), (1184, 768, 3072), (5760, 768, 768),
+              (5120, 256, 768), (5120, 512, 512), (5120, 384, 384), (5120, 1536, 384), (5120, 384, 1536),
+              (5120, 256, 256), (5120, 1024, 256), (5120, 256, 1024), (11520, 512, 128)]
+for (M, N, K) in SHAPES:
     x = torch.randn(M, K, device=dev).bfloat16()
     w = (torch.randn(N, K, device=dev) * 0.05).bfloat16()
     b = torch.randn(N, device=dev)

@@ -98,6 +98,22 @@ __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
 
+// One lane of a CONVERGED warp.  The producer and MMA warps run their loops with all 32 lanes (uniform control flow)
+// and elect only around the issue instructions: TMA / tcgen05 take their operands from uniform registers, and
+// inside an `if (lane == 0)` region ptxas cannot prove uniformity, so every UTMALDG / UTCHMMA was wrapped in an
+// ELECT + R2UR.BROADCAST + BRA.U.ANY waterfall loop (~170 cycles per issued MMA, measured).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred P;\n"
+      "elect.sync _|P, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, P;\n"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // ---- CTA pair (cta_group::2): two CTAs of a cluster on one TPC share the operands of a 256 x BN tile -----------
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
@@ -523,19 +539,20 @@ __global__ void __launch_bounds__(NTHREADS, 1)
   if (threadIdx.x == 0) stamp(P, 1);
 
   if (warp == 0) {
-    if (lane == 0) {
-      // ===== TMA producer =====
-      int s = 0;
-      uint32_t ph = 0;
-      for (int work = wfirst; work < total_work; work += wstride) {
-        const int tile = work % (P.m_tiles * P.n_tiles), ks = work / (P.m_tiles * P.n_tiles);
-        const int m0 = (tile / P.n_tiles) * (BM * CTAS) + crank * BM, n0 = (tile % P.n_tiles) * BN + crank * B_ROWS;
-        const int kb0 = ks * P.kb_per_split, kb1 = min(P.total_kb, kb0 + P.kb_per_split);
-        for (int kb = kb0; kb < kb1; kb++) {
-          mbar_wait(&empty[s], ph ^ 1);
-          uint8_t* a_dst = sA + s * A_BYTES;
-          uint8_t* b_dst = sB + s * B_BYTES;
-          const int k0 = kb * BK;
+    // ===== TMA producer (whole warp walks the loop, one elected lane issues) =====
+    int s = 0;
+    uint32_t ph = 0;
+    for (int work = wfirst; work < total_work; work += wstride) {
+      const int tile = work % (P.m_tiles * P.n_tiles), ks = work / (P.m_tiles * P.n_tiles);
+      const int m0 = (tile / P.n_tiles) * (BM * CTAS) + crank * BM, n0 = (tile % P.n_tiles) * BN + crank * B_ROWS;
+      const int kb0 = ks * P.kb_per_split, kb1 = min(P.total_kb, kb0 + P.kb_per_split);
+      for (int kb = kb0; kb < kb1; kb++) {
+        mbar_wait(&empty[s], ph ^ 1);
+        uint8_t* a_dst = sA + s * A_BYTES;
+        uint8_t* b_dst = sB + s * B_BYTES;
+        const int k0 = kb * BK;
+        if (elect_one()) {
+          if (work == 0 && kb == kb0) stamp(P, 14);
           if (CTAS == 2) {
             // both CTAs' bytes land on the leader's barrier; only the leader posts the expected count
             if (leader) mbar_expect_tx(&full[s], 2 * (A_BYTES + B_BYTES));
@@ -552,32 +569,34 @@ __global__ void __launch_bounds__(NTHREADS, 1)
               for (int j = 0; j < B_ROWS / 64; j++)
                 tma_load_2d_pair(&tmap_b, &full[s], b_dst + j * 64 * BK * 2, n0 + 64 * j, k0);
             }
-            if (++s == stages) { s = 0; ph ^= 1; }
-            continue;
-          }
-          mbar_expect_tx(&full[s], A_BYTES + B_BYTES);
-          if (!P.a_mn) {
-            tma_load_2d(&tmap_a, &full[s], a_dst, k0, m0);  // box {64 k, 128 rows}
           } else {
-            tma_load_2d(&tmap_a, &full[s], a_dst, m0, k0);  // box {64 m, 64 k} x 2
-            tma_load_2d(&tmap_a, &full[s], a_dst + 64 * BK * 2, m0 + 64, k0);
-          }
-          if (!P.b_mn) {
-            tma_load_2d(&tmap_b, &full[s], b_dst, k0, n0);  // box {64 k, BN rows}
-          } else {
+            mbar_expect_tx(&full[s], A_BYTES + B_BYTES);
+            if (!P.a_mn) {
+              tma_load_2d(&tmap_a, &full[s], a_dst, k0, m0);  // box {64 k, 128 rows}
+            } else {
+              tma_load_2d(&tmap_a, &full[s], a_dst, m0, k0);  // box {64 m, 64 k} x 2
+              tma_load_2d(&tmap_a, &full[s], a_dst + 64 * BK * 2, m0 + 64, k0);
+            }
+            if (!P.b_mn) {
+              tma_load_2d(&tmap_b, &full[s], b_dst, k0, n0);  // box {64 k, BN rows}
+            } else {
 #pragma unroll
-            for (int j = 0; j < BN / 64; j++)
-              tma_load_2d(&tmap_b, &full[s], b_dst + j * 64 * BK * 2, n0 + 64 * j, k0);
+              for (int j = 0; j < BN / 64; j++)
+                tma_load_2d(&tmap_b, &full[s], b_dst + j * 64 * BK * 2, n0 + 64 * j, k0);
+            }
           }
-          if (++s == stages) { s = 0; ph ^= 1; }
           if (work == 0 && kb == kb0) stamp(P, 2);
         }
+        __syncwarp();
+        if (++s == stages) { s = 0; ph ^= 1; }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0 && leader) {
-      // ===== MMA issuer (pair: the leader CTA only) =====
+    if (leader) {
+      // ===== MMA issuer (pair: the leader CTA only; whole warp walks the loop, one elected lane issues) =====
       const uint32_t idesc = make_idesc(BM * CTAS, BN, P.a_mn, P.b_mn);
+      const uint32_t rs_idesc = make_idesc(BM, RS_COLS, P.a_mn, 0);
+      const uint64_t ones_desc = make_desc(smem_u32(sOnes), 16, 1024);
       int s = 0;
       uint32_t ph = 0;
       int it = 0;
@@ -588,9 +607,7 @@ __global__ void __launch_bounds__(NTHREADS, 1)
         const uint32_t aph = (it >> 1) & 1;
         // bias gradient: the CTAs of the first tile column also multiply A by a tile of ones
         const bool rs_tile = rowsum && (work % (P.m_tiles * P.n_tiles)) % P.n_tiles == 0;
-        const uint32_t rs_idesc = make_idesc(BM, RS_COLS, P.a_mn, 0);
         const uint32_t tmem_rs = tmem_base + (uint32_t)(2 * BN + as * RS_COLS);
-        const uint64_t ones_desc = make_desc(smem_u32(sOnes), 16, 1024);
         if (CTAS == 2) mbar_wait_cluster(&tmem_empty[as], aph ^ 1);  // both CTAs have drained this buffer
         else mbar_wait(&tmem_empty[as], aph ^ 1);                   // epilogue has drained this accumulator buffer
         tc_fence_after();
@@ -598,30 +615,37 @@ __global__ void __launch_bounds__(NTHREADS, 1)
         for (int kb = kb0; kb < kb1; kb++) {
           mbar_wait(&full[s], ph);
           tc_fence_after();
-          if (work == 0 && kb == kb0) stamp(P, 3);
           const uint32_t a_base = smem_u32(sA + s * A_BYTES), b_base = smem_u32(sB + s * B_BYTES);
+          if (elect_one()) {
+            if (work == 0 && kb == kb0) stamp(P, 3);
+            if (work == 0 && kb == kb0 + 1) stamp(P, 13);
 #pragma unroll
-          for (int k = 0; k < BK / 16; k++) {
-            // K-major: +32 B per UMMA_K inside the 128 B swizzle row; MN-major: +16 k-rows * 128 B
-            const uint64_t adesc =
-                P.a_mn ? make_desc(a_base + k * 2048, 8192, 1024) : make_desc(a_base + k * 32, 16, 1024);
-            const uint64_t bdesc =
-                P.b_mn ? make_desc(b_base + k * 2048, 8192, 1024) : make_desc(b_base + k * 32, 16, 1024);
-            if (CTAS == 2) {
-              umma_bf16_pair(tmem_c, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
-            } else {
-              umma_bf16(tmem_c, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
-              if (rs_tile) umma_bf16(tmem_rs, adesc, ones_desc, rs_idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            for (int k = 0; k < BK / 16; k++) {
+              // K-major: +32 B per UMMA_K inside the 128 B swizzle row; MN-major: +16 k-rows * 128 B
+              const uint64_t adesc =
+                  P.a_mn ? make_desc(a_base + k * 2048, 8192, 1024) : make_desc(a_base + k * 32, 16, 1024);
+              const uint64_t bdesc =
+                  P.b_mn ? make_desc(b_base + k * 2048, 8192, 1024) : make_desc(b_base + k * 32, 16, 1024);
+              if (CTAS == 2) {
+                umma_bf16_pair(tmem_c, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+              } else {
+                umma_bf16(tmem_c, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+                if (rs_tile) umma_bf16(tmem_rs, adesc, ones_desc, rs_idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+              }
+            }
+            // frees this smem stage (in both CTAs of a pair) once the MMAs above have read it
+            if (CTAS == 2) umma_commit_pair(&empty[s]);
+            else umma_commit(&empty[s]);
+            if (work == 0 && kb == kb0) stamp(P, 12);
+            if (kb == kb1 - 1) {  // accumulator complete (pair: both CTAs' epilogues wake)
+              if (CTAS == 2) umma_commit_pair(&tmem_full[as]);
+              else umma_commit(&tmem_full[as]);
+              if (work == 0) stamp(P, 4);
             }
           }
-          // frees this smem stage (in both CTAs of a pair) once the MMAs above have read it
-          if (CTAS == 2) umma_commit_pair(&empty[s]);
-          else umma_commit(&empty[s]);
+          __syncwarp();
           if (++s == stages) { s = 0; ph ^= 1; }
         }
-        if (CTAS == 2) umma_commit_pair(&tmem_full[as]);  // accumulator complete (both CTAs' epilogues wake)
-        else umma_commit(&tmem_full[as]);
-        if (work == 0) stamp(P, 4);
       }
     }
   } else {
@@ -694,7 +718,7 @@ __global__ void __launch_bounds__(NTHREADS, 1)
           continue;
         }
         // staging buffers: at most one store group may still be reading (the other buffer)
-        if (lane == 0) {
+        if (elect_one()) {  // (elect.sync is deterministic per member mask: the same lane owns the bulk groups)
           if (has_pre) bulk_wait_read<0>();
           else bulk_wait_read<1>();
         }
@@ -730,16 +754,17 @@ __global__ void __launch_bounds__(NTHREADS, 1)
         if (tr && u == hf) stamp(P, 7);
         fence_proxy_async();
         __syncwarp();
-        if (lane == 0) {
+        if (elect_one()) {
           if (P.reduce) tma_reduce_add_2d(&tmap_c, bufc, nu, m0 + q * 32);
           else tma_store_2d(&tmap_c, bufc, nu, m0 + q * 32);
           if (has_pre) tma_store_2d(&tmap_pre, bufp, nu, m0 + q * 32);
           bulk_commit();
         }
+        __syncwarp();
         if (tr && u == hf) stamp(P, 8);
       }
     }
-    if (lane == 0) bulk_wait_read<0>();  // smem must outlive the stores' reads; the writes land before grid completion
+    if (elect_one()) bulk_wait_read<0>();  // smem must outlive the stores' reads; the writes land before grid completion
   }
   if (warp == 2 && lane == 0) stamp(P, 9);
   tc_fence_before();
@@ -972,10 +997,11 @@ int gemm_tc_dispatch(const void* A, const void* B, void* C, int c_dt, int M, int
   }
   if (force_bn() == 64 || force_bn() == 128 || force_bn() == 256) BN = force_bn();
   if (epi.rowsum && BN > 128) BN = 128;  // the row-sum accumulators need TMEM columns beyond the two tile buffers
-  // CTA pairs (256 x 256 tiles, cta_group::2) for the wide GEMMs with a real reduction depth: bf16 C, no bias-gradient
-  // rider, and enough pair tiles to occupy at least half of the 74 pairs
+  // CTA pairs (256 x 256 tiles, cta_group::2) for the wide GEMMs with a real reduction depth (K >= 512): bf16 C, no
+  // bias-gradient rider, and enough pair tiles to occupy at least half of the 74 pairs.  Measured crossover
+  // (scripts/pair_check.py small): below ~2.4 M outputs or at K <= 384 the single-CTA tiles are 0.3-1.4 us faster
   bool pair = false;
-  if (pair_mode() != 0 && c_dt == MAGIC_BF16 && !epi.rowsum && epi.beta == 0.f && N >= 256 && M >= 512 && P.total_kb >= 4) {
+  if (pair_mode() != 0 && c_dt == MAGIC_BF16 && !epi.rowsum && epi.beta == 0.f && N >= 256 && M >= 512 && P.total_kb >= 8) {
     const long pt = (long)((M + 255) / 256) * ((N + 255) / 256);
     pair = pt * 4 >= sms || pair_mode() == 2;
   }

@@ -200,9 +200,9 @@ class _Ctx:
         return float(dropout_module.p) if self.training else 0.0
 
 
-def _ln(x, m, fc, res=None, p_in=0.0, p_out=0.0):
+def _ln(x, m, fc, res=None, p_in=0.0, p_out=0.0, link=None):
     return ops.layer_norm(x, m.weight, m.bias, m.eps, res=res, p_in=p_in, salt_in=fc.salt(), p_out=p_out,
-                          salt_out=fc.salt())
+                          salt_out=fc.salt(), link=link)
 
 
 def _attn_block(att, x, ctx_kv, B, Lq, Lk, key_lens, fc, dists=None, sprel=None):
@@ -214,26 +214,29 @@ def _attn_block(att, x, ctx_kv, B, Lq, Lk, key_lens, fc, dists=None, sprel=None)
     pdrop = fc.p(sa.dropout)
     sw = sprel.weight if sprel is not None else None
     sb = sprel.bias if sprel is not None else None
+    # y = LN(x + f(x)): the residual-branch gradient rides the dgrad GEMM of f's first linear (ops.GradLink)
+    link = ops.GradLink() if (x.requires_grad and torch.is_grad_enabled()) else None
     if ctx_kv is None:
         qkv = ops.packed_linear(x, [sa.query.weight, sa.key.weight, sa.value.weight],
-                                [sa.query.bias, sa.key.bias, sa.value.bias])
+                                [sa.query.bias, sa.key.bias, sa.value.bias], link=link)
         o, pbar = ops.attention(qkv, None, 0, h, 2 * h, B, H, Lq, Lk, key_lens, dists, sw, sb, fc.want_attn, pdrop,
                                 fc.salt())
     else:
-        q = ops.linear(x, sa.query.weight, sa.query.bias)
+        q = ops.linear(x, sa.query.weight, sa.query.bias, link=link)
         kv = ops.packed_linear(ctx_kv, [sa.key.weight, sa.value.weight], [sa.key.bias, sa.value.bias])
         o, pbar = ops.attention(q, kv, 0, 0, h, B, H, Lq, Lk, key_lens, None, None, None, fc.want_attn, pdrop,
                                 fc.salt())
     so = att.output
     d = ops.linear(o, so.dense.weight, so.dense.bias)
-    y = _ln(d, so.LayerNorm, fc, res=x, p_in=fc.p(so.dropout))
+    y = _ln(d, so.LayerNorm, fc, res=x, p_in=fc.p(so.dropout), link=link)
     return y, pbar
 
 
 def _ffn_block(layer, x, fc):
+    link = ops.GradLink() if (x.requires_grad and torch.is_grad_enabled()) else None
     f = ops.ffn(x, layer.intermediate.dense.weight, layer.intermediate.dense.bias, layer.output.dense.weight,
-                layer.output.dense.bias, act=L.ACT_GELU)
-    return _ln(f, layer.output.LayerNorm, fc, res=x, p_in=fc.p(layer.output.dropout))
+                layer.output.dense.bias, act=L.ACT_GELU, link=link)
+    return _ln(f, layer.output.LayerNorm, fc, res=x, p_in=fc.p(layer.output.dropout), link=link)
 
 
 def _cross_encoder(enc, x, ctx, B, Lx, Lc, x_lens, c_lens, fc, dists=None, sprel=None):

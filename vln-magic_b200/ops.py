@@ -114,12 +114,29 @@ def _rows2d(t):
     return t
 
 
-def _lin_dgrad(dy2, w, dx, act=0, dact_pre=None, drop_p=0.0, salt=0, seed=None):
+def _lin_dgrad(dy2, w, dx, act=0, dact_pre=None, drop_p=0.0, salt=0, seed=None, residual=None):
     M, N = dy2.shape
     K = w.shape[1]
     wo = _wop(w)
     gemm(dy2, dy2.stride(0), 1, wo, K, 1, dx, M, K, N, act=act, dact_pre=dact_pre, drop_p=drop_p, salt=salt,
-         seed=seed)
+         seed=seed, residual=residual)
+
+
+class GradLink:
+    """Side channel between the two consumers of a sublayer input x in `y = LN(x + f(x))`: LayerNorm's backward
+    parks the residual-branch gradient here (and reports None to autograd), the first linear of f picks it up and
+    adds it in the epilogue of its dgrad GEMM, so x receives ONE gradient and autograd launches no `add` kernel.
+    LayerNorm's backward always runs before f's first linear (f's output feeds the LayerNorm)."""
+    __slots__ = ("dres",)
+
+    def __init__(self):
+        self.dres = None
+
+    def take(self, like):
+        d, self.dres = self.dres, None
+        if d is not None and (d.dtype != like.dtype or d.shape != like.shape or not d.is_contiguous()):
+            d = d.to(like.dtype).reshape(like.shape).contiguous()
+        return d
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -221,7 +238,8 @@ class LinearFn(torch.autograd.Function):
     """y = drop(act(x W^T + b)) (+ residual)."""
 
     @staticmethod
-    def forward(ctx, x, w, bias, act, residual, drop_p, salt, pad_out=False):
+    def forward(ctx, x, w, bias, act, residual, drop_p, salt, pad_out=False, link=None):
+        ctx.link = link
         x2 = x.reshape(-1, x.shape[-1]).contiguous()
         M, N = x2.shape[0], w.shape[0]
         if pad_out and N % 8 != 0:
@@ -251,22 +269,25 @@ class LinearFn(torch.autograd.Function):
         else:
             dz = dy2
         dx = None
+        gres = ctx.link.take(x2) if ctx.link is not None else None
         if ctx.needs_input_grad[0]:
             if dz.shape[1] >= 4096 and x2.dtype != torch.float32:
                 # vocabulary-sized reduction with a tiny output (MLM decoder dgrad): fp32 C so the GEMM may split K
                 dx32 = torch.empty(x2.shape, dtype=torch.float32, device=x2.device)
                 _lin_dgrad(dz, w, dx32)
                 dx = dx32.to(x2.dtype)
+                if gres is not None:
+                    dx.add_(gres)
             else:
                 dx = torch.empty_like(x2)
-                _lin_dgrad(dz, w, dx)
+                _lin_dgrad(dz, w, dx, residual=gres)
             dx = dx.view(xshape)
         rw, rb = _lin_wgrad(dz, x2, w, bias)
-        return dx, rw, rb, None, dres, None, None, None
+        return dx, rw, rb, None, dres, None, None, None, None
 
 
-def linear(x, w, bias=None, act=0, residual=None, drop_p=0.0, salt=0, pad_out=False):
-    return LinearFn.apply(x, w, bias, act, residual, drop_p if _DROP_ON else 0.0, salt, pad_out)
+def linear(x, w, bias=None, act=0, residual=None, drop_p=0.0, salt=0, pad_out=False, link=None):
+    return LinearFn.apply(x, w, bias, act, residual, drop_p if _DROP_ON else 0.0, salt, pad_out, link)
 
 
 def _adjacent(ts):
@@ -284,7 +305,8 @@ class PackedLinearFn(torch.autograd.Function):
     If the weights (and their grad sinks) are adjacent in the arena this is a single GEMM each way."""
 
     @staticmethod
-    def forward(ctx, x, n, *wb):
+    def forward(ctx, x, n, link, *wb):
+        ctx.link = link
         ws, bs = wb[:n], wb[n:]
         K = x.shape[-1]
         x2 = x.reshape(-1, K).contiguous()
@@ -314,15 +336,18 @@ class PackedLinearFn(torch.autograd.Function):
         dy2 = dy.reshape(M, Nt).contiguous()
         wops = [_wop(w) for w in ws]
         dx = None
+        gres = ctx.link.take(x2) if ctx.link is not None else None
         if ctx.needs_input_grad[0]:
             dx = torch.empty_like(x2)
             if _adjacent(wops):
-                gemm(dy2, Nt, 1, wops[0], K, 1, dx, M, K, Nt)
+                gemm(dy2, Nt, 1, wops[0], K, 1, dx, M, K, Nt, residual=gres)
             else:
                 off = 0
                 for i, (w, Ni) in enumerate(zip(wops, Ns)):
                     gemm(dy2[:, off:off + Ni], Nt, 1, w, K, 1, dx, M, K, Ni, beta=0.0 if i == 0 else 1.0)
                     off += Ni
+                if gres is not None:
+                    dx.add_(gres)
             dx = dx.view(xshape)
         gws = [getattr(w, "_magic_grad", None) for w in ws]
         gbs = [getattr(b, "_magic_grad", None) for b in bs]
@@ -341,11 +366,11 @@ class PackedLinearFn(torch.autograd.Function):
                 gb, rbs[i], _ = _sink(b)
                 gemm_wgrad(dv, x2, gw, gb, M, Ni, K, beta)
                 off += Ni
-        return (dx, None, *rws, *rbs)
+        return (dx, None, None, *rws, *rbs)
 
 
-def packed_linear(x, ws, bs):
-    return PackedLinearFn.apply(x, len(ws), *ws, *bs)
+def packed_linear(x, ws, bs, link=None):
+    return PackedLinearFn.apply(x, len(ws), link, *ws, *bs)
 
 
 class FFNFn(torch.autograd.Function):
@@ -353,7 +378,8 @@ class FFNFn(torch.autograd.Function):
     epilogue of the dgrad GEMM."""
 
     @staticmethod
-    def forward(ctx, x, w1, b1, w2, b2, act, residual, drop_p, salt, drop_out_p, salt_out):
+    def forward(ctx, x, w1, b1, w2, b2, act, residual, drop_p, salt, drop_out_p, salt_out, link=None):
+        ctx.link = link
         x2 = x.reshape(-1, x.shape[-1]).contiguous()
         M = x2.shape[0]
         I, N = w1.shape[0], w2.shape[0]
@@ -383,25 +409,27 @@ class FFNFn(torch.autograd.Function):
         _lin_dgrad(dy2, w2, dz, act=act, dact_pre=pre, drop_p=drop_p, salt=salt, seed=seed)
         rw2, rb2 = _lin_wgrad(dy2, hmid, w2, b2)
         dx = None
+        gres = ctx.link.take(x2) if ctx.link is not None else None
         if ctx.needs_input_grad[0]:
             dx = torch.empty_like(x2)
-            _lin_dgrad(dz, w1, dx)
+            _lin_dgrad(dz, w1, dx, residual=gres)
             dx = dx.view(xshape)
         rw1, rb1 = _lin_wgrad(dz, x2, w1, b1)
-        return dx, rw1, rb1, rw2, rb2, None, (dy if has_res else None), None, None, None, None
+        return dx, rw1, rb1, rw2, rb2, None, (dy if has_res else None), None, None, None, None, None
 
 
-def ffn(x, w1, b1, w2, b2, act=L.ACT_GELU, residual=None, drop_p=0.0, salt=0, drop_out_p=0.0, salt_out=0):
+def ffn(x, w1, b1, w2, b2, act=L.ACT_GELU, residual=None, drop_p=0.0, salt=0, drop_out_p=0.0, salt_out=0, link=None):
     if not _DROP_ON:
         drop_p = drop_out_p = 0.0
-    return FFNFn.apply(x, w1, b1, w2, b2, act, residual, drop_p, salt, drop_out_p, salt_out)
+    return FFNFn.apply(x, w1, b1, w2, b2, act, residual, drop_p, salt, drop_out_p, salt_out, link)
 
 
 class LayerNormFn(torch.autograd.Function):
     """y = drop_out(LN(drop_in(x) + res))."""
 
     @staticmethod
-    def forward(ctx, x, res, gamma, beta, eps, p_in, salt_in, p_out, salt_out):
+    def forward(ctx, x, res, gamma, beta, eps, p_in, salt_in, p_out, salt_out, link=None):
+        ctx.link = link
         h = x.shape[-1]
         x2 = x.reshape(-1, h).contiguous()
         r2 = res.reshape(-1, h).contiguous() if res is not None else None
@@ -432,13 +460,16 @@ class LayerNormFn(torch.autograd.Function):
         dresv = None
         if r2 is not None:
             dresv = dres.view(shape) if dres is not None else dxv
-        return dxv, dresv, rg, rb, None, None, None, None, None
+            if ctx.link is not None and ctx.needs_input_grad[1]:
+                ctx.link.dres = dres if dres is not None else dx  # consumed by the dgrad GEMM of the sublayer's first linear
+                dresv = None
+        return dxv, dresv, rg, rb, None, None, None, None, None, None
 
 
-def layer_norm(x, gamma, beta, eps, res=None, p_in=0.0, salt_in=0, p_out=0.0, salt_out=0):
+def layer_norm(x, gamma, beta, eps, res=None, p_in=0.0, salt_in=0, p_out=0.0, salt_out=0, link=None):
     if not _DROP_ON:
         p_in = p_out = 0.0
-    return LayerNormFn.apply(x, res, gamma, beta, eps, p_in, salt_in, p_out, salt_out)
+    return LayerNormFn.apply(x, res, gamma, beta, eps, p_in, salt_in, p_out, salt_out, link)
 
 
 class EmbedLNFn(torch.autograd.Function):

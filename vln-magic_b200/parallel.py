@@ -52,10 +52,14 @@ class FlatAllReduce:
     def __call__(self):
         if self.world == 1:
             return
-        handles = [dist.all_reduce(self.flat[lo:hi], op=dist.ReduceOp.SUM, async_op=True) for lo, hi in self.bounds]
+        # NCCL averages inside the collective (no extra pass over the arena); gloo (CPU tests) has no AVG
+        avg = dist.get_backend() == "nccl"
+        op = dist.ReduceOp.AVG if avg else dist.ReduceOp.SUM
+        handles = [dist.all_reduce(self.flat[lo:hi], op=op, async_op=True) for lo, hi in self.bounds]
         for h in handles:
             h.wait()
-        self.flat.mul_(1.0 / self.world)
+        if not avg:
+            self.flat.mul_(1.0 / self.world)
 
 
 def broadcast_flat(flat, src=0):
