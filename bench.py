@@ -69,9 +69,13 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+                                          "-i", str(self.index), "-lms", "20"], stdout=subprocess.PIPE, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
+            t0 = time.time()
+            while not self.rows and time.time() - t0 < 2.0:  # nvidia-smi takes ~0.1 s to come up: be live first
+                time.sleep(0.005)
+            self.rows.clear()
         except Exception:
             self.proc = None
 
@@ -210,6 +214,7 @@ def family_cost(name, a):
 
 
 OUTLIERS = {}
+WORKLOAD_NAME = None
 
 
 def summarise_profile(prof, n_steps, pk):
@@ -256,6 +261,17 @@ def summarise_profile(prof, n_steps, pk):
         ach = v["bytes"] / (v["ms_per_step"] * 1e-3) / 1e9
         roof = dict(kernel=name, bound="hbm", achieved=ach, peak=pk["hbm"], unit="GB/s", frac=ach / pk["hbm"],
                     traffic=None, peak_source=pk["src"])
+    # DRAM traffic per launch of the dominant kernel from the committed `ncu --set full` capture of this workload
+    # (profiles/traffic.json, written by scripts/summarize_ncu.py traffic); null when no capture covers it
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        ent = tr.get(WORKLOAD_NAME, {}).get(name)
+        if ent:
+            roof["traffic"] = ent["dram_bytes_per_launch"]
+            roof["traffic_source"] = ent["source"]
+            roof["algorithmic_bytes_per_launch"] = v["bytes"] / max(v["calls_per_step"], 1)
+    except Exception:
+        pass
     roof["avg_launch_us"] = v["ms_per_step"] * 1e3 / max(v["calls_per_step"], 1)
     roof["share_of_step_kernel_time"] = v["share"]
     fams = {k: dict(ms_per_step=round(x["ms_per_step"], 4), calls=round(x["calls_per_step"], 1),
@@ -353,6 +369,8 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     w = WORKLOADS[args.workload]
+    global WORKLOAD_NAME
+    WORKLOAD_NAME = args.workload
     pk = peaks()
     cfg_s, cfg_t = make_cfgs(w, args.dropout)
     dtype = torch.bfloat16 if args.dtype == "bf16" else torch.float32
@@ -437,8 +455,8 @@ def run_ours(args):
     sync_all()
     ms = e0.elapsed_time(e1)
     launches = _lib.COUNTERS["launches"] - c0["launches"]
-    clocks = clk.stop() if rank == 0 else None
     if args.timed_only:
+        clk.stop() if rank == 0 else None
         sys.stderr.write(f"timed-only: {ms / args.steps:.3f} ms/step, {launches} launches\n")
         if world > 1:
             dist.destroy_process_group()
@@ -453,6 +471,7 @@ def run_ours(args):
     f1.record()
     sync_all()
     ms_e2e = max(f0.elapsed_time(f1), (time.perf_counter() - t0) * 1e3)
+    clocks = clk.stop() if rank == 0 else None  # sampled (20 ms period) across BOTH timed regions: device-resident and e2e
     t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)

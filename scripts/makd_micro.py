@@ -43,7 +43,7 @@ def timeit(fn):
 
 
 def main():
-    dtype = torch.float32 if (len(sys.argv) > 1 and sys.argv[1] == "f32") else torch.bfloat16
+    dtype = torch.float32 if "f32" in sys.argv else torch.bfloat16
     B, L, T, G, V, h = 64, 80, 5, 20, 37, 768
     hid = [(B, L * h), (B * T, 36 * h), (B * T, h), (B, G * h), (B, V * h)]
     maps = [(B, L * L)] * 6 + [(B * T, 36 * 36)] * 2 + [(B, G * G), (B, G * L)] * 3 + [(B, V * V), (B, V * L)] * 3
@@ -69,6 +69,22 @@ def main():
     segs_f = [ops._mk_segs(ps, False) for ps in sets]
     segs_b = [ops._mk_segs(ps, True) for ps in sets]
     pk = peak()
+    if "once" in sys.argv:  # profiling aid: every kernel twice, eagerly, nothing else (ncu -k regex:makd -c 8)
+        R, C, ld = 768, 50265, 50272
+        ss = torch.randn(R, ld, device=dev).to(dtype)[:, :C]
+        ts = torch.randn(R, ld, device=dev).to(dtype)[:, :C]
+        ds = torch.empty(R, ld, device=dev, dtype=dtype)[:, :C]
+        w = torch.rand(R, device=dev)
+        stats, kl, g1 = torch.empty(R, 2, device=dev), torch.empty(1, device=dev), torch.ones(1, device=dev)
+        for i in range(2):
+            _lib.call("magic_makd_mse_fwd", segs_f[i], n, loss.data_ptr(), _lib.stream())
+            _lib.call("magic_makd_mse_bwd", segs_b[i], n, None, gtot.data_ptr(), _lib.stream())
+            _lib.call("magic_makd_kl_fwd", ss.data_ptr(), ts.data_ptr(), R, C, ld, 2.0, w.data_ptr(), 4.0 / R, None,
+                      stats.data_ptr(), kl.data_ptr(), _lib.dt(ss), _lib.stream())
+            _lib.call("magic_makd_kl_bwd", ss.data_ptr(), ts.data_ptr(), ds.data_ptr(), R, C, ld, 2.0, w.data_ptr(),
+                      4.0 / R, None, stats.data_ptr(), g1.data_ptr(), _lib.dt(ss), _lib.stream())
+        torch.cuda.synchronize()
+        return
     us = timeit(lambda i: _lib.call("magic_makd_mse_fwd", segs_f[i], n, loss.data_ptr(), _lib.stream()))
     print(f"makd_mse fwd  {n} segments {by / 1e6:7.1f} MB: {us:7.2f} us  {by / us / 1e3:7.1f} GB/s  "
           f"{by / us / 1e3 / pk:.3f} of {pk:.0f}")

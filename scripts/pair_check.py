@@ -14,6 +14,8 @@ if len(sys.argv) > 1 and sys.argv[1] == "small":
               (2560, 3072, 768), (2560, 768, 3072), (1184, 3072, 768), (1184, 768, 3072), (5760, 768, 768),
               (5120, 256, 768), (5120, 512, 512), (5120, 384, 384), (5120, 1536, 384), (5120, 384, 1536),
               (5120, 256, 256), (5120, 1024, 256), (5120, 256, 1024), (11520, 512, 128)]
+if len(sys.argv) > 1 and sys.argv[1] == "pair_only":
+    SHAPES = [(5120, 768, 3072), (5120, 3072, 768), (11520, 768, 768), (8192, 8192, 8192)]
 for (M, N, K) in SHAPES:
     x = torch.randn(M, K, device=dev).bfloat16()
     w = (torch.randn(N, K, device=dev) * 0.05).bfloat16()

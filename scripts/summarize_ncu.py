@@ -66,8 +66,15 @@ WANT = [
 
 
 def full(path):
-    out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    """`path`: a .ncu-rep, or the `ncu -i <rep> --page raw --csv` dump of one (scripts/profile_round.sh reduces the
+    captures to CSV on the GPU box: the reports themselves are too large to bring back)."""
+    if path.endswith(".csv"):
+        out = open(path).read()
+    else:
+        out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(out)))
+    while rows and (not rows[0] or rows[0][0] != "ID"):
+        rows.pop(0)
     hdr, units = rows[0], rows[1]
     cols = [(lab, hdr.index(m)) for m, lab in WANT if m in hdr]
     ki = hdr.index("Kernel Name")
@@ -81,13 +88,31 @@ def full(path):
             except ValueError:
                 vals.append(r[i])
         print(f"| {n} | `{short(r[ki])}` | " + " | ".join(vals) + " |")
-    tens = [h for h in hdr if "tensor" in h or "tmem" in h.lower()]
-    if tens:
+    if "--tensor" in sys.argv:
+        tens = [h for h in hdr if "tensor" in h or "tmem" in h.lower()]
         print("\nTensor / TMEM metrics present in the capture:")
         for h in tens[:24]:
             i = hdr.index(h)
             print(f"* `{h}` ({units[i]}): " + ", ".join(r[i] for r in rows[2:]))
 
 
+def traffic(path):
+    """Average DRAM bytes (read + write) per launch over the launches of a raw-CSV capture -> one JSON object."""
+    import json
+    out = open(path).read()
+    rows = list(csv.reader(io.StringIO(out)))
+    while rows and (not rows[0] or rows[0][0] != "ID"):
+        rows.pop(0)
+    hdr, units = rows[0], rows[1]
+    ir, iw = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
+    mul = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    tot = 0.0
+    for r in rows[2:]:
+        tot += float(r[ir].replace(",", "")) * mul.get(units[ir], 1.0) + float(r[iw].replace(",", "")) * mul.get(units[iw], 1.0)
+    n = len(rows) - 2
+    print(json.dumps(dict(dram_bytes_per_launch=tot / max(n, 1), launches=n, source=os.path.basename(path))))
+
+
 if __name__ == "__main__":
-    {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2])
+    import os
+    {"launches": launches, "full": full, "traffic": traffic}[sys.argv[1]](sys.argv[2])

@@ -345,6 +345,51 @@ def test_makd_mse_kl_vs_oracle():
     assert abs(got.item() - exp.item()) <= 1e-4 * abs(exp.item()) + 1e-7
 
 
+def test_makd_edge_cases():
+    """Empty segment, rows shorter than one 16-byte vector, many small rows that make one CTA's chunk range span
+    segments, and vocabulary-sized bf16 KL rows with a padded leading dimension (single-pass forward)."""
+    torch.manual_seed(11)
+    B = 5
+    w = torch.rand(B, device=DEV)
+    s0, t0 = torch.zeros(0, 64, device=DEV, requires_grad=True), torch.zeros(0, 64, device=DEV)
+    s1 = torch.randn(B, 3, device=DEV).requires_grad_()
+    t1 = torch.randn(B, 3, device=DEV)
+    s2 = torch.randn(3000, 40, device=DEV).bfloat16().requires_grad_()
+    t2 = torch.randn(3000, 40, device=DEV).bfloat16()
+    s3 = torch.randn(B, 8192 * 2 + 24, device=DEV).bfloat16().requires_grad_()
+    t3 = torch.randn(B, 8192 * 2 + 24, device=DEV).bfloat16()
+    per, tot = ops.makd_mse([(s0, t0, None, 1.0), (s1, t1, w, 1.0 / s1.numel()), (s2, t2, None, 1.0 / s2.numel()),
+                             (s3, t3, w, 1.0 / s3.numel())])
+    refs = [torch.zeros((), device=DEV)]
+    leaves = []
+    for s, t, ww in ((s1, t1, w), (s2, t2, None), (s3, t3, w)):
+        r = s.detach().float().requires_grad_()
+        leaves.append(r)
+        refs.append(KO.mse_loss(r, t.float(), ww))
+    close(per, torch.stack(refs), 1e-2, "makd edge fwd")
+    assert abs(per[0].item()) == 0.0
+    tot.backward()
+    sum(refs[1:]).backward()
+    close(s1.grad, leaves[0].grad, 1e-5, "makd edge ds1")
+    close(s2.grad, leaves[1].grad, 2e-2, "makd edge ds2")
+    close(s3.grad, leaves[2].grad, 2e-2, "makd edge ds3")
+    # vocabulary-sized rows, bf16, leading dimension padded to 50272, masked columns, per-row weights
+    R, C = 24, 50265
+    sl = (torch.randn(R, 50272, device=DEV) * 2).bfloat16()[:, :C]
+    tl = (torch.randn(R, 50272, device=DEV) * 2).bfloat16()[:, :C]
+    sl[:, 100:200] = float("-inf")
+    tl[:, 100:200] = float("-inf")
+    wr = torch.rand(R, device=DEV)
+    x = sl.clone().requires_grad_()  # clone() of a column slice is dense: ops re-pads it
+    got = KD.kd_loss(x, tl, temperature=2, t_sample_weights=wr)
+    y = sl.float().clone().requires_grad_()
+    exp = KO.kd_loss(y, tl.float(), temperature=2, t_sample_weights=wr)
+    assert abs(got.item() - exp.item()) <= 2e-3 * abs(exp.item()), (got.item(), exp.item())
+    got.backward()
+    exp.backward()
+    close(x.grad, y.grad, 2e-2, "kd bf16 vocab grad")
+
+
 def test_dropout_is_consistent_between_fwd_and_bwd():
     """The backward regenerates the forward mask: check d(out)/d(x) numerically along a random direction."""
     torch.manual_seed(8)

@@ -14,12 +14,13 @@
 
 namespace {
 
-constexpr int CH = 4096;        // elements per chunk
 constexpr int NT = 256;         // threads per CTA
+constexpr int CH_ELEMS = 4096;  // elements per chunk (measured: 8192-element bf16 chunks balance worse over the grid)
 
 struct Args {
   MagicMseSeg seg[MAGIC_MAKD_MAX_SEGS];
   long long chunk0[MAGIC_MAKD_MAX_SEGS + 1];
+  int ch[MAGIC_MAKD_MAX_SEGS];  // elements per chunk of segment i
   int nseg;
 };
 
@@ -38,6 +39,7 @@ template <typename T, bool BWD>
 __device__ __forceinline__ float mse_chunk(const MagicMseSeg& S, size_t sb, size_t tb, long long c0, long long c1,
                                            float coef) {
   constexpr int VN = RowVec<T>::N;
+  constexpr int CH = CH_ELEMS;
   constexpr int UN = CH / (NT * VN);  // 4 (fp32) / 2 (bf16) independent 16-byte loads per tensor per thread
   const T* sp = (const T*)S.s + sb;
   const T* tp = (const T*)S.t + tb;
@@ -91,11 +93,13 @@ __global__ void __launch_bounds__(NT) makd_mse_kernel(const __grid_constant__ Ar
   __shared__ float red[32];
   const long long total = A.chunk0[A.nseg];
   const long long ch_beg = total * blockIdx.x / gridDim.x, ch_end = total * (blockIdx.x + 1) / gridDim.x;
-  int si = 0;
+  int si = -1;          // current segment (none yet)
+  long long row = 0, c0 = 0, seg_end = 0;  // position inside it: advanced incrementally, the 64-bit divisions that
+  int CH = 1;                              // locate a chunk run once per (CTA, segment), not once per chunk
   float seg_acc = 0.f;  // this thread's share of segment si, already multiplied by row weight * scale
   for (long long ch = ch_beg; ch < ch_end; ch++) {
-    if (ch >= A.chunk0[si + 1]) {
-      if (!BWD) {
+    if (ch >= seg_end) {
+      if (!BWD && si >= 0) {
         const float tot = block_sum(seg_acc, red);
         if (threadIdx.x == 0 && tot != 0.f) {
           atomicAdd(loss + si, tot);
@@ -103,13 +107,16 @@ __global__ void __launch_bounds__(NT) makd_mse_kernel(const __grid_constant__ Ar
         }
         seg_acc = 0.f;
       }
+      if (si < 0) si = 0;
       while (ch >= A.chunk0[si + 1]) si++;
+      seg_end = A.chunk0[si + 1];
+      CH = A.ch[si];
+      const long long cpr = (A.seg[si].inner + CH - 1) / CH;
+      const long long local = ch - A.chunk0[si];
+      row = local / cpr;
+      c0 = (local % cpr) * CH;
     }
     const MagicMseSeg& S = A.seg[si];
-    const long long cpr = (S.inner + CH - 1) / CH;
-    const long long local = ch - A.chunk0[si];
-    const long long row = local / cpr;
-    const long long c0 = (local % cpr) * CH;
     const long long c1 = min(S.inner, c0 + CH);
     const float wr = (S.w ? S.w[row] : 1.f) * (S.scale_dev ? S.scale_dev[0] : 1.f) * S.scale;
     const size_t sb = (size_t)row * S.s_rs, tb = (size_t)row * S.t_rs;
@@ -127,8 +134,13 @@ __global__ void __launch_bounds__(NT) makd_mse_kernel(const __grid_constant__ Ar
       }
     }
     if (!BWD) seg_acc = fmaf(acc, wr, seg_acc);
+    c0 += CH;  // next chunk of this segment
+    if (c0 >= S.inner) {
+      c0 = 0;
+      row++;
+    }
   }
-  if (!BWD && ch_end > ch_beg) {
+  if (!BWD && si >= 0) {
     const float tot = block_sum(seg_acc, red);
     if (threadIdx.x == 0 && tot != 0.f) {
       atomicAdd(loss + si, tot);
@@ -138,21 +150,29 @@ __global__ void __launch_bounds__(NT) makd_mse_kernel(const __grid_constant__ Ar
 }
 
 // ---- KL on logits: one CTA per row -----------------------------------------------------------------
-__device__ __forceinline__ float fix_inf(float v, float invT) { return (v == -INFINITY ? -1e6f : v) * invT; }
 
 // ONE pass over both rows: per thread an online triple for the teacher (max m_t, z_t = sum e^{x_t - m_t},
 // a = sum e^{x_t - m_t} (x_t - x_s)) and an online pair for the student (m_s, z_s); then
 //   KL(row) = a / z_t - (m_t - m_s) - log(z_t / z_s)          [= sum_c p_t (log p_t - log p_s)]
 // so each logit is read from HBM exactly once (the two-pass form re-read both rows).  The running maxima are
 // updated once per 16-byte vector (vector max first), which removes the per-element branches.
+// The pass works in the log2 domain (u = logit * (1/T) * log2 e): an exponential is then one FADD + one MUFU.EX2,
+// and the kernel is MUFU-bound (2 exponentials per logit pair at 16 / clk / SM), so every saved instruction counts.
 struct KlAcc {
-  float ms, zs, mt, zt, a;
+  float ms, zs, mt, zt, a;  // maxima in log2 units; a = sum 2^{u_t - m_t} (u_t - u_s)
 };
+__device__ __forceinline__ float fast_ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// -inf -> -1e6 (kd_loss.py:21-22) and the temperature / log2 e scale in two instructions
+__device__ __forceinline__ float fix2(float v, float c) { return fmaxf(v, -1e6f) * c; }
 __device__ __forceinline__ void kl_merge(KlAcc& x, const KlAcc& y) {
   const float ms = fmaxf(x.ms, y.ms), mt = fmaxf(x.mt, y.mt);
-  if (ms > -INFINITY) x.zs = x.zs * __expf(x.ms - ms) + y.zs * __expf(y.ms - ms);
+  if (ms > -INFINITY) x.zs = x.zs * fast_ex2(x.ms - ms) + y.zs * fast_ex2(y.ms - ms);
   if (mt > -INFINITY) {
-    const float fx = __expf(x.mt - mt), fy = __expf(y.mt - mt);
+    const float fx = fast_ex2(x.mt - mt), fy = fast_ex2(y.mt - mt);
     x.zt = x.zt * fx + y.zt * fy;
     x.a = x.a * fx + y.a * fy;
   }
@@ -168,19 +188,19 @@ __device__ __forceinline__ void kl_push(KlAcc& k, const float (&xs)[VN], const f
     vt = fmaxf(vt, xt[i]);
   }
   if (vs > k.ms) {
-    k.zs *= __expf(k.ms - vs);  // m = -inf: z is 0 and exp(-inf) = 0
+    k.zs *= fast_ex2(k.ms - vs);  // m = -inf: z is 0 and 2^-inf = 0
     k.ms = vs;
   }
   if (vt > k.mt) {
-    const float f = __expf(k.mt - vt);
+    const float f = fast_ex2(k.mt - vt);
     k.zt *= f;
     k.a *= f;
     k.mt = vt;
   }
 #pragma unroll
   for (int i = 0; i < VN; i++) {
-    k.zs += __expf(xs[i] - k.ms);
-    const float e = __expf(xt[i] - k.mt);
+    k.zs += fast_ex2(xs[i] - k.ms);
+    const float e = fast_ex2(xt[i] - k.mt);
     k.zt += e;
     k.a = fmaf(e, xt[i] - xs[i], k.a);  // e == 0 (masked / far below the max) contributes exactly 0
   }
@@ -197,6 +217,8 @@ __global__ void __launch_bounds__(NT)
   const T* tr = t + (size_t)r * ld;
   constexpr int VN = RowVec<T>::N;
   const int cv = vec ? (C / VN) * VN : 0;
+  const float c2 = invT * 1.4426950408889634f;
+  constexpr float LN2 = 0.6931471805599453f;
   KlAcc k{-INFINITY, 0.f, -INFINITY, 0.f, 0.f};
   int c = threadIdx.x * VN;
   for (; c + NT * VN < cv; c += 2 * NT * VN) {  // two independent 16-byte loads per row in flight
@@ -207,8 +229,8 @@ __global__ void __launch_bounds__(NT)
     RowVec<T>::load_cs(tr + c + NT * VN, b1);
 #pragma unroll
     for (int i = 0; i < VN; i++) {
-      a0[i] = fix_inf(a0[i], invT); b0[i] = fix_inf(b0[i], invT);
-      a1[i] = fix_inf(a1[i], invT); b1[i] = fix_inf(b1[i], invT);
+      a0[i] = fix2(a0[i], c2); b0[i] = fix2(b0[i], c2);
+      a1[i] = fix2(a1[i], c2); b1[i] = fix2(b1[i], c2);
     }
     kl_push<VN>(k, a0, b0);
     kl_push<VN>(k, a1, b1);
@@ -219,12 +241,12 @@ __global__ void __launch_bounds__(NT)
     RowVec<T>::load_cs(tr + c, b0);
 #pragma unroll
     for (int i = 0; i < VN; i++) {
-      a0[i] = fix_inf(a0[i], invT); b0[i] = fix_inf(b0[i], invT);
+      a0[i] = fix2(a0[i], c2); b0[i] = fix2(b0[i], c2);
     }
     kl_push<VN>(k, a0, b0);
   }
-  for (int c2 = cv + threadIdx.x; c2 < C; c2 += NT) {
-    const float xs[1] = {fix_inf(ldf(sr, c2), invT)}, xt[1] = {fix_inf(ldf(tr, c2), invT)};
+  for (int cc = cv + threadIdx.x; cc < C; cc += NT) {
+    const float xs[1] = {fix2(ldf(sr, cc), c2)}, xt[1] = {fix2(ldf(tr, cc), c2)};
     kl_push<1>(k, xs, xt);
   }
 #pragma unroll
@@ -242,9 +264,9 @@ __global__ void __launch_bounds__(NT)
   __syncthreads();
   if (threadIdx.x == 0) {
     for (int i = 1; i < NT / 32; i++) kl_merge(k, part[i]);
-    const float kl = k.a / k.zt - (k.mt - k.ms) - logf(k.zt / k.zs);
-    stats[2 * r] = k.ms + logf(k.zs);
-    stats[2 * r + 1] = k.mt + logf(k.zt);
+    const float kl = LN2 * (k.a / k.zt - (k.mt - k.ms)) - logf(k.zt / k.zs);
+    stats[2 * r] = LN2 * k.ms + logf(k.zs);  // natural-log log-sum-exp of the scaled rows, as backward expects
+    stats[2 * r + 1] = LN2 * k.mt + logf(k.zt);
     atomicAdd(loss, kl * (w ? w[r] : 1.f) * scale * (scale_dev ? scale_dev[0] : 1.f));
   }
 }
@@ -258,7 +280,9 @@ __global__ void __launch_bounds__(NT)
   const T* sr = s + (size_t)r * ld;
   const T* tr = t + (size_t)r * ld;
   T* dr = ds + (size_t)r * ld;
-  const float lse_s = stats[2 * r], lse_t = stats[2 * r + 1];
+  // softmax probabilities as 2^(u - lse * log2 e): one FFMA + one MUFU.EX2 each
+  const float c2 = invT * 1.4426950408889634f;
+  const float l2s = stats[2 * r] * 1.4426950408889634f, l2t = stats[2 * r + 1] * 1.4426950408889634f;
   const float coef = gout[0] * scale * (scale_dev ? scale_dev[0] : 1.f) * (w ? w[r] : 1.f) * invT;
   constexpr int VN = RowVec<T>::N;
   const int cv = vec ? (C / VN) * VN : 0;
@@ -268,13 +292,13 @@ __global__ void __launch_bounds__(NT)
     RowVec<T>::load(tr + c, b);
 #pragma unroll
     for (int i = 0; i < VN; i++)
-      a[i] = a[i] != -INFINITY ? coef * (expf(a[i] * invT - lse_s) - expf(fix_inf(b[i], invT) - lse_t)) : 0.f;
+      a[i] = a[i] != -INFINITY ? coef * (fast_ex2(a[i] * c2 - l2s) - fast_ex2(fix2(b[i], c2) - l2t)) : 0.f;
     RowVec<T>::store(dr + c, a);
   }
   for (int c = cv + threadIdx.x; c < C; c += NT) {
     const float sv = ldf(sr, c);
     float g = 0.f;
-    if (sv != -INFINITY) g = coef * (expf(sv * invT - lse_s) - expf(fix_inf(ldf(tr, c), invT) - lse_t));
+    if (sv != -INFINITY) g = coef * (fast_ex2(sv * c2 - l2s) - fast_ex2(fix2(ldf(tr, c), c2) - l2t));
     stf(dr, c, g);
   }
 }
@@ -314,9 +338,11 @@ int build_args(const MagicMseSeg* segs, int nseg, Args& A, const char* name) {
     A.seg[i] = segs[i];
     A.chunk0[i] = c;
     MAGIC_CHECK_ARG(segs[i].rows >= 0 && segs[i].inner >= 0, "%s: negative extent in segment %d", name, i);
-    c += segs[i].rows * ((segs[i].inner + CH - 1) / CH);
     // 128-bit path: same dtype, 16-byte aligned bases and row strides
     const int esz = segs[i].s_dt == MAGIC_BF16 ? 2 : 4;
+    const int CH = CH_ELEMS;
+    A.ch[i] = CH;
+    c += segs[i].rows * ((segs[i].inner + CH - 1) / CH);
     const int v = 16 / esz;
     bool ok = segs[i].s_dt == segs[i].t_dt && segs[i].s_rs % v == 0 && segs[i].t_rs % v == 0 &&
               ((uintptr_t)segs[i].s % 16 == 0) && ((uintptr_t)segs[i].t % 16 == 0) &&
@@ -338,7 +364,7 @@ int magic_makd_mse_fwd(const MagicMseSeg* segs, int nseg, float* loss, cudaStrea
   MAGIC_CUDA(cudaMemsetAsync(loss, 0, sizeof(float) * (MAGIC_MAKD_MAX_SEGS + 1), st), "magic_makd_mse_fwd");
   const long long total = A.chunk0[nseg];
   if (total == 0) return MAGIC_OK;
-  const long long cap = 16LL * magic_num_sms();
+  const long long cap = 16LL * magic_num_sms();  // measured: 16 x SMs beats one resident wave (8 x SMs) by 4-8 %
   makd_mse_kernel<false><<<(int)(total < cap ? total : cap), NT, 0, st>>>(A, loss, nullptr, nullptr);
   MAGIC_CHECK_LAUNCH("magic_makd_mse_fwd");
   return MAGIC_OK;
@@ -348,7 +374,9 @@ int magic_makd_mse_bwd(const MagicMseSeg* segs, int nseg, const float* gseg, con
   Args A;
   int rc = build_args(segs, nseg, A, "magic_makd_mse_bwd");
   if (rc) return rc;
-  for (int i = 0; i < nseg; i++) MAGIC_CHECK_ARG(segs[i].ds != nullptr, "magic_makd_mse_bwd: segment %d has no ds", i);
+  for (int i = 0; i < nseg; i++)
+    MAGIC_CHECK_ARG(segs[i].ds != nullptr || segs[i].rows * segs[i].inner == 0, "magic_makd_mse_bwd: segment %d has no ds",
+                    i);
   const long long total = A.chunk0[nseg];
   if (total == 0) return MAGIC_OK;
   const long long cap = 16LL * magic_num_sms();
