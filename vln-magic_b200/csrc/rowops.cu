@@ -3,6 +3,8 @@
 // N=1 heads (rowdot), bias-gradient column sums, dtype casts.
 // One warp owns one row of h <= 768 elements held in registers (lane i owns columns i, i+32, ...):
 // every global access of a warp is a contiguous 128 B (fp32) / 64 B (bf16) segment.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "../../include/magic_b200.h"
 
@@ -989,7 +991,12 @@ int magic_ln_bwd(const void* dy, const void* x, const void* res, const float* ga
   const size_t smem = 2 * (size_t)h * sizeof(float);
   if (vec_h(h) && vec_ok(dy, x, res, dx, dres) && vec_ok(gamma, nullptr, nullptr, nullptr, nullptr)) {
     // several rows per warp at the narrow widths: fewer CTAs -> fewer column reductions into dgamma / dbeta
-    const int rpw = h <= 128 ? 4 : h <= 256 ? 2 : 1;
+    static int rpw_env = -1;
+    if (rpw_env < 0) {
+      const char* e = getenv("MAGIC_LN_RPW");  // measurement aid
+      rpw_env = e ? atoi(e) : 0;
+    }
+    const int rpw = rpw_env > 0 ? rpw_env : (h <= 128 ? 4 : h <= 256 ? 2 : 1);
     int grid = (M + ROW_WARPS * rpw - 1) / (ROW_WARPS * rpw);
     const int cap = magic_num_sms() * 4;
     grid = grid < 1 ? 1 : (grid > cap ? cap : grid);
