@@ -31,13 +31,8 @@ typedef __nv_bfloat16 bf16;
 
 constexpr int D = 64;
 constexpr int PITCH = 72;   // bf16 elements per shared row (144 B: 16-byte aligned, ldmatrix conflict-free)
-// rows (queries or keys) per CTA = 16 per warp; the launch picks 1..8 warps so that ONE CTA covers every row of a
-// (batch, head) up to L = 128 (two CTAs at L = 160): K/V (resp. Q/dO) are staged once per (batch, head) instead of once per 64-row tile
-// (at H = 12, L = 160 the 64-row tiling re-read 226 MB per call from L2) and no CTA is left with a single live warp
-constexpr int MAX_WARPS = 8;   // 256 threads keep the 255-register budget the 160-key instantiations need
-constexpr int MAX_THREADS = MAX_WARPS * 32;
-#define TILE ((int)(blockDim.x >> 1))
-#define NTHREADS ((int)blockDim.x)
+constexpr int TILE = 64;    // rows (queries or keys) per CTA: 4 warps x 16
+constexpr int NTHREADS = 128;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -154,7 +149,7 @@ __device__ __forceinline__ void store_rows(bf16* ra, bf16* rb, const float (&o)[
 // forward
 // ===================================================================================================
 template <int NT>
-__global__ void __launch_bounds__(MAX_THREADS) attn_mma_fwd_kernel(AttnParams P, int hc, int csize) {
+__global__ void __launch_bounds__(NTHREADS) attn_mma_fwd_kernel(AttnParams P, int hc, int csize) {
   extern __shared__ __align__(16) uint8_t smraw[];
   pdl_trigger();
   pdl_wait();
@@ -316,7 +311,7 @@ __global__ void __launch_bounds__(MAX_THREADS) attn_mma_fwd_kernel(AttnParams P,
 // backward pass 1 (query-major): delta, dQ, d(sprel)
 // ===================================================================================================
 template <int NT>
-__global__ void __launch_bounds__(MAX_THREADS) attn_mma_bwd_q_kernel(AttnParams P) {
+__global__ void __launch_bounds__(NTHREADS) attn_mma_bwd_q_kernel(AttnParams P) {
   extern __shared__ __align__(16) uint8_t smraw[];
   pdl_trigger();
   pdl_wait();
@@ -435,7 +430,7 @@ __global__ void __launch_bounds__(MAX_THREADS) attn_mma_bwd_q_kernel(AttnParams 
 // backward pass 2 (key-major): dK, dV from the transposed tile
 // ===================================================================================================
 template <int NTQ>
-__global__ void __launch_bounds__(MAX_THREADS) attn_mma_bwd_kv_kernel(AttnParams P) {
+__global__ void __launch_bounds__(NTHREADS) attn_mma_bwd_kv_kernel(AttnParams P) {
   extern __shared__ __align__(16) uint8_t smraw[];
   pdl_trigger();
   pdl_wait();
@@ -565,12 +560,6 @@ bool mma_disabled() {
   return v == 1;
 }
 
-// warps per CTA: one per 16 rows, at most MAX_WARPS (longer row ranges take several CTAs)
-int pick_warps(int rows) {
-  const int nw = (rows + 15) / 16;
-  return nw < 1 ? 1 : (nw > MAX_WARPS ? MAX_WARPS : nw);
-}
-
 int pick_nt(int L) { return L <= 32 ? 4 : L <= 48 ? 6 : L <= 80 ? 10 : L <= 160 ? 20 : 0; }
 
 bool al16(const void* p) { return ((uintptr_t)p & 15) == 0; }
@@ -589,41 +578,38 @@ int launch_fwd(const AttnParams& P, cudaStream_t st) {
   // >= 2 heads (below that the cluster barrier costs more than the serial head walk it replaces: measured)
   int csize = 1;
   if (P.pbar && P.H >= 4) csize = (P.H % 4 == 0 && P.H >= 8) ? 4 : (P.H % 2 == 0) ? 2 : 1;
-  const int nw = pick_warps(P.Lq), tile = nw * 16;
-  const size_t smem = (size_t)(2 * NT * 8 + tile) * PITCH * 2 + (P.pbar ? (size_t)tile * (NT * 8 + 8) * 4 : 0);
+  const size_t smem = (size_t)(2 * NT * 8 + TILE) * PITCH * 2 + (P.pbar ? (size_t)TILE * (NT * 8 + 8) * 4 : 0);
   int rc = set_smem(attn_mma_fwd_kernel<NT>, smem, "magic_attn_fwd");
   if (rc) return rc;
   const int hc = P.pbar ? P.H / csize : 1;
-  dim3 grid((P.Lq + tile - 1) / tile, P.H / hc, P.B);
+  dim3 grid((P.Lq + TILE - 1) / TILE, P.H / hc, P.B);
   if (csize > 1) {
-    MAGIC_CUDA(magic_launch_cluster(attn_mma_fwd_kernel<NT>, grid, dim3(nw * 32), smem, st, dim3(1, csize, 1), P, hc,
+    MAGIC_CUDA(magic_launch_cluster(attn_mma_fwd_kernel<NT>, grid, dim3(NTHREADS), smem, st, dim3(1, csize, 1), P, hc,
                                     csize),
                "magic_attn_fwd(mma, cluster)");
   } else {
-    MAGIC_CUDA(magic_launch(attn_mma_fwd_kernel<NT>, grid, dim3(nw * 32), smem, st, P, hc, 1), "magic_attn_fwd(mma)");
+    MAGIC_CUDA(magic_launch(attn_mma_fwd_kernel<NT>, grid, dim3(NTHREADS), smem, st, P, hc, 1), "magic_attn_fwd(mma)");
   }
   return MAGIC_OK;
 }
 
 template <int NT>
 int launch_bwd_q(const AttnParams& P, cudaStream_t st) {
-  const int nw = pick_warps(P.Lq), tile = nw * 16;
-  const size_t smem = (size_t)(2 * NT * 8 + 2 * tile) * PITCH * 2;
+  const size_t smem = (size_t)(2 * NT * 8 + 2 * TILE) * PITCH * 2;
   int rc = set_smem(attn_mma_bwd_q_kernel<NT>, smem, "magic_attn_bwd");
   if (rc) return rc;
-  dim3 grid((P.Lq + tile - 1) / tile, P.H, P.B);
-  MAGIC_CUDA(magic_launch(attn_mma_bwd_q_kernel<NT>, grid, dim3(nw * 32), smem, st, P), "magic_attn_bwd(mma q)");
+  dim3 grid((P.Lq + TILE - 1) / TILE, P.H, P.B);
+  MAGIC_CUDA(magic_launch(attn_mma_bwd_q_kernel<NT>, grid, dim3(NTHREADS), smem, st, P), "magic_attn_bwd(mma q)");
   return MAGIC_OK;
 }
 
 template <int NTQ>
 int launch_bwd_kv(const AttnParams& P, cudaStream_t st) {
-  const int nw = pick_warps(P.Lk), tile = nw * 16;
-  const size_t smem = (size_t)(2 * NTQ * 8 + 2 * tile) * PITCH * 2 + (size_t)2 * NTQ * 8 * 4;
+  const size_t smem = (size_t)(2 * NTQ * 8 + 2 * TILE) * PITCH * 2 + (size_t)2 * NTQ * 8 * 4;
   int rc = set_smem(attn_mma_bwd_kv_kernel<NTQ>, smem, "magic_attn_bwd");
   if (rc) return rc;
-  dim3 grid((P.Lk + tile - 1) / tile, P.H, P.B);
-  MAGIC_CUDA(magic_launch(attn_mma_bwd_kv_kernel<NTQ>, grid, dim3(nw * 32), smem, st, P), "magic_attn_bwd(mma kv)");
+  dim3 grid((P.Lk + TILE - 1) / TILE, P.H, P.B);
+  MAGIC_CUDA(magic_launch(attn_mma_bwd_kv_kernel<NTQ>, grid, dim3(NTHREADS), smem, st, P), "magic_attn_bwd(mma kv)");
   return MAGIC_OK;
 }
 

@@ -996,7 +996,7 @@ int magic_ln_bwd(const void* dy, const void* x, const void* res, const float* ga
       const char* e = getenv("MAGIC_LN_RPW");  // measurement aid
       rpw_env = e ? atoi(e) : 0;
     }
-    const int rpw = rpw_env > 0 ? rpw_env : (h <= 128 ? 4 : h <= 256 ? 2 : 1);
+    const int rpw = rpw_env > 0 ? rpw_env : (h <= 256 ? 2 : 1);  // measured at h = 128: 2 rows/warp 5.9 us, 1: 7.3, 4: 8.2
     int grid = (M + ROW_WARPS * rpw - 1) / (ROW_WARPS * rpw);
     const int cap = magic_num_sms() * 4;
     grid = grid < 1 ? 1 : (grid > cap ? cap : grid);
