@@ -994,6 +994,8 @@ int gemm_tc_dispatch(const void* A, const void* B, void* C, int c_dt, int M, int
     const long t256 = (long)P.m_tiles * ((N + 255) / 256);
     if (N > 128 && t256 >= sms && P.total_kb >= 4) BN = 256;
     else if (t128 < sms / 2) BN = 64;
+    // (tried: 64-wide tiles where 128-wide ones spill into a mostly empty extra wave, e.g. M = 5120, N = 512 --
+    // slower, 12.7 vs 12.1 us: at BN = 64 only half of the epilogue warps have a 128-byte unit to drain)
   }
   if (force_bn() == 64 || force_bn() == 128 || force_bn() == 256) BN = force_bn();
   if (epi.rowsum && BN > 128) BN = 128;  // the row-sum accumulators need TMEM columns beyond the two tile buffers
