@@ -71,6 +71,14 @@ int magic_attn_bwd(const void* q, const void* k, const void* v, long q_ld, long 
                    int Lk, const int* key_lens, const float* dists, const float* sprel_w, const float* sprel_b,
                    float scale, int dtype, float drop_p, unsigned salt, const unsigned long long* seed_ptr,
                    cudaStream_t st);
+/* One half of the bf16 tensor-core attention backward (run the halves on two streams): part 1 = query-major kernel
+ * (delta, dQ, d sprel), part 2 = key-major kernel (dK, dV) with delta = dO . O from the forward output `out`.  Without a
+ * KD-map gradient only.  Returns MAGIC_ERR_UNSUPPORTED (nothing launched) when not covered: use magic_attn_bwd then. */
+int magic_attn_bwd_part(const void* q, const void* k, const void* v, long q_ld, long k_ld, long v_ld, const void* dout,
+                        const void* out, const float* lse, float* delta, void* dq, void* dk, void* dv, long dq_ld,
+                        long dk_ld, long dv_ld, float* dsprel, int B, int H, int Lq, int Lk, const int* key_lens,
+                        const float* dists, const float* sprel_w, const float* sprel_b, float scale, int dtype,
+                        float drop_p, unsigned salt, const unsigned long long* seed_ptr, int part, cudaStream_t st);
 
 /* ---- LayerNorm (+residual, +dropout): BertSelfOutput / BertOutput / norm1,norm2 / head LNs ---------
  * y = drop_out(LN(drop_in(x) + res) * gamma + beta); stats[r] = (mean, rstd). Parameter grads ACCUMULATE. */

@@ -345,6 +345,45 @@ def test_makd_mse_kl_vs_oracle():
     assert abs(got.item() - exp.item()) <= 1e-4 * abs(exp.item()) + 1e-7
 
 
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 2e-5), (torch.bfloat16, 3e-2)])
+def test_grad_link_matches_autograd_sum(dtype, tol):
+    """y = LN(x + f(x)) with ops.GradLink (the residual-branch gradient rides the dgrad GEMM epilogue of f's first
+    linear, LayerNorm reports None for the residual) gives the same gradients as letting autograd add the two
+    branches -- for the FFN block, the packed-QKV block and a plain linear, and launches no torch add kernel."""
+    torch.manual_seed(21)
+    M, h, I = 300, 128, 512
+    x0 = torch.randn(M, h, device=DEV)
+    gamma, beta = torch.rand(h, device=DEV) + 0.5, torch.randn(h, device=DEV) * 0.1
+    w1, b1 = torch.randn(I, h, device=DEV) * 0.05, torch.randn(I, device=DEV) * 0.05
+    w2, b2 = torch.randn(h, I, device=DEV) * 0.05, torch.randn(h, device=DEV) * 0.05
+    wq = [torch.randn(h, h, device=DEV) * 0.05 for _ in range(3)]
+    bq = [torch.randn(h, device=DEV) * 0.05 for _ in range(3)]
+    g = torch.randn(M, h, device=DEV).to(dtype)
+
+    def run(use_link):
+        x = x0.clone().requires_grad_()
+        xs = x.to(dtype) * 1.0  # non-leaf sublayer input, as inside the model
+        ps = [t.clone().requires_grad_() for t in (w1, b1, w2, b2, gamma, beta)]
+        l1 = ops.GradLink() if use_link else None
+        f = ops.ffn(xs, ps[0], ps[1], ps[2], ps[3], link=l1)
+        y1 = ops.layer_norm(f, ps[4], ps[5], 1e-12, res=xs, link=l1)
+        qs = [t.clone().requires_grad_() for t in wq + bq]
+        l2 = ops.GradLink() if use_link else None
+        qkv = ops.packed_linear(y1, qs[:3], qs[3:], link=l2)
+        d = ops.linear(qkv[:, :h].contiguous() + qkv[:, h:2 * h] + qkv[:, 2 * h:], ps[2][:, :h].contiguous(), None)
+        y2 = ops.layer_norm(d, ps[4], ps[5], 1e-12, res=y1, link=l2)
+        l3 = ops.GradLink() if use_link else None
+        q = ops.linear(y2, qs[0], qs[3], link=l3)
+        y3 = ops.layer_norm(q, ps[4], ps[5], 1e-12, res=y2, link=l3)
+        y3.backward(g)
+        assert all(l is None or l.dres is None for l in (l1, l2, l3))  # every parked gradient was consumed
+        return [x.grad] + [p.grad for p in ps] + [p.grad for p in qs]
+
+    a, b = run(True), run(False)
+    for i, (ga, gb) in enumerate(zip(a, b)):
+        close(ga, gb, tol, f"grad_link tensor {i}")
+
+
 def test_makd_edge_cases():
     """Empty segment, rows shorter than one 16-byte vector, many small rows that make one CTA's chunk range span
     segments, and vocabulary-sized bf16 KL rows with a padded leading dimension (single-pass forward)."""

@@ -79,6 +79,7 @@ class MagicError(RuntimeError):
 
 # kernels launched per C-ABI call (for the launch counter bench.py reports as gpu_launches)
 _LAUNCHES = {"magic_attn_bwd": 2, "magic_scatter_rows": 1, "magic_gmap_aggregate_bwd": 1}
+ERR_UNSUPPORTED = 3
 COUNTERS = {"calls": 0, "launches": 0}
 _PROFILE = None  # {name: [(start_event, end_event, args)]} when bench.py profiles kernel families
 _PROFILE_EVERY = 0  # > 0: keep the stream busy with a delay kernel every N calls so the host stays ahead of the GPU
@@ -120,6 +121,20 @@ def call(name, *args):
         rc = getattr(lib, name)(*args)
     if rc != 0:
         raise MagicError(f"{name} failed (rc={rc}): {lib.magic_last_error().decode()}")
+
+
+def call_rc(name, *args):
+    """Like `call`, for entry points that may decline a shape: returns 0, or ERR_UNSUPPORTED when NOTHING was launched
+    (the caller then takes the general entry point); any other status raises."""
+    lib = load()
+    rc = getattr(lib, name)(*args)
+    if rc == ERR_UNSUPPORTED:
+        return rc
+    if rc != 0:
+        raise MagicError(f"{name} failed (rc={rc}): {lib.magic_last_error().decode()}")
+    COUNTERS["calls"] += 1
+    COUNTERS["launches"] += _LAUNCHES.get(name, 1)
+    return 0
 
 
 def ptr(t):

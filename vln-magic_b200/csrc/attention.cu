@@ -533,4 +533,26 @@ int magic_attn_bwd(const void* q, const void* k, const void* v, long q_ld, long 
   return MAGIC_OK;
 }
 
+
+/* One half of the bf16 tensor-core backward, so the caller can run the two halves on different streams: part 1 =
+ * query-major kernel (delta, dQ, d sprel), part 2 = key-major kernel (dK, dV) with delta recomputed as dO . O from the
+ * forward output `out`.  Only without a KD-map gradient; MAGIC_ERR_UNSUPPORTED (no launch) when the shape / dtype is
+ * not covered -- the caller then uses magic_attn_bwd. */
+int magic_attn_bwd_part(const void* q, const void* k, const void* v, long q_ld, long k_ld, long v_ld, const void* dout,
+                        const void* out, const float* lse, float* delta, void* dq, void* dk, void* dv, long dq_ld,
+                        long dk_ld, long dv_ld, float* dsprel, int B, int H, int Lq, int Lk, const int* key_lens,
+                        const float* dists, const float* sprel_w, const float* sprel_b, float scale, int dtype,
+                        float drop_p, unsigned salt, const unsigned long long* seed_ptr, int part, cudaStream_t st) {
+  if (dtype != MAGIC_BF16 || Lq <= 0 || Lk <= 0 || Lq > MAXL || Lk > MAXL || (part != 1 && part != 2))
+    return MAGIC_ERR_UNSUPPORTED;
+  if (B <= 0) return MAGIC_OK;
+  AttnParams P = make_params(q, k, v, q_ld, k_ld, v_ld, B, H, Lq, Lk, key_lens, dists, sprel_w, sprel_b, scale, drop_p,
+                             salt, seed_ptr);
+  P.lse = const_cast<float*>(lse); P.dout = dout; P.dpbar = nullptr; P.pbar_bs = 0; P.pbar_rs = 0;
+  P.out = const_cast<void*>(out);
+  P.delta = delta; P.dq = dq; P.dk = dk; P.dv = dv; P.dq_ld = dq_ld; P.dk_ld = dk_ld; P.dv_ld = dv_ld;
+  P.dsprel = dsprel;
+  return attn_mma_bwd_part(P, part, st);
+}
+
 }  // extern "C"

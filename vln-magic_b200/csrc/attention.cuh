@@ -25,9 +25,13 @@ struct AttnParams {
   void *dq, *dk, *dv;
   long dq_ld, dk_ld, dv_ld;
   float* dsprel;                // [2] : dw, db
+  int delta_from_out;           // key-major backward: delta[i] = dO_i . O_i from `out` (no KD-map gradient) instead of
+                                // reading `delta` written by the query-major kernel, so the two kernels are independent
 };
 
 // bf16 mma.sync path (attention_mma.cu).  Return MAGIC_ERR_UNSUPPORTED when the shape / alignment is outside
 // what the tensor-core kernels cover; the caller then uses the SIMT kernels.
 int attn_mma_fwd(const AttnParams& P, cudaStream_t st);
 int attn_mma_bwd(const AttnParams& P, cudaStream_t st);
+// part 1: query-major kernel only (delta, dQ, d sprel); part 2: key-major kernel only (dK, dV), delta from dO . O
+int attn_mma_bwd_part(const AttnParams& P, int part, cudaStream_t st);

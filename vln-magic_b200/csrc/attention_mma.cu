@@ -441,6 +441,7 @@ __global__ void __launch_bounds__(NTHREADS) attn_mma_bwd_kv_kernel(AttnParams P)
   bf16* Vs = Ks + TILE * PITCH;
   float* ls = reinterpret_cast<float*>(Vs + TILE * PITCH);  // [LQP] lse
   float* dl = ls + LQP;                                     // [LQP] delta
+  bf16* Os = reinterpret_cast<bf16*>(dl + LQP);             // [LQP][PITCH] forward output, only when delta_from_out
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
   const int b = blockIdx.z, hd = blockIdx.y, k0 = blockIdx.x * TILE;
   const int Lq = P.Lq, Lk = P.Lk, H = P.H;
@@ -454,12 +455,39 @@ __global__ void __launch_bounds__(NTHREADS) attn_mma_bwd_kv_kernel(AttnParams P)
   load_rows(Gs, (const bf16*)P.dout + (size_t)b * Lq * (size_t)(H * D) + hd * D, (long)H * D, Lq, LQP);
   load_rows(Ks, (const bf16*)P.k + ((size_t)b * Lk + k0) * P.k_ld + hd * D, P.k_ld, rows_k, TILE);
   load_rows(Vs, (const bf16*)P.v + ((size_t)b * Lk + k0) * P.v_ld + hd * D, P.v_ld, rows_k, TILE);
+  if (P.delta_from_out)
+    load_rows(Os, (const bf16*)P.out + (size_t)b * Lq * (size_t)(H * D) + hd * D, (long)H * D, Lq, LQP);
   for (int i = threadIdx.x; i < LQP; i += NTHREADS) {
     ls[i] = i < Lq ? P.lse[((size_t)b * H + hd) * Lq + i] : 0.f;
-    dl[i] = i < Lq ? P.delta[((size_t)b * H + hd) * Lq + i] : 0.f;
+    if (!P.delta_from_out) dl[i] = i < Lq ? P.delta[((size_t)b * H + hd) * Lq + i] : 0.f;
   }
   cp_async_wait_all();
   __syncthreads();
+  if (P.delta_from_out) {
+    // delta_i = sum_j P_ij dP_ij = dO_i . O_i (dropout included: O was formed with the same mask), so this kernel
+    // does not wait for the query-major one and the two run as concurrent graph branches
+    for (int i = threadIdx.x; i < LQP; i += NTHREADS) {
+      float acc = 0.f;
+      if (i < Lq) {
+        const uint4* gp = reinterpret_cast<const uint4*>(Gs + i * PITCH);
+        const uint4* op = reinterpret_cast<const uint4*>(Os + i * PITCH);
+#pragma unroll
+        for (int c = 0; c < 8; c++) {
+          const uint4 gv = gp[c], ov = op[c];
+          const __nv_bfloat162* gh = reinterpret_cast<const __nv_bfloat162*>(&gv);
+          const __nv_bfloat162* oh = reinterpret_cast<const __nv_bfloat162*>(&ov);
+#pragma unroll
+          for (int e = 0; e < 4; e++) {
+            const float2 a = __bfloat1622float2(gh[e]), o2 = __bfloat1622float2(oh[e]);
+            acc = fmaf(a.x, o2.x, acc);
+            acc = fmaf(a.y, o2.y, acc);
+          }
+        }
+      }
+      dl[i] = acc;
+    }
+    __syncthreads();
+  }
   if (w * 16 >= rows_k) return;  // no barriers below
 
   const int ja = k0 + w * 16 + g, jb = ja + 8;
@@ -605,7 +633,8 @@ int launch_bwd_q(const AttnParams& P, cudaStream_t st) {
 
 template <int NTQ>
 int launch_bwd_kv(const AttnParams& P, cudaStream_t st) {
-  const size_t smem = (size_t)(2 * NTQ * 8 + 2 * TILE) * PITCH * 2 + (size_t)2 * NTQ * 8 * 4;
+  const size_t smem = (size_t)(2 * NTQ * 8 + 2 * TILE) * PITCH * 2 + (size_t)2 * NTQ * 8 * 4 +
+                      (P.delta_from_out ? (size_t)NTQ * 8 * PITCH * 2 : 0);
   int rc = set_smem(attn_mma_bwd_kv_kernel<NTQ>, smem, "magic_attn_bwd");
   if (rc) return rc;
   dim3 grid((P.Lk + TILE - 1) / TILE, P.H, P.B);
@@ -631,6 +660,28 @@ int attn_mma_fwd(const AttnParams& P, cudaStream_t st) {
   const int nt = pick_nt(P.Lk);
   if (mma_disabled() || nt == 0 || !operands_ok(P) || ((uintptr_t)P.out & 3)) return MAGIC_ERR_UNSUPPORTED;
   DISPATCH_NT(nt, launch_fwd, P, st);
+}
+
+int attn_mma_bwd_part(const AttnParams& P0, int part, cudaStream_t st) {
+  AttnParams P = P0;
+  const int nt = pick_nt(P.Lk), ntq = pick_nt(P.Lq);
+  if (mma_disabled() || nt == 0 || ntq == 0 || !operands_ok(P) || !al16(P.dout) || P.dpbar != nullptr)
+    return MAGIC_ERR_UNSUPPORTED;
+  if (((uintptr_t)P.dq & 3) || ((uintptr_t)P.dk & 3) || ((uintptr_t)P.dv & 3) || (P.dq_ld & 1) || (P.dk_ld & 1) ||
+      (P.dv_ld & 1))
+    return MAGIC_ERR_UNSUPPORTED;
+  if (part == 1) {
+    P.delta_from_out = 0;
+    switch (nt) {
+      case 4: return launch_bwd_q<4>(P, st);
+      case 6: return launch_bwd_q<6>(P, st);
+      case 10: return launch_bwd_q<10>(P, st);
+      default: return launch_bwd_q<20>(P, st);
+    }
+  }
+  if (P.out == nullptr || !al16(P.out)) return MAGIC_ERR_UNSUPPORTED;
+  P.delta_from_out = 1;
+  DISPATCH_NT(ntq, launch_bwd_kv, P, st);
 }
 
 int attn_mma_bwd(const AttnParams& P, cudaStream_t st) {
