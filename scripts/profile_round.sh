@@ -17,8 +17,9 @@ cap() {  # name, kernel regex, skip, count, command...
   rm -f $TMP/$name.ncu-rep
 }
 cap gemm_s gemm_tc 500 24 $B
-MAGIC_TC_PAIR=1 cap gemm_pair gemm_tc 0 8 python scripts/pair_check.py
-cap makd makd 0 12 python scripts/makd_micro.py bf16
-cap attn attn_mma 0 12 python scripts/graph_micro.py attn
+cap gemm_pair gemm_tc 0 8 python scripts/pair_check.py pair_only
+cap makd makd 0 8 python scripts/makd_micro.py bf16 once
+cap attn attn_mma_fwd 0 6 python scripts/graph_micro.py attn
+cap attn_bwd attn_mma_bwd 0 6 python scripts/graph_micro.py attn
 ls -la $OUT | tail -20
 du -sh $OUT

@@ -145,9 +145,14 @@ def distill_step_loss(student, teacher, batch, task, rw, kdl=None):
     """Forward of the (missing upstream) distillation step, SURVEY.md 3.2.
     Returns (mix [total, sup_mean, kd_total], kd result dict, s_out, t_out)."""
     k = kdl_config(kdl)
-    with torch.no_grad():
-        t_out = teacher(batch, task, True, output_kd=True)
-    s_out = student(batch, task, True, output_kd=True)
+
+    def t_fwd():
+        with torch.no_grad():
+            return teacher(batch, task, True, output_kd=True)
+
+    # the frozen teacher's forward and the student's forward are independent until the losses: two stream branches
+    # (the student's small latency-bound kernels fill the gaps of the teacher's wide GEMMs)
+    t_out, s_out = ops.run_branches(t_fwd, lambda: student(batch, task, True, output_kd=True))
     t_w = mktd_weights(t_out["sample_loss"], k["t_sample_preprocess_exp_decay"]) if k["teacher_sample_hard_mining"] \
         else None
     res = compute_kd_losses(student, s_out, t_out, task, rw, t_w, k)

@@ -184,9 +184,13 @@ def enable_branch_streams(flag=True):
 def _record(obj, stream):
     """Tell the caching allocator that tensors produced on the branch stream are consumed on `stream`."""
     if torch.is_tensor(obj):
-        obj.record_stream(stream)
+        if obj.is_cuda:
+            obj.record_stream(stream)
     elif isinstance(obj, (tuple, list)):
         for o in obj:
+            _record(o, stream)
+    elif isinstance(obj, dict):
+        for o in obj.values():
             _record(o, stream)
 
 
@@ -209,9 +213,12 @@ def run_branches(side_fn, main_fn):
         a = side_fn()
         return a, main_fn()
     main = torch.cuda.current_stream()
-    if _BRANCH["stream"] is None:
-        _BRANCH["stream"] = torch.cuda.Stream()
-    side = _BRANCH["stream"]
+    # one side stream per LAUNCHING stream, so branches nest (teacher || student, and inside each text || panorama)
+    # without sharing a stream and picking up each other's work as false dependencies
+    pool = _BRANCH.setdefault("pool", {})
+    side = pool.get(main.cuda_stream)
+    if side is None:
+        side = pool[main.cuda_stream] = torch.cuda.Stream()
     side.wait_stream(main)
     with torch.cuda.stream(side):
         a = side_fn()
