@@ -535,13 +535,17 @@ __global__ void __launch_bounds__(NTHREADS, 1)
   else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
-  pdl_wait();  // everything above overlapped the previous kernel's tail; global memory is touched only below
+  // Programmatic dependent launch: everything above overlapped the previous kernel's tail.  griddepcontrol.wait is
+  // executed per ROLE, as late as possible: the producer walks to its first TMA issue (tile coordinates, first
+  // empty-slot wait -- which also pulls that code into the instruction cache) before it waits, the MMA warp never
+  // touches global memory and does not wait at all, the epilogue warps wait before their first global access.
   if (threadIdx.x == 0) stamp(P, 1);
 
   if (warp == 0) {
     // ===== TMA producer (whole warp walks the loop, one elected lane issues) =====
     int s = 0;
     uint32_t ph = 0;
+    bool pdl_done = false;
     for (int work = wfirst; work < total_work; work += wstride) {
       const int tile = work % (P.m_tiles * P.n_tiles), ks = work / (P.m_tiles * P.n_tiles);
       const int m0 = (tile / P.n_tiles) * (BM * CTAS) + crank * BM, n0 = (tile % P.n_tiles) * BN + crank * B_ROWS;
@@ -551,6 +555,10 @@ __global__ void __launch_bounds__(NTHREADS, 1)
         uint8_t* a_dst = sA + s * A_BYTES;
         uint8_t* b_dst = sB + s * B_BYTES;
         const int k0 = kb * BK;
+        if (!pdl_done) {  // first k-block of this CTA: the operands are the predecessor's outputs
+          pdl_wait();
+          pdl_done = true;
+        }
         if (elect_one()) {
           if (work == 0 && kb == kb0) stamp(P, 14);
           if (CTAS == 2) {
@@ -654,6 +662,7 @@ __global__ void __launch_bounds__(NTHREADS, 1)
     const int hf = (warp - 2) >> 2;
     const int et = (int)threadIdx.x - 64;  // 0..255 within the epilogue warps
     uint8_t* stg = sStage + (warp - 2) * (STG_BUFS * STG_BYTES);
+    pdl_wait();  // bias / residual / seed loads and the stores below touch global memory
     const Dropout dr = make_dropout(P.epi.drop_p, P.epi.seed_ptr, P.epi.salt);
     const bool has_pre = P.epi.pre_out != nullptr;
     const bool use_bias = !DACT && P.epi.bias != nullptr;
