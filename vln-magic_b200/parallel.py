@@ -49,17 +49,27 @@ class FlatAllReduce:
             hi = lo
         self.world = world_size()
 
-    def __call__(self):
+    def start(self):
+        """Issue the bucket all-reduces (asynchronously, on the backend's own stream)."""
+        self._handles, self._avg = [], True
         if self.world == 1:
             return
         # NCCL averages inside the collective (no extra pass over the arena); gloo (CPU tests) has no AVG
-        avg = dist.get_backend() == "nccl"
-        op = dist.ReduceOp.AVG if avg else dist.ReduceOp.SUM
-        handles = [dist.all_reduce(self.flat[lo:hi], op=op, async_op=True) for lo, hi in self.bounds]
-        for h in handles:
+        self._avg = dist.get_backend() == "nccl"
+        op = dist.ReduceOp.AVG if self._avg else dist.ReduceOp.SUM
+        self._handles = [dist.all_reduce(self.flat[lo:hi], op=op, async_op=True) for lo, hi in self.bounds]
+
+    def finish(self):
+        """Order the current stream after the exchange started by `start()`."""
+        for h in self._handles:
             h.wait()
-        if not avg:
+        if self._handles and not self._avg:
             self.flat.mul_(1.0 / self.world)
+        self._handles = []
+
+    def __call__(self):
+        self.start()
+        self.finish()
 
 
 def broadcast_flat(flat, src=0):

@@ -66,12 +66,17 @@ class PretrainStepper:
     # -- the device side of one step -------------------------------------------------------------
     def _finish(self):
         """Gradient exchange + optimizer (kept outside the captured graph when world > 1)."""
+        # both exchanges are issued up front: the teacher's all-reduce (ICoD) runs under the student's optimizer
         if self.allreduce is not None:
-            self.allreduce()
+            self.allreduce.start()
+        if self.co_update and self.t_allreduce is not None:
+            self.t_allreduce.start()
+        if self.allreduce is not None:
+            self.allreduce.finish()
         self.opt.apply()
         if self.co_update:  # agent_base.py:271-274: clip + step the student, then clip + step the teacher
             if self.t_allreduce is not None:
-                self.t_allreduce()
+                self.t_allreduce.finish()
             self.t_opt.apply()
 
     def _device_step(self, task, batch, rw, finish=True):
