@@ -139,6 +139,10 @@ int magic_segsum(const float* vals, const long long* seg, const float* seg_scale
 /* MKTD sample weights: exponential_decay (kd_loss.py:43-44), invert_normalized_losses (kd_loss.py:46-54) */
 int magic_exp_decay(const float* in, float* out, int n, float rate, cudaStream_t st);
 int magic_invert_norm(const float* in, float* out, int n, cudaStream_t st);
+/* per-row KD weights: out[i] = (src ? src[idx ? idx[i] : i] : 1) * (scale ? scale[i] : 1); idx < 0 -> 0.  The
+   gather is the per-row form of t_sample_weights (kd_loss.py:31-40, agent.py:1019); `scale` masks padded rows */
+int magic_row_weights(const float* src, const long long* idx, const float* scale, float* out, int n,
+                      cudaStream_t st);
 /* dz = dy * dropscale * act'(pre): backward of a stand-alone Linear+activation (ClsPrediction, MLM transform) */
 int magic_act_bwd(const void* dy, const void* pre, void* dz, long long n, int act, int dtype, float drop_p,
                   unsigned salt, const unsigned long long* seed_ptr, cudaStream_t st);

@@ -398,6 +398,15 @@ class GlocalTextPathCMT(nn.Module):
             for name in ("txt_emb_w", "kdl_img_w", "kdl_avg_img_w", "global_cross_w", "local_cross_w",
                          "vp_txt_w", "gmap_txt_w"):
                 setattr(self, name, nn.Linear(c.hidden_size, ht))
+            kdl = getattr(c, "kdl", None) or {}
+            kind = kdl.get("kdl_adaptive_ability_weight_type") if hasattr(kdl, "get") else \
+                getattr(kdl, "kdl_adaptive_ability_weight_type", None)
+            if kind == "learned_weight":
+                # learned ability weights used through softplus (agent.py:585,618,678,681,713)
+                # [DECISION] scalars initialised so that softplus(.) = 1
+                for name in ("kdl_txt_weight", "kdl_img_weight", "kdl_global_weight", "kdl_local_weight",
+                             "kdl_predict_weight"):
+                    setattr(self, name, nn.Parameter(torch.full((1,), 0.5413248546129181)))
 
     def forward_text(self, txt_ids, txt_lens):
         x = self.embeddings(txt_ids)
@@ -635,9 +644,10 @@ class GlocalTextPathCMTPreTraining(nn.Module):
 # ----------------------------------------------------------------------------------------------
 # MAKD (pretraining composition of the pinned pieces)
 # ----------------------------------------------------------------------------------------------
-KDL_DEFAULT = dict(kd_alpha=0.5, kd_temperature=2.0, rw_temp=4.0, t_sample_preprocess_exp_decay=0.7,
-                   teacher_sample_hard_mining=True, kdl_tasks=("txt", "img", "local", "global", "predict"),
-                   kdl_task_types=("emb", "attn"))
+KDL_DEFAULT = dict(kd_alpha=0.5, kd_temperature=2.0, rw_temp=4.0, t_sample_preprocess="exp",
+                   t_sample_preprocess_exp_decay=0.7, teacher_sample_hard_mining=True,
+                   kdl_adaptive_ability_weight=True, kdl_adaptive_ability_weight_type="RW",
+                   kdl_tasks=("txt", "img", "local", "global", "predict"), kdl_task_types=("emb", "attn"))
 
 
 def mkrw_weights(gen=None, rw_temp=4.0, device="cpu"):
@@ -645,9 +655,23 @@ def mkrw_weights(gen=None, rw_temp=4.0, device="cpu"):
     return torch.softmax(torch.randn(5, generator=gen).to(device) / rw_temp, 0) * 5
 
 
-def mktd_weights(t_sample_loss, decay=0.7):
-    """agent.py:1013-1020 with optim/kd_loss.py:43-44."""
+def mktd_weights(t_sample_loss, decay=0.7, preprocess="exp"):
+    """agent.py:1013-1020 with optim/kd_loss.py:43-44 ('exp') or :46-54 ('norm'; agent_base.py:172-175)."""
+    if preprocess == "norm":
+        return KD.invert_normalized_losses(t_sample_loss.detach(), decay_rate=decay)
     return KD.exponential_decay(t_sample_loss.detach(), decay_rate=decay)
+
+
+def ability_weights(student, k, rw):
+    """-> (5 multipliers, divisor of the two image embedding losses): agent.py:583-593, 616-625, 675-693, 710-717."""
+    if not k.get("kdl_adaptive_ability_weight", True):
+        return [1.0] * 5, 2.0
+    kind = k.get("kdl_adaptive_ability_weight_type", "RW")
+    if kind == "learned_weight":
+        b = student.bert
+        return [F.softplus(getattr(b, n)).squeeze(0) for n in ("kdl_txt_weight", "kdl_img_weight", "kdl_global_weight",
+                                                               "kdl_local_weight", "kdl_predict_weight")], 2.0
+    return rw, 1.0
 
 
 def makd_losses(student, s_out, t_out, task, rw, t_w, kdl=None, role="t2s"):
@@ -663,6 +687,7 @@ def makd_losses(student, s_out, t_out, task, rw, t_w, kdl=None, role="t2s"):
     if kdl:
         k.update(kdl)
     bert = student.bert
+    rw, img_div = ability_weights(student, k, rw)
     T = k["kd_temperature"]
     emb = "emb" in k["kdl_task_types"]
     att = "attn" in k["kdl_task_types"]
@@ -685,9 +710,9 @@ def makd_losses(student, s_out, t_out, task, rw, t_w, kdl=None, role="t2s"):
         L["txt_emb_loss"] = e(bert.txt_emb_w, "txt_embeds", 0)
         L["txt_attn_loss"] = KD.mse_loss(s_out["txt_attns"][:, :min_len], t_out["txt_attns"][:, :min_len].detach(), t_w) * rw[0] if att else z
     if "img" in k["kdl_tasks"]:
-        # agent.py:620-622: under RW the two image emb losses are NOT halved
-        L["img_emb_loss"] = e(bert.kdl_img_w, "pano_embeds", 1)
-        L["avg_img_emb_loss"] = e(bert.kdl_avg_img_w, "pano_fused_embeds", 1)
+        # agent.py:620-622: under RW the two image emb losses are NOT halved; :618-619, :624-625 otherwise halved
+        L["img_emb_loss"] = e(bert.kdl_img_w, "pano_embeds", 1) / img_div
+        L["avg_img_emb_loss"] = e(bert.kdl_avg_img_w, "pano_fused_embeds", 1) / img_div
         L["img_attn_loss"] = KD.mse_loss(s_out["img_attns"], t_out["img_attns"].detach(), t_w) * rw[1] if att else z  # agent.py:628 unsliced
     gw, lw = (bert.gmap_txt_w, bert.vp_txt_w) if task.startswith("mlm") else (bert.global_cross_w, bert.local_cross_w)
     if "global" in k["kdl_tasks"]:
@@ -713,7 +738,8 @@ def distill_step_loss(student, teacher, batch, task, rw, kdl=None):
         t_out = teacher(batch, task, True)
     s_out = student(batch, task, True)
     sup = s_out["loss"].mean()
-    t_w = mktd_weights(t_out["sample_loss"], k["t_sample_preprocess_exp_decay"]) if k["teacher_sample_hard_mining"] else None
+    t_w = mktd_weights(t_out["sample_loss"], k["t_sample_preprocess_exp_decay"], k["t_sample_preprocess"]) \
+        if k["teacher_sample_hard_mining"] else None
     L = makd_losses(student, s_out, t_out, task, rw, t_w, k)
     kd_total = sum(L.values())
     total = k["kd_alpha"] * kd_total + (1 - k["kd_alpha"]) * sup  # agent.py:1119
@@ -736,8 +762,9 @@ def icod_step_loss(student, teacher, batch, task, rw, t_rw, kdl=None):
         k.update(kdl)
     t_out = teacher(batch, task, True)
     s_out = student(batch, task, True)
-    t_w = mktd_weights(t_out["sample_loss"], k["t_sample_preprocess_exp_decay"]) if k["teacher_sample_hard_mining"] else None
-    s_w = mktd_weights(s_out["sample_loss"], k["t_sample_preprocess_exp_decay"]) if k["teacher_sample_hard_mining"] else None
+    pre = k["t_sample_preprocess"]
+    t_w = mktd_weights(t_out["sample_loss"], k["t_sample_preprocess_exp_decay"], pre) if k["teacher_sample_hard_mining"] else None
+    s_w = mktd_weights(s_out["sample_loss"], k["t_sample_preprocess_exp_decay"], pre) if k["teacher_sample_hard_mining"] else None
     Ls = makd_losses(student, s_out, t_out, task, rw, t_w, k, role="t2s")
     Lt = makd_losses(student, t_out, s_out, task, t_rw, s_w, k, role="s2t")
     total_s = k["kd_alpha"] * sum(Ls.values()) + (1 - k["kd_alpha"]) * s_out["loss"].mean()

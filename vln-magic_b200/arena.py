@@ -49,6 +49,8 @@ class ParamArena:
             if lowp:
                 p._magic_lowp = self.flat_lowp[o:o + k].view(p.shape)
         self.model = model
+        model._magic_arena = self  # the model's forward calls sync_lowp() through this (stale-shadow guard)
+        self._versions = None
         if lowp:
             self.refresh_lowp()
 
@@ -56,21 +58,49 @@ class ParamArena:
         if self.flat_g is not None:
             self.flat_g.zero_()
 
+    def _version_sum(self):
+        return sum(p._version for _, p, _, _ in self.entries)
+
     def refresh_lowp(self):
+        """Recompute the bf16 shadow (the weight operand of every tensor-core GEMM) from the fp32 parameters.
+        The fused optimizer keeps it current; ANY other in-place parameter write (load_state_dict, manual
+        re-initialisation, an EMA copy) must be followed by this -- `sync_lowp()` does it automatically."""
         if self.flat_lowp is not None:
             call("magic_cast", ptr(self.flat_p), F32, ptr(self.flat_lowp), BF16, self.total, stream())
+        self._versions = self._version_sum()
+
+    def sync_lowp(self):
+        """Refresh the shadow if a parameter was written through torch since the last refresh (autograd version
+        counters: `load_state_dict`, `p.copy_()`, `p.data = ...` re-attached by check()).  The fused AdamW writes
+        through raw pointers and refreshes the shadow itself, so the training loop never triggers this.
+        Called at the start of every model forward and every PretrainStepper.step (a ~20 us host loop)."""
+        if self.flat_lowp is None:
+            return False
+        moved = self.check()
+        if moved or self._versions != self._version_sum():
+            self.refresh_lowp()
+            return True
+        return False
 
     def check(self):
-        """Re-attach if something (e.g. .to(), load_state_dict on a new storage) detached the views."""
+        """Re-attach if something (e.g. .to(), load_state_dict on a new storage) detached the views.
+        -> True if any parameter had to be copied back into the arena."""
+        moved = False
         for n, p, o, k in self.entries:
             if p.data.data_ptr() != self.flat_p.data_ptr() + o * 4:
                 view = self.flat_p[o:o + k].view(p.shape)
                 view.copy_(p.data)
                 p.data = view
+                moved = True
             if self.flat_g is not None and (p.grad is None or p.grad.data_ptr() != self.flat_g.data_ptr() + o * 4):
                 p.grad = p._magic_grad
+        if moved and self.flat_lowp is not None:
+            self.refresh_lowp()
+        return moved
 
     def release(self):
+        if getattr(self.model, "_magic_arena", None) is self:
+            del self.model._magic_arena
         for n, p, o, k in self.entries:
             p.data = p.data.clone()
             p.grad = None

@@ -192,8 +192,9 @@ __device__ __forceinline__ float fast_ex2(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-// -inf -> -1e6 (kd_loss.py:21-22) and the temperature / log2 e scale in two instructions
-__device__ __forceinline__ float fix2(float v, float c) { return fmaxf(v, -1e6f) * c; }
+// -inf -> -1e6 (kd_loss.py:21-22: torch.where(x == -inf, -1e6, x) -- NaN and finite values below -1e6 pass through
+// unchanged, as in the reference) and the temperature / log2 e scale
+__device__ __forceinline__ float fix2(float v, float c) { return (v == -INFINITY ? -1e6f : v) * c; }
 __device__ __forceinline__ void kl_merge(KlAcc& x, const KlAcc& y) {
   const float ms = fmaxf(x.ms, y.ms), mt = fmaxf(x.mt, y.mt);
   if (ms > -INFINITY) x.zs = x.zs * fast_ex2(x.ms - ms) + y.zs * fast_ex2(y.ms - ms);

@@ -870,6 +870,20 @@ __global__ void segsum_kernel(const float* __restrict__ vals, const long long* _
   }
 }
 
+// out[i] = (src ? src[idx ? idx[i] : i] : 1) * (scale ? scale[i] : 1): per-row KD weights (MKTD sample weight of
+// the row's sample x the padding mask / count correction of graph_index.pad_batch)
+__global__ void row_weights_kernel(const float* __restrict__ src, const long long* __restrict__ idx,
+                                   const float* __restrict__ scale, float* __restrict__ out, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float v = 1.f;
+  if (src) {
+    const long long j = idx ? idx[i] : (long long)i;
+    v = j >= 0 ? src[j] : 0.f;
+  }
+  out[i] = v * (scale ? scale[i] : 1.f);
+}
+
 __global__ void exp_decay_kernel(const float* __restrict__ in, float* __restrict__ out, int n, float rate) {
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
     out[i] = expf(-rate * in[i]);
@@ -1183,6 +1197,14 @@ int magic_exp_decay(const float* in, float* out, int n, float rate, cudaStream_t
   if (n <= 0) return MAGIC_OK;
   exp_decay_kernel<<<(n + 255) / 256, 256, 0, st>>>(in, out, n, rate);
   MAGIC_CHECK_LAUNCH("magic_exp_decay");
+  return MAGIC_OK;
+}
+
+int magic_row_weights(const float* src, const long long* idx, const float* scale, float* out, int n,
+                      cudaStream_t st) {
+  if (n <= 0) return MAGIC_OK;
+  row_weights_kernel<<<(n + 255) / 256, 256, 0, st>>>(src, idx, scale, out, n);
+  MAGIC_CHECK_LAUNCH("magic_row_weights");
   return MAGIC_OK;
 }
 

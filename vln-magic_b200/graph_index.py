@@ -149,7 +149,8 @@ def pad_batch(batch, n_panos=None, n_masked=None, n_entries=None, n_sources=None
     """Pad a prepared CPU batch to fixed capacities so every batch of a task has the same tensor shapes
     (one CUDA graph per task).  Padded panoramas have a single all-zero view and are referenced by no index
     table; padded masked-token rows gather a zero row, carry label -1 (ignored) and are excluded from the
-    mean through `mlm_inv_n`."""
+    supervised mean through `mlm_inv_n`.  Padding must not change the distillation objective either:
+    `pano_row_scale` / `mlm_row_scale` are per-row KD weights (0 on padding, capacity / real count elsewhere)."""
     ix = batch[INDEX_KEY]
     if n_panos is not None:
         R = batch["traj_view_img_fts"].shape[0]
@@ -163,6 +164,10 @@ def pad_batch(batch, n_panos=None, n_masked=None, n_entries=None, n_sources=None
                 batch[k] = padr(batch[k])
             batch["traj_vp_view_lens"] = padr(batch["traj_vp_view_lens"], 1)
             ix["key_lens_pano"] = padr(ix["key_lens_pano"], 1)
+        # KD row weights of the panorama tensors: 0 on padded panoramas, n_panos / R on real ones, so that a mean over
+        # the padded tensor equals the mean over the real rows (makd.compute_kd_losses)
+        ix["pano_row_scale"] = torch.cat([torch.full((R,), n_panos / max(R, 1), dtype=torch.float32),
+                                          torch.zeros(n_panos - R, dtype=torch.float32)])
     if n_entries is not None:
         if ix["entries"].numel() > n_entries:
             raise ValueError("gmap entry capacity too small")
@@ -188,6 +193,9 @@ def pad_batch(batch, n_panos=None, n_masked=None, n_entries=None, n_sources=None
                 ix["mlm_rows"] = torch.cat([ix["mlm_rows"], torch.full((pad,), -1, dtype=torch.int64)])
                 ix["mlm_labels"] = torch.cat([ix["mlm_labels"], torch.full((pad,), -1, dtype=torch.int64)])
                 ix["mlm_row_sample"] = torch.cat([ix["mlm_row_sample"], torch.zeros(pad, dtype=torch.int64)])
+            # KD row weights of the [n_masked, vocab] logits: padded rows 0, real rows n_masked / n
+            ix["mlm_row_scale"] = torch.cat([torch.full((n,), n_masked / max(n, 1), dtype=torch.float32),
+                                             torch.zeros(n_masked - n, dtype=torch.float32)])
     return batch
 
 

@@ -6,14 +6,16 @@ a second, and the alpha mix (agent.py:1119) through a third."""
 import torch
 
 from . import ops
-from .kd_loss import exponential_decay
+from .kd_loss import exponential_decay, invert_normalized_losses
 
-KDL_DEFAULT = dict(kd_alpha=0.5, t_kd_alpha=0.5, kd_temperature=2.0, rw_temp=4.0, t_sample_preprocess_exp_decay=0.7,
-                   teacher_sample_hard_mining=True, kdl_tasks=("txt", "img", "local", "global", "predict"),
-                   kdl_task_types=("emb", "attn"))
+KDL_DEFAULT = dict(kd_alpha=0.5, t_kd_alpha=0.5, kd_temperature=2.0, rw_temp=4.0,
+                   t_sample_preprocess="exp", t_sample_preprocess_exp_decay=0.7, teacher_sample_hard_mining=True,
+                   kdl_adaptive_ability_weight=True, kdl_adaptive_ability_weight_type="RW",
+                   kdl_tasks=("txt", "img", "local", "global", "predict"), kdl_task_types=("emb", "attn"))
 
 NAMES = ("txt_emb_loss", "txt_attn_loss", "img_emb_loss", "avg_img_emb_loss", "img_attn_loss", "global_emb_loss",
          "global_attn_loss", "local_emb_loss", "local_attn_loss", "predict_loss")
+LEARNED_WEIGHTS = ("kdl_txt_weight", "kdl_img_weight", "kdl_global_weight", "kdl_local_weight", "kdl_predict_weight")
 
 
 def kdl_config(kdl=None):
@@ -38,12 +40,73 @@ def mkrw_weights(rw_temp=4.0, device="cuda", generator=None, out=None, ring=None
     return out
 
 
-def mktd_weights(t_sample_loss, decay=0.7):
-    return exponential_decay(t_sample_loss, decay_rate=decay)
+def grad_weights(current_iter_grads, rw_temp=4.0):
+    """The 'grad' flavour of the adaptive ability weights (agent.py:856-863): softmax(-grads / rw_temp) * 5 over the
+    per-ability gradient magnitudes of the previous iteration, key order [txt, img, local, global, action] as in the
+    reference (:858) -- the result is used positionally like the RW draw."""
+    g = torch.tensor([-float(current_iter_grads[key]) for key in ("txt", "img", "local", "global", "action")])
+    return (torch.softmax(g / rw_temp, 0) * 5).tolist()
+
+
+def mktd_weights(t_sample_loss, decay=0.7, preprocess="exp"):
+    """MKTD per-sample weights (agent_base.py:172-175 selects the function, agent.py:1009,1019 call it with
+    `decay_rate=`): 'exp' -> exponential_decay, 'norm' -> invert_normalized_losses (which ignores decay_rate)."""
+    if preprocess == "exp":
+        return exponential_decay(t_sample_loss, decay_rate=decay)
+    if preprocess == "norm":
+        return invert_normalized_losses(t_sample_loss, decay_rate=decay)
+    raise ValueError("t_sample_preprocess must be 'exp' or 'norm' (map_nav_src/r2r/parser.py:169)")
+
+
+def _sample_weights(out, k):
+    if not k["teacher_sample_hard_mining"]:
+        return None
+    return mktd_weights(out["sample_loss"], k["t_sample_preprocess_exp_decay"], k.get("t_sample_preprocess", "exp"))
 
 
 def _w_for(x, w):
     return w if (w is not None and x.shape[0] == w.shape[0]) else None
+
+
+class _Softplus5(torch.autograd.Function):
+    """w = softplus(p) for the five learned ability weights (agent.py:585,618,678,681,713).  Five scalars of glue on
+    the non-default 'learned_weight' branch: plain tensor arithmetic, no kernel of ours."""
+
+    @staticmethod
+    def forward(ctx, *ps):
+        p = torch.cat([x.detach().reshape(1).float() for x in ps])
+        ctx.save_for_backward(p)
+        return torch.where(p > 20, p, torch.log1p(torch.exp(p)))
+
+    @staticmethod
+    def backward(ctx, dw):
+        (p,) = ctx.saved_tensors
+        g = dw * torch.sigmoid(p)
+        return tuple(g[i:i + 1] for i in range(p.numel()))
+
+
+def ability_weights(student, k, rw):
+    """-> (host multipliers [5], device multipliers [5] or None, divisor of the two image embedding losses).
+    agent.py:583-593, 616-625, 675-693, 710-717: 'RW' / 'grad' multiply by softmax_weights[a] (image embedding losses
+    NOT halved); 'learned_weight' multiplies by softplus(s_model.kdl_<a>_weight) and halves the two image embedding
+    losses; without kdl_adaptive_ability_weight every weight is 1 and the two image embedding losses are halved."""
+    if not k.get("kdl_adaptive_ability_weight", True):
+        return [1.0] * 5, None, 2.0
+    kind = k.get("kdl_adaptive_ability_weight_type", "RW")
+    if kind in ("RW", "grad"):
+        if rw is None:
+            raise ValueError("adaptive ability weights of type %s need the step's weights (mkrw_weights / grad_weights)"
+                             % kind)
+        if torch.is_tensor(rw):
+            return [1.0] * 5, rw.float().contiguous(), 1.0
+        return [float(x) for x in rw], None, 1.0
+    if kind == "learned_weight":
+        ps = [getattr(student.bert, n, None) for n in LEARNED_WEIGHTS]
+        if any(p is None for p in ps):
+            raise ValueError("kdl_adaptive_ability_weight_type='learned_weight' needs the student's kdl_*_weight "
+                             "parameters (build the student with that kdl config)")
+        return [1.0] * 5, _Softplus5.apply(*[p.reshape(1) for p in ps]), 2.0
+    raise ValueError("kdl_adaptive_ability_weight_type must be RW, grad or learned_weight")
 
 
 def compute_kd_losses(student, s_out, t_out, task, rw, t_w, kdl=None, role="t2s"):
@@ -54,22 +117,28 @@ def compute_kd_losses(student, s_out, t_out, task, rw, t_w, kdl=None, role="t2s"
     model learns, prediction = proj(s_out), target = t_out.detach().  role 's2t' (agent.py:553-556, ICoD): the
     LARGE model learns; pass (s_out, t_out) = (large model's outputs, small model's outputs) as agent.py:1022
     does; prediction = s_out, target = proj(t_out).detach() (agent.py:571,605-606,647,665) and `t_w` are the small
-    model's MKTD weights."""
+    model's MKTD weights.
+    Batches padded by graph_index.pad_batch carry `pano_row_scale` / `row_scale` (model outputs): padded panoramas
+    and padded masked-token rows get weight 0 and the means are taken over the real rows."""
     k = kdl_config(kdl)
-    rw_dev = rw if torch.is_tensor(rw) else None
-    if rw_dev is not None:
-        rw_dev = rw_dev.float().contiguous()
-        rw = [1.0] * 5
+    aw, aw_dev, img_div = ability_weights(student, k, rw)
 
     def sdev(i):
-        return rw_dev[i:i + 1] if rw_dev is not None else None
+        return aw_dev.detach()[i:i + 1] if aw_dev is not None else None
 
     bert = student.bert
     emb, att = "emb" in k["kdl_task_types"], "attn" in k["kdl_task_types"]
     tasks = k["kdl_tasks"]
-    pairs, owner = [], []
+    pairs, owner, ability = [], [], []
+    pano_scale = s_out.get("pano_row_scale")
 
-    def add_emb(name, proj, s, t, ri):
+    def row_w(x, pano):
+        w = _w_for(x, t_w)
+        if pano and pano_scale is not None and pano_scale.shape[0] == x.shape[0]:
+            return ops.row_weights(w, None, pano_scale, x.shape[0])
+        return w
+
+    def add_emb(name, proj, s, t, ri, div=1.0, pano=False):
         if not emb:
             return
         if role == "t2s":
@@ -78,10 +147,11 @@ def compute_kd_losses(student, s_out, t_out, task, rw, t_w, kdl=None, role="t2s"
         else:
             with torch.no_grad():
                 ps, t = s, ops.linear(t.detach(), proj.weight, proj.bias)
-        pairs.append((ps, t, _w_for(ps, t_w), rw[ri] / ps.numel(), sdev(ri)))
+        pairs.append((ps, t, row_w(ps, pano), aw[ri] / (ps.numel() * div), sdev(ri)))
         owner.append(name)
+        ability.append(ri)
 
-    def add_attn(name, s_list, t_list, ri, n_layers):
+    def add_attn(name, s_list, t_list, ri, n_layers, pano=False):
         if not att or not s_list:
             return
         items = []
@@ -91,9 +161,11 @@ def compute_kd_losses(student, s_out, t_out, task, rw, t_w, kdl=None, role="t2s"
             else:
                 items.append((sl, tl))
         numel = sum(a.numel() for a, _ in items)
+        w = row_w(items[0][0], pano) if items else None
         for a, b in items:
-            pairs.append((a, b.detach(), _w_for(a, t_w), rw[ri] / numel, sdev(ri)))
+            pairs.append((a, b.detach(), w, aw[ri] / numel, sdev(ri)))
             owner.append(name)
+            ability.append(ri)
 
     # agent.py:560 -- the attention maps are compared on their first min(layers) layers
     min_len = min(len(s_out["txt_attn_list"]), len(t_out["txt_attn_list"])) if att else 0
@@ -101,11 +173,13 @@ def compute_kd_losses(student, s_out, t_out, task, rw, t_w, kdl=None, role="t2s"
         add_emb("txt_emb_loss", bert.txt_emb_w, s_out["txt_embeds"], t_out["txt_embeds"], 0)
         add_attn("txt_attn_loss", s_out["txt_attn_list"], t_out["txt_attn_list"], 0, min_len)
     if "img" in tasks:
-        add_emb("img_emb_loss", bert.kdl_img_w, s_out["pano_embeds"], t_out["pano_embeds"], 1)
-        add_emb("avg_img_emb_loss", bert.kdl_avg_img_w, s_out["pano_fused_embeds"], t_out["pano_fused_embeds"], 1)
+        add_emb("img_emb_loss", bert.kdl_img_w, s_out["pano_embeds"], t_out["pano_embeds"], 1, img_div, pano=True)
+        add_emb("avg_img_emb_loss", bert.kdl_avg_img_w, s_out["pano_fused_embeds"], t_out["pano_fused_embeds"], 1,
+                img_div, pano=True)
         if att and len(s_out["img_attn_list"]) != len(t_out["img_attn_list"]):
             raise ValueError("img_attns of teacher and student must have the same shape (agent.py:628)")
-        add_attn("img_attn_loss", s_out["img_attn_list"], t_out["img_attn_list"], 1, len(s_out["img_attn_list"]))
+        add_attn("img_attn_loss", s_out["img_attn_list"], t_out["img_attn_list"], 1, len(s_out["img_attn_list"]),
+                 pano=True)
     mlm = task.startswith("mlm")
     gw, lw = (bert.gmap_txt_w, bert.vp_txt_w) if mlm else (bert.global_cross_w, bert.local_cross_w)
     nx = min(len(s_out["gmap_attn_list"]), len(t_out["gmap_attn_list"]), max(min_len, 0)) if att else 0
@@ -115,17 +189,20 @@ def compute_kd_losses(student, s_out, t_out, task, rw, t_w, kdl=None, role="t2s"
     if "local" in tasks:
         add_emb("local_emb_loss", lw, s_out["vp_embeds"], t_out["vp_embeds"], 3)
         add_attn("local_attn_loss", s_out["vp_attn_list"], t_out["vp_attn_list"], 3, nx)
-    per_seg, mse_total = ops.makd_mse(pairs) if pairs else (None, None)
+    per_seg, mse_total = ops.makd_mse(pairs, aw_dev, ability) if pairs else (None, None)
     kl = None
     if "predict" in tasks:
-        w = t_w
-        if w is not None and mlm:
-            w = ops.gather_rows(t_w.reshape(-1, 1), s_out["row_sample"]).reshape(-1)  # per-row weights
         s_log, t_log = s_out["logits"], t_out["logits"].detach()
         R, C = s_log.shape
+        w = t_w
+        if mlm:
+            # per-row weights for the [n_masked, vocab] logits: the row's sample weight x the padding mask
+            rs = s_out.get("row_scale")
+            if t_w is not None or rs is not None:
+                w = ops.row_weights(t_w, s_out["row_sample"] if t_w is not None else None, rs, R)
         T = float(k["kd_temperature"])
-        scale = (T * T / R if w is not None else T * T / (R * C)) * rw[4]
-        kl = ops.makd_kl(s_log, t_log, T, w, scale, sdev(4))
+        scale = (T * T / R if t_w is not None else T * T / (R * C)) * aw[4]
+        kl = ops.makd_kl(s_log, t_log, T, w, scale, sdev(4), aw_dev)
     return dict(per_seg=per_seg, owner=owner, mse_total=mse_total, kl=kl)
 
 
@@ -153,8 +230,7 @@ def distill_step_loss(student, teacher, batch, task, rw, kdl=None):
     # the frozen teacher's forward and the student's forward are independent until the losses: two stream branches
     # (the student's small latency-bound kernels fill the gaps of the teacher's wide GEMMs)
     t_out, s_out = ops.run_branches(t_fwd, lambda: student(batch, task, True, output_kd=True))
-    t_w = mktd_weights(t_out["sample_loss"], k["t_sample_preprocess_exp_decay"]) if k["teacher_sample_hard_mining"] \
-        else None
+    t_w = _sample_weights(t_out, k)
     res = compute_kd_losses(student, s_out, t_out, task, rw, t_w, k)
     mix = ops.loss_mix(res["mse_total"], res["kl"], s_out["loss"], k["kd_alpha"], s_out.get("loss_inv_n"))
     return mix, res, s_out, t_out
@@ -168,9 +244,7 @@ def icod_step_loss(student, teacher, batch, task, rw, t_rw, kdl=None):
     k = kdl_config(kdl)
     t_out = teacher(batch, task, True, output_kd=True)
     s_out = student(batch, task, True, output_kd=True)
-    hard = k["teacher_sample_hard_mining"]
-    t_w = mktd_weights(t_out["sample_loss"], k["t_sample_preprocess_exp_decay"]) if hard else None
-    s_w = mktd_weights(s_out["sample_loss"], k["t_sample_preprocess_exp_decay"]) if hard else None
+    t_w, s_w = _sample_weights(t_out, k), _sample_weights(s_out, k)
     res_s = compute_kd_losses(student, s_out, t_out, task, rw, t_w, k, role="t2s")
     res_t = compute_kd_losses(student, t_out, s_out, task, t_rw, s_w, k, role="s2t")
     mix_s = ops.loss_mix(res_s["mse_total"], res_s["kl"], s_out["loss"], k["kd_alpha"], s_out.get("loss_inv_n"))

@@ -180,6 +180,16 @@ class _MLMHead(nn.Module):
 
 
 KD_HEADS = ("txt_emb_w", "kdl_img_w", "kdl_avg_img_w", "global_cross_w", "local_cross_w", "vp_txt_w", "gmap_txt_w")
+# learned ability weights, used through softplus (agent.py:585,618,678,681,713); order = the RW weight order
+KD_LEARNED_WEIGHTS = ("kdl_txt_weight", "kdl_img_weight", "kdl_global_weight", "kdl_local_weight", "kdl_predict_weight")
+SOFTPLUS_ONE = 0.5413248546129181  # softplus(x) = 1: a learned ability weight starts at the non-adaptive value
+
+
+def _kdl_get(c, key, default=None):
+    kdl = getattr(c, "kdl", None)
+    if kdl is None:
+        return default
+    return kdl.get(key, default) if hasattr(kdl, "get") else getattr(kdl, key, default)
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -262,6 +272,9 @@ class GlocalTextPathCMT(nn.Module):
         if _cfg(c, "role", "student") == "student" and _cfg(c, "kd", False) and ht:
             for name in KD_HEADS:
                 setattr(self, name, nn.Linear(c.hidden_size, ht))
+            if _kdl_get(c, "kdl_adaptive_ability_weight_type") == "learned_weight":
+                for name in KD_LEARNED_WEIGHTS:  # [DECISION] one scalar each, initialised so that softplus = 1
+                    setattr(self, name, nn.Parameter(torch.full((1,), SOFTPLUS_ONE)))
 
     # -- text ------------------------------------------------------------------------------------
     def forward_text(self, batch, ix, fc):
@@ -371,7 +384,7 @@ class GlocalTextPathCMT(nn.Module):
             g, v = g.view(B, Lt, h), v.view(B, Lt, h)
         return dict(txt_embeds=txt.view(B, Lt, h), txt_attn_list=txt_attns, pano_embeds=pano,
                     pano_fused_embeds=fused, img_attn_list=img_attns, gmap_embeds=g, gmap_attn_list=g_attn,
-                    vp_embeds=v, vp_attn_list=v_attn)
+                    vp_embeds=v, vp_attn_list=v_attn, pano_row_scale=ix.get("pano_row_scale"))
 
 
 def stack_attns(lst):
@@ -474,6 +487,9 @@ class GlocalTextPathCMTPreTraining(nn.Module):
 
     def forward(self, batch, task, compute_loss=True, output_kd=None):
         """`output_kd` (ours): also return the KD attention maps; default = config.kd (train_r2r_magic.py:134,159)."""
+        arena = getattr(self, "_magic_arena", None)
+        if arena is not None and not torch.cuda.is_current_stream_capturing():
+            arena.sync_lowp()  # a checkpoint loaded after the arena was built must reach the bf16 GEMM operands
         if output_kd is not None:
             prev, self.output_kd = self.output_kd, bool(output_kd)
             try:
@@ -512,7 +528,7 @@ class GlocalTextPathCMTPreTraining(nn.Module):
             return {"predict": logits.float() if logits.dtype != torch.float32 else logits}
         loss = ops.cross_entropy(logits, ix["mlm_labels"], -1)
         o.update(loss=loss, logits=logits, predict=logits, row_sample=ix["mlm_row_sample"],
-                 loss_inv_n=ix.get("mlm_inv_n"),
+                 loss_inv_n=ix.get("mlm_inv_n"), row_scale=ix.get("mlm_row_scale"),
                  sample_loss=ops.segment_mean(loss.detach(), ix["mlm_row_sample"], ix["mlm_inv_count"], B))
         return o
 

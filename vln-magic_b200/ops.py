@@ -872,10 +872,12 @@ def _mk_segs(pairs, with_ds):
 
 
 class MakdMseFn(torch.autograd.Function):
-    """One launch for all MSE segments.  Returns (per-segment losses [n], total scalar)."""
+    """One launch for all MSE segments.  Returns (per-segment losses [n], total scalar).  `aw_dev` (optional device
+    tensor [5]) holds the ability multipliers the segments read through `scale_dev`; when it requires grad (learned
+    ability weights, agent.py:585) backward also returns d total / d aw_dev."""
 
     @staticmethod
-    def forward(ctx, meta, *tensors):
+    def forward(ctx, meta, aw_dev, *tensors):
         n = len(meta)
         ss, ts, ws = tensors[:n], tensors[n:2 * n], tensors[2 * n:3 * n]
         pairs = []
@@ -892,6 +894,8 @@ class MakdMseFn(torch.autograd.Function):
         segs = _mk_segs(pairs, False)
         call("magic_makd_mse_fwd", segs, n, ptr(loss), stream())
         ctx.pairs = pairs
+        ctx.ability = [m.get("ability") for m in meta]
+        ctx.aw = (aw_dev.detach(), loss) if (aw_dev is not None and aw_dev.requires_grad) else None
         return loss[:n], loss[L.MAKD_MAX_SEGS]
 
     @staticmethod
@@ -906,15 +910,23 @@ class MakdMseFn(torch.autograd.Function):
             outs.append(p["ds"])
         segs = _mk_segs(pairs, True)
         call("magic_makd_mse_bwd", segs, n, ptr(dseg), ptr(dtot), stream())
+        g_aw = None
+        if ctx.aw is not None:  # learned ability weights: d/d aw[a] = sum over the ability's segments of (raw loss)
+            aw, loss = ctx.aw
+            idx = torch.tensor(ctx.ability, dtype=torch.int64, device=aw.device)
+            up = (dseg if dseg is not None else 0) + (dtot if dtot is not None else 0)
+            g_aw = torch.zeros_like(aw).index_add_(0, idx, up * loss[:n] / aw[idx])
         ctx.pairs = None
-        return (None, *outs, *([None] * (2 * n)))
+        return (None, g_aw, *outs, *([None] * (2 * n)))
 
 
-def makd_mse(pairs):
+def makd_mse(pairs, aw_dev=None, ability=None):
     """pairs: list of (s, t, w_or_None, scale[, scale_dev]). `scale_dev` is an optional 1-element DEVICE tensor
-    multiplied into the host `scale` (device-resident MKRW weight).  Returns (per-segment losses [n], their sum)."""
-    meta = [dict(scale=float(p[3]), sdev=(p[4] if len(p) > 4 else None)) for p in pairs]
-    return MakdMseFn.apply(meta, *[p[0] for p in pairs], *[p[1] for p in pairs], *[p[2] for p in pairs])
+    multiplied into the host `scale` (device-resident ability weight; a slice of `aw_dev`, `ability[i]` = its index).
+    Returns (per-segment losses [n], their sum)."""
+    meta = [dict(scale=float(p[3]), sdev=(p[4] if len(p) > 4 else None),
+                 ability=(ability[i] if ability is not None else None)) for i, p in enumerate(pairs)]
+    return MakdMseFn.apply(meta, aw_dev, *[p[0] for p in pairs], *[p[1] for p in pairs], *[p[2] for p in pairs])
 
 
 class LossMixFn(torch.autograd.Function):
@@ -947,7 +959,7 @@ def loss_mix(mse_total, kl, sup, alpha, inv_n=None):
 
 class MakdKlFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, s, t, temperature, w, scale, sdev):
+    def forward(ctx, s, t, temperature, w, scale, sdev, aw_dev):
         R, C = s.shape
         s, t = _rows2d(s), _rows2d(t)
         if t.dtype != s.dtype:
@@ -962,6 +974,7 @@ class MakdKlFn(torch.autograd.Function):
              ptr(loss), dt(s), stream())
         ctx.save_for_backward(s, t, w, stats, sdev)
         ctx.meta = (temperature, scale)
+        ctx.aw = (aw_dev.detach(), loss) if (aw_dev is not None and aw_dev.requires_grad) else None
         return loss.view(())
 
     @staticmethod
@@ -973,11 +986,16 @@ class MakdKlFn(torch.autograd.Function):
         ds = torch.empty_strided(s.shape, s.stride(), dtype=s.dtype, device=s.device)
         call("magic_makd_kl_bwd", ptr(s), ptr(t), ptr(ds), R, C, s.stride(0), temperature, ptr(w), scale, ptr(sdev),
              ptr(stats), ptr(g), dt(s), stream())
-        return ds, None, None, None, None, None
+        g_aw = None
+        if ctx.aw is not None:  # the predict ability is index 4 of the ability weights
+            aw, loss = ctx.aw
+            g_aw = torch.zeros_like(aw)
+            g_aw[4:5] = g * loss / aw[4:5]
+        return ds, None, None, None, None, None, g_aw
 
 
-def makd_kl(s, t, temperature, w, scale, scale_dev=None):
-    return MakdKlFn.apply(s, t, float(temperature), w, float(scale), scale_dev)
+def makd_kl(s, t, temperature, w, scale, scale_dev=None, aw_dev=None):
+    return MakdKlFn.apply(s, t, float(temperature), w, float(scale), scale_dev, aw_dev)
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -1129,6 +1147,14 @@ class Cat2Fn(torch.autograd.Function):
 
 def cat2(a, b):
     return Cat2Fn.apply(a, b)
+
+
+def row_weights(src, idx, scale, n):
+    """out[i] = (src[idx[i]] or src[i] or 1) * (scale[i] or 1), fp32 [n]; idx < 0 gives 0.  No autograd (KD weights)."""
+    dev = (src if src is not None else scale).device
+    out = torch.empty(n, dtype=torch.float32, device=dev)
+    call("magic_row_weights", ptr(src), ptr(idx), ptr(scale), ptr(out), n, stream())
+    return out
 
 
 def segment_mean(vals, seg, inv_count, n_seg):

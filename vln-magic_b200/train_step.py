@@ -25,7 +25,7 @@ class _Prefetched:
 class PretrainStepper:
     def __init__(self, student, teacher=None, kdl=None, lr=5e-5, betas=(0.9, 0.98), weight_decay=0.01,
                  max_grad_norm=5.0, use_graphs=False, rw_generator=None, side_stream=True,
-                 branch_streams=True, co_update=False, t_lr=None):
+                 branch_streams=True, co_update=False, t_lr=None, max_graphs=16):
         """co_update=True is ICoD (`--train_kdl_teacher`, agent_base.py:260-279): the teacher is trained too, from
         the s2t losses, with its own arena / AdamW state / clip, and both models step once per batch."""
         self.student, self.teacher = student, teacher
@@ -48,6 +48,8 @@ class PretrainStepper:
         ops.enable_side_stream(side_stream)
         ops.enable_branch_streams(branch_streams)
         self.graphs = {}
+        self.max_graphs = int(max_graphs)  # shape signatures beyond this many run eagerly (no unbounded cache)
+        self._graph_overflow_warned = False
         self.rw_generator = rw_generator
         self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
         self.device = self.arena.device
@@ -161,9 +163,20 @@ class PretrainStepper:
         if self.co_update:
             self.t_opt.set_hyper(None)
         ops.bump_seed(self.device)
-        if not self.use_graphs:
-            return self._device_step(task, batch, rw)
-        return self._graph_step(task, batch, rw)
+        for a in (self.arena, self.t_arena):  # parameters written through torch since the last step (resume, EMA)
+            if a is not None:
+                a.sync_lowp()
+        if self.use_graphs:
+            sig = self._signature(task, batch)
+            if sig in self.graphs or len(self.graphs) < self.max_graphs:
+                return self._graph_step(task, batch, rw, sig)
+            if not self._graph_overflow_warned:
+                self._graph_overflow_warned = True
+                import warnings
+                warnings.warn(f"PretrainStepper: more than {self.max_graphs} batch shape signatures; further shapes run "
+                              "eagerly -- pad batches to fixed capacities (graph_index.pad_batch) to replay one graph "
+                              "per task")
+        return self._device_step(task, batch, rw)
 
     # -- CUDA-graph replay ------------------------------------------------------------------------
     @staticmethod
@@ -179,8 +192,8 @@ class PretrainStepper:
                 sig.append(tuple((kk, tuple(vv.shape) if torch.is_tensor(vv) else vv) for kk, vv in sorted(v.items())))
         return tuple(sig)
 
-    def _graph_step(self, task, batch, rw):
-        sig = self._signature(task, batch)
+    def _graph_step(self, task, batch, rw, sig=None):
+        sig = self._signature(task, batch) if sig is None else sig
         entry = self.graphs.get(sig)
         if entry is None:
             dev = self.device
