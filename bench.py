@@ -4,8 +4,12 @@
   python bench.py --gpus N --steps K --warmup W            our arm (CUDA kernels), one JSON line on rank 0
   python bench.py --impl reference ...                     the oracle port of the reference path on host cores
 
-A "step" = one optimisation step (forward + loss + backward + [all-reduce] + clip + AdamW) of the MAGIC-S
-student on one synthetic batch, tasks alternating MLM / SAP 1:1 (BASELINE.json configs[1]).
+  python bench.py --impl torch_gpu ...                     the same oracle port with stock torch ops on cuda:0 (bf16 autocast)
+
+A "step" = one optimisation step of the distillation hot path on one synthetic batch: frozen teacher (h = 768, 9/2/4)
+forward, MAGIC-S student forward, MAKD losses, backward, [gradient exchange], clip + AdamW; tasks alternate MLM / SAP
+1:1 (BASELINE.json configs[2], the configuration the metric "MLM+SAP+distill step" names).  The other configs ride
+along in the `workloads` sub-dict of the same JSON line.
 """
 import argparse
 import json
@@ -37,6 +41,10 @@ WORKLOADS = {
     "rxr_stress_distill_b128": dict(hidden=128, n_l=6, n_x=3, n_p=2, B=128, L=160, T_max=12, G_max=50,
                                     teacher=dict(hidden=768, n_l=9, n_x=4, n_p=2)),
 }
+# the headline: BASELINE.json's metric is "pretrain samples/s (MLM+SAP+distill step)" = configs[2]
+DEFAULT_WORKLOAD = "magic_s_distill_t768_b64"
+# BASELINE.json configs[1], [2], [3], [4] (in that order): carried in the JSON line's `workloads` sub-dict
+SUB_WORKLOADS = ("magic_s_pretrain_b64", "magic_s_distill_t768_b64", "magic_l_icod_b32", "rxr_stress_distill_b128")
 # forward GFLOP per sample, keyed (hidden, n_l, L): student / teacher shapes of the workloads above
 FWD_GFLOP = {(128, 6, 80): 0.669, (768, 6, 80): 17.29, (768, 9, 80): 22.08, (128, 6, 160): 1.42, (768, 9, 160): 44.9}
 
@@ -176,14 +184,18 @@ def family_cost(name, a):
     if name == "magic_gemm_wgrad":
         M, N, K = a[9], a[10], a[11]
         return 2.0 * M * N * K, M * N * esz(a[1]) + M * K * esz(a[4]) + N * K * 4
-    if name in ("magic_attn_fwd", "magic_attn_bwd"):
+    if name in ("magic_attn_fwd", "magic_attn_bwd", "magic_attn_bwd_part"):
         if name == "magic_attn_fwd":
             B, H, Lq, Lk, dtc = a[11], a[12], a[13], a[14], a[20]
             mul = 1
-        else:
+        elif name == "magic_attn_bwd":
             B, H, Lq, Lk, dtc = a[19], a[20], a[21], a[22], a[28]
             mul = 2.5
-        return 4.0 * B * H * Lq * Lk * 64 * mul, (2 * B * Lq + 2 * B * Lk) * H * 64 * esz(dtc) * (2 if mul > 1 else 1)
+        else:  # one half (query-major or key-major) of the split backward
+            B, H, Lq, Lk, dtc = a[17], a[18], a[19], a[20], a[26]
+            mul = 1.25
+        # bytes: Q, O (+dO, dQ) and K, V (+dK, dV) once each; a backward half touches half of the backward's tensors
+        return 4.0 * B * H * Lq * Lk * 64 * mul, (2 * B * Lq + 2 * B * Lk) * H * 64 * esz(dtc) * (2 if mul > 2 else 1)
     if name in ("magic_ln_fwd", "magic_ln_bwd"):
         M, h, dtc = (a[6], a[7], a[9]) if name == "magic_ln_fwd" else (a[9], a[10], a[11])
         return 0.0, M * h * esz(dtc) * (3 if name == "magic_ln_fwd" else 5)
@@ -213,248 +225,394 @@ def family_cost(name, a):
     return 0.0, 0.0
 
 
-OUTLIERS = {}
 WORKLOAD_NAME = None
 
 
-def summarise_profile(prof, n_steps, pk):
-    fam = {}
-    for name, recs in prof.items():
-        if name == "magic_delay":
-            continue
-        per_call = [e0.elapsed_time(e1) for e0, e1, _ in recs]
-        # one-off stalls inside a bracket (seen: a single 39 ms gap in one attention-backward call of the eager
-        # distillation pass, 1000x its median) are not kernel time: a call above max(20 x median, 1 ms) counts as
-        # the family's median and is reported in `profile_outliers`
-        med = sorted(per_call)[len(per_call) // 2]
-        lim = max(20.0 * med, 1.0)
-        n_out = sum(1 for x in per_call if x > lim)
-        if n_out:
-            OUTLIERS[name] = OUTLIERS.get(name, 0) + n_out
-            per_call = [med if x > lim else x for x in per_call]
-        ms = sum(per_call)
-        if os.environ.get("BENCH_DEBUG_PROFILE"):
-            srt = sorted(per_call)
-            sys.stderr.write(f"[profile] {name}: n={len(srt)} sum={ms:.3f} ms median={srt[len(srt) // 2] * 1e3:.1f} us "
-                             f"max={srt[-1] * 1e3:.1f} us top5={[round(x * 1e3, 1) for x in srt[-5:]]}\n")
-        fl = by = 0.0
-        for _, _, a in recs:
-            f, b = family_cost(name, a)
-            fl += f
-            by += b
-        key = "magic_gemm" if name == "magic_gemm_wgrad" else name  # one kernel (gemm_tc_kernel), one family
-        d = fam.setdefault(key, dict(ms_per_step=0.0, calls_per_step=0.0, flops=0.0, bytes=0.0))
-        d["ms_per_step"] += ms / n_steps
-        d["calls_per_step"] += len(recs) / n_steps
-        d["flops"] += fl / n_steps
-        d["bytes"] += by / n_steps
-    tot = sum(v["ms_per_step"] for v in fam.values()) or 1.0
-    for v in fam.values():
-        v["share"] = v["ms_per_step"] / tot
-    top = max(fam.items(), key=lambda kv: kv[1]["ms_per_step"])
-    name, v = top
-    if v["flops"] > 0 and name == "magic_gemm":
-        ach = v["flops"] / (v["ms_per_step"] * 1e-3) / 1e12
-        roof = dict(kernel=name, bound="tensor", achieved=ach, peak=pk["tf_sus"], unit="TFLOP/s",
-                    frac=ach / pk["tf_sus"], traffic=None, peak_source=pk["src"] + " (sustained)")
-    else:
-        ach = v["bytes"] / (v["ms_per_step"] * 1e-3) / 1e9
-        roof = dict(kernel=name, bound="hbm", achieved=ach, peak=pk["hbm"], unit="GB/s", frac=ach / pk["hbm"],
-                    traffic=None, peak_source=pk["src"])
-    # DRAM traffic per launch of the dominant kernel from the committed `ncu --set full` capture of this workload
-    # (profiles/traffic.json, written by scripts/summarize_ncu.py traffic); null when no capture covers it
-    try:
-        tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-        ent = tr.get(WORKLOAD_NAME, {}).get(name)
-        if ent:
-            roof["traffic"] = ent["dram_bytes_per_launch"]
-            roof["traffic_source"] = ent["source"]
-            roof["algorithmic_bytes_per_launch"] = v["bytes"] / max(v["calls_per_step"], 1)
-    except Exception:
-        pass
-    roof["avg_launch_us"] = v["ms_per_step"] * 1e3 / max(v["calls_per_step"], 1)
-    roof["share_of_step_kernel_time"] = v["share"]
-    fams = {k: dict(ms_per_step=round(x["ms_per_step"], 4), calls=round(x["calls_per_step"], 1),
-                    share=round(x["share"], 3),
-                    tflops=round(x["flops"] / (x["ms_per_step"] * 1e-3) / 1e12, 2) if x["flops"] else None,
-                    gbs=round(x["bytes"] / (x["ms_per_step"] * 1e-3) / 1e9, 1) if x["bytes"] else None)
-            for k, x in sorted(fam.items(), key=lambda kv: -kv[1]["ms_per_step"])[:8]}
-    return roof, fams
-
-
 # ---------------------------------------------------------------------------------------------------
-# CPU arms
+# baselines: the oracle port on the host cores (reference arm / cpu_baseline) and on the GPU (gpu_baseline)
 # ---------------------------------------------------------------------------------------------------
-def cpu_step_rate(w, seconds_budget, sample_B, dropout=0.0, train=True):
-    """Oracle port (fp32 PyTorch) of the same step on the host cores: student fwd+bwd+AdamW, MLM/SAP 1:1."""
+def oracle_step_fn(w, device, dropout, autocast=False, fused_opt=False):
+    """-> (step(i) -> None, batch size): one optimisation step of workload `w` written with stock PyTorch ops only
+    (the oracle port of the missing reference model + the reference's kd_loss arithmetic): frozen-teacher forward,
+    student forward, MAKD losses, alpha mix, backward, clip 5.0, AdamW; ICoD co-update trains both models.
+    MLM / SAP alternate 1:1."""
     from oracle import magic_oracle as O
     from magic_b200 import synth
-    torch.set_num_threads(os.cpu_count())
-    cfg_s, _ = make_cfgs(w, dropout)
+    cfg_s, cfg_t = make_cfgs(w, dropout)
     torch.manual_seed(1)
-    model = O.GlocalTextPathCMTPreTraining(cfg_s).train()
-    opt = torch.optim.AdamW(model.parameters(), lr=5e-5, betas=(0.9, 0.98), eps=1e-6, weight_decay=0.01)
-    batches = [(t, synth.make_batch(t, sample_B, L=w["L"], T_max=w["T_max"], G_max=w["G_max"], seed=9 + i))
-               for i, t in enumerate(("mlm", "sap"))]
-    times, n, t_start = [], 0, time.time()
+    student = O.GlocalTextPathCMTPreTraining(cfg_s).to(device).train()
+    teacher = None
+    co = bool(w.get("co_update"))
+    if cfg_t is not None:
+        torch.manual_seed(0)
+        teacher = O.GlocalTextPathCMTPreTraining(cfg_t).to(device)
+        teacher = teacher.train() if co else teacher.eval()
+    kw = dict(lr=5e-5, betas=(0.9, 0.98), eps=1e-6, weight_decay=0.01)
+    if fused_opt:
+        kw["fused"] = True
+    opts = [torch.optim.AdamW(student.parameters(), **kw)]
+    if co:
+        opts.append(torch.optim.AdamW(teacher.parameters(), **kw))
+    B = w["B"]
+    batches = []
+    for i, t in enumerate(("mlm", "sap")):
+        b = synth.make_batch(t, B, L=w["L"], T_max=w["T_max"], G_max=w["G_max"], seed=9 + i)
+        batches.append((t, {k: (v.to(device) if torch.is_tensor(v) else v) for k, v in b.items()}))
+    gen = torch.Generator().manual_seed(5)
+
+    def step(i):
+        task, b = batches[i % 2]
+        for o in opts:
+            o.zero_grad(set_to_none=True)
+        with torch.autocast(device_type="cuda", dtype=torch.bfloat16, enabled=autocast):
+            if teacher is None:
+                loss = student(b, task, True)["loss"].float().mean()
+            else:
+                rw = O.mkrw_weights(gen, 4.0, device)
+                if co:
+                    tot_s, tot_t = O.icod_step_loss(student, teacher, b, task, rw, rw)[:2]
+                    loss = tot_s.float() + tot_t.float()
+                else:
+                    loss = O.distill_step_loss(student, teacher, b, task, rw)[0].float()
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(student.parameters(), 5.0)
+        if co:
+            torch.nn.utils.clip_grad_norm_(teacher.parameters(), 5.0)
+        for o in opts:
+            o.step()
+
+    return step, B
+
+
+def kind_of(w):
+    return "MLM+SAP step" if w["teacher"] is None else ("MLM+SAP+distill step, ICoD co-update" if w.get("co_update")
+                                                        else "MLM+SAP+distill step")
+
+
+def cpu_step_rate(w, seconds_budget, dropout=0.0):
+    """Bounded sample of the workload on the host cores (same batch size, same models): >= 2 steps (one MLM, one SAP),
+    more while the budget lasts."""
+    torch.set_num_threads(os.cpu_count())
+    step, B = oracle_step_fn(w, "cpu", dropout)
+    times, t_start = [], time.time()
     while True:
-        task, b = batches[n % 2]
         t0 = time.time()
-        opt.zero_grad()
-        loss = model(b, task, True)["loss"].mean()
-        if train:
-            loss.backward()
-            torch.nn.utils.clip_grad_norm_(model.parameters(), 5.0)
-            opt.step()
+        step(len(times))
         times.append(time.time() - t0)
-        n += 1
-        if n >= 4 and (time.time() - t_start > seconds_budget or n >= 40):
+        if len(times) >= 2 and (time.time() - t_start > seconds_budget or len(times) >= 40):
             break
-    t = statistics.median(times[2:]) if len(times) > 3 else statistics.median(times)
-    return sample_B / t, n, t
+    use = times[1:] if len(times) > 2 else times  # the first step pays the allocator / thread-pool start-up
+    t = sum(use) / len(use)
+    return B / t, len(times), t
 
 
 def run_reference(args):
+    """The reference arm: the oracle port (the reference's model files are absent upstream, readme.md:75; its KD loss
+    arithmetic is the reference's own) running THE SAME workload -- same models, same batch size, same step --
+    in fp32 on all host cores.  Rank 0 alone runs it."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     w = WORKLOADS[args.workload]
-    sample_B = 8
-    times = []
-    from oracle import magic_oracle as O
-    from magic_b200 import synth
     torch.set_num_threads(os.cpu_count())
-    cfg_s, _ = make_cfgs(w, args.dropout)
-    torch.manual_seed(1)
-    model = O.GlocalTextPathCMTPreTraining(cfg_s).train()
-    opt = torch.optim.AdamW(model.parameters(), lr=5e-5, betas=(0.9, 0.98), eps=1e-6, weight_decay=0.01)
-    batches = [(t, synth.make_batch(t, sample_B, L=w["L"], T_max=w["T_max"], G_max=w["G_max"], seed=9 + i))
-               for i, t in enumerate(("mlm", "sap"))]
+    step, B = oracle_step_fn(w, "cpu", args.dropout)
+    times = []
     for i in range(args.warmup + args.steps):
-        task, b = batches[i % 2]
         t0 = time.time()
-        opt.zero_grad()
-        loss = model(b, task, True)["loss"].mean()
-        loss.backward()
-        torch.nn.utils.clip_grad_norm_(model.parameters(), 5.0)
-        opt.step()
+        step(i)
         if i >= args.warmup:
             times.append(time.time() - t0)
     tot = sum(times)
-    v = sample_B * len(times) / tot
-    sample = f"fp32 PyTorch oracle port (reference model files absent upstream), student step fwd+bwd+clip+AdamW, " \
-             f"batch {sample_B} per step (bounded sample of the batch-{w['B']} workload), MLM/SAP 1:1"
+    v = B * len(times) / tot
+    t = w["teacher"]
+    sample = f"fp32 PyTorch oracle port (reference model files absent upstream) of the same step at the same batch " \
+             f"size {B}: " + ("frozen teacher forward + " if t and not w.get("co_update") else "") + \
+             "student forward/backward" + (" + teacher forward/backward (ICoD)" if w.get("co_update") else "") + \
+             (" + MAKD losses" if t else "") + " + clip + AdamW, MLM/SAP 1:1"
     emit(OUT_FD, (dict(
-        impl="reference", metric="pretrain samples/s (MLM+SAP step)", value=v, unit="samples/s", n_gpus=args.gpus,
+        impl="reference", metric=f"pretrain samples/s ({kind_of(w)})", value=v, unit="samples/s", n_gpus=args.gpus,
         steps=args.steps, warmup=args.warmup, ms_per_step=1e3 * tot / len(times), higher_is_better=True,
         scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
-        config=dict(workload=args.workload, hidden=w["hidden"], layers=f"{w['n_l']}/{w['n_p']}/{w['n_x']}",
-                    batch_per_step=sample_B, seq_len=w["L"], graph_nodes=w["G_max"]),
+        config=workload_config(args.workload, w, 1, args.dropout, cuda_graphs=False),
         cpu_baseline=dict(value=v, unit="samples/s", cores=os.cpu_count(), kind="port", sample=sample),
         e2e=dict(value=v, unit="samples/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))))
+
+
+def torch_gpu_rate(w, dropout, steps=6, warmup=2, compiled=False):
+    """Stock-PyTorch-on-GPU baseline (SURVEY.md 8d "the number our sm_100a kernels must beat"): the same oracle port
+    on cuda:0 under bf16 autocast (cuBLASLt GEMMs, ATen softmax / LayerNorm, fused torch AdamW), eager."""
+    step, B = oracle_step_fn(w, "cuda", dropout, autocast=True, fused_opt=True)
+    if compiled:
+        step = torch.compile(step, dynamic=False)
+    for i in range(warmup):
+        step(i)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        step(i)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    return B / (ms * 1e-3), ms
+
+
+def run_torch_gpu(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    w = WORKLOADS[args.workload]
+    torch.cuda.set_device(0)
+    v, ms = torch_gpu_rate(w, args.dropout, max(args.steps, 2), max(args.warmup, 2), compiled=bool(args.compile))
+    emit(OUT_FD, dict(impl="torch_gpu", metric=f"pretrain samples/s ({kind_of(w)})", value=v, unit="samples/s",
+                      n_gpus=1, steps=args.steps, warmup=args.warmup, ms_per_step=ms, higher_is_better=True,
+                      scaling="weak", vs_baseline=None, dtype="bf16 autocast", data="synthetic",
+                      config=workload_config(args.workload, w, 1, args.dropout, cuda_graphs=False),
+                      kind="oracle port, stock torch ops on cuda" + (", torch.compile" if args.compile else ", eager")))
+
+
+def workload_config(name, w, world, dropout, cuda_graphs=True, pool_n=None, in_bytes=None):
+    B = w["B"]
+    cfg = dict(workload=name, hidden=w["hidden"], layers=f"{w['n_l']}/{w['n_p']}/{w['n_x']}",
+               batch_per_gpu=B, global_batch=B * world, seq_len=w["L"], views=36, graph_nodes=w["G_max"],
+               traj_steps_max=w["T_max"], tasks="mlm:sap 1:1", dropout=dropout,
+               teacher=("h%d %d/%d/%d%s" % (w["teacher"]["hidden"], w["teacher"]["n_l"], w["teacher"]["n_p"],
+                                            w["teacher"]["n_x"], " (trained, ICoD)" if w.get("co_update")
+                                            else " (frozen)")) if w["teacher"] else None,
+               optimizer="fused AdamW + clip 5.0", cuda_graphs=bool(cuda_graphs), parallelism=f"dp{world}")
+    if pool_n is not None:
+        cfg["l2"] = "inputs cycle through a pool of %d batches/task (~%.0f MB) > 126 MB L2" % (
+            pool_n, 2 * pool_n * in_bytes / 1e6)
+    return cfg
 
 
 # ---------------------------------------------------------------------------------------------------
 # our arm
 # ---------------------------------------------------------------------------------------------------
-def run_ours(args):
-    import torch.distributed as dist
-    import magic_b200
-    from magic_b200 import _lib, ops
-    from magic_b200.graph_index import flatten_batch
-    from magic_b200.train_step import PretrainStepper
+class Runner:
+    """One workload on this rank: models, stepper, input pools, and the step loops bench.py times."""
 
-    from magic_b200.parallel import init_distributed
-    rank, world, local = init_distributed()
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    w = WORKLOADS[args.workload]
-    global WORKLOAD_NAME
-    WORKLOAD_NAME = args.workload
-    pk = peaks()
-    cfg_s, cfg_t = make_cfgs(w, args.dropout)
-    dtype = torch.bfloat16 if args.dtype == "bf16" else torch.float32
-    torch.manual_seed(1)
-    student = magic_b200.GlocalTextPathCMTPreTraining(cfg_s).to(dev).train().set_compute_dtype(dtype)
-    teacher = None
-    if cfg_t is not None:
-        torch.manual_seed(0)
-        teacher = magic_b200.GlocalTextPathCMTPreTraining(cfg_t).to(dev).set_compute_dtype(dtype)
-        teacher = teacher.train() if w.get("co_update") else teacher.eval()
-    stepper = PretrainStepper(student, teacher, use_graphs=bool(args.graphs), co_update=bool(w.get("co_update")),
-                              side_stream=bool(args.side_stream), branch_streams=bool(args.branch_streams))
-    ops.set_seed(dev, 1234 + rank)
+    def __init__(self, name, args, rank, world, dev):
+        import magic_b200
+        from magic_b200 import ops
+        from magic_b200.graph_index import flatten_batch
+        from magic_b200.train_step import PretrainStepper
+        self.name, self.args, self.rank, self.world, self.dev = name, args, rank, world, dev
+        w = self.w = WORKLOADS[name]
+        cfg_s, cfg_t = make_cfgs(w, args.dropout)
+        dtype = torch.bfloat16 if args.dtype == "bf16" else torch.float32
+        torch.manual_seed(1)
+        student = magic_b200.GlocalTextPathCMTPreTraining(cfg_s).to(dev).train().set_compute_dtype(dtype)
+        teacher = None
+        if cfg_t is not None:
+            torch.manual_seed(0)
+            teacher = magic_b200.GlocalTextPathCMTPreTraining(cfg_t).to(dev).set_compute_dtype(dtype)
+            teacher = teacher.train() if w.get("co_update") else teacher.eval()
+        self.stepper = PretrainStepper(student, teacher, use_graphs=bool(args.graphs),
+                                       co_update=bool(w.get("co_update")), side_stream=bool(args.side_stream),
+                                       branch_streams=bool(args.branch_streams), overlap=bool(args.overlap))
+        ops.set_seed(dev, 1234 + rank)
+        n = self.pool_n = args.pool
+        pools = {t: make_pool(t, n, w, 1234 + rank * 1000 + (0 if t == "mlm" else 500)) for t in ("mlm", "sap")}
+        # flat batches: every tensor of a batch is a view into one buffer, so staging a batch is ONE copy
+        self.dev_pools = {t: [flatten_batch(b, device=dev) for b in bs] for t, bs in pools.items()}
+        self.pin_pools = {t: [flatten_batch(b, pin=True) for b in bs] for t, bs in pools.items()}
+        self.in_bytes = sum(nbytes(b) for bs in pools.values() for b in bs) / (2 * n)
+        self.host_loss = [torch.zeros(1).pin_memory() for _ in range(2)]
+        self.loss_ev = [torch.cuda.Event() for _ in range(2)]
 
-    pool_n = args.pool
-    pools = {t: make_pool(t, pool_n, w, 1234 + rank * 1000 + (0 if t == "mlm" else 500)) for t in ("mlm", "sap")}
-    # flat batches: every tensor of a batch is a view into one buffer, so staging a batch is ONE copy
-    dev_pools = {t: [flatten_batch(b, device=dev) for b in bs] for t, bs in pools.items()}
-    pin_pools = {t: [flatten_batch(b, pin=True) for b in bs] for t, bs in pools.items()}
-    in_bytes = sum(nbytes(b) for bs in pools.values() for b in bs) / (2 * pool_n)
+    def pick(self, i):
+        return ("mlm" if i % 2 == 0 else "sap"), (i // 2) % self.pool_n
 
-    def sync_all():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    host_loss = [torch.zeros(1).pin_memory() for _ in range(2)]
-    loss_ev = [torch.cuda.Event() for _ in range(2)]
-
-    def pick(i):
-        return ("mlm" if i % 2 == 0 else "sap"), (i // 2) % pool_n
-
-    def run_steps(n, first, from_host, delay_cycles=0):
-        out = None
-        nxt = None
+    def run_steps(self, n, first, from_host):
+        stepper, out, nxt = self.stepper, None, None
         if from_host:
-            task, j = pick(first)
-            nxt = stepper.prefetch(task, pin_pools[task][j])
+            task, j = self.pick(first)
+            nxt = stepper.prefetch(task, self.pin_pools[task][j])
         for i in range(first, first + n):
-            if delay_cycles:
-                # keep the GPU busy while the host queues this step's launches, so per-call CUDA events bracket
-                # back-to-back device execution rather than host launch latency
-                _lib.COUNTERS["launches"] -= 1
-                _lib.call("magic_delay", int(delay_cycles), _lib.stream())
-            task, j = pick(i)
+            task, j = self.pick(i)
             if from_host:
                 # end to end: every step's inputs start in pinned host memory; the copy of step i+1 is issued on the
                 # copy stream before step i's loss is read back, as the reference's PrefetchLoader does
                 b = nxt
                 if i + 1 < first + n:
-                    t2, j2 = pick(i + 1)
-                    nxt = stepper.prefetch(t2, pin_pools[t2][j2])
+                    t2, j2 = self.pick(i + 1)
+                    nxt = stepper.prefetch(t2, self.pin_pools[t2][j2])
             else:
-                b = dev_pools[task][j]
+                b = self.dev_pools[task][j]
             out = stepper.step(task, b)
             if from_host:
                 # device -> host read of EVERY step's loss, one step late (async copy into pinned memory + event),
                 # so the host queues step i+1 while step i runs instead of draining the GPU each step
                 k = i % 2
-                host_loss[k].copy_(out[0:1], non_blocking=True)
-                loss_ev[k].record()
+                self.host_loss[k].copy_(out[0:1], non_blocking=True)
+                self.loss_ev[k].record()
                 if i > first:
-                    loss_ev[1 - k].synchronize()
-                    _ = host_loss[1 - k].item()
+                    self.loss_ev[1 - k].synchronize()
+                    _ = self.host_loss[1 - k].item()
         if from_host:
-            loss_ev[(first + n - 1) % 2].synchronize()
-            _ = host_loss[(first + n - 1) % 2].item()
+            self.loss_ev[(first + n - 1) % 2].synchronize()
+            _ = self.host_loss[(first + n - 1) % 2].item()
         return out
 
+    def sync_all(self):
+        import torch.distributed as dist
+        if self.world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(self, steps, from_host):
+        """-> (ms for `steps` steps: CUDA events bracketed by barrier + synchronize, max over ranks), launches."""
+        import torch.distributed as dist
+        from magic_b200 import _lib
+        c0 = _lib.COUNTERS["launches"]
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        self.sync_all()
+        t0 = time.perf_counter()
+        e0.record()
+        self.run_steps(steps, 100, from_host)
+        e1.record()
+        self.sync_all()
+        ms = e0.elapsed_time(e1)
+        if from_host:
+            ms = max(ms, (time.perf_counter() - t0) * 1e3)
+        t = torch.tensor([ms], device=self.dev, dtype=torch.float64)
+        if self.world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()), _lib.COUNTERS["launches"] - c0
+
+    def profile_graph(self, nprof):
+        """Per-kernel durations of the REPLAYED graphs: the step graphs are re-captured with an external event-record
+        node before and after every C-ABI call (`_lib.profile_start(graph=True)`), replayed `nprof` times per task,
+        and every bracket is read with cudaEventElapsedTime after each replay.  Every rank runs the pass (the
+        gradient exchange stays matched); rank 0 reports."""
+        from magic_b200 import _lib
+        st = self.stepper
+        saved = st.graphs
+        st.graphs = {}
+        _lib.profile_start(graph=True)
+        try:
+            for i in range(2):  # capture (+ first replay) of the MLM and the SAP graph
+                _lib.profile_tag(self.pick(i)[0])
+                self.run_steps(1, i, False)
+            torch.cuda.synchronize()
+            prof = _lib._PROFILE
+            acc = {name: [0.0] * len(recs) for name, recs in prof.items()}
+            wall = 0.0
+            for i in range(2 * nprof):
+                task = self.pick(i)[0]
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                self.run_steps(1, 100 + i, False)
+                e1.record()
+                torch.cuda.synchronize()
+                wall += e0.elapsed_time(e1)
+                for name, recs in prof.items():
+                    a = acc[name]
+                    for k, r in enumerate(recs):
+                        if r[3] == task:
+                            a[k] += r[0].elapsed_time(r[1])
+        finally:
+            prof = _lib.profile_stop()
+            st.graphs = saved
+        # per record: mean ms per replay of ITS task's graph -> per step (MLM and SAP alternate: each runs nprof times)
+        out = {name: [(a / nprof, r[2]) for a, r in zip(acc[name], recs)] for name, recs in prof.items()}
+        return out, wall / (2 * nprof)
+
+
+FAMILY_OF = {"magic_gemm_wgrad": "magic_gemm", "magic_attn_bwd_part": "magic_attn_bwd"}
+
+
+def summarise_graph_profile(prof, ms_profiled_step, pk, workload):
+    """prof: {name: [(ms summed over one MLM+SAP pair ... per record, args)]}; each record ran in ONE of the two task
+    graphs, so a record's mean duration contributes half of it to the average step."""
+    fam, shapes = {}, {}
+    for name, recs in prof.items():
+        key = FAMILY_OF.get(name, name)
+        d = fam.setdefault(key, dict(ms_per_step=0.0, calls_per_step=0.0, flops=0.0, bytes=0.0))
+        for ms, a in recs:
+            f, b = family_cost(name, a)
+            d["ms_per_step"] += ms / 2
+            d["calls_per_step"] += 0.5
+            d["flops"] += f / 2
+            d["bytes"] += b / 2
+            if key == "magic_gemm":
+                M, N, K = (a[11], a[12], a[13]) if name == "magic_gemm" else (a[10], a[11], a[9])
+                sh = shapes.setdefault((name[6:], M, N, K), [0.0, 0, 0.0])
+                sh[0] += ms / 2
+                sh[1] += 1
+                sh[2] += f / 2
+    tot = sum(v["ms_per_step"] for v in fam.values()) or 1.0
+    for v in fam.values():
+        v["share"] = v["ms_per_step"] / tot
+
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(workload, {})
+    except Exception:
+        traffic = {}
+
+    def roof(names, bound, label):
+        ms = sum(fam[n]["ms_per_step"] for n in names if n in fam)
+        if ms <= 0:
+            return None
+        calls = sum(fam[n]["calls_per_step"] for n in names if n in fam)
+        if bound == "tensor":
+            work = sum(fam[n]["flops"] for n in names if n in fam)
+            ach, peak, unit = work / (ms * 1e-3) / 1e12, pk["tf_sus"], "TFLOP/s"
+            src = pk["src"] + " (sustained: timed inside a long step)"
+        else:
+            work = sum(fam[n]["bytes"] for n in names if n in fam)
+            ach, peak, unit = work / (ms * 1e-3) / 1e9, pk["hbm"], "GB/s"
+            src = pk["src"]
+        r = dict(kernel=label, bound=bound, achieved=ach, peak=peak, unit=unit, frac=ach / peak, traffic=None,
+                 peak_source=src, avg_launch_us=ms * 1e3 / max(calls, 1e-9), launches_per_step=calls,
+                 ms_per_step=ms, share_of_step_kernel_time=ms / tot,
+                 algorithmic_per_launch=work / max(calls, 1e-9))
+        ent = traffic.get(label)
+        if ent:
+            r["traffic"] = ent["dram_bytes_per_launch"]
+            r["traffic_source"] = ent["source"]
+        return r
+
+    rooflines = [r for r in (roof(["magic_gemm"], "tensor", "magic_gemm"),
+                             roof(["magic_attn_fwd", "magic_attn_bwd"], "hbm", "magic_attn"),
+                             roof(["magic_makd_mse_fwd", "magic_makd_mse_bwd", "magic_makd_kl_fwd",
+                                   "magic_makd_kl_bwd"], "hbm", "magic_makd")) if r]
+    top = max(rooflines, key=lambda r: r["ms_per_step"]) if rooflines else None
+    fams = {k: dict(ms_per_step=round(x["ms_per_step"], 4), calls=round(x["calls_per_step"], 1),
+                    share=round(x["share"], 3),
+                    tflops=round(x["flops"] / (x["ms_per_step"] * 1e-3) / 1e12, 2) if x["flops"] else None,
+                    gbs=round(x["bytes"] / (x["ms_per_step"] * 1e-3) / 1e9, 1) if x["bytes"] else None)
+            for k, x in sorted(fam.items(), key=lambda kv: -kv[1]["ms_per_step"])[:10]}
+    gshapes = [dict(op=k[0], M=k[1], N=k[2], K=k[3], launches_per_step=v[1] / 2, ms_per_step=round(v[0], 4),
+                    tflops=round(v[2] / (v[0] * 1e-3) / 1e12, 1) if v[0] > 0 else None)
+               for k, v in sorted(shapes.items(), key=lambda kv: -kv[1][0])[:12]]
+    note = dict(mode="events inside the replayed CUDA graph", sum_kernel_ms=round(tot, 4),
+                profiled_step_ms=round(ms_profiled_step, 4), overlap=round(tot / max(ms_profiled_step, 1e-9), 3),
+                note="brackets on concurrent stream branches overlap in time, so the sum of kernel durations may "
+                     "exceed the step; an event node between two kernels removes their PDL overlap")
+    return top, rooflines, fams, gshapes, note
+
+
+def run_ours(args):
+    import torch.distributed as dist
+    from magic_b200 import _lib
+    from magic_b200.parallel import init_distributed
+    rank, world, local = init_distributed()
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    global WORKLOAD_NAME
+    WORKLOAD_NAME = args.workload
+    pk = peaks()
+    R = Runner(args.workload, args, rank, world, dev)
+    w = R.w
     # warm-up (also builds the CUDA graphs, one per task/shape)
-    run_steps(max(args.warmup, 3), 0, False)
-    sync_all()
+    R.run_steps(max(args.warmup, 3), 0, False)
+    R.sync_all()
     clk = ClockSampler(local)
     if rank == 0:
         clk.start()
-    c0 = dict(_lib.COUNTERS)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    sync_all()
-    e0.record()
-    run_steps(args.steps, 100, False)
-    e1.record()
-    sync_all()
-    ms = e0.elapsed_time(e1)
-    launches = _lib.COUNTERS["launches"] - c0["launches"]
+    ms, launches = R.timed(args.steps, False)
     if args.timed_only:
         clk.stop() if rank == 0 else None
         sys.stderr.write(f"timed-only: {ms / args.steps:.3f} ms/step, {launches} launches\n")
@@ -462,73 +620,76 @@ def run_ours(args):
             dist.destroy_process_group()
         return
     # end-to-end: host (pinned) buffers -> H2D -> step -> D2H loss, through the public stepper API
-    run_steps(2, 0, True)
-    sync_all()
-    t0 = time.perf_counter()
-    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    f0.record()
-    run_steps(args.steps, 100, True)
-    f1.record()
-    sync_all()
-    ms_e2e = max(f0.elapsed_time(f1), (time.perf_counter() - t0) * 1e3)
-    clocks = clk.stop() if rank == 0 else None  # sampled (20 ms period) across BOTH timed regions: device-resident and e2e
-    t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms, ms_e2e = t.tolist()
+    R.run_steps(2, 0, True)
+    ms_e2e, _ = R.timed(args.steps, True)
+    clocks = clk.stop() if rank == 0 else None  # sampled (20 ms period) across BOTH timed regions
     B = w["B"]
     value = world * B * args.steps / (ms * 1e-3)
     e2e_v = world * B * args.steps / (ms_e2e * 1e-3)
 
-    roof, fams = None, None
+    top = rooflines = fams = gshapes = note = None
+    if args.graphs and not args.no_profile:
+        try:
+            prof, ms_prof = R.profile_graph(args.profile_steps)
+            if rank == 0:
+                top, rooflines, fams, gshapes, note = summarise_graph_profile(prof, ms_prof, pk, args.workload)
+        except Exception as e:  # keep the headline numbers if the stopwatch graph cannot be built
+            note = dict(mode="unavailable", error=repr(e)[:300])
+    line = None
     if rank == 0:
-        # instrumented pass (eager, per-call CUDA events on the launch stream) for the roofline numbers
-        # (single stream, eager; a delay kernel every 32 calls keeps the host ahead of the GPU -- see _lib.profile_start)
-        g = stepper.use_graphs
-        stepper.use_graphs = False
-        # rank 0 runs this pass ALONE: it must not issue the gradient all-reduce (the other ranks are not in it)
-        stepper.allreduce = stepper.t_allreduce = None
-        ops.enable_side_stream(False)
-        ops.enable_branch_streams(False)
-        run_steps(2, 0, False)
-        torch.cuda.synchronize()
-        _lib.profile_start(delay_every=32, delay_cycles=2e6)
-        nprof = 4
-        run_steps(nprof, 100, False)
-        torch.cuda.synchronize()
-        roof, fams = summarise_profile(_lib.profile_stop(), nprof, pk)
-        stepper.use_graphs = g
-        ops.enable_side_stream(bool(args.side_stream))
-        ops.enable_branch_streams(bool(args.branch_streams))
-    cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu:
-        v, n, tstep = cpu_step_rate(w, 12.0, 8, args.dropout)
-        cpu = dict(value=v, unit="samples/s", cores=os.cpu_count(), kind="port",
-                   sample=f"fp32 PyTorch oracle port, student step fwd+bwd+clip+AdamW at batch 8 (bounded sample of the "
-                          f"batch-{B} workload), MLM/SAP 1:1, {n} steps, median {tstep * 1e3:.0f} ms/step")
-    if rank == 0:
-        train_gflop = train_gflop_per_sample(w)
-        kind = "MLM+SAP step" if w["teacher"] is None else ("MLM+SAP+distill step, ICoD co-update" if w.get("co_update")
-                                                            else "MLM+SAP+distill step")
+        cfg = workload_config(args.workload, w, world, args.dropout, R.stepper.use_graphs, R.pool_n, R.in_bytes)
+        cfg["model_tflops"] = value * train_gflop_per_sample(w) / 1e3
+        cfg["gradient_exchange"] = R.stepper.exchange_description() if world > 1 else None
         line = dict(
-            metric=f"pretrain samples/s ({kind})", value=value, unit="samples/s", n_gpus=world, steps=args.steps,
+            metric=f"pretrain samples/s ({kind_of(w)})", value=value, unit="samples/s", n_gpus=world, steps=args.steps,
             warmup=max(args.warmup, 3), ms_per_step=ms / args.steps, higher_is_better=True, scaling="weak",
-            vs_baseline=None, dtype=args.dtype, data="synthetic",
-            config=dict(workload=args.workload, hidden=w["hidden"], layers=f"{w['n_l']}/{w['n_p']}/{w['n_x']}",
-                        batch_per_gpu=B, global_batch=B * world, seq_len=w["L"], views=36, graph_nodes=w["G_max"],
-                        traj_steps_max=w["T_max"], tasks="mlm:sap 1:1", dropout=args.dropout,
-                        teacher=("h%d %d/%d/%d%s" % (w["teacher"]["hidden"], w["teacher"]["n_l"], w["teacher"]["n_p"],
-                                                     w["teacher"]["n_x"], " (trained, ICoD)" if w.get("co_update")
-                                                     else " (frozen)")) if w["teacher"] else None,
-                        optimizer="fused AdamW + clip 5.0", cuda_graphs=bool(stepper.use_graphs),
-                        parallelism=f"dp{world}",
-                        l2="inputs cycle through a pool of %d batches/task (~%.0f MB) > 126 MB L2" % (
-                            pool_n, 2 * pool_n * in_bytes / 1e6),
-                        model_tflops=value * train_gflop / 1e3),
-            roofline=roof, kernel_families=fams, profile_outliers=OUTLIERS or None, cpu_baseline=cpu,
-            e2e=dict(value=e2e_v, unit="samples/s", h2d_bytes_per_step=int(in_bytes), d2h_bytes_per_step=4,
+            vs_baseline=None, dtype=args.dtype, data="synthetic", config=cfg,
+            roofline=top, rooflines=rooflines, kernel_families=fams, gemm_shapes=gshapes, profile=note,
+            e2e=dict(value=e2e_v, unit="samples/s", h2d_bytes_per_step=int(R.in_bytes), d2h_bytes_per_step=4,
                      ms_per_step=ms_e2e / args.steps),
             gpu_launches=int(launches), clocks=clocks)
+    del R
+    torch.cuda.empty_cache()
+
+    # the other BASELINE.json configs that fit this GPU count, short runs (device-resident inputs, graph replay)
+    subs = {}
+    names = [] if args.sub_workloads == "none" else (
+        [n for n in SUB_WORKLOADS if n != args.workload] if args.sub_workloads == "auto"
+        else [n for n in args.sub_workloads.split(",") if n])
+    for name in names:
+        try:
+            Rs = Runner(name, args, rank, world, dev)
+            Rs.run_steps(4, 0, False)
+            sms, sl = Rs.timed(args.sub_steps, False)
+            ws = Rs.w
+            v = world * ws["B"] * args.sub_steps / (sms * 1e-3)
+            subs[name] = dict(metric=f"pretrain samples/s ({kind_of(ws)})", value=v, unit="samples/s",
+                              ms_per_step=sms / args.sub_steps, steps=args.sub_steps, n_gpus=world,
+                              gpu_launches=int(sl), model_tflops=v * train_gflop_per_sample(ws) / 1e3,
+                              config=workload_config(name, ws, world, args.dropout, Rs.stepper.use_graphs))
+            del Rs
+        except Exception as e:
+            subs[name] = dict(error=repr(e)[:300])
+        torch.cuda.empty_cache()
+    if rank == 0:
+        line["workloads"] = subs or None
+        line["cpu_baseline"] = line["gpu_baseline"] = None
+        if world == 1 and not args.no_gpu_baseline:
+            try:
+                v, gms = torch_gpu_rate(w, args.dropout)
+                line["gpu_baseline"] = dict(value=v, unit="samples/s", ms_per_step=gms,
+                                            kind="oracle port, stock torch ops on cuda, bf16 autocast, eager, "
+                                                 "fused torch AdamW (bench.py --impl torch_gpu)")
+            except Exception as e:
+                line["gpu_baseline"] = dict(error=repr(e)[:300])
+            torch.cuda.empty_cache()
+        if world == 1 and not args.no_cpu:
+            v, n, tstep = cpu_step_rate(w, args.cpu_seconds, args.dropout)
+            line["cpu_baseline"] = dict(
+                value=v, unit="samples/s", cores=os.cpu_count(), kind="port",
+                sample=f"fp32 PyTorch oracle port of the same step at the same batch size {B} "
+                       f"(teacher forward + student forward/backward + MAKD + clip + AdamW), MLM/SAP 1:1, {n} steps "
+                       f"on the host cores, mean {tstep * 1e3:.0f} ms/step after the first")
         emit(OUT_FD, line)
     if world > 1:
         dist.destroy_process_group()
@@ -558,8 +719,17 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=4)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="magic_s_pretrain_b64", choices=sorted(WORKLOADS))
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "torch_gpu"])
+    ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
+    ap.add_argument("--sub-workloads", default="auto",
+                    help="'auto' = the other BASELINE.json configs, 'none', or a comma-separated list")
+    ap.add_argument("--sub-steps", type=int, default=10)
+    ap.add_argument("--profile-steps", type=int, default=3)
+    ap.add_argument("--no-profile", action="store_true")
+    ap.add_argument("--no-gpu-baseline", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=15.0)
+    ap.add_argument("--compile", type=int, default=0, help="--impl torch_gpu: wrap the step in torch.compile")
+    ap.add_argument("--overlap", type=int, default=1, help="N > 1: exchange gradient buckets during backward")
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "f32"])
     ap.add_argument("--dropout", type=float, default=0.1)
     ap.add_argument("--graphs", type=int, default=1)
@@ -572,6 +742,8 @@ def main():
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.impl == "torch_gpu":
+        run_torch_gpu(args)
     else:
         run_ours(args)
 

@@ -211,6 +211,15 @@ int magic_loss_mix_bwd(const float* g, int n, float alpha, const float* inv_n, f
 int magic_gemm_set_trace(unsigned long long* dev_buf);
 /* measurement aid: keeps the stream busy for ~cycles SM clocks so the host can queue launches ahead of the GPU */
 int magic_delay(long long cycles, cudaStream_t st);
+/* measurement aid (no reference counterpart): events recordable inside a captured CUDA graph (external event-record
+ * nodes), so bench.py times every kernel of the REPLAYED step with CUDA events on the launching stream */
+int magic_event_create(void** ev);
+int magic_event_destroy(void* ev);
+int magic_event_record(void* ev, cudaStream_t st);
+int magic_event_elapsed_ms(void* e0, void* e1, float* ms);
+/* make `st` (a stream OUTSIDE the graph, e.g. the one NCCL is issued from) wait for an event-record node of the graph
+ * launched before this call: the gradient exchange of a finished layer group starts while the graph still runs */
+int magic_stream_wait_event(cudaStream_t st, void* ev);
 /* scale_dev: optional device scalar multiplied into `scale` (see MagicMseSeg.scale_dev) */
 int magic_makd_kl_fwd(const void* s, const void* t, int R, int C, long ld, float temperature, const float* w,
                       float scale, const float* scale_dev, float* stats /* [R,2] */,

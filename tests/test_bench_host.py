@@ -11,41 +11,40 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 
-class _Ev:
-    def __init__(self, t):
-        self.t = t
-
-    def elapsed_time(self, other):
-        return other.t - self.t
-
-
-def _rec(ms, args):
-    return (_Ev(0.0), _Ev(ms), args)
-
-
-def test_summarise_profile_clips_one_off_stalls_and_reports_traffic():
+def test_graph_profile_summary_three_rooflines_and_shapes():
+    """bench.summarise_graph_profile: records are (mean ms per replay of the record's task graph, C-ABI args); MLM and
+    SAP graphs alternate, so each record weighs one half in the average step."""
     bench = importlib.import_module("bench")
-    bench.OUTLIERS.clear()
-    bench.WORKLOAD_NAME = "magic_s_pretrain_b64"
-    # magic_ln_fwd args: (..., M at [6], h at [7], ..., dtype at [9]); 40 normal calls and one 39 ms stall
-    ln_args = (0, 0, 0, 0, 0, 0, 5120, 128, 1e-12, 1)
-    prof = {"magic_ln_fwd": [_rec(0.005, ln_args) for _ in range(40)] + [_rec(39.0, ln_args)],
-            "magic_delay": [_rec(1.0, ())]}
     pk = dict(hbm=6546.2, tf=1661.3, tf_sus=1403.5, src="measured")
-    roof, fams = bench.summarise_profile(prof, 1, pk)
-    assert bench.OUTLIERS == {"magic_ln_fwd": 1}
-    assert roof["kernel"] == "magic_ln_fwd" and roof["bound"] == "hbm"
-    assert abs(fams["magic_ln_fwd"]["ms_per_step"] - 41 * 0.005) < 1e-6  # the stall counts as the median
-    by = 41 * 5120 * 128 * 2 * 3
-    assert abs(roof["achieved"] - by / (41 * 0.005e-3) / 1e9) / roof["achieved"] < 1e-6
-    assert roof["peak"] == 6546.2 and 0 < roof["frac"] < 1
-    # GEMM family: traffic comes from the committed ncu capture
-    g_args = (0, 1, 128, 1, 0, 1, 1, 128, 0, 1, 128, 5120, 128, 128)
-    prof = {"magic_gemm": [_rec(0.004, g_args) for _ in range(10)]}
-    roof, _ = bench.summarise_profile(prof, 1, pk)
+    # magic_gemm args: M, N, K at [11], [12], [13]; dtypes at [1], [5], [9]
+    g_args = (0, 1, 768, 1, 0, 1, 1, 768, 0, 1, 768, 5120, 768, 768)
+    # magic_gemm_wgrad args: (dy, dy_dt, dy_ld, x, x_dt, x_ld, dw, dw_ld, dbias, M, N, K)
+    w_args = (0, 1, 768, 0, 1, 768, 0, 768, 0, 5120, 768, 768)
+    # magic_attn_fwd: B, H, Lq, Lk at [11..14], dtype at [20]
+    a_args = (0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 64, 12, 80, 80, 0, 0, 0, 0, 0, 1)
+    prof = {"magic_gemm": [(0.010, g_args)] * 20, "magic_gemm_wgrad": [(0.012, w_args)] * 4,
+            "magic_attn_fwd": [(0.008, a_args)] * 10}
+    top, roofs, fams, shapes, note = bench.summarise_graph_profile(prof, 0.2, pk, "no_such_workload")
+    assert top["kernel"] == "magic_gemm" and top["bound"] == "tensor" and top["traffic"] is None
+    gemm_ms = (20 * 0.010 + 4 * 0.012) / 2
+    assert abs(fams["magic_gemm"]["ms_per_step"] - gemm_ms) < 1e-4
+    fl = 2.0 * 5120 * 768 * 768 * 24 / 2
+    assert abs(top["achieved"] - fl / (gemm_ms * 1e-3) / 1e12) / top["achieved"] < 1e-6
+    assert abs(top["frac"] - top["achieved"] / 1403.5) < 1e-9
+    assert abs(top["avg_launch_us"] - gemm_ms * 1e3 / 12) < 1e-6
+    kinds = {r["kernel"]: r for r in roofs}
+    assert set(kinds) == {"magic_gemm", "magic_attn"} and kinds["magic_attn"]["bound"] == "hbm"
+    assert kinds["magic_attn"]["peak"] == 6546.2
+    assert {(d["op"], d["M"], d["N"], d["K"]) for d in shapes} == {("gemm", 5120, 768, 768), ("gemm_wgrad", 768, 768, 5120)}
+    assert abs(note["sum_kernel_ms"] - (gemm_ms + 10 * 0.008 / 2)) < 1e-4 and note["overlap"] > 0
+    # the traffic of a roofline comes from the committed ncu capture of THAT workload, when there is one
     tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-    assert roof["bound"] == "tensor" and roof["traffic"] == tr["magic_s_pretrain_b64"]["magic_gemm"]["dram_bytes_per_launch"]
-    assert abs(roof["achieved"] - 2.0 * 5120 * 128 * 128 / 0.004e-3 / 1e12) < 1e-6
+    for wl, ents in tr.items():
+        for label, ent in ents.items():
+            fam_prof = {"magic_gemm": [(0.010, g_args)]} if label == "magic_gemm" else None
+            if fam_prof:
+                t2 = bench.summarise_graph_profile(fam_prof, 0.01, pk, wl)[0]
+                assert t2["traffic"] == ent["dram_bytes_per_launch"]
 
 
 def test_train_gflop_accounting():

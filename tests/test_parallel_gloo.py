@@ -36,6 +36,41 @@ idx = parallel.shard_indices(101, rank, world, seed=3)
 both = [None, None]
 dist.all_gather_object(both, idx)
 assert len(both[0]) == len(both[1]) == 51 and set(both[0]) | set(both[1]) == set(range(101))
+# overlapped exchange: the stage plan + StageSync's issue / rest / wait on a fake two-group arena (CPU, gloo)
+from types import SimpleNamespace
+names = ["bert.embeddings.word_embeddings.weight", "bert.lang_encoder.layer.0.attention.self.query.weight",
+         "bert.lang_encoder.layer.1.attention.self.query.weight", "bert.local_encoder.vp_pos_embeddings.0.weight",
+         "bert.local_encoder.encoder.crossattention.0.attention.self.query.weight",
+         "bert.global_encoder.gmap_step_embeddings.weight",
+         "bert.global_encoder.encoder.crossattention.0.attention.self.query.weight", "bert.txt_emb_w.weight",
+         "global_sap_head.net.0.weight"]
+entries, off = [], 0
+for i, n in enumerate(names):
+    k = 37 + 11 * i
+    entries.append((n, None, off, k))
+    off += (k + 7) // 8 * 8
+n_decay = off
+entries.append(("bert.lang_encoder.layer.1.attention.self.query.bias", None, off, 5))
+off += 8
+torch.manual_seed(200 + rank)
+arena = SimpleNamespace(entries=entries, n_decay=n_decay, total=off, flat_g=torch.randn(off))
+before = [torch.zeros(off) for _ in range(world)]
+dist.all_gather(before, arena.flat_g.clone())
+sy = parallel.StageSync(arena, 2, bucket_bytes=64 * 4)
+st0 = [entries[i][2] for i in (4, 6, 7, 8)]
+assert [lo for lo, hi in sy.stages[0]] == [entries[4][2], entries[6][2]] and sy.stages[1] == [(entries[2][2], entries[3][2])]
+cover = sorted(sy.stages[0] + sy.stages[1] + sy.rest)
+assert cover[0][0] == 0 and cover[-1][1] == off and all(a[1] == b[0] for a, b in zip(cover[:-1], cover[1:]))
+sy.begin("eager")
+sy.expect(0, "txt"); sy.expect(0, "g_in"); sy.expect(1, "txt_mid")
+fired = []
+sy._ready = lambda st: (fired.append(st), sy._issue(st))
+sy.fire(0, "txt"); assert fired == []
+sy.fire(0, "g_in"); assert fired == [0]
+sy.fire(0, "g_in"); assert fired == [0]          # a stage starts once
+sy.issue_rest(sy.fired)                           # stage 1 never completed: its range travels with the rest
+sy.wait()
+assert torch.allclose(arena.flat_g, (before[0] + before[1]) / 2, atol=1e-6)
 dist.barrier()
 sys.stdout.write("rank " + str(rank) + " ok\n")
 sys.stdout.flush()
@@ -57,7 +92,8 @@ def test_reference_arm_runs_on_rank0_only():
     env = dict(os.environ, OMP_NUM_THREADS="4")
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
                         "--master-addr", "127.0.0.1", "--master-port", "29732", os.path.join(ROOT, "bench.py"),
-                        "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "1"],
+                        "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "1", "--workload",
+                        "magic_s_pretrain_b64"],
                        capture_output=True, text=True, timeout=600, env=env)
     assert r.returncode == 0, r.stderr[-2000:]
     lines = [l for l in r.stdout.splitlines() if l.startswith("{")]

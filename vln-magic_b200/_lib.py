@@ -81,25 +81,89 @@ class MagicError(RuntimeError):
 _LAUNCHES = {"magic_attn_bwd": 2, "magic_scatter_rows": 1, "magic_gmap_aggregate_bwd": 1}
 ERR_UNSUPPORTED = 3
 COUNTERS = {"calls": 0, "launches": 0}
-_PROFILE = None  # {name: [(start_event, end_event, args)]} when bench.py profiles kernel families
+_PROFILE = None  # {name: [record]} when bench.py profiles kernel families
 _PROFILE_EVERY = 0  # > 0: keep the stream busy with a delay kernel every N calls so the host stays ahead of the GPU
 _PROFILE_N = 0
+_PROFILE_GRAPH = False  # True: brackets are external event-record NODES of the graph being captured
+_PROFILE_TAG = None
 
 
-def profile_start(delay_every=0, delay_cycles=3e6):
-    """Per-call CUDA-event timing of every C-ABI call (bench.py's roofline pass).  In eager mode the host issues
-    launches more slowly than the GPU retires these small kernels; a short `magic_delay` kernel every
-    `delay_every` calls (outside the event brackets) lets the host queue the next calls while the stream is
-    busy, so each bracket measures back-to-back device execution and not host launch latency."""
-    global _PROFILE, _PROFILE_EVERY, _PROFILE_N, _PROFILE_CYCLES
+class GraphEvent:
+    """A CUDA event of libmagic_b200 (magic_event_*): recorded with cudaEventRecordExternal while a stream is being
+    captured, so it becomes a node of the graph and is re-stamped by every replay."""
+    __slots__ = ("h",)
+
+    def __init__(self):
+        h = ctypes.c_void_p()
+        rc = load().magic_event_create(ctypes.byref(h))
+        if rc != 0:
+            raise MagicError(f"magic_event_create failed: {load().magic_last_error().decode()}")
+        self.h = h
+
+    def record(self):
+        rc = load().magic_event_record(self.h, stream())
+        if rc != 0:
+            raise MagicError(f"magic_event_record failed: {load().magic_last_error().decode()}")
+
+    def elapsed_time(self, other):
+        ms = ctypes.c_float()
+        rc = load().magic_event_elapsed_ms(self.h, other.h, ctypes.byref(ms))
+        if rc != 0:
+            raise MagicError(f"magic_event_elapsed_ms failed: {load().magic_last_error().decode()}")
+        return ms.value
+
+
+def profile_start(delay_every=0, delay_cycles=3e6, graph=False):
+    """Per-call CUDA-event timing of every C-ABI call (bench.py's roofline pass).
+
+    graph=True (the default pass of bench.py): nothing is recorded in eager execution; while a stream is being
+    CAPTURED every call is bracketed by two external event-record nodes, so the captured graph carries its own
+    stopwatch and each replay yields the duration of every kernel of the replayed step -- same graph topology
+    (stream branches) as the timed region; an event node between two kernels removes their programmatic-dependent-
+    launch overlap, which is the only difference.
+
+    graph=False: eager mode.  The host issues launches more slowly than the GPU retires small kernels; a short
+    `magic_delay` kernel every `delay_every` calls (outside the event brackets) lets the host queue the next calls
+    while the stream is busy, so each bracket measures back-to-back device execution and not host launch latency."""
+    global _PROFILE, _PROFILE_EVERY, _PROFILE_N, _PROFILE_CYCLES, _PROFILE_GRAPH
     _PROFILE = {}
+    _PROFILE_GRAPH = bool(graph)
     _PROFILE_EVERY, _PROFILE_N, _PROFILE_CYCLES = int(delay_every), 0, int(delay_cycles)
 
 
 def profile_stop():
-    global _PROFILE
+    global _PROFILE, _PROFILE_GRAPH
     p, _PROFILE = _PROFILE, None
+    _PROFILE_GRAPH = False
     return p
+
+
+def profile_tag(tag):
+    global _PROFILE_TAG
+    _PROFILE_TAG = tag
+
+
+def _profiled(lib, name, args):
+    global _PROFILE_N
+    if _PROFILE_GRAPH:
+        if not torch.cuda.is_current_stream_capturing():
+            return getattr(lib, name)(*args)
+        e0, e1 = GraphEvent(), GraphEvent()
+        e0.record()
+        rc = getattr(lib, name)(*args)
+        e1.record()
+        _PROFILE.setdefault(name, []).append((e0, e1, args, _PROFILE_TAG))
+        return rc
+    if _PROFILE_EVERY > 0 and name != "magic_delay":
+        if _PROFILE_N % _PROFILE_EVERY == 0:
+            lib.magic_delay(_PROFILE_CYCLES, stream())
+        _PROFILE_N += 1
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    rc = getattr(lib, name)(*args)
+    e1.record()
+    _PROFILE.setdefault(name, []).append((e0, e1, args, _PROFILE_TAG))
+    return rc
 
 
 def call(name, *args):
@@ -107,16 +171,7 @@ def call(name, *args):
     COUNTERS["calls"] += 1
     COUNTERS["launches"] += _LAUNCHES.get(name, 1)
     if _PROFILE is not None:
-        global _PROFILE_N
-        if _PROFILE_EVERY > 0 and name != "magic_delay":
-            if _PROFILE_N % _PROFILE_EVERY == 0:
-                lib.magic_delay(_PROFILE_CYCLES, stream())
-            _PROFILE_N += 1
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        rc = getattr(lib, name)(*args)
-        e1.record()
-        _PROFILE.setdefault(name, []).append((e0, e1, args))
+        rc = _profiled(lib, name, args)
     else:
         rc = getattr(lib, name)(*args)
     if rc != 0:
@@ -127,7 +182,12 @@ def call_rc(name, *args):
     """Like `call`, for entry points that may decline a shape: returns 0, or ERR_UNSUPPORTED when NOTHING was launched
     (the caller then takes the general entry point); any other status raises."""
     lib = load()
-    rc = getattr(lib, name)(*args)
+    if _PROFILE is not None:
+        rc = _profiled(lib, name, args)
+        if rc == ERR_UNSUPPORTED and _PROFILE.get(name):
+            _PROFILE[name].pop()  # nothing was launched inside that bracket
+    else:
+        rc = getattr(lib, name)(*args)
     if rc == ERR_UNSUPPORTED:
         return rc
     if rc != 0:

@@ -90,4 +90,35 @@ int magic_gemm_wgrad(const void* dy, int dy_dt, long dy_ld, const void* x, int x
   return magic_colsum(dy, dbias, M, N, dy_ld, dy_dt, st);
 }
 
+/* ---- measurement aid: CUDA events that can be recorded INSIDE a captured graph ---------------------------------
+ * cudaEventRecordWithFlags(..., cudaEventRecordExternal) turns the record into a graph node during stream capture, so
+ * every replay re-stamps the event and the host reads kernel durations of the REPLAYED graph (bench.py). */
+int magic_event_create(void** ev) {
+  cudaEvent_t e;
+  MAGIC_CUDA(cudaEventCreate(&e), "magic_event_create");
+  *ev = (void*)e;
+  return MAGIC_OK;
+}
+int magic_event_destroy(void* ev) {
+  MAGIC_CUDA(cudaEventDestroy((cudaEvent_t)ev), "magic_event_destroy");
+  return MAGIC_OK;
+}
+int magic_event_record(void* ev, cudaStream_t st) {
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  MAGIC_CUDA(cudaStreamIsCapturing(st, &cs), "magic_event_record");
+  if (cs == cudaStreamCaptureStatusActive)
+    MAGIC_CUDA(cudaEventRecordWithFlags((cudaEvent_t)ev, st, cudaEventRecordExternal), "magic_event_record(external)");
+  else
+    MAGIC_CUDA(cudaEventRecord((cudaEvent_t)ev, st), "magic_event_record");
+  return MAGIC_OK;
+}
+int magic_stream_wait_event(cudaStream_t st, void* ev) {
+  MAGIC_CUDA(cudaStreamWaitEvent(st, (cudaEvent_t)ev, 0), "magic_stream_wait_event");
+  return MAGIC_OK;
+}
+int magic_event_elapsed_ms(void* e0, void* e1, float* ms) {
+  MAGIC_CUDA(cudaEventElapsedTime(ms, (cudaEvent_t)e0, (cudaEvent_t)e1), "magic_event_elapsed_ms");
+  return MAGIC_OK;
+}
+
 }  // extern "C"

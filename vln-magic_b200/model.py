@@ -260,6 +260,19 @@ def _cross_encoder(enc, x, ctx, B, Lx, Lc, x_lens, c_lens, fc, dists=None, sprel
 
 
 class GlocalTextPathCMT(nn.Module):
+    # data-parallel training: an object with expect(stage, key) / fire(stage, key) (parallel.StageSync).  The forward
+    # marks the activations at which backward has FINISHED a group of layers; the tensor hook fires when that
+    # activation's gradient is complete, i.e. every layer above it has issued its weight gradients, so the gradient
+    # arena range of those layers can be exchanged while the layers below still back-propagate.
+    stage_cb = None
+
+    def _mark(self, t, stage, key):
+        cb = self.stage_cb
+        if cb is not None and torch.is_grad_enabled() and t.requires_grad:
+            cb.expect(stage, key)
+            t.register_hook(lambda g, s=stage, k=key: cb.fire(s, k))
+        return t
+
     def __init__(self, c):
         super().__init__()
         self.config = c
@@ -287,7 +300,10 @@ class GlocalTextPathCMT(nn.Module):
                          e.LayerNorm.bias, e.LayerNorm.eps, fc.dtype, fc.p(e.dropout), fc.salt())
         x = x.view(B * Lt, -1)
         attns = []
-        for layer in self.lang_encoder.layer:
+        mid = len(self.lang_encoder.layer) // 2
+        for li, layer in enumerate(self.lang_encoder.layer):
+            if li == mid and li > 0:
+                self._mark(x, 1, "txt_mid")  # gradient complete <=> text layers mid.. have finished backward
             a, p = _attn_block(layer.attention, x, None, B, Lt, Lt, ix["key_lens_txt"], fc)
             x = _ffn_block(layer, a, fc)
             attns.append(p)
@@ -370,6 +386,10 @@ class GlocalTextPathCMT(nn.Module):
 
         (pano, fused, img_attns, g_in, v_in), (txt, txt_attns) = ops.run_branches(
             visual, lambda: self.forward_text(batch, ix, fc))
+        # stage 0 of the gradient exchange: the cross-modal encoders and every head have finished backward once the
+        # gradients of their three inputs are complete
+        for t_, k_ in ((txt, "txt"), (g_in, "g_in"), (v_in, "v_in")):
+            self._mark(t_, 0, k_)
         if mode == "nav":
             dists = batch["gmap_pair_dists"] if ge.sprel_linear is not None else None
             (v, v_attn), (g, g_attn) = ops.run_branches(

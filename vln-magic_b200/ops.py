@@ -709,7 +709,7 @@ class AttentionFn(torch.autograd.Function):
         sw = sprel_w.reshape(-1) if sprel_w is not None else None
         sb = sprel_b.reshape(-1) if sprel_b is not None else None
         done = False
-        if (dpbar is None and qsrc.dtype == torch.bfloat16 and _BRANCH["on"] and L._PROFILE is None
+        if (dpbar is None and qsrc.dtype == torch.bfloat16 and _BRANCH["on"] and (L._PROFILE is None or L._PROFILE_GRAPH)
                 and B * H * Lq <= 24576):  # latency-bound sizes only: at H = 12 the halves fill the GPU on their own
             # no KD-map gradient: the key-major kernel (dK, dV) recomputes delta = dO . O itself, so it does not depend
             # on the query-major kernel (dQ) and the two run concurrently -- a forked branch of the captured graph

@@ -72,6 +72,170 @@ class FlatAllReduce:
         self.finish()
 
 
+# ---------------------------------------------------------------------------------------------------
+# gradient exchange overlapped with backward (DDP's bucketed overlap, pretrain_src/utils/misc.py:57-71)
+# ---------------------------------------------------------------------------------------------------
+STAGE0_PREFIXES = ("bert.local_encoder.encoder.", "bert.global_encoder.encoder.", "bert.global_encoder.sprel_linear",
+                   "bert.txt_emb_w", "bert.kdl_img_w", "bert.kdl_avg_img_w", "bert.global_cross_w",
+                   "bert.local_cross_w", "bert.vp_txt_w", "bert.gmap_txt_w", "mlm_head.", "global_sap_head.",
+                   "local_sap_head.", "sap_fuse_linear.", "image_classifier.", "cfp_", "og_head.")
+
+
+def stage_ranges(arena, n_text_layers):
+    """-> ([ranges of stage 0, ranges of stage 1], rest ranges) as (lo, hi) element offsets of the gradient arena.
+
+    Stage 0 = every weight-decay-group parameter of the cross-modal encoders, the KD projections and the task heads:
+    complete when the gradients of the cross encoders' inputs (text output, gmap input, vp input) are complete.
+    Stage 1 = the upper half of the text encoder: complete when the gradient of the activation entering text layer
+    n/2 is complete.  (The position / step embedding weights of the two cross encoders produce gmap / vp INPUTS, so
+    their gradients arrive after the stage-0 point: they stay in the rest, with the biases and LayerNorm parameters
+    of the no-decay group, the embeddings, the lower text layers and the panorama encoder.)"""
+    mid = n_text_layers // 2
+    upper = tuple(f"bert.lang_encoder.layer.{i}." for i in range(mid, n_text_layers)) if mid > 0 else ()
+    stages = [[], []]
+    for n, p, o, k in arena.entries:
+        if o >= arena.n_decay:
+            continue
+        st = 0 if n.startswith(STAGE0_PREFIXES) else (1 if upper and n.startswith(upper) else None)
+        if st is None:
+            continue
+        hi = o + (k + 7) // 8 * 8  # the arena pads every entry to 8 elements
+        r = stages[st]
+        if r and r[-1][1] == o:
+            r[-1] = (r[-1][0], hi)
+        else:
+            r.append((o, hi))
+    covered = sorted(x for r in stages for x in r)
+    rest, pos = [], 0
+    for lo, hi in covered:
+        if lo > pos:
+            rest.append((pos, lo))
+        pos = hi
+    if pos < arena.total:
+        rest.append((pos, arena.total))
+    return stages, rest
+
+
+class StageSync:
+    """Receives the model's backward stage marks (model.GlocalTextPathCMT._mark) for ONE model / gradient arena and
+    starts the all-reduce of a stage's arena ranges as soon as the stage is complete.
+
+    mode 'eager'   : the hook orders the current stream after every helper stream and issues the NCCL all-reduce.
+    mode 'capture' : the step is being captured into a CUDA graph.  NCCL is NOT captured; instead the hook adds an
+                     external event-record node (on a marker stream that depends on every capturing stream) to the
+                     graph.  After each replay the host makes the communication stream wait for that event and
+                     issues the all-reduce there: the exchange starts in the middle of the running graph.
+    mode None      : marks are ignored (warm-up, single GPU)."""
+
+    def __init__(self, arena, n_text_layers, bucket_bytes=64 << 20):
+        self.arena = arena
+        self.stages, self.rest = stage_ranges(arena, n_text_layers)
+        self.bucket = max(1, bucket_bytes // 4)
+        self.mode = None
+        self.pending = [set(), set()]
+        self.expected = [False, False]
+        self.fired = []          # stages completed during the current backward, in order
+        self.events = {}         # capture mode: stage -> GraphEvent
+        self.handles = []
+        self.marker = None
+
+    # -- called by the model ------------------------------------------------------------------------------
+    def expect(self, stage, key):
+        if self.mode is None:
+            return
+        self.pending[stage].add(key)
+        self.expected[stage] = True
+
+    def fire(self, stage, key):
+        if self.mode is None:
+            return
+        self.pending[stage].discard(key)
+        if self.expected[stage] and not self.pending[stage] and stage not in self.fired:
+            self.fired.append(stage)
+            self._ready(stage)
+
+    # -- stepper interface ----------------------------------------------------------------------------------
+    def begin(self, mode):
+        self.mode = mode
+        self.pending = [set(), set()]
+        self.expected = [False, False]
+        self.fired = []
+        if mode == "capture":
+            self.events = {}
+
+    def _streams(self):
+        from . import ops
+        out = list(ops._BRANCH.get("pool", {}).values()) + list(ops._ATTN_STREAMS.values())
+        if ops._SIDE["stream"] is not None:
+            out.append(ops._SIDE["stream"])
+        return out
+
+    def _ready(self, stage):
+        cur = torch.cuda.current_stream()
+        if self.mode == "eager":
+            for s in self._streams():
+                cur.wait_stream(s)
+            self._issue(stage)
+            return
+        from ._lib import GraphEvent
+        if self.marker is None:
+            self.marker = torch.cuda.Stream()
+        mk = self.marker
+        mk.wait_stream(cur)
+        for s in self._streams():
+            with torch.cuda.stream(s):
+                capturing = torch.cuda.is_current_stream_capturing()
+            if capturing:
+                mk.wait_stream(s)  # an edge from the stream's last node; adds no work to that stream
+        ev = GraphEvent()
+        with torch.cuda.stream(mk):
+            ev.record()            # external event-record node: re-stamped by every replay
+        self.events[stage] = ev
+
+    def join_marker(self):
+        """Capture mode: the marker stream must rejoin the origin stream before the capture ends."""
+        if self.marker is not None and self.mode == "capture" and self.events:
+            torch.cuda.current_stream().wait_stream(self.marker)
+
+    def _issue(self, stage_or_ranges):
+        ranges = self.stages[stage_or_ranges] if isinstance(stage_or_ranges, int) else stage_or_ranges
+        g = self.arena.flat_g
+        avg = dist.get_backend() == "nccl"
+        op = dist.ReduceOp.AVG if avg else dist.ReduceOp.SUM
+        for lo, hi in ranges:
+            pos = lo
+            while pos < hi:
+                end = min(hi, pos + self.bucket)
+                self.handles.append((dist.all_reduce(g[pos:end], op=op, async_op=True), pos, end, avg))
+                pos = end
+
+    def after_replay(self, comm_stream, fired, events):
+        """Graph mode, called right after g.replay(): the communication stream waits for each stage's in-graph event
+        and issues that stage's all-reduce (NCCL orders its own stream after the stream it is called from)."""
+        from ._lib import load
+        lib = load()
+        with torch.cuda.stream(comm_stream):
+            for st in fired:
+                lib.magic_stream_wait_event(comm_stream.cuda_stream, events[st].h)
+                self._issue(st)
+
+    def issue_rest(self, fired):
+        """Everything that was not exchanged during backward (call when backward has been issued completely)."""
+        ranges = list(self.rest)
+        for st in (0, 1):
+            if st not in fired:
+                ranges += self.stages[st]
+        self._issue(sorted(ranges))
+
+    def wait(self):
+        world = world_size()
+        for h, lo, hi, avg in self.handles:
+            h.wait()
+            if not avg:
+                self.arena.flat_g[lo:hi].mul_(1.0 / world)
+        self.handles = []
+
+
 def broadcast_flat(flat, src=0):
     """DDP's parameter broadcast at wrap time (utils/misc.py:63-66) on the flat parameter arena."""
     if world_size() > 1:

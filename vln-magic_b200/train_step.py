@@ -12,7 +12,7 @@ from . import _lib, makd, ops
 from .graph_index import FLAT_KEY, INDEX_KEY, alloc_like, copy_batch_
 from .optim import FusedAdamW
 from .arena import ParamArena
-from .parallel import FlatAllReduce, broadcast_flat
+from .parallel import FlatAllReduce, StageSync, broadcast_flat
 
 
 class _Prefetched:
@@ -25,7 +25,7 @@ class _Prefetched:
 class PretrainStepper:
     def __init__(self, student, teacher=None, kdl=None, lr=5e-5, betas=(0.9, 0.98), weight_decay=0.01,
                  max_grad_norm=5.0, use_graphs=False, rw_generator=None, side_stream=True,
-                 branch_streams=True, co_update=False, t_lr=None, max_graphs=16):
+                 branch_streams=True, co_update=False, t_lr=None, max_graphs=16, overlap=True):
         """co_update=True is ICoD (`--train_kdl_teacher`, agent_base.py:260-279): the teacher is trained too, from
         the s2t losses, with its own arena / AdamW state / clip, and both models step once per batch."""
         self.student, self.teacher = student, teacher
@@ -61,13 +61,48 @@ class PretrainStepper:
             if self.co_update:
                 broadcast_flat(self.t_arena.flat_p, 0)
                 self.t_arena.refresh_lowp()
+        # gradient exchange overlapped with backward (DDP's bucketed overlap, utils/misc.py:57-71): the model marks the
+        # points of backward at which a group of layers is complete (model._mark), parallel.StageSync starts that
+        # group's all-reduce there; the rest follows when backward has been issued
+        self.overlap = bool(overlap) and self.world > 1
+        self.syncs = []
+        self.comm_stream = None
+        if self.overlap:
+            self.comm_stream = torch.cuda.Stream()
+            pairs = [(student, self.arena)] + ([(teacher, self.t_arena)] if self.co_update else [])
+            for m, a in pairs:
+                sy = StageSync(a, len(m.bert.lang_encoder.layer))
+                m.bert.stage_cb = sy
+                self.syncs.append(sy)
         self.launches_per_step = None
         self._copy_stream, self._staging = None, {}
         self._rw_dev = None
 
+    def exchange_description(self):
+        if self.world == 1:
+            return None
+        if self.overlap:
+            mb = sum((hi - lo) * 4 for sy in self.syncs for st in sy.stages for lo, hi in st) / 1e6
+            tot = sum(sy.arena.total * 4 for sy in self.syncs) / 1e6
+            return (f"NCCL all-reduce(AVG) of the flat fp32 gradient arena in 64 MB buckets; {mb:.0f} of {tot:.0f} MB "
+                    "(cross-modal encoders + heads, upper text layers) start DURING backward from in-graph event "
+                    "nodes, the rest when backward has been issued")
+        n = len(self.allreduce.bounds) + (len(self.t_allreduce.bounds) if self.t_allreduce is not None else 0)
+        return f"NCCL all-reduce(AVG) of the flat fp32 gradient arena, {n} buckets, issued after backward"
+
     # -- the device side of one step -------------------------------------------------------------
-    def _finish(self):
+    def _finish(self, fired=None):
         """Gradient exchange + optimizer (kept outside the captured graph when world > 1)."""
+        if self.overlap:
+            # what backward did not already exchange; the teacher's exchange (ICoD) runs under the student's optimizer
+            for i, sy in enumerate(self.syncs):
+                sy.issue_rest(sy.fired if fired is None else fired[i])
+            self.syncs[0].wait()
+            self.opt.apply()
+            if self.co_update:
+                self.syncs[1].wait()
+                self.t_opt.apply()
+            return
         # both exchanges are issued up front: the teacher's all-reduce (ICoD) runs under the student's optimizer
         if self.allreduce is not None:
             self.allreduce.start()
@@ -81,7 +116,9 @@ class PretrainStepper:
                 self.t_allreduce.finish()
             self.t_opt.apply()
 
-    def _device_step(self, task, batch, rw, finish=True):
+    def _device_step(self, task, batch, rw, finish=True, mode="eager"):
+        for sy in self.syncs:
+            sy.begin(mode)
         self.arena.zero_grad()
         if self.co_update:
             self.t_arena.zero_grad()
@@ -92,6 +129,8 @@ class PretrainStepper:
             # produces exactly those gradients
             (mix[0] + mix_t[0]).backward()
             ops.join_side_stream()
+            for sy in self.syncs:
+                sy.join_marker()
             if finish:
                 self._finish()
             return torch.cat([mix, mix_t])
@@ -102,6 +141,8 @@ class PretrainStepper:
             mix = ops.loss_mix(None, None, s_out["loss"], 0.0, s_out.get("loss_inv_n"))
         mix[0].backward()
         ops.join_side_stream()
+        for sy in self.syncs:
+            sy.join_marker()
         if finish:
             self._finish()
         return mix
@@ -207,7 +248,7 @@ class PretrainStepper:
             snap = [(a.flat_p.clone(), o.m.clone(), o.v.clone()) for a, o in pairs]
             with torch.cuda.stream(s):
                 for _ in range(2):
-                    self._device_step(task, static, rw, finish=self.world == 1)
+                    self._device_step(task, static, rw, finish=self.world == 1, mode=None)
                     if self.world > 1:
                         for _, o in pairs:
                             o.apply()
@@ -220,13 +261,17 @@ class PretrainStepper:
             g = torch.cuda.CUDAGraph()
             n0 = _lib.COUNTERS["launches"]
             with torch.cuda.graph(g):
-                out = self._device_step(task, static, rw, finish=self.world == 1)
-            entry = (g, static, out, _lib.COUNTERS["launches"] - n0)
+                out = self._device_step(task, static, rw, finish=self.world == 1, mode="capture")
+            marks = [(list(sy.fired), dict(sy.events)) for sy in self.syncs]
+            entry = (g, static, out, _lib.COUNTERS["launches"] - n0, marks)
             self.graphs[sig] = entry
-        g, static, out, n_launch = entry
+        g, static, out, n_launch, marks = entry
         copy_batch_(static, batch)
         g.replay()
         _lib.COUNTERS["launches"] += n_launch  # kernels replayed inside the graph
         if self.world > 1:
-            self._finish()
+            # the exchange of every stage that completed inside the graph starts at its in-graph event
+            for sy, (fired, events) in zip(self.syncs, marks):
+                sy.after_replay(self.comm_stream, fired, events)
+            self._finish([f for f, _ in marks] if self.overlap else None)
         return out
