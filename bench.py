@@ -410,7 +410,9 @@ class Runner:
             teacher = teacher.train() if w.get("co_update") else teacher.eval()
         self.stepper = PretrainStepper(student, teacher, use_graphs=bool(args.graphs),
                                        co_update=bool(w.get("co_update")), side_stream=bool(args.side_stream),
-                                       branch_streams=bool(args.branch_streams), overlap=bool(args.overlap))
+                                       branch_streams=bool(args.branch_streams), overlap=bool(args.overlap),
+                                       pipeline_teacher=bool(args.pipeline), teacher_sm_budget=args.teacher_sms,
+                                       pdl=None if args.pdl < 0 else ((args.pdl & 1) != 0, (args.pdl & 2) != 0))
         ops.set_seed(dev, 1234 + rank)
         n = self.pool_n = args.pool
         pools = {t: make_pool(t, n, w, 1234 + rank * 1000 + (0 if t == "mlm" else 500)) for t in ("mlm", "sap")}
@@ -440,7 +442,13 @@ class Runner:
                     nxt = stepper.prefetch(t2, self.pin_pools[t2][j2])
             else:
                 b = self.dev_pools[task][j]
-            out = stepper.step(task, b)
+            # a prefetching loader knows the next batch: announce it so a frozen teacher's forward of step i+1 can run
+            # under step i's backward (PretrainStepper.step)
+            ahead = None
+            if i + 1 < first + n:
+                t2, j2 = self.pick(i + 1)
+                ahead = (t2, nxt if from_host else self.dev_pools[t2][j2])
+            out = stepper.step(task, b, next=ahead)
             if from_host:
                 # device -> host read of EVERY step's loss, one step late (async copy into pinned memory + event),
                 # so the host queues step i+1 while step i runs instead of draining the GPU each step
@@ -481,15 +489,21 @@ class Runner:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item()), _lib.COUNTERS["launches"] - c0
 
-    def profile_graph(self, nprof):
+    def profile_graph(self, nprof, serial=True):
         """Per-kernel durations of the REPLAYED graphs: the step graphs are re-captured with an external event-record
         node before and after every C-ABI call (`_lib.profile_start(graph=True)`), replayed `nprof` times per task,
         and every bracket is read with cudaEventElapsedTime after each replay.  Every rank runs the pass (the
         gradient exchange stays matched); rank 0 reports."""
-        from magic_b200 import _lib
+        from magic_b200 import _lib, ops
         st = self.stepper
-        saved = st.graphs
-        st.graphs = {}
+        saved = st.graphs, st.pipeline_teacher, st._t_inflight
+        st.graphs, st._t_inflight = {}, None
+        if serial:
+            # one chain: no stream branches, no weight-gradient side stream, teacher inside the step's graph -- every
+            # bracket then measures ITS kernel alone on the GPU and the brackets add up to the (serial) step
+            st.pipeline_teacher = False
+            ops.enable_branch_streams(False)
+            ops.enable_side_stream(False)
         _lib.profile_start(graph=True)
         try:
             for i in range(2):  # capture (+ first replay) of the MLM and the SAP graph
@@ -514,7 +528,9 @@ class Runner:
                             a[k] += r[0].elapsed_time(r[1])
         finally:
             prof = _lib.profile_stop()
-            st.graphs = saved
+            st.graphs, st.pipeline_teacher, st._t_inflight = saved[0], saved[1], None
+            ops.enable_branch_streams(bool(self.args.branch_streams))
+            ops.enable_side_stream(bool(self.args.side_stream))
         # per record: mean ms per replay of ITS task's graph -> per step (MLM and SAP alternate: each runs nprof times)
         out = {name: [(a / nprof, r[2]) for a, r in zip(acc[name], recs)] for name, recs in prof.items()}
         return out, wall / (2 * nprof)
@@ -587,10 +603,11 @@ def summarise_graph_profile(prof, ms_profiled_step, pk, workload):
     gshapes = [dict(op=k[0], M=k[1], N=k[2], K=k[3], launches_per_step=v[1] / 2, ms_per_step=round(v[0], 4),
                     tflops=round(v[2] / (v[0] * 1e-3) / 1e12, 1) if v[0] > 0 else None)
                for k, v in sorted(shapes.items(), key=lambda kv: -kv[1][0])[:12]]
-    note = dict(mode="events inside the replayed CUDA graph", sum_kernel_ms=round(tot, 4),
-                profiled_step_ms=round(ms_profiled_step, 4), overlap=round(tot / max(ms_profiled_step, 1e-9), 3),
-                note="brackets on concurrent stream branches overlap in time, so the sum of kernel durations may "
-                     "exceed the step; an event node between two kernels removes their PDL overlap")
+    note = dict(mode="CUDA events inside a replayed graph of the same step captured on ONE stream (no branches): each "
+                     "bracket times its kernel alone on the GPU", sum_kernel_ms=round(tot, 4),
+                profiled_step_ms=round(ms_profiled_step, 4),
+                note="the timed region replays the multi-branch graphs (value / ms_per_step); the sum of these "
+                     "single-stream kernel times is the serial length of the same step")
     return top, rooflines, fams, gshapes, note
 
 
@@ -730,6 +747,12 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--compile", type=int, default=0, help="--impl torch_gpu: wrap the step in torch.compile")
     ap.add_argument("--overlap", type=int, default=1, help="N > 1: exchange gradient buckets during backward")
+    ap.add_argument("--pdl", type=int, default=-1,
+                    help="programmatic dependent launch: -1 stepper default, bit 0 = student graph, bit 1 = teacher graph")
+    ap.add_argument("--teacher-sms", type=int, default=0,
+                    help="SMs the pipelined teacher graph's persistent GEMMs may occupy (0 = all)")
+    ap.add_argument("--pipeline", type=int, default=1,
+                    help="frozen teacher: run the next batch's teacher forward under this batch's student backward")
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "f32"])
     ap.add_argument("--dropout", type=float, default=0.1)
     ap.add_argument("--graphs", type=int, default=1)

@@ -30,9 +30,12 @@ typedef struct CUstream_st* cudaStream_t;
 #define MAGIC_ACT_GELU 1
 #define MAGIC_ACT_RELU 2
 #define MAGIC_MAKD_MAX_SEGS 32
+#define MAGIC_SUMSQ_SCRATCH 2048
 
 const char* magic_last_error(void);
 int magic_version(void);
+/* programmatic dependent launch for subsequent launches: 1 on, 0 off, -1 follow env MAGIC_PDL (default on) */
+int magic_set_pdl(int on);
 /* 1 if the tcgen05/TMA GEMM path is compiled in and usable for (M,N,K) bf16 operands */
 int magic_gemm_tc_supported(int M, int N, int K);
 
@@ -143,6 +146,9 @@ int magic_invert_norm(const float* in, float* out, int n, cudaStream_t st);
    gather is the per-row form of t_sample_weights (kd_loss.py:31-40, agent.py:1019); `scale` masks padded rows */
 int magic_row_weights(const float* src, const long long* idx, const float* scale, float* out, int n,
                       cudaStream_t st);
+/* out[i] = valid[i] ? x[i] : fill -- object-grounding logits (`obj_logits.masked_fill_(obj_masks.logical_not(), -inf)`,
+   the OG head of the DUET lineage; batch schema data/tasks.py:503-559); its backward uses fill = 0 */
+int magic_mask_fill(const float* x, const unsigned char* valid, float* out, int n, float fill, cudaStream_t st);
 /* dz = dy * dropscale * act'(pre): backward of a stand-alone Linear+activation (ClsPrediction, MLM transform) */
 int magic_act_bwd(const void* dy, const void* pre, void* dz, long long n, int act, int dtype, float drop_p,
                   unsigned salt, const unsigned long long* seed_ptr, cudaStream_t st);
@@ -209,6 +215,9 @@ int magic_loss_mix_bwd(const float* g, int n, float alpha, const float* inv_n, f
 /* measurement aid: when dev_buf (32 x u64, device) is non-NULL, CTA 0 of every tensor-core GEMM launched afterwards
  * stamps clock64() at its phase boundaries into it (scripts/gemm_trace.py); NULL switches tracing off */
 int magic_gemm_set_trace(unsigned long long* dev_buf);
+/* scheduling hint: SMs the persistent tcgen05 GEMM may occupy from now on (0 = all).  The stepper lowers it while it
+ * captures a graph that runs beside another one, so both make progress instead of queueing SM by SM. */
+int magic_gemm_set_sm_budget(int sms);
 /* measurement aid: keeps the stream busy for ~cycles SM clocks so the host can queue launches ahead of the GPU */
 int magic_delay(long long cycles, cudaStream_t st);
 /* measurement aid (no reference counterpart): events recordable inside a captured CUDA graph (external event-record
@@ -229,6 +238,9 @@ int magic_makd_kl_bwd(const void* s, const void* t, void* ds, int R, int C, long
                       int dtype, cudaStream_t st);
 
 /* ---- optimizer (pretrain_src/optim/adamw.py:53-112, clip grad_norm r2r_magic_pretrain.json:22) ----- */
+/* out[0] (+)= sum g^2, deterministic (two-stage, no floating-point atomics: data-parallel replicas with identical
+ * gradients compute the identical clip coefficient).  `out` must hold 1 + MAGIC_SUMSQ_SCRATCH floats: out[1..] is the
+ * scratch of the per-CTA partials. */
 int magic_sumsq(const float* g, long long n, float* out, int zero_first, cudaStream_t st);
 int magic_adamw(float* p, const float* g, float* m, float* v, void* bf16_shadow, long long n, const float* hyper,
                 float weight_decay, const float* sumsq, cudaStream_t st);

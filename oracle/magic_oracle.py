@@ -268,15 +268,27 @@ class ImageEmbeddings(nn.Module):
         self.loc_linear = nn.Linear(c.angle_feat_size + 3, h)
         self.loc_layer_norm = nn.LayerNorm(h, eps=c.layer_norm_eps)
         self.nav_type_embedding = nn.Embedding(3, h)
+        if getattr(c, "obj_feat_size", 0) > 0:  # object tokens (REVERIE / SOON), DUET-lineage names
+            self.obj_linear = nn.Linear(c.obj_feat_size, h)
+            self.obj_layer_norm = nn.LayerNorm(h, eps=c.layer_norm_eps)
+        else:
+            self.obj_linear = self.obj_layer_norm = None
         self.layer_norm = nn.LayerNorm(h, eps=c.layer_norm_eps)
         self.dropout = nn.Dropout(c.hidden_dropout_prob)
         self.pano_encoder = PanoEncoder(c) if c.num_pano_layers > 0 else None
         # [DECISION] adaptive pano fusion = learned attention pooling over the valid views (A.2)
         self.adaptive_pano_attn = nn.Linear(h, 1) if c.adaptive_pano_fusion else None
 
-    def forward(self, img_fts, loc_fts, nav_types, view_lens, type_embed):
-        e = self.img_layer_norm(self.img_linear(img_fts)) + self.loc_layer_norm(self.loc_linear(loc_fts)) \
-            + self.nav_type_embedding(nav_types) + type_embed
+    def forward(self, img_fts, loc_fts, nav_types, view_lens, type_embed, obj_fts=None, obj_lens=None):
+        img = self.img_layer_norm(self.img_linear(img_fts))
+        if obj_fts is not None and self.obj_linear is not None:
+            # tokens of a panorama = its views followed by its objects (dataset.py:447,494-508), padded to the longest
+            obj = self.obj_layer_norm(self.obj_linear(obj_fts))
+            rows = [torch.cat([img[r, :int(view_lens[r])], obj[r, :int(obj_lens[r])]], 0) for r in range(img.shape[0])]
+            n = loc_fts.shape[1]
+            img = torch.stack([F.pad(x, (0, 0, 0, n - x.shape[0])) for x in rows], 0)
+            view_lens = view_lens + obj_lens
+        e = img + self.loc_layer_norm(self.loc_linear(loc_fts)) + self.nav_type_embedding(nav_types) + type_embed
         e = self.dropout(self.layer_norm(e))
         mask = gen_seq_masks(view_lens, e.shape[1])
         attns = []
@@ -345,11 +357,14 @@ def aggregate_gmap_features(pano_embeds, pano_fused, batch):
 
 
 def vp_lens_of(batch):
-    """Number of valid local tokens = views of the LAST step + 1 ([stop]) -- DUET lineage computes this inside
+    """Number of valid local tokens = tokens (views + objects) of the LAST step + 1 ([stop]) -- DUET lineage computes this inside
     the model from traj_vp_view_lens.  NB the reference collate's own batch['vp_lens'] is `len(x[-1])` of a
     [Vp,14] tensor, i.e. the constant 14 (pretrain_src/data/tasks.py:153); it is not usable as a length."""
     rows = last_step_rows(batch)
-    return batch["traj_vp_view_lens"][rows] + 1
+    lens = batch["traj_vp_view_lens"][rows]
+    if batch.get("traj_vp_obj_lens") is not None:
+        lens = lens + batch["traj_vp_obj_lens"][rows]
+    return lens + 1
 
 
 def last_step_rows(batch):
@@ -423,7 +438,8 @@ class GlocalTextPathCMT(nn.Module):
     def forward_pano(self, batch):
         type_embed = self.embeddings.token_type_embeddings.weight[0]  # [DECISION] type index 0 (A.2)
         return self.img_embeddings(batch["traj_view_img_fts"], batch["traj_loc_fts"], batch["traj_nav_types"],
-                                   batch["traj_vp_view_lens"], type_embed)
+                                   batch["traj_vp_view_lens"], type_embed, batch.get("traj_obj_img_fts"),
+                                   batch.get("traj_vp_obj_lens"))
 
     def gmap_input(self, pano_embeds, pano_fused, batch):
         ge = self.global_encoder
@@ -527,6 +543,8 @@ class GlocalTextPathCMTPreTraining(nn.Module):
         if "cfp" in tasks:
             for n in ("cfp_gmap_proj", "cfp_vp_proj", "cfp_txt_proj"):
                 setattr(self, n, nn.Linear(c.hidden_size, c.hidden_size))
+        if "og" in tasks:
+            self.og_head = ClsPrediction(c.hidden_size, eps=c.layer_norm_eps)
         self.apply(self._init)
 
     def _init(self, m):
@@ -552,7 +570,26 @@ class GlocalTextPathCMTPreTraining(nn.Module):
             return self.forward_mrc(batch, compute_loss)
         if task.startswith("cfp"):
             return self.forward_cfp(batch, compute_loss)
+        if task.startswith("og"):
+            return self.forward_og(batch, compute_loss)
         raise ValueError("invalid task")
+
+    def forward_og(self, batch, compute_loss):
+        """[INFERRED, DUET lineage forward_og] object tokens of the last panorama, read from the local branch
+        (vp_embeds[b, 1 + view_len : 1 + view_len + obj_len]), scored by og_head, -inf on padded slots, CE with
+        ignore_index -100 (dataset.py:318)."""
+        o = self.bert(batch, "nav")
+        rows = last_step_rows(batch)
+        vl, ol = batch["traj_vp_view_lens"][rows], batch["traj_vp_obj_lens"][rows]
+        O = batch["traj_obj_img_fts"].shape[1]
+        v = o["vp_embeds"]
+        obj = torch.stack([F.pad(v[b, 1 + int(vl[b]): 1 + int(vl[b]) + int(ol[b])], (0, 0, 0, O - int(ol[b])))
+                           for b in range(v.shape[0])], 0)
+        logits = self.og_head(obj).squeeze(2).masked_fill(~gen_seq_masks(ol, O), float("-inf"))
+        if not compute_loss:
+            return logits
+        o.update(loss=F.cross_entropy(logits, batch["obj_labels"], reduction="none", ignore_index=-100), logits=logits)
+        return o
 
     def forward_mlm(self, batch, compute_loss):
         o = self.bert(batch, "lang")

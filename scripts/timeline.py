@@ -23,6 +23,8 @@ def main():
     ap.add_argument("--graphs", type=int, default=1)
     ap.add_argument("--dropout", type=float, default=0.1)
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "timeline.csv"))
+    ap.add_argument("--lookahead", type=int, default=1)
+    ap.add_argument("--sync", type=int, default=0, help="synchronize after every step (isolates the steps)")
     args = ap.parse_args()
     import magic_b200
     from magic_b200 import ops
@@ -42,9 +44,13 @@ def main():
     pools = {t: [batch_to_device(b, dev) for b in bench.make_pool(t, 2, w, 1234 + (0 if t == "mlm" else 500))]
              for t in ("mlm", "sap")}
 
-    def step(i):
+    def pick(i):
         task = "mlm" if i % 2 == 0 else "sap"
-        return stepper.step(task, pools[task][(i // 2) % 2])
+        return task, pools[task][(i // 2) % 2]
+
+    def step(i):
+        task, b = pick(i)
+        return stepper.step(task, b, next=pick(i + 1) if args.lookahead else None)
 
     for i in range(6):
         step(i)
@@ -53,7 +59,9 @@ def main():
     with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
         for i in range(args.steps):
             step(i)
-            torch.cuda.synchronize()
+            if args.sync:
+                torch.cuda.synchronize()
+        torch.cuda.synchronize()
     evs = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA]
     rows = []
     for e in evs:

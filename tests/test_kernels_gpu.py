@@ -517,8 +517,11 @@ def test_adamw_matches_reference_update_order():
     lr, b1, b2, eps, wd, maxn = 5e-5, 0.9, 0.98, 1e-6, 0.01, 5.0
     rm, rv, rp = torch.zeros(n, device=DEV), torch.zeros(n, device=DEV), p0.clone()
     for step in range(1, 4):
-        ss = torch.zeros(1, device=DEV)
+        ss = torch.zeros(1 + 2048, device=DEV)  # [0] = sum g^2, the rest is the kernel's scratch (MAGIC_SUMSQ_SCRATCH)
         L.call("magic_sumsq", g.data_ptr(), n, ss.data_ptr(), 1, L.stream())
+        ss2 = torch.zeros(1 + 2048, device=DEV)
+        L.call("magic_sumsq", g.data_ptr(), n, ss2.data_ptr(), 1, L.stream())
+        assert torch.equal(ss[0], ss2[0])  # deterministic: no floating-point atomics
         bc1, bc2 = 1 - b1 ** step, 1 - b2 ** step
         hyper = torch.tensor([lr, lr * math.sqrt(bc2) / bc1, b1, b2, eps, maxn, 0, 0], device=DEV)
         shadow = torch.empty(n, device=DEV, dtype=torch.bfloat16)

@@ -284,6 +284,54 @@ def test_cfp_head(dtype, tol, gtol):
         assert prod.cfp_txt_proj.weight.grad.abs().max() > 0
 
 
+@pytest.mark.parametrize("dtype,tol,gtol", [(torch.float32, 1e-4, 2e-3), (torch.bfloat16, 2e-2, None)])
+def test_og_head(dtype, tol, gtol):
+    """OG (a9): object tokens appended to every panorama (og_collate, data/tasks.py:503-559), obj_linear + LN token
+    embeddings, the OG head on the local branch, -inf on padded object slots, CE with ignore -100."""
+    oracle, prod = build_pair(128, seed=12, pretrain_tasks=("mlm", "sap", "og"), obj_feat_size=48)
+    prod.set_compute_dtype(dtype)
+    b = synth.make_batch("og", 6, seed=23, obj_dim=48, max_objects=5)
+    prepare_batch(b)
+    b = batch_to_device(b, DEV)
+    assert b["traj_loc_fts"].shape[1] == 36 + 5 and b["vp_pos_fts"].shape[1] == 36 + 5 + 1
+    b["obj_labels"][1] = -100  # an ignored sample (dataset.py:318: ground-truth object not among the kept objects)
+    assert (b["obj_labels"] >= 0).any()
+    with torch.no_grad():
+        rl, pl = oracle(oracle_batch(b), "og", False), prod(b, "og", False)
+    assert pl.shape == rl.shape == (6, 5)
+    assert torch.equal(torch.isinf(pl), torch.isinf(rl))          # padded object slots: bit-exact masks
+    fin = torch.isfinite(rl)
+    assert rel(pl[fin], rl[fin]) < tol
+    if dtype == torch.float32:
+        has = fin.any(1)
+        assert torch.equal(pl[has].argmax(1), rl[has].argmax(1))
+    oracle.train()
+    prod.train()
+    ro, po = oracle(oracle_batch(b), "og", True), prod(b, "og", True)
+    assert rel(po["loss"], ro["loss"]) < tol
+    assert rel(po["pano_embeds"], ro["pano_embeds"]) < tol and rel(po["vp_embeds"], ro["vp_embeds"]) < tol
+    # the SAP masks of the same batch: object tokens (nav type 2) are never navigable
+    if gtol is not None:
+        ro["loss"].mean().backward()
+        po["loss"].mean().backward()
+        go = dict(oracle.named_parameters())
+        bad = [(n, rel(p.grad, go[n].grad)) for n, p in prod.named_parameters()
+               if go[n].grad is not None and go[n].grad.norm() > 1e-7 and rel(p.grad, go[n].grad) > gtol]
+        assert not bad, bad[:10]
+        assert prod.og_head.net[0].weight.grad.abs().max() > 0
+        assert prod.bert.img_embeddings.obj_linear.weight.grad.abs().max() > 0
+        assert torch.isfinite(torch.stack([p.grad.abs().max() for p in prod.parameters() if p.grad is not None])).all()
+
+
+def test_og_needs_object_features():
+    _, prod = build_pair(128, seed=13, pretrain_tasks=("mlm", "sap", "og"), obj_feat_size=48)
+    b = get_batch("sap", B=2, seed=5)
+    with pytest.raises(ValueError):
+        prod(b, "og", True)
+    with pytest.raises(ValueError):  # the shipped R2R / RxR config has obj_feat_size 0
+        build_pair(128, seed=13, pretrain_tasks=("mlm", "og"))
+
+
 def test_unknown_task_raises_like_reference():
     _, prod = build_pair(128, seed=11)
     b = get_batch("sap", B=2, seed=5)

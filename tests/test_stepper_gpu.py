@@ -48,23 +48,36 @@ def host_pool(n=3, B=4):
     return pools
 
 
-def run(teacher, n_steps=4, prefetch=False, **kw):
+def run(teacher, n_steps=4, prefetch=False, lookahead=False, order=None, **kw):
+    """`lookahead`: announce the next batch to step() (frozen-teacher pipelining: its teacher forward runs under the
+    current step's backward).  `order`: task sequence (default MLM / SAP alternating)."""
     s, t = models(teacher)
     g = torch.Generator().manual_seed(7)
     st = PretrainStepper(s, t, lr=1e-3, rw_generator=g, **kw)
     pools = host_pool()
-    losses = []
-    for i in range(n_steps):
-        task = "mlm" if i % 2 == 0 else "sap"
-        hb = pools[task][(i // 2) % len(pools[task])]
+    order = order or ["mlm" if i % 2 == 0 else "sap" for i in range(n_steps)]
+    seen = {"mlm": 0, "sap": 0}
+
+    def stage(task):
+        hb = pools[task][seen[task] % len(pools[task])]
+        seen[task] += 1
         if prefetch:
             pinned = {k: (v.pin_memory() if torch.is_tensor(v) else
                           ({kk: (vv.pin_memory() if torch.is_tensor(vv) else vv) for kk, vv in v.items()}
                            if k == magic_b200.INDEX_KEY else v)) for k, v in hb.items()}
-            b = st.prefetch(task, pinned)
+            return st.prefetch(task, pinned)
+        return batch_to_device(hb, DEV)
+
+    losses = []
+    nxt = stage(order[0])
+    for i, task in enumerate(order):
+        b = nxt
+        nxt = stage(order[i + 1]) if i + 1 < len(order) else None
+        if lookahead and nxt is not None:
+            torch.cuda.synchronize()  # a batch announced as `next` must be resident
+            losses.append(st.step(task, b, next=(order[i + 1], nxt)).clone())
         else:
-            b = batch_to_device(hb, DEV)
-        losses.append(st.step(task, b).clone())
+            losses.append(st.step(task, b).clone())
     torch.cuda.synchronize()
     return torch.stack(losses).cpu(), st.arena.flat_p.clone().cpu()
 
@@ -82,6 +95,21 @@ def test_graph_streams_prefetch_match_plain_eager(teacher):
         l, p = run(teacher, **kw)
         assert rel(l, base_l) < 2e-5, (kw, l, base_l)
         assert rel(p, base_p) < 2e-5, kw
+
+
+def test_teacher_pipelining_matches_serial_order():
+    """Frozen teacher + graphs: the teacher forward of the announced next batch runs on its own stream under the
+    current step's backward.  Same losses and parameters as the plain eager step -- alternating tasks (teacher output
+    buffers of the two tasks are disjoint) and a sequence with repeated tasks (the next teacher forward must wait
+    for the step that still reads those buffers), with resident batches and with prefetched ones."""
+    for order in (None, ["sap", "sap", "mlm", "mlm", "mlm", "sap"]):
+        n = 6
+        base_l, base_p = run(True, n_steps=n, order=order, use_graphs=False, side_stream=False, branch_streams=False)
+        for kw in (dict(lookahead=True), dict(lookahead=True, prefetch=True), dict(lookahead=False),
+                   dict(lookahead=True, pipeline_teacher=False)):
+            l, p = run(True, n_steps=n, order=order, use_graphs=True, **kw)
+            assert rel(l, base_l) < 2e-5, (order, kw, l, base_l)
+            assert rel(p, base_p) < 2e-5, (order, kw)
 
 
 def test_graph_replay_follows_per_step_mkrw_draw():

@@ -1,5 +1,6 @@
 """Host logic: the synthetic batch generator's collate must reproduce the reference collate functions
-(pretrain_src/data/tasks.py:110-166 mlm_collate, :392-451 sap_collate) key by key, bit-exactly."""
+(pretrain_src/data/tasks.py:110-166 mlm_collate, :263-324 mrc_collate, :392-451 sap_collate, :503-559 og_collate,
+:618-677 cfp_collate) key by key, bit-exactly."""
 import os
 import sys
 import types
@@ -34,10 +35,10 @@ def _ref_tasks():
 
 
 @pytest.mark.skipif(not os.path.exists(REF), reason="reference not mounted")
-@pytest.mark.parametrize("task", ["mlm", "sap", "mrc", "cfp"])
+@pytest.mark.parametrize("task", ["mlm", "sap", "mrc", "cfp", "og"])
 def test_collate_matches_reference(task):
     tasks = _ref_tasks()
-    samples = synth.make_samples(task, 6, seed=5)
+    samples = synth.make_samples(task, 6, seed=5, obj_dim=32 if task == "og" else 0)
     ours = synth.collate([dict(s) for s in samples])
     ref_samples = [dict(s) for s in samples]
     if task == "cfp":  # CfpDataset adds a per-sample config echo (data/tasks.py:606); not a model input

@@ -869,6 +869,20 @@ int get_map(const void* ptr, uint64_t inner, uint64_t outer, uint64_t stride, ui
   return MAGIC_OK;
 }
 
+// SMs the persistent GEMM may occupy (MAGIC_TC_MAX_SMS, default all; magic_gemm_set_sm_budget overrides per call site)
+int g_sm_budget = 0;
+int tc_sm_budget() {
+  static int env = -1;
+  if (env < 0) {
+    const char* e = getenv("MAGIC_TC_MAX_SMS");
+    env = e ? atoi(e) : 0;
+  }
+  int v = g_sm_budget > 0 ? g_sm_budget : env;
+  const int sms = magic_num_sms();
+  if (v <= 0 || v > sms) v = sms;
+  return v < 2 ? 2 : v;
+}
+
 constexpr size_t SMEM_MAX = 227 * 1024;
 constexpr size_t SMEM_FIXED = 1024 /*align slack*/ + NUM_EPI_WARPS * STG_BUFS * STG_BYTES + ONES_BYTES + BIAS_BYTES +
                               (2 * MAX_STAGES + 4) * 8 + 16;
@@ -881,8 +895,13 @@ int launch_tc_k(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap&
   if (stages > MAX_STAGES) stages = MAX_STAGES;
   // never more stages than k-blocks a CTA will ever load
   const long work = (long)P.m_tiles * P.n_tiles * P.splits;
-  const int slots = magic_num_sms() / CTAS;  // CTAs (CTAS = 1) or CTA pairs (CTAS = 2) that run at once
-  const int groups = (int)(work < slots ? work : slots);
+  const int slots = tc_sm_budget() / CTAS;  // CTAs (CTAS = 1) or CTA pairs (CTAS = 2) that run at once
+  // balanced waves: the SMALLEST grid that still finishes in ceil(work / slots) rounds.  5120-row GEMMs of the
+  // h = 768 encoders make 60 / 180 / 240 pair tiles: 60 CTA pairs need 1 / 3 / 4 rounds, exactly like 74 would, and
+  // the 28 SMs left alone run the kernels of the concurrent branches (student, panorama encoder, next teacher) that
+  // would otherwise queue behind a persistent CTA holding an SM's whole shared memory and TMEM
+  const long waves = (work + slots - 1) / slots;
+  const int groups = (int)((work + waves - 1) / waves);
   const long per_cta_kb = ((work + groups - 1) / groups) * (long)P.kb_per_split;
   if (stages > per_cta_kb) stages = (int)(per_cta_kb < 2 ? 2 : per_cta_kb);
   P.stages = stages;
@@ -955,6 +974,11 @@ int force_bn() {
 }
 
 }  // namespace
+
+extern "C" int magic_gemm_set_sm_budget(int sms) {
+  g_sm_budget = sms;
+  return MAGIC_OK;
+}
 
 extern "C" int magic_gemm_set_trace(unsigned long long* dev_buf) {
   g_trace = dev_buf;

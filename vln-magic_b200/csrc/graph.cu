@@ -222,6 +222,14 @@ __global__ void __launch_bounds__(256)
   T* drow = dlogits + (size_t)r * ld;
   constexpr int VN = RowVec<T>::N;
   const int cv = vec ? (C / VN) * VN : 0;
+  if (y == ignore_index) {  // exact zeros, also for a row whose logits are all -inf (lse = -inf would give NaN)
+    float z[VN];
+#pragma unroll
+    for (int i = 0; i < VN; i++) z[i] = 0.f;
+    for (int c = threadIdx.x * VN; c < cv; c += blockDim.x * VN) RowVec<T>::store(drow + c, z);
+    for (int c = cv + threadIdx.x; c < C; c += blockDim.x) stf(drow, c, 0.f);
+    return;
+  }
   for (int c = threadIdx.x * VN; c < cv; c += blockDim.x * VN) {
     float v[VN];
     RowVec<T>::load(row + c, v);

@@ -8,7 +8,12 @@
 
 namespace {
 
-__global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ g, long long n, float* __restrict__ out) {
+// Sum of squares in TWO deterministic stages: every CTA writes its partial to `partials[blockIdx.x]` (fixed grid,
+// fixed per-thread element order), then one CTA adds the partials in index order.  No floating-point atomics: the
+// clip coefficient is a function of the gradient values alone, so data-parallel replicas that hold bit-identical
+// gradients after the exchange stay bit-identical after the step.
+__global__ void __launch_bounds__(256) sumsq_partial_kernel(const float* __restrict__ g, long long n,
+                                                            float* __restrict__ partials) {
   __shared__ float red[32];
   float a = 0.f;
   const long long n4 = n / 4;
@@ -21,7 +26,15 @@ __global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ g,
        i += (long long)gridDim.x * blockDim.x)
     a += g[i] * g[i];
   a = block_sum(a, red);
-  if (threadIdx.x == 0) atomicAdd(out, a);
+  if (threadIdx.x == 0) partials[blockIdx.x] = a;
+}
+__global__ void __launch_bounds__(256) sumsq_final_kernel(const float* __restrict__ partials, int np,
+                                                          float* __restrict__ out, int accumulate) {
+  __shared__ float red[32];
+  float a = 0.f;
+  for (int i = threadIdx.x; i < np; i += blockDim.x) a += partials[i];  // fixed assignment, fixed order
+  a = block_sum(a, red);
+  if (threadIdx.x == 0) out[0] = accumulate ? out[0] + a : a;
 }
 
 // hyper (device, fp32): [0] lr  [1] step_size = lr*sqrt(1-b2^t)/(1-b1^t)  [2] beta1  [3] beta2  [4] eps
@@ -73,15 +86,21 @@ int magic_delay(long long cycles, cudaStream_t st) {
 
 
 int magic_sumsq(const float* g, long long n, float* out, int zero_first, cudaStream_t st) {
-  if (zero_first) MAGIC_CUDA(cudaMemsetAsync(out, 0, sizeof(float), st), "magic_sumsq");
-  if (n <= 0) return MAGIC_OK;
+  if (n <= 0) {
+    if (zero_first) MAGIC_CUDA(cudaMemsetAsync(out, 0, sizeof(float), st), "magic_sumsq");
+    return MAGIC_OK;
+  }
   MAGIC_CHECK_ARG(((uintptr_t)g % 16) == 0, "magic_sumsq: pointer must be 16-byte aligned");
   long long blocks = (n / 4 + 255) / 256;
   const long long cap = 8LL * magic_num_sms();
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
-  sumsq_kernel<<<(int)blocks, 256, 0, st>>>(g, n, out);
+  if (blocks > MAGIC_SUMSQ_SCRATCH) blocks = MAGIC_SUMSQ_SCRATCH;
+  float* partials = out + 1;  // the caller's buffer carries the scratch: out[1 .. MAGIC_SUMSQ_SCRATCH]
+  sumsq_partial_kernel<<<(int)blocks, 256, 0, st>>>(g, n, partials);
   MAGIC_CHECK_LAUNCH("magic_sumsq");
+  sumsq_final_kernel<<<1, 256, 0, st>>>(partials, (int)blocks, out, zero_first ? 0 : 1);
+  MAGIC_CHECK_LAUNCH("magic_sumsq(final)");
   return MAGIC_OK;
 }
 

@@ -884,6 +884,13 @@ __global__ void row_weights_kernel(const float* __restrict__ src, const long lon
   out[i] = v * (scale ? scale[i] : 1.f);
 }
 
+// out[i] = valid[i] ? x[i] : fill   (object-grounding logits: -inf on padded object slots; backward: fill = 0)
+__global__ void mask_fill_kernel(const float* __restrict__ x, const unsigned char* __restrict__ valid,
+                                 float* __restrict__ out, int n, float fill) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = valid[i] ? x[i] : fill;
+}
+
 __global__ void exp_decay_kernel(const float* __restrict__ in, float* __restrict__ out, int n, float rate) {
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
     out[i] = expf(-rate * in[i]);
@@ -1205,6 +1212,13 @@ int magic_row_weights(const float* src, const long long* idx, const float* scale
   if (n <= 0) return MAGIC_OK;
   row_weights_kernel<<<(n + 255) / 256, 256, 0, st>>>(src, idx, scale, out, n);
   MAGIC_CHECK_LAUNCH("magic_row_weights");
+  return MAGIC_OK;
+}
+
+int magic_mask_fill(const float* x, const unsigned char* valid, float* out, int n, float fill, cudaStream_t st) {
+  if (n <= 0) return MAGIC_OK;
+  mask_fill_kernel<<<(n + 255) / 256, 256, 0, st>>>(x, valid, out, n, fill);
+  MAGIC_CHECK_LAUNCH("magic_mask_fill");
   return MAGIC_OK;
 }
 

@@ -20,12 +20,17 @@ def build_index(batch):
     """-> dict of CPU tensors (int32 / uint8 / int64 / float32) + python ints."""
     steps = batch["traj_step_lens"]
     B = len(steps)
-    V = batch["traj_view_img_fts"].shape[1]
+    Vv = batch["traj_view_img_fts"].shape[1]
+    # tokens per panorama: the views, followed by the panorama's object tokens when the batch carries objects
+    # (og_collate, data/tasks.py:503-559; token order dataset.py:447)
+    V = batch["traj_loc_fts"].shape[1]
     G = batch["gmap_step_ids"].shape[1]
     Vp = batch["vp_pos_fts"].shape[1]
     gmap_lens = _cpu(batch["gmap_lens"]).tolist()
     visited_masks = _cpu(batch["gmap_visited_masks"]).numpy().astype(bool)
     view_lens = _cpu(batch["traj_vp_view_lens"])
+    obj_lens = _cpu(batch["traj_vp_obj_lens"]) if batch.get("traj_vp_obj_lens") is not None else None
+    tok_lens = view_lens if obj_lens is None else view_lens + obj_lens
     nav_types = _cpu(batch["traj_nav_types"]).numpy()
 
     node_ptr, entries = [0], []
@@ -52,7 +57,7 @@ def build_index(batch):
     n_rows = row0
     # valid local tokens = views of the last step + [stop] (DUET lineage; the reference collate's 'vp_lens' key is
     # the constant 14 = len(x[-1]) of a [Vp,14] tensor, pretrain_src/data/tasks.py:153, and is not a length)
-    vp_lens_t = view_lens[torch.as_tensor(last_rows, dtype=torch.int64)] + 1
+    vp_lens_t = tok_lens[torch.as_tensor(last_rows, dtype=torch.int64)] + 1
     vp_lens = vp_lens_t.tolist()
 
     # reverse CSR (unique source -> nodes, weights 1/count(node)) for the deterministic backward
@@ -111,9 +116,27 @@ def build_index(batch):
         last_rows=torch.from_numpy(np.asarray(last_rows, dtype=np.int64)),
         stop_rows_g=torch.arange(B, dtype=torch.int64) * G, stop_rows_v=torch.arange(B, dtype=torch.int64) * Vp,
         key_lens_txt=_cpu(batch["txt_lens"]).to(torch.int32), key_lens_gmap=_cpu(batch["gmap_lens"]).to(torch.int32),
-        key_lens_vp=vp_lens_t.to(torch.int32), key_lens_pano=_cpu(batch["traj_vp_view_lens"]).to(torch.int32),
+        key_lens_vp=vp_lens_t.to(torch.int32), key_lens_pano=tok_lens.to(torch.int32),
         n_nodes=B * G, n_src=int(len(src_ids)),
     )
+    if obj_lens is not None:
+        # panorama token t of row r comes from view t (t < view_len) or object t - view_len; -1 = padding (zero row)
+        R, O = n_rows, batch["traj_obj_img_fts"].shape[1]
+        tt = np.arange(V)[None, :]
+        vl, ol = view_lens.numpy()[:, None], obj_lens.numpy()[:, None]
+        rr = np.arange(R)[:, None]
+        idx["pano_view_src"] = torch.from_numpy(np.where(tt < vl, rr * Vv + tt, -1).astype(np.int64).reshape(-1))
+        idx["pano_obj_src"] = torch.from_numpy(
+            np.where((tt >= vl) & (tt < vl + ol), rr * O + (tt - vl), -1).astype(np.int64).reshape(-1))
+        idx["pano_lens"] = tok_lens.to(torch.int64)
+        # OG head: the object tokens of the LAST panorama inside the local sequence ([stop] + views + objects)
+        last = np.asarray(last_rows)
+        kk = np.arange(O)[None, :]
+        lv, lo = view_lens.numpy()[last][:, None], obj_lens.numpy()[last][:, None]
+        ok = kk < lo
+        idx["og_rows"] = torch.from_numpy(
+            np.where(ok, np.arange(B)[:, None] * Vp + 1 + lv + kk, -1).astype(np.int64).reshape(-1))
+        idx["og_valid"] = torch.from_numpy(ok.astype(np.uint8))
     Lt = batch["txt_ids"].shape[1]
     idx["cls_rows_txt"] = torch.arange(B, dtype=torch.int64) * Lt
     idx["arange_b"] = torch.arange(B, dtype=torch.int64)
@@ -156,6 +179,8 @@ def pad_batch(batch, n_panos=None, n_masked=None, n_entries=None, n_sources=None
         R = batch["traj_view_img_fts"].shape[0]
         if n_panos < R:
             raise ValueError(f"pano capacity {n_panos} < {R}")
+        if n_panos > R and batch.get("traj_obj_img_fts") is not None:
+            raise NotImplementedError("pad_batch: object-grounding batches are not padded (og is not an R2R / RxR task)")
         if n_panos > R:
             def padr(t, value=0):
                 pad = torch.full((n_panos - R, *t.shape[1:]), value, dtype=t.dtype)

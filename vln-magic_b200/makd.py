@@ -236,6 +236,25 @@ def distill_step_loss(student, teacher, batch, task, rw, kdl=None):
     return mix, res, s_out, t_out
 
 
+def teacher_forward(teacher, batch, task):
+    """The frozen teacher's half of the distillation step (no grad, KD outputs on)."""
+    with torch.no_grad():
+        return teacher(batch, task, True, output_kd=True)
+
+
+def student_distill_loss(student, t_out, batch, task, rw, kdl=None):
+    """The student's half: forward, MAKD losses against the given teacher outputs, alpha mix.
+    `distill_step_loss` == `student_distill_loss(student, teacher_forward(teacher, batch, task), ...)`; the split
+    lets the stepper run the frozen teacher's forward of the NEXT batch while this batch back-propagates.
+    Returns (mix [total, sup_mean, kd_total], kd result dict, s_out)."""
+    k = kdl_config(kdl)
+    s_out = student(batch, task, True, output_kd=True)
+    t_w = _sample_weights(t_out, k)
+    res = compute_kd_losses(student, s_out, t_out, task, rw, t_w, k)
+    mix = ops.loss_mix(res["mse_total"], res["kl"], s_out["loss"], k["kd_alpha"], s_out.get("loss_inv_n"))
+    return mix, res, s_out
+
+
 def icod_step_loss(student, teacher, batch, task, rw, t_rw, kdl=None):
     """ICoD co-update (`--train_kdl_teacher`; agent.py:1019-1022, 1136-1149, agent_base.py:260-279): the large
     model's forward runs WITH grad and one step produces two losses, one per model, from two disjoint autograd

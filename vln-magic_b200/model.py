@@ -127,6 +127,11 @@ class _ImageEmbeddings(nn.Module):
         self.loc_linear = nn.Linear(c.angle_feat_size + 3, h)
         self.loc_layer_norm = nn.LayerNorm(h, eps=c.layer_norm_eps)
         self.nav_type_embedding = nn.Embedding(3, h)
+        if _cfg(c, "obj_feat_size", 0) > 0:  # REVERIE / SOON object tokens (DUET lineage names)
+            self.obj_linear = nn.Linear(c.obj_feat_size, h)
+            self.obj_layer_norm = nn.LayerNorm(h, eps=c.layer_norm_eps)
+        else:
+            self.obj_linear = self.obj_layer_norm = None
         self.layer_norm = nn.LayerNorm(h, eps=c.layer_norm_eps)
         self.dropout = nn.Dropout(c.hidden_dropout_prob)
         self.pano_encoder = _PanoEncoder(c) if c.num_pano_layers > 0 else None
@@ -323,6 +328,18 @@ class GlocalTextPathCMT(nn.Module):
             x_in = x_in.to(fc.dtype)  # TODO(fuse): fp32 -> bf16 cast of the CLIP features into the GEMM loader
         z = ops.linear(x_in, ie.img_linear.weight, ie.img_linear.bias)
         a = _ln(z, ie.img_layer_norm, fc)
+        view_lens = batch["traj_vp_view_lens"]
+        if batch.get("traj_obj_img_fts") is not None and ie.obj_linear is not None:
+            # object tokens follow each panorama's views ([cand_views, noncand_views, objs], dataset.py:447): embed
+            # them with their own linear + LN and interleave by the host-built row tables (-1 = padding -> zero row)
+            ofts = batch["traj_obj_img_fts"]
+            o_in = ofts.reshape(-1, ofts.shape[-1])
+            if o_in.dtype != fc.dtype:
+                o_in = o_in.to(fc.dtype)
+            ao = _ln(ops.linear(o_in, ie.obj_linear.weight, ie.obj_linear.bias), ie.obj_layer_norm, fc)
+            a = ops.add(ops.gather_rows(a, ix["pano_view_src"]), ops.gather_rows(ao, ix["pano_obj_src"]))
+            V = batch["traj_loc_fts"].shape[1]
+            view_lens = ix["pano_lens"]
         typ = e.token_type_embeddings.weight if e.token_type_embeddings.weight.shape[0] == 1 else \
             e.token_type_embeddings.weight[0].contiguous()
         s = ops.posfuse(a, batch["traj_nav_types"].reshape(-1), ie.nav_type_embedding.weight, typ,
@@ -349,7 +366,7 @@ class GlocalTextPathCMT(nn.Module):
         x3 = x.view(R, V, h)
         ap = ie.adaptive_pano_attn
         fused = ops.pano_fuse(x3, ap.weight if ap is not None else None, ap.bias if ap is not None else None,
-                              batch["traj_vp_view_lens"])
+                              view_lens)
         return x3, fused, attns
 
     def gmap_input(self, pano, fused, batch, ix, fc):
@@ -444,6 +461,11 @@ class GlocalTextPathCMTPreTraining(nn.Module):
         if "cfp" in tasks:
             for n in ("cfp_gmap_proj", "cfp_vp_proj", "cfp_txt_proj"):
                 setattr(self, n, nn.Linear(h, h))
+        if "og" in tasks:
+            if _cfg(c, "obj_feat_size", 0) <= 0:
+                raise ValueError("the og task needs obj_feat_size > 0 (r2r_magic_model_config.json:48 sets 0: R2R / RxR "
+                                 "have no object features)")
+            self.og_head = _ClsPrediction(h, eps=c.layer_norm_eps)
         self.compute_dtype = torch.float32
         self.output_kd = bool(_cfg(c, "kd", False))
         self.apply(self._init_weights)
@@ -525,8 +547,7 @@ class GlocalTextPathCMTPreTraining(nn.Module):
         if task.startswith("cfp"):
             return self.forward_cfp(batch, compute_loss)
         if task.startswith("og"):
-            raise NotImplementedError("og (object grounding) needs obj_feat_size > 0; R2R/RxR configs set it to 0 "
-                                      "(r2r_magic_model_config.json:48)")
+            return self.forward_og(batch, compute_loss)
         raise ValueError("invalid task")
 
     def forward_mlm(self, batch, compute_loss=True):
@@ -608,6 +629,27 @@ class GlocalTextPathCMTPreTraining(nn.Module):
         if not compute_loss:
             return (logits.float() if logits.dtype != torch.float32 else logits), targets, None, None
         o.update(loss=ops.soft_cross_entropy(logits, targets), logits=logits, view_targets=targets)
+        return o
+
+    def forward_og(self, batch, compute_loss=True):
+        """Object grounding (batch schema data/tasks.py:503-559; DUET-lineage head): the object tokens of the last
+        panorama, taken from the local branch ([stop] + views + objects), are scored by `og_head`; padded object
+        slots get -inf; loss = CE against `obj_labels` (ignore -100, dataset.py:318).
+        compute_loss=False returns the `[B, max_objects]` logits."""
+        if not hasattr(self, "og_head"):
+            raise ValueError("this model was built without the og task (config.pretrain_tasks)")
+        ix = self._index(batch)
+        if "og_rows" not in ix:
+            raise ValueError("og needs a batch with object features (traj_obj_img_fts / traj_vp_obj_lens)")
+        fc = self._fc(False)
+        o = self.bert(batch, "nav", fc, ix)
+        B, Vp, h = o["vp_embeds"].shape
+        x = ops.gather_rows(o["vp_embeds"].reshape(B * Vp, h), ix["og_rows"])
+        raw = self._cls(self.og_head, x).reshape(B, -1)
+        logits = ops.mask_fill(raw, ix["og_valid"])
+        if not compute_loss:
+            return logits
+        o.update(loss=ops.cross_entropy(logits, batch["obj_labels"], -100), logits=logits, obj_logits=logits)
         return o
 
     def forward_cfp(self, batch, compute_loss=True):

@@ -1149,6 +1149,31 @@ def cat2(a, b):
     return Cat2Fn.apply(a, b)
 
 
+class MaskFillFn(torch.autograd.Function):
+    """out = valid ? x : fill (fp32); gradient passes where valid."""
+
+    @staticmethod
+    def forward(ctx, x, valid, fill):
+        x = x.contiguous().float()
+        valid = valid.contiguous()
+        out = torch.empty_like(x)
+        call("magic_mask_fill", ptr(x), ptr(valid), ptr(out), x.numel(), fill, stream())
+        ctx.save_for_backward(valid)
+        return out
+
+    @staticmethod
+    def backward(ctx, dy):
+        (valid,) = ctx.saved_tensors
+        dy = dy.contiguous().float()
+        dx = torch.empty_like(dy)
+        call("magic_mask_fill", ptr(dy), ptr(valid), ptr(dx), dy.numel(), 0.0, stream())
+        return dx, None, None
+
+
+def mask_fill(x, valid, fill=float("-inf")):
+    return MaskFillFn.apply(x, valid, float(fill))
+
+
 def row_weights(src, idx, scale, n):
     """out[i] = (src[idx[i]] or src[i] or 1) * (scale[i] or 1), fp32 [n]; idx < 0 gives 0.  No autograd (KD weights)."""
     dev = (src if src is not None else scale).device

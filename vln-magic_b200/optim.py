@@ -11,6 +11,8 @@ from ._lib import call, ptr, stream
 from .arena import ParamArena
 from .ops import PinnedRing
 
+SUMSQ_SCRATCH = 2048  # MAGIC_SUMSQ_SCRATCH (include/magic_b200.h)
+
 
 def warmup_linear(step, warmup_step, tot_step):
     if step < warmup_step:
@@ -33,7 +35,7 @@ class FusedAdamW:
         self.v = torch.zeros(arena.total, dtype=torch.float32, device=dev)
         self.hyper = torch.zeros(8, dtype=torch.float32, device=dev)
         self.hyper_ring = PinnedRing(8)
-        self.sumsq = torch.zeros(1, dtype=torch.float32, device=dev)
+        self.sumsq = torch.zeros(1 + SUMSQ_SCRATCH, dtype=torch.float32, device=dev)  # [0] = sum g^2, rest = scratch
         self.step_count = 0
         self.param_groups = [dict(lr=lr)]  # so `for g in optimizer.param_groups: g['lr'] = ...` keeps working
 
@@ -71,7 +73,7 @@ class FusedAdamW:
         self.arena.zero_grad()
 
     def grad_norm(self):
-        return float(self.sumsq.sqrt())
+        return float(self.sumsq[0].sqrt())
 
 
 def build_optimizer(model, opts, lowp=None):

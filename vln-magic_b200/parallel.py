@@ -138,6 +138,7 @@ class StageSync:
         self.events = {}         # capture mode: stage -> GraphEvent
         self.handles = []
         self.marker = None
+        self.main = None
 
     # -- called by the model ------------------------------------------------------------------------------
     def expect(self, stage, key):
@@ -157,6 +158,8 @@ class StageSync:
     # -- stepper interface ----------------------------------------------------------------------------------
     def begin(self, mode):
         self.mode = mode
+        # the step's (capture) origin stream; None on the CPU (gloo tests of the bucket plan)
+        self.main = torch.cuda.current_stream() if (mode is not None and torch.cuda.is_available()) else None
         self.pending = [set(), set()]
         self.expected = [False, False]
         self.fired = []
@@ -168,6 +171,8 @@ class StageSync:
         out = list(ops._BRANCH.get("pool", {}).values()) + list(ops._ATTN_STREAMS.values())
         if ops._SIDE["stream"] is not None:
             out.append(ops._SIDE["stream"])
+        if self.main is not None:
+            out.append(self.main)
         return out
 
     def _ready(self, stage):

@@ -101,7 +101,9 @@ def _gmap(path, cands):
     return vpids, step_ids, vmask
 
 
-def make_samples(task, B, L=80, T_max=5, G_max=20, seed=1234, with_labels=None):
+def make_samples(task, B, L=80, T_max=5, G_max=20, seed=1234, with_labels=None, obj_dim=0, max_objects=6):
+    """task 'og' (object grounding, data/tasks.py:455-501): every panorama additionally carries 0..max_objects object
+    tokens after its 36 views (token order [cand_views, noncand_views, objs], data/dataset.py:447,494-508)."""
     rs = np.random.RandomState(seed)
     rng = random.Random(seed)
     samples = []
@@ -124,10 +126,26 @@ def make_samples(task, B, L=80, T_max=5, G_max=20, seed=1234, with_labels=None):
             out["txt_ids"] = torch.LongTensor(toks)
         out["traj_view_img_fts"] = [torch.from_numpy(rs.randn(N_VIEWS, IMG_DIM).astype(np.float32)) for _ in range(T)]
         loc, nav = [], []
+        n_objs = [int(rs.randint(0, max_objects + 1)) for _ in range(T)] if task == "og" else [0] * T
+        if task == "og" and b == full_idx:
+            n_objs[-1] = max_objects
         for t in range(T):
-            ang = _angle_fts(rs.uniform(-math.pi, math.pi, N_VIEWS), rs.uniform(-math.pi / 6, math.pi / 6, N_VIEWS))
-            loc.append(torch.from_numpy(np.concatenate([ang, np.ones((N_VIEWS, 3), np.float32)], 1)))
-            nav.append(torch.LongTensor([1] * len(cands[t]) + [0] * (N_VIEWS - len(cands[t]))))
+            nt = N_VIEWS + n_objs[t]
+            ang = _angle_fts(rs.uniform(-math.pi, math.pi, nt), rs.uniform(-math.pi / 6, math.pi / 6, nt))
+            box = np.ones((nt, 3), np.float32)
+            if n_objs[t]:
+                box[N_VIEWS:] = rs.uniform(0.05, 1.0, (n_objs[t], 3)).astype(np.float32)  # dataset.py:489-491
+            loc.append(torch.from_numpy(np.concatenate([ang, box], 1)))
+            nav.append(torch.LongTensor([1] * len(cands[t]) + [0] * (N_VIEWS - len(cands[t])) + [2] * n_objs[t]))
+        if task == "og":
+            if obj_dim <= 0:
+                raise ValueError("task 'og' needs obj_dim > 0 (config.obj_feat_size)")
+            out["traj_obj_img_fts"] = [torch.from_numpy(rs.randn(n, obj_dim).astype(np.float32)) for n in n_objs]
+            # dataset.py:487,493: the object-name ids, [0] for a panorama without objects
+            out["traj_reverie_obj_names"] = [torch.from_numpy(rs.randint(1, 400, size=n).astype(np.int64)) if n
+                                             else torch.zeros(1, dtype=torch.int64) for n in n_objs]
+            # get_obj_label (dataset.py:307-320): index among the last panorama's objects, -100 if not present
+            out["obj_labels"] = int(rs.randint(0, n_objs[-1])) if (n_objs[-1] and rs.rand() > 0.1) else -100
         if task == "mrc":
             # MrcDataset.__getitem__ (data/tasks.py:220-223): mask >= 1 view of the last panorama, zero its feature,
             # soft labels over image_prob_size classes for every view (no [stop])
@@ -159,7 +177,7 @@ def make_samples(task, B, L=80, T_max=5, G_max=20, seed=1234, with_labels=None):
         d[:, 0] = 0
         out["gmap_pair_dists"] = torch.from_numpy(d)
         K = len(cands[-1])
-        vp = np.zeros((N_VIEWS + 1, 14), np.float32)
+        vp = np.zeros((N_VIEWS + n_objs[-1] + 1, 14), np.float32)  # vp_ft_len = tokens of the last panorama
         start = np.concatenate([_angle_fts(rs.uniform(-math.pi, math.pi, 1), rs.uniform(-0.5, 0.5, 1)),
                                 rs.uniform(0, 1, (1, 3)).astype(np.float32)], 1)
         vp[:, :7] = start
@@ -203,6 +221,11 @@ def collate(samples):
         batch["txt_labels"] = _pad_1d(batch["txt_labels"], -1)
     batch["traj_step_lens"] = [len(x) for x in batch["traj_view_img_fts"]]
     batch["traj_vp_view_lens"] = torch.LongTensor(sum([[len(y) for y in x] for x in batch["traj_view_img_fts"]], []))
+    if "traj_obj_img_fts" in batch:  # og_collate, data/tasks.py:515-524, 557
+        batch["traj_vp_obj_lens"] = torch.LongTensor(sum([[len(y) for y in x] for x in batch["traj_obj_img_fts"]], []))
+        batch["traj_obj_img_fts"] = pad_tensors(sum(batch["traj_obj_img_fts"], []))
+        batch["traj_reverie_obj_names"] = pad_tensors(sum(batch["traj_reverie_obj_names"], []))
+        batch["obj_labels"] = torch.LongTensor(batch["obj_labels"])
     batch["traj_view_img_fts"] = pad_tensors(sum(batch["traj_view_img_fts"], []))
     batch["traj_loc_fts"] = pad_tensors(sum(batch["traj_loc_fts"], []))
     batch["traj_nav_types"] = _pad_1d(sum(batch["traj_nav_types"], []), 0)
@@ -229,8 +252,8 @@ def collate(samples):
     return batch
 
 
-def make_batch(task, B, L=80, T_max=5, G_max=20, seed=1234):
-    return collate(make_samples(task, B, L, T_max, G_max, seed))
+def make_batch(task, B, L=80, T_max=5, G_max=20, seed=1234, obj_dim=0, max_objects=6):
+    return collate(make_samples(task, B, L, T_max, G_max, seed, obj_dim=obj_dim, max_objects=max_objects))
 
 
 def batch_to(batch, device, non_blocking=False):

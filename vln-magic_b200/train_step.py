@@ -25,7 +25,8 @@ class _Prefetched:
 class PretrainStepper:
     def __init__(self, student, teacher=None, kdl=None, lr=5e-5, betas=(0.9, 0.98), weight_decay=0.01,
                  max_grad_norm=5.0, use_graphs=False, rw_generator=None, side_stream=True,
-                 branch_streams=True, co_update=False, t_lr=None, max_graphs=16, overlap=True):
+                 branch_streams=True, co_update=False, t_lr=None, max_graphs=16, overlap=True,
+                 pipeline_teacher=True, teacher_sm_budget=0, pdl=None):
         """co_update=True is ICoD (`--train_kdl_teacher`, agent_base.py:260-279): the teacher is trained too, from
         the s2t losses, with its own arena / AdamW state / clip, and both models step once per batch."""
         self.student, self.teacher = student, teacher
@@ -64,7 +65,10 @@ class PretrainStepper:
         # gradient exchange overlapped with backward (DDP's bucketed overlap, utils/misc.py:57-71): the model marks the
         # points of backward at which a group of layers is complete (model._mark), parallel.StageSync starts that
         # group's all-reduce there; the rest follows when backward has been issued
-        self.overlap = bool(overlap) and self.world > 1
+        # (below ~64 MB of gradients the extra collectives and event waits cost more than they hide: measured at
+        # 2 GPUs, 39 MB arena: 2.17 ms/step plain vs 2.25 overlapped; 1.4 GB arena: 19.7 vs 19.0)
+        big = self.arena.total * 4 + (self.t_arena.total * 4 if self.co_update else 0) >= (64 << 20)
+        self.overlap = (overlap == "force" or (bool(overlap) and big)) and self.world > 1
         self.syncs = []
         self.comm_stream = None
         if self.overlap:
@@ -74,9 +78,25 @@ class PretrainStepper:
                 sy = StageSync(a, len(m.bert.lang_encoder.layer))
                 m.bert.stage_cb = sy
                 self.syncs.append(sy)
+        # frozen teacher + CUDA graphs: the teacher's forward is its own graph on its own stream, and the forward of
+        # the NEXT batch (announced through step(..., next=)) runs while this batch's student back-propagates.  The
+        # teacher does not depend on the student's update, so every result is identical to the serial order.
+        self.pipeline_teacher = bool(pipeline_teacher) and use_graphs and teacher is not None and not self.co_update
+        self._t_stream = None
+        self._t_inflight = None
+        # SMs the teacher graph's persistent GEMMs may occupy (0 = all): the teacher graph runs beside the student
+        # graph, and a persistent CTA holds an SM's whole shared memory and TMEM for the length of its kernel
+        self.teacher_sm_budget = int(teacher_sm_budget)
+        # programmatic dependent launch: a win for a lone chain of small kernels, a loss when graph branches of two
+        # models compete for the SMs (an early-launched grid holds SM slots while it waits).  Default: on without a
+        # teacher, off with one.  (student_pdl, teacher_pdl) or one bool for both.
+        if pdl is None:
+            pdl = teacher is None
+        self.pdl = (bool(pdl), bool(pdl)) if not isinstance(pdl, (tuple, list)) else (bool(pdl[0]), bool(pdl[1]))
         self.launches_per_step = None
         self._copy_stream, self._staging = None, {}
         self._rw_dev = None
+        self._next = None
 
     def exchange_description(self):
         if self.world == 1:
@@ -116,7 +136,7 @@ class PretrainStepper:
                 self.t_allreduce.finish()
             self.t_opt.apply()
 
-    def _device_step(self, task, batch, rw, finish=True, mode="eager"):
+    def _device_step(self, task, batch, rw, finish=True, mode="eager", t_out=None):
         for sy in self.syncs:
             sy.begin(mode)
         self.arena.zero_grad()
@@ -134,7 +154,9 @@ class PretrainStepper:
             if finish:
                 self._finish()
             return torch.cat([mix, mix_t])
-        if self.teacher is not None:
+        if self.teacher is not None and t_out is not None:  # teacher outputs computed by the teacher's own graph
+            mix, res, s_out = makd.student_distill_loss(self.student, t_out, batch, task, rw, self.kdl)
+        elif self.teacher is not None:
             mix, res, s_out, t_out = makd.distill_step_loss(self.student, self.teacher, batch, task, rw, self.kdl)
         else:
             s_out = self.student(batch, task, True)
@@ -175,13 +197,21 @@ class PretrainStepper:
             ready.record(self._copy_stream)
         return _Prefetched(task, dst, ready, slot, i)
 
-    def step(self, task, batch, lr=None):
+    def step(self, task, batch, lr=None, next=None):
         """batch: device batch with index tables (graph_index.prepare_batch + batch_to_device), or the handle
-        returned by `prefetch()`.  Returns the device tensor [total, supervised_mean, kd_total] (no host sync)."""
+        returned by `prefetch()`.  Returns the device tensor [total, supervised_mean, kd_total] (no host sync).
+        `next` = (task, batch or prefetch handle) of the FOLLOWING step, if known (a prefetching loader knows it):
+        with a frozen teacher and CUDA graphs its teacher forward is started now, under this step's backward.  A
+        device batch announced this way must already be resident (not still being written on the current stream)."""
         handle = None
         if isinstance(batch, _Prefetched):
             handle, batch = batch, batch.batch
             torch.cuda.current_stream().wait_event(handle.ready)
+        nxt = None
+        if next is not None and self.pipeline_teacher:
+            t2, b2 = next
+            nxt = (t2, b2.batch, b2.ready) if isinstance(b2, _Prefetched) else (t2, b2, None)
+        self._next = nxt
         out = self._step(task, batch, lr)
         if handle is not None:
             done = torch.cuda.Event()
@@ -233,11 +263,56 @@ class PretrainStepper:
                 sig.append(tuple((kk, tuple(vv.shape) if torch.is_tensor(vv) else vv) for kk, vv in sorted(v.items())))
         return tuple(sig)
 
+    def _capture_teacher(self, task, batch):
+        """The frozen teacher's forward as its own graph: static inputs, static outputs (the dict the student graph
+        reads), two events -- `ready` (outputs valid) and `done` (the student step that read them has been issued)."""
+        static = alloc_like(batch, self.device)
+        copy_batch_(static, batch)
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        lib = _lib.load()
+        lib.magic_gemm_set_sm_budget(self.teacher_sm_budget)
+        lib.magic_set_pdl(int(self.pdl[1]))
+        try:
+            with torch.cuda.stream(s):
+                makd.teacher_forward(self.teacher, static, task)  # warm-up (allocator, lazy init)
+            torch.cuda.current_stream().wait_stream(s)
+            g = torch.cuda.CUDAGraph()
+            n0 = _lib.COUNTERS["launches"]
+            with torch.cuda.graph(g):
+                t_out = makd.teacher_forward(self.teacher, static, task)
+        finally:
+            lib.magic_gemm_set_sm_budget(0)
+            lib.magic_set_pdl(-1)
+        return dict(g=g, static=static, t_out=t_out, n=_lib.COUNTERS["launches"] - n0, ready=torch.cuda.Event(),
+                    done=torch.cuda.Event())
+
+    def _launch_teacher(self, t_ent, batch, ready=None, serial=False):
+        if self._t_stream is None:
+            self._t_stream = torch.cuda.Stream()
+        T = self._t_stream
+        if serial:  # not announced in advance: the batch may still be in flight on the current stream
+            T.wait_stream(torch.cuda.current_stream())
+        if ready is not None:
+            T.wait_event(ready)          # host -> device copy of a prefetched batch
+        T.wait_event(t_ent["done"])      # the previous step that read these outputs (a never-recorded event is a no-op)
+        with torch.cuda.stream(T):
+            copy_batch_(t_ent["static"], batch)
+            t_ent["g"].replay()
+            t_ent["ready"].record(T)
+        _lib.COUNTERS["launches"] += t_ent["n"]
+
     def _graph_step(self, task, batch, rw, sig=None):
         sig = self._signature(task, batch) if sig is None else sig
         entry = self.graphs.get(sig)
         if entry is None:
             dev = self.device
+            t_ent = None
+            self._t_inflight = None
+            if self.pipeline_teacher:
+                t_ent = self._capture_teacher(task, batch)
+                t_ent["g"].replay()  # valid teacher outputs for the student's warm-up runs and capture
+            t_out = t_ent["t_out"] if t_ent is not None else None
             static = alloc_like(batch, dev)
             copy_batch_(static, batch)
             s = torch.cuda.Stream()
@@ -248,7 +323,7 @@ class PretrainStepper:
             snap = [(a.flat_p.clone(), o.m.clone(), o.v.clone()) for a, o in pairs]
             with torch.cuda.stream(s):
                 for _ in range(2):
-                    self._device_step(task, static, rw, finish=self.world == 1, mode=None)
+                    self._device_step(task, static, rw, finish=self.world == 1, mode=None, t_out=t_out)
                     if self.world > 1:
                         for _, o in pairs:
                             o.apply()
@@ -260,15 +335,34 @@ class PretrainStepper:
             torch.cuda.current_stream().wait_stream(s)
             g = torch.cuda.CUDAGraph()
             n0 = _lib.COUNTERS["launches"]
-            with torch.cuda.graph(g):
-                out = self._device_step(task, static, rw, finish=self.world == 1, mode="capture")
+            _lib.load().magic_set_pdl(int(self.pdl[0]))
+            try:
+                with torch.cuda.graph(g):
+                    out = self._device_step(task, static, rw, finish=self.world == 1, mode="capture", t_out=t_out)
+            finally:
+                _lib.load().magic_set_pdl(-1)
             marks = [(list(sy.fired), dict(sy.events)) for sy in self.syncs]
-            entry = (g, static, out, _lib.COUNTERS["launches"] - n0, marks)
+            entry = (g, static, out, _lib.COUNTERS["launches"] - n0, marks, t_ent)
             self.graphs[sig] = entry
-        g, static, out, n_launch, marks = entry
+        g, static, out, n_launch, marks, t_ent = entry
+        cur = torch.cuda.current_stream()
+        if t_ent is not None:
+            if self._t_inflight != (sig, id(batch)):
+                self._launch_teacher(t_ent, batch, serial=True)
+            self._t_inflight = None
+            cur.wait_event(t_ent["ready"])
         copy_batch_(static, batch)
         g.replay()
         _lib.COUNTERS["launches"] += n_launch  # kernels replayed inside the graph
+        if t_ent is not None:
+            t_ent["done"].record(cur)
+            if self._next is not None:  # the next batch's teacher forward starts now, under this step's backward
+                t2, b2, ready2 = self._next
+                sig2 = self._signature(t2, b2)
+                e2 = self.graphs.get(sig2)
+                if e2 is not None and e2[5] is not None:
+                    self._launch_teacher(e2[5], b2, ready=ready2)
+                    self._t_inflight = (sig2, id(b2))
         if self.world > 1:
             # the exchange of every stage that completed inside the graph starts at its in-graph event
             for sy, (fired, events) in zip(self.syncs, marks):
