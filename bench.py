@@ -637,8 +637,11 @@ def run_ours(args):
             dist.destroy_process_group()
         return
     # end-to-end: host (pinned) buffers -> H2D -> step -> D2H loss, through the public stepper API
-    R.run_steps(2, 0, True)
-    ms_e2e, _ = R.timed(args.steps, True)
+    if args.no_e2e:
+        ms_e2e = ms
+    else:
+        R.run_steps(2, 0, True)
+        ms_e2e, _ = R.timed(args.steps, True)
     clocks = clk.stop() if rank == 0 else None  # sampled (20 ms period) across BOTH timed regions
     B = w["B"]
     value = world * B * args.steps / (ms * 1e-3)
@@ -647,10 +650,12 @@ def run_ours(args):
     top = rooflines = fams = gshapes = note = None
     if args.graphs and not args.no_profile:
         try:
-            prof, ms_prof = R.profile_graph(args.profile_steps)
+            prof, ms_prof = R.profile_graph(args.profile_steps, serial=bool(args.profile_serial))
             if rank == 0:
                 top, rooflines, fams, gshapes, note = summarise_graph_profile(prof, ms_prof, pk, args.workload)
         except Exception as e:  # keep the headline numbers if the stopwatch graph cannot be built
+            import traceback
+            traceback.print_exc()
             note = dict(mode="unavailable", error=repr(e)[:300])
     line = None
     if rank == 0:
@@ -743,6 +748,9 @@ def main():
     ap.add_argument("--sub-steps", type=int, default=10)
     ap.add_argument("--profile-steps", type=int, default=3)
     ap.add_argument("--no-profile", action="store_true")
+    ap.add_argument("--profile-serial", type=int, default=1,
+                    help="1: the stopwatch graph is captured on one stream (kernels timed alone); 0: same branches as the timed graphs")
+    ap.add_argument("--no-e2e", action="store_true", help="debug aid: skip the end-to-end region")
     ap.add_argument("--no-gpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--compile", type=int, default=0, help="--impl torch_gpu: wrap the step in torch.compile")

@@ -1,0 +1,69 @@
+"""CPU tests of the loop library's host logic (train_loop.py): RunningMeter and ModelSaver semantics of the reference
+(pretrain_src/utils/logger.py:66-94, utils/save.py:23-74), and the seeded MetaLoader."""
+import math
+import os
+
+import torch
+import torch.nn as nn
+
+import magic_b200  # noqa: F401
+from magic_b200.train_loop import MetaLoader, ModelSaver, RunningMeter
+
+REF = "/root/reference/pretrain_src"
+
+
+def test_running_meter_matches_reference_semantics():
+    m = RunningMeter("loss/mlm/total_loss")
+    assert m.val == 0 and m.name == "loss/mlm/total_loss"
+    m(2.0)
+    assert m.val == 2.0                      # first value is taken as is
+    m(4.0)
+    assert abs(m.val - (4.0 * 0.01 + 2.0 * 0.99)) < 1e-12
+    before = m.val
+    m(float("nan"))
+    assert m.val == before                   # NaN updates are dropped (logger.py:80-81)
+    assert str(m).startswith("loss/mlm/total_loss: ")
+    if os.path.exists(os.path.join(REF, "utils", "logger.py")):  # live check against the reference class
+        src = open(os.path.join(REF, "utils", "logger.py")).read()
+        i = src.index("class RunningMeter")
+        ns = {"math": math}
+        exec(src[i:], ns)
+        r = ns["RunningMeter"]("x")
+        ours = RunningMeter("x")
+        for v in (1.0, 3.0, float("nan"), -2.0, 0.5):
+            r(v), ours(v)
+            assert r.val == ours.val
+
+
+class _Opt:
+    def state_dict(self):
+        return {"step": 3, "x": torch.ones(2)}
+
+
+def test_model_saver_layout(tmp_path):
+    model = nn.Sequential(nn.Linear(3, 2))
+    wrapped = nn.Module()
+    wrapped.module = model       # a DDP-like wrapper: keys gain the `module.` prefix
+    saver = ModelSaver(str(tmp_path))
+    saver.save(wrapped, 7, _Opt())
+    saver.save_latest(wrapped, 8, _Opt())
+    saver.save_latest(wrapped, 9, _Opt(), is_max=True)
+    files = sorted(os.listdir(tmp_path))
+    assert files == ["model_step_7.pt", "model_step_best.pt", "model_step_latest.pt", "train_state_7.pt",
+                     "train_state_best_9.pt", "train_state_latest.pt"]
+    sd = torch.load(tmp_path / "model_step_7.pt")
+    assert set(sd) == {"0.weight", "0.bias"} and all(v.device.type == "cpu" for v in sd.values())
+    assert torch.equal(sd["0.weight"], model[0].weight.detach())
+    st = torch.load(tmp_path / "train_state_7.pt")
+    assert st["step"] == 7 and st["optimizer"]["step"] == 3
+
+
+def test_meta_loader_is_seeded_and_cycles():
+    loaders = {"mlm": [1, 2], "sap": [10], "cfp": [100, 200, 300]}
+    a = [x for x in MetaLoader(loaders, [1, 1, 1], seed=5, num_steps=30)]
+    b = [x for x in MetaLoader(loaders, [1, 1, 1], seed=5, num_steps=30)]
+    assert a == b and len(a) == 30 and {t for t, _ in a} == {"mlm", "sap", "cfp"}
+    mlm = [v for t, v in a if t == "mlm"]
+    assert mlm[:4] == [1, 2, 1, 2][:len(mlm[:4])]          # a task's loader restarts when exhausted
+    only = [t for t, _ in MetaLoader(loaders, [1, 0, 0], seed=1, num_steps=10)]
+    assert set(only) == {"mlm"}

@@ -265,7 +265,9 @@ class LinearFn(torch.autograd.Function):
             out = torch.empty(M, (N + 7) // 8 * 8, dtype=x.dtype, device=x.device)[:, :N]
         else:
             out = torch.empty(M, N, dtype=x.dtype, device=x.device)
-        pre = torch.empty_like(out) if act != 0 else None
+        # the pre-activation copy is only needed by backward: a no-grad forward (frozen teacher, validation) skips the
+        # second output tile of the epilogue and its HBM write
+        pre = torch.empty_like(out) if (act != 0 and any(ctx.needs_input_grad)) else None
         seed = seed_tensor(x.device) if drop_p > 0 else None
         res2 = residual.reshape(-1, N).contiguous() if residual is not None else None
         _lin_fwd(x2, w, bias, out, act, pre, res2, drop_p, salt, seed)
@@ -402,7 +404,7 @@ class FFNFn(torch.autograd.Function):
         M = x2.shape[0]
         I, N = w1.shape[0], w2.shape[0]
         hmid = torch.empty(M, I, dtype=x.dtype, device=x.device)
-        pre = torch.empty_like(hmid)
+        pre = torch.empty_like(hmid) if any(ctx.needs_input_grad) else None  # backward only (see LinearFn)
         seed = seed_tensor(x.device) if (drop_p > 0 or drop_out_p > 0) else None
         _lin_fwd(x2, w1, b1, hmid, act, pre, None, drop_p, salt, seed)
         out = torch.empty(M, N, dtype=x.dtype, device=x.device)

@@ -72,6 +72,20 @@ class FusedAdamW:
     def zero_grad(self):
         self.arena.zero_grad()
 
+    def state_dict(self):
+        """{step, exp_avg, exp_avg_sq} on the CPU, flat in arena order, plus the layout that makes them meaningful
+        (ModelSaver dumps this next to the weights, utils/save.py:41-45)."""
+        return dict(step=self.step_count, exp_avg=self.m.detach().cpu().clone(), exp_avg_sq=self.v.detach().cpu().clone(),
+                    layout=[(n, o, k) for n, _, o, k in self.arena.entries], lr=self.param_groups[0]["lr"])
+
+    def load_state_dict(self, sd):
+        if [(n, o, k) for n, _, o, k in self.arena.entries] != [tuple(x) for x in sd["layout"]]:
+            raise ValueError("optimizer state was saved for a different parameter layout")
+        self.step_count = int(sd["step"])
+        self.m.copy_(sd["exp_avg"])
+        self.v.copy_(sd["exp_avg_sq"])
+        self.param_groups[0]["lr"] = sd.get("lr", self.lr)
+
     def grad_norm(self):
         return float(self.sumsq[0].sqrt())
 
