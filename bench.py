@@ -124,17 +124,22 @@ def make_cfgs(w, dropout):
     return cfg_s, cfg_t
 
 
-def make_pool(task, n, w, seed0):
+def make_pool(task, n, w, seed0, store=None):
+    """`store`: a CPU copy of the panorama feature database; the batches then carry panorama rows + view orders instead
+    of the 36 x 768 features per step (featurizer.py) and the model gathers the features on the device."""
     import magic_b200
     from magic_b200 import synth
+    from magic_b200.featurizer import compact_batch
     from magic_b200.graph_index import prepare_batch
     from magic_b200.graph_index import pad_batch
     out = []
     for i in range(n):
-        b = synth.make_batch(task, w["B"], L=w["L"], T_max=w["T_max"], G_max=w["G_max"], seed=seed0 + i)
+        b = synth.make_batch(task, w["B"], L=w["L"], T_max=w["T_max"], G_max=w["G_max"], seed=seed0 + i, store=store)
+        if store is not None:
+            b = compact_batch(b)
         out.append(prepare_batch(b))
     # identical shapes across the pool (one CUDA graph per task): pad to the pool maxima, rounded up
-    rcap = max(b["traj_view_img_fts"].shape[0] for b in out)
+    rcap = max(b["traj_vp_view_lens"].shape[0] for b in out)
     rcap = (rcap + 7) // 8 * 8
     mcap = None
     if task == "mlm":
@@ -381,8 +386,8 @@ def workload_config(name, w, world, dropout, cuda_graphs=True, pool_n=None, in_b
                                             else " (frozen)")) if w["teacher"] else None,
                optimizer="fused AdamW + clip 5.0", cuda_graphs=bool(cuda_graphs), parallelism=f"dp{world}")
     if pool_n is not None:
-        cfg["l2"] = "inputs cycle through a pool of %d batches/task (~%.0f MB) > 126 MB L2" % (
-            pool_n, 2 * pool_n * in_bytes / 1e6)
+        cfg["l2"] = ("the step's working set (weights + activations + logits, > 1 GB at h = 768) exceeds the 126 MB L2; "
+                     "inputs cycle through a pool of %d batches/task" % pool_n)
     return cfg
 
 
@@ -415,7 +420,17 @@ class Runner:
                                        pdl=None if args.pdl < 0 else ((args.pdl & 1) != 0, (args.pdl & 2) != 0))
         ops.set_seed(dev, 1234 + rank)
         n = self.pool_n = args.pool
-        pools = {t: make_pool(t, n, w, 1234 + rank * 1000 + (0 if t == "mlm" else 500)) for t in ("mlm", "sap")}
+        store_cpu = None
+        self.store = None
+        if args.feature_store > 0:
+            # GPU batch featuriser: the panorama features are resident in HBM (bf16 in bf16 mode), a batch names
+            # panorama rows and view orders, and the model gathers its inputs on the device
+            from magic_b200 import synth
+            from magic_b200.featurizer import FeatureStore
+            store_cpu = synth.make_store(args.feature_store, seed=77, dtype=dtype)
+            self.store = FeatureStore(store_cpu, device=dev, dtype=dtype).attach(student, teacher)
+        pools = {t: make_pool(t, n, w, 1234 + rank * 1000 + (0 if t == "mlm" else 500), store_cpu)
+                 for t in ("mlm", "sap")}
         # flat batches: every tensor of a batch is a view into one buffer, so staging a batch is ONE copy
         self.dev_pools = {t: [flatten_batch(b, device=dev) for b in bs] for t, bs in pools.items()}
         self.pin_pools = {t: [flatten_batch(b, pin=True) for b in bs] for t, bs in pools.items()}
@@ -661,6 +676,10 @@ def run_ours(args):
     if rank == 0:
         cfg = workload_config(args.workload, w, world, args.dropout, R.stepper.use_graphs, R.pool_n, R.in_bytes)
         cfg["model_tflops"] = value * train_gflop_per_sample(w) / 1e3
+        cfg["features"] = ("device-resident store of %d panoramas x 36 x 768 %s (%.0f MB); a batch carries panorama rows + "
+                           "view orders and the model gathers its inputs in HBM" % (
+                               R.store.N, args.dtype, R.store.nbytes / 1e6)) if R.store is not None else \
+            "fp32 36 x 768 view features travel host->device every step (reference loader layout)"
         cfg["gradient_exchange"] = R.stepper.exchange_description() if world > 1 else None
         line = dict(
             metric=f"pretrain samples/s ({kind_of(w)})", value=value, unit="samples/s", n_gpus=world, steps=args.steps,
@@ -755,6 +774,9 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--compile", type=int, default=0, help="--impl torch_gpu: wrap the step in torch.compile")
     ap.add_argument("--overlap", type=int, default=1, help="N > 1: exchange gradient buckets during backward")
+    ap.add_argument("--feature-store", type=int, default=2048,
+                    help="panoramas in the device-resident feature store (0: batches carry fp32 features, as the "
+                         "reference loader ships them)")
     ap.add_argument("--pdl", type=int, default=-1,
                     help="programmatic dependent launch: -1 stepper default, bit 0 = student graph, bit 1 = teacher graph")
     ap.add_argument("--teacher-sms", type=int, default=0,

@@ -237,6 +237,15 @@ int magic_makd_kl_bwd(const void* s, const void* t, void* ds, int R, int C, long
                       const float* w, float scale, const float* scale_dev, const float* stats, const float* gout,
                       int dtype, cudaStream_t st);
 
+/* ---- GPU batch featuriser (feature half): replaces the host-side per-sample feature read + collate + 36 x 768 fp32
+ * H2D copy of pretrain_src/data/dataset.py:210-244,742-756 / data/tasks.py:121-133 with a gather from a device-
+ * resident store.  out[r, j, :] = perm[r, j] >= 0 ? store[vp[r], perm[r, j], :] : 0  (store [n_store, V, D]);
+ * gmap_pair_dists[b, i, j] = dist[v_i, v_j] from the resident all-pairs matrix (dataset.py:545-549), 0 for [stop]/pad */
+int magic_gather_views(const void* store, int store_dt, long long n_store, const long long* vp, const int* perm,
+                       void* out, int out_dt, long long R, int V, int D, cudaStream_t st);
+int magic_gather_pair_dists(const float* dist, long long N, const long long* node_vp, float* out, int B, int G,
+                            cudaStream_t st);
+
 /* ---- optimizer (pretrain_src/optim/adamw.py:53-112, clip grad_norm r2r_magic_pretrain.json:22) ----- */
 /* out[0] (+)= sum g^2, deterministic (two-stage, no floating-point atomics: data-parallel replicas with identical
  * gradients compute the identical clip coefficient).  `out` must hold 1 + MAGIC_SUMSQ_SCRATCH floats: out[1..] is the

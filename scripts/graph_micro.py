@@ -143,5 +143,9 @@ if which in ("all", "gemm_l"):
 if which in ("all", "attn"):
     attn_cases([(64, 2, 80, 80, False), (224, 2, 36, 36, False), (64, 2, 20, 20, True), (64, 2, 20, 80, False),
                 (64, 2, 37, 80, False), (64, 2, 80, 37, False), (64, 12, 80, 80, False)])
+if which == "attn_l":
+    attn_cases([(64, 12, 80, 80, False), (64, 2, 80, 80, False), (128, 12, 160, 160, False), (128, 2, 160, 160, False),
+                (320, 12, 36, 36, False), (64, 12, 20, 20, True), (128, 12, 50, 160, False), (64, 12, 37, 80, False),
+                (128, 2, 50, 50, True), (1536, 2, 36, 36, False)])
 if which in ("all", "ln"):
     ln_cases([(5120, 128), (8064, 128), (5120, 768), (11520, 768)])

@@ -308,6 +308,216 @@ __global__ void __launch_bounds__(NTHREADS) attn_mma_fwd_kernel(AttnParams P, in
 }
 
 // ===================================================================================================
+// forward, version 2: one CTA owns ALL query rows of a (batch, head) item (ceil(Lq / 16) warps, at most 10), so K and V
+// are staged once per item instead of once per 64-row query tile; the CTA walks a list of items -- the heads of its
+// cluster slice when the KD map is requested, a grid-strided range of (batch, head) pairs otherwise -- and, when two
+// operand sets fit in shared memory, cp.async-prefetches the next item's Q / K / V while the current one is in the
+// tensor cores.  Each warp stages its 16 output rows in the shared rows its Q slab came from (dead once the A
+// fragments are in registers) and writes them with 16-byte row-contiguous stores.
+// ===================================================================================================
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+// like load_rows, for any block size
+__device__ __forceinline__ void load_rows_n(bf16* dst, const bf16* src, long ld, int rows_valid, int rows_pad) {
+  for (int e = threadIdx.x; e < rows_pad * 8; e += blockDim.x) {
+    const int r = e >> 3, c = e & 7;
+    const int rs = r < rows_valid ? r : rows_valid - 1;
+    cp_async16(dst + r * PITCH + c * 8, src + (size_t)rs * ld + c * 8, r < rows_valid ? 16 : 0);
+  }
+}
+
+template <int NT, bool DB>
+__global__ void __launch_bounds__(320) attn_fwd2_kernel(AttnParams P, int hc, int csize) {
+  extern __shared__ __align__(16) uint8_t smraw[];
+  pdl_trigger();
+  pdl_wait();
+  constexpr int LKP = NT * 8;
+  const int nw = blockDim.x >> 5, QP = nw * 16;
+  const int set_elems = (2 * LKP + QP) * PITCH;
+  bf16* sets = reinterpret_cast<bf16*>(smraw);
+  float* pb = reinterpret_cast<float*>(sets + (DB ? 2 : 1) * set_elems);  // [QP][LKP + 8], only when P.pbar
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
+  const int Lq = P.Lq, Lk = P.Lk, H = P.H;
+  const bool kd = P.pbar != nullptr;
+  // item list of this CTA
+  const int b_fixed = blockIdx.z, h_begin = blockIdx.y * hc;
+  const int n_items = kd ? hc : ((P.B * H - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x);
+  auto item = [&](int k, int& b, int& hd) {
+    if (kd) { b = b_fixed; hd = h_begin + k; }
+    else { const int idx = blockIdx.x + k * gridDim.x; b = idx / H; hd = idx - b * H; }
+  };
+  auto load_item = [&](int set, int k) {
+    int b, hd;
+    item(k, b, hd);
+    bf16* Ks = sets + set * set_elems;
+    bf16* Vs = Ks + LKP * PITCH;
+    bf16* Qs = Vs + LKP * PITCH;
+    load_rows_n(Ks, (const bf16*)P.k + (size_t)b * Lk * P.k_ld + hd * D, P.k_ld, Lk, LKP);
+    load_rows_n(Vs, (const bf16*)P.v + (size_t)b * Lk * P.v_ld + hd * D, P.v_ld, Lk, LKP);
+    load_rows_n(Qs, (const bf16*)P.q + (size_t)b * Lq * P.q_ld + hd * D, P.q_ld, Lq, QP);
+    cp_async_commit();
+  };
+  const bool wact = w * 16 < Lq;
+  const float sw = P.dists ? P.sprel_w[0] : 0.f, sb = P.dists ? P.sprel_b[0] : 0.f;
+  const Dropout dr = make_dropout(P.drop_p, P.seed_ptr, P.salt);
+  const float invH = 1.f / (float)H;
+  const int ia = w * 16 + g, ib = ia + 8;
+  const bool va = ia < Lq, vb = ib < Lq;
+  constexpr int PBP = LKP + 8;
+  float* pba = pb + (w * 16 + g) * PBP + 2 * t;
+  float* pbb = pba + 8 * PBP;
+
+  if (n_items > 0) load_item(0, 0);
+  for (int k = 0; k < n_items; k++) {
+    const int set = DB ? (k & 1) : 0;
+    if (DB && k + 1 < n_items) {
+      load_item((k + 1) & 1, k + 1);  // the other set was released by the barrier that closed iteration k - 1
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    __syncthreads();
+    int b, hd;
+    item(k, b, hd);
+    bf16* Ks = sets + set * set_elems;
+    bf16* Vs = Ks + LKP * PITCH;
+    bf16* Qs = Vs + LKP * PITCH;
+    const int klen = P.key_lens ? min(Lk, P.key_lens[b]) : Lk;
+    if (wact) {
+      float s[NT][4];
+      {
+        uint32_t qa[4][4];
+        load_a_frags(Qs, w * 16, lane, qa);
+        mma_a_yt<NT>(s, qa, Ks, lane);
+      }
+      const size_t da = ((size_t)b * Lq + (va ? ia : 0)) * Lk, db = ((size_t)b * Lq + (vb ? ib : 0)) * Lk;
+      float mxa = -INFINITY, mxb = -INFINITY;
+#pragma unroll
+      for (int j = 0; j < NT; j++) {
+#pragma unroll
+        for (int e = 0; e < 2; e++) {
+          const int c = j * 8 + 2 * t + e;
+          float x0 = s[j][e] * P.scale, x1 = s[j][2 + e] * P.scale;
+          if (c < klen) {
+            if (P.dists) {
+              x0 += sw * P.dists[da + c] + sb;
+              x1 += sw * P.dists[db + c] + sb;
+            }
+          } else {
+            x0 = x1 = -INFINITY;
+          }
+          s[j][e] = x0;
+          s[j][2 + e] = x1;
+          mxa = fmaxf(mxa, x0);
+          mxb = fmaxf(mxb, x1);
+        }
+      }
+      mxa = quad_max(mxa);
+      mxb = quad_max(mxb);
+      float suma = 0.f, sumb = 0.f;
+#pragma unroll
+      for (int j = 0; j < NT; j++) {
+#pragma unroll
+        for (int e = 0; e < 2; e++) {
+          const float e0 = (s[j][e] == -INFINITY) ? 0.f : __expf(s[j][e] - mxa);
+          const float e1 = (s[j][2 + e] == -INFINITY) ? 0.f : __expf(s[j][2 + e] - mxb);
+          s[j][e] = e0;
+          s[j][2 + e] = e1;
+          suma += e0;
+          sumb += e1;
+        }
+      }
+      suma = quad_sum(suma);
+      sumb = quad_sum(sumb);
+      const float inva = 1.f / suma, invb = 1.f / sumb;
+      if (t == 0) {
+        if (va) P.lse[((size_t)b * H + hd) * Lq + ia] = mxa + __logf(suma);
+        if (vb) P.lse[((size_t)b * H + hd) * Lq + ib] = mxb + __logf(sumb);
+      }
+#pragma unroll
+      for (int j = 0; j < NT; j++) {
+        s[j][0] *= inva; s[j][1] *= inva;  // normalised probabilities: exactly 0 for masked / padded keys
+        s[j][2] *= invb; s[j][3] *= invb;
+      }
+      if (kd) {
+        if (k == 0) {  // the first head stores, later heads add: nothing is zero-filled
+#pragma unroll
+          for (int j = 0; j < NT; j++) {
+            *reinterpret_cast<float2*>(pba + j * 8) = make_float2(s[j][0] * invH, s[j][1] * invH);
+            *reinterpret_cast<float2*>(pbb + j * 8) = make_float2(s[j][2] * invH, s[j][3] * invH);
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < NT; j++) {
+            float2 a = *reinterpret_cast<float2*>(pba + j * 8), c2 = *reinterpret_cast<float2*>(pbb + j * 8);
+            a.x += s[j][0] * invH; a.y += s[j][1] * invH;
+            c2.x += s[j][2] * invH; c2.y += s[j][3] * invH;
+            *reinterpret_cast<float2*>(pba + j * 8) = a;
+            *reinterpret_cast<float2*>(pbb + j * 8) = c2;
+          }
+        }
+      }
+      if (dr.p > 0.f) {
+        const size_t dia = (((size_t)b * H + hd) * Lq + ia) * Lk, dib = (((size_t)b * H + hd) * Lq + ib) * Lk;
+#pragma unroll
+        for (int j = 0; j < NT; j++) {
+#pragma unroll
+          for (int e = 0; e < 2; e++) {
+            const int c = j * 8 + 2 * t + e;
+            s[j][e] *= dr.scale(dia + c);
+            s[j][2 + e] *= dr.scale(dib + c);
+          }
+        }
+      }
+      float o[8][4];
+      mma_c_y<NT>(o, s, Vs, lane, klen);
+      // stage this warp's 16 x 64 output slab in its own (now dead) Q rows, then 16-byte row-contiguous stores
+      __syncwarp();
+      bf16* stg = Qs + w * 16 * PITCH;
+      store_rows(stg + g * PITCH, stg + (g + 8) * PITCH, o, 1.f, t);
+      __syncwarp();
+      bf16* ob = (bf16*)P.out + ((size_t)b * Lq + w * 16) * (size_t)(H * D) + hd * D;
+#pragma unroll
+      for (int i = 0; i < 4; i++) {
+        const int r = i * 4 + (lane >> 3), c = lane & 7;
+        if (w * 16 + r < Lq)
+          *reinterpret_cast<uint4*>(ob + (size_t)r * (H * D) + c * 8) = *reinterpret_cast<const uint4*>(stg + r * PITCH + c * 8);
+      }
+    }
+    __syncthreads();  // every warp is done with this set before the loads of iteration k + 1 / k + 2 overwrite it
+    if (!DB && k + 1 < n_items) load_item(0, k + 1);
+  }
+  if (kd) {
+    const int b = b_fixed;
+    if (csize == 1) {
+      for (int e = threadIdx.x; e < Lq * Lk; e += blockDim.x) {
+        const int r = e / Lk, c = e - r * Lk;
+        P.pbar[(size_t)b * P.pbar_bs + (size_t)r * P.pbar_rs + c] = pb[r * PBP + c];
+      }
+    } else {
+      namespace cg = cooperative_groups;
+      cg::cluster_group cluster = cg::this_cluster();
+      cluster.sync();  // every peer's partial head-mean is complete and visible cluster-wide
+      const int rank = (int)cluster.block_rank();
+      const float* peer[4];
+      for (int r = 0; r < csize; r++) peer[r] = cluster.map_shared_rank(pb, r);
+      const int total = Lq * Lk, per = (total + csize - 1) / csize;
+      const int e0 = rank * per, e1 = min(total, e0 + per);
+      for (int e = e0 + threadIdx.x; e < e1; e += blockDim.x) {
+        const int r = e / Lk, c = e - r * Lk;
+        float acc = 0.f;
+        for (int kk = 0; kk < csize; kk++) acc += peer[kk][r * PBP + c];  // fixed rank order: deterministic
+        P.pbar[(size_t)b * P.pbar_bs + (size_t)r * P.pbar_rs + c] = acc;
+      }
+      cluster.sync();  // keep this CTA's shared memory alive until the peers have read it
+    }
+  }
+}
+
+// ===================================================================================================
 // backward pass 1 (query-major): delta, dQ, d(sprel)
 // ===================================================================================================
 template <int NT>
@@ -600,8 +810,17 @@ int set_smem(K kernel, size_t bytes, const char* name) {
   return MAGIC_OK;
 }
 
+bool fwd_v1() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("MAGIC_ATTN_V1");
+    v = (e && e[0] == '1') ? 1 : 0;
+  }
+  return v == 1;
+}
+
 template <int NT>
-int launch_fwd(const AttnParams& P, cudaStream_t st) {
+int launch_fwd_v1(const AttnParams& P, cudaStream_t st) {
   // KD attention map: the heads of a query tile are shared out over a cluster of 4 / 2 CTAs when each still gets
   // >= 2 heads (below that the cluster barrier costs more than the serial head walk it replaces: measured)
   int csize = 1;
@@ -619,6 +838,56 @@ int launch_fwd(const AttnParams& P, cudaStream_t st) {
     MAGIC_CUDA(magic_launch(attn_mma_fwd_kernel<NT>, grid, dim3(NTHREADS), smem, st, P, hc, 1), "magic_attn_fwd(mma)");
   }
   return MAGIC_OK;
+}
+
+template <int NT, bool DB>
+int launch_fwd2_k(const AttnParams& P, int nw, size_t smem, int hc, int csize, cudaStream_t st) {
+  int rc = set_smem(attn_fwd2_kernel<NT, DB>, smem, "magic_attn_fwd");
+  if (rc) return rc;
+  if (P.pbar) {
+    dim3 grid(1, P.H / hc, P.B);
+    if (csize > 1) {
+      MAGIC_CUDA(magic_launch_cluster(attn_fwd2_kernel<NT, DB>, grid, dim3(nw * 32), smem, st, dim3(1, csize, 1), P, hc,
+                                      csize),
+                 "magic_attn_fwd(v2, cluster)");
+    } else {
+      MAGIC_CUDA(magic_launch(attn_fwd2_kernel<NT, DB>, grid, dim3(nw * 32), smem, st, P, hc, 1), "magic_attn_fwd(v2)");
+    }
+    return MAGIC_OK;
+  }
+  // persistent walk over the (batch, head) pairs: about as many CTAs as fit on the GPU at once
+  int per_sm = (int)((200 * 1024) / smem);
+  const int by_threads = 1536 / (nw * 32);
+  if (per_sm > by_threads) per_sm = by_threads;
+  if (per_sm < 1) per_sm = 1;
+  if (per_sm > 4) per_sm = 4;
+  const long items = (long)P.B * P.H;
+  long ctas = (long)magic_num_sms() * per_sm;
+  if (ctas > items) ctas = items;
+  MAGIC_CUDA(magic_launch(attn_fwd2_kernel<NT, DB>, dim3((unsigned)ctas), dim3(nw * 32), smem, st, P, 1, 1),
+             "magic_attn_fwd(v2)");
+  return MAGIC_OK;
+}
+
+template <int NT>
+int launch_fwd(const AttnParams& P, cudaStream_t st) {
+  // measured (B200, graph-replayed, scripts/graph_micro.py attn_l): the one-CTA-per-item kernel wins where a 64-row
+  // tiling would stage K / V twice or more (Lq 80: 29.7 -> 24.8 us, Lq 160: 206 -> 166 us at H = 12 with the KD map;
+  // 43.8 -> 29.8 us at H = 2) and loses on short query ranges (36 x 36: 31 -> 38 us, 50 x 160: 55 -> 90 us), where its
+  // 2 - 4 warp CTAs leave the SM under-occupied
+  if (fwd_v1() || P.Lq > 160 || P.Lq <= 64) return launch_fwd_v1<NT>(P, st);
+  const int nw = (P.Lq + 15) / 16;
+  int csize = 1;
+  if (P.pbar && P.H >= 4) csize = (P.H % 4 == 0 && P.H >= 8) ? 4 : (P.H % 2 == 0) ? 2 : 1;
+  const int hc = P.pbar ? P.H / csize : 1;
+  const size_t set_bytes = (size_t)(2 * NT * 8 + nw * 16) * PITCH * 2;
+  const size_t pb_bytes = P.pbar ? (size_t)nw * 16 * (NT * 8 + 8) * 4 : 0;
+  const long my_items = P.pbar ? hc : 2;  // plain mode: a CTA usually walks several pairs
+  // two operand sets (prefetch of the next item) when they fit beside the KD-map accumulator and pay off
+  const bool db = my_items > 1 && 2 * set_bytes + pb_bytes <= 200 * 1024;
+  if (db) return launch_fwd2_k<NT, true>(P, nw, 2 * set_bytes + pb_bytes, hc, csize, st);
+  if (set_bytes + pb_bytes > 220 * 1024) return launch_fwd_v1<NT>(P, st);
+  return launch_fwd2_k<NT, false>(P, nw, set_bytes + pb_bytes, hc, csize, st);
 }
 
 template <int NT>

@@ -20,7 +20,9 @@ def build_index(batch):
     """-> dict of CPU tensors (int32 / uint8 / int64 / float32) + python ints."""
     steps = batch["traj_step_lens"]
     B = len(steps)
-    Vv = batch["traj_view_img_fts"].shape[1]
+    # views per panorama (compact batches carry the view order instead of the features: featurizer.py)
+    Vv = batch["traj_view_img_fts"].shape[1] if batch.get("traj_view_img_fts") is not None \
+        else batch["traj_view_perm"].shape[1]
     # tokens per panorama: the views, followed by the panorama's object tokens when the batch carries objects
     # (og_collate, data/tasks.py:503-559; token order dataset.py:447)
     V = batch["traj_loc_fts"].shape[1]
@@ -144,7 +146,7 @@ def build_index(batch):
         # MRC: masked views of the last-step panorama, row-major (b, view) order = boolean-mask order of
         # `vp_view_probs[mask]` (train_r2r_magic.py:483; data/tasks.py:183-187)
         m = _cpu(batch["vp_view_mrc_masks"]).bool()
-        V = batch["traj_view_img_fts"].shape[1]
+        V = Vv
         bb, jj = m.nonzero(as_tuple=True)
         last = torch.from_numpy(np.asarray(last_rows, dtype=np.int64))
         idx["mrc_rows"] = (bb * Vp + 1 + jj).to(torch.int64)          # rows of vp_embeds [B*Vp, h]
@@ -176,7 +178,7 @@ def pad_batch(batch, n_panos=None, n_masked=None, n_entries=None, n_sources=None
     `pano_row_scale` / `mlm_row_scale` are per-row KD weights (0 on padding, capacity / real count elsewhere)."""
     ix = batch[INDEX_KEY]
     if n_panos is not None:
-        R = batch["traj_view_img_fts"].shape[0]
+        R = batch["traj_vp_view_lens"].shape[0]
         if n_panos < R:
             raise ValueError(f"pano capacity {n_panos} < {R}")
         if n_panos > R and batch.get("traj_obj_img_fts") is not None:
@@ -185,8 +187,11 @@ def pad_batch(batch, n_panos=None, n_masked=None, n_entries=None, n_sources=None
             def padr(t, value=0):
                 pad = torch.full((n_panos - R, *t.shape[1:]), value, dtype=t.dtype)
                 return torch.cat([t, pad], 0)
-            for k in ("traj_view_img_fts", "traj_loc_fts", "traj_nav_types"):
-                batch[k] = padr(batch[k])
+            for k in ("traj_view_img_fts", "traj_loc_fts", "traj_nav_types", "traj_vp_index"):
+                if batch.get(k) is not None:
+                    batch[k] = padr(batch[k])
+            if batch.get("traj_view_perm") is not None:  # padded panoramas: every view masked (-1 -> zero row)
+                batch["traj_view_perm"] = padr(batch["traj_view_perm"], -1)
             batch["traj_vp_view_lens"] = padr(batch["traj_vp_view_lens"], 1)
             ix["key_lens_pano"] = padr(ix["key_lens_pano"], 1)
         # KD row weights of the panorama tensors: 0 on padded panoramas, n_panos / R on real ones, so that a mean over

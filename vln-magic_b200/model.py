@@ -320,7 +320,12 @@ class GlocalTextPathCMT(nn.Module):
     def forward_pano(self, batch, ix, fc, img_fts=None):
         ie = self.img_embeddings
         e = self.embeddings
-        fts = batch["traj_view_img_fts"] if img_fts is None else img_fts
+        if img_fts is not None:
+            fts = img_fts
+        elif batch.get("traj_view_img_fts") is not None:
+            fts = batch["traj_view_img_fts"]
+        else:
+            fts = self.view_features(batch, fc.dtype)
         R, V, Fd = fts.shape
         h = self.config.hidden_size
         x_in = fts.reshape(R * V, Fd)
@@ -368,6 +373,17 @@ class GlocalTextPathCMT(nn.Module):
         fused = ops.pano_fuse(x3, ap.weight if ap is not None else None, ap.bias if ap is not None else None,
                               view_lens)
         return x3, fused, attns
+
+    feature_store = None
+
+    def view_features(self, batch, dtype):
+        """Compact batches (featurizer.py) carry panorama rows + view orders instead of 36 x 768 features per step: the
+        features are gathered from the device-resident store, directly in the compute dtype."""
+        store = getattr(self, "feature_store", None)
+        if store is None or batch.get("traj_vp_index") is None:
+            raise ValueError("the batch has no traj_view_img_fts and no feature store is attached "
+                             "(featurizer.FeatureStore.attach)")
+        return store.gather_views(batch["traj_vp_index"], batch["traj_view_perm"], out_dtype=dtype)
 
     def gmap_input(self, pano, fused, batch, ix, fc):
         ge = self.global_encoder
@@ -468,6 +484,7 @@ class GlocalTextPathCMTPreTraining(nn.Module):
             self.og_head = _ClsPrediction(h, eps=c.layer_norm_eps)
         self.compute_dtype = torch.float32
         self.output_kd = bool(_cfg(c, "kd", False))
+        self.feature_store = None  # featurizer.FeatureStore.attach(model)
         self.apply(self._init_weights)
 
     # -- construction ------------------------------------------------------------------------------
@@ -616,7 +633,9 @@ class GlocalTextPathCMTPreTraining(nn.Module):
         `image_prob_size` classes against the soft labels `vp_view_probs[mask]` with KL."""
         ix = self._index(batch)
         fc = self._fc(False)
-        fts = batch["traj_view_img_fts"]
+        fts = batch.get("traj_view_img_fts")
+        if fts is None:
+            fts = self.bert.view_features(batch, fc.dtype)
         R, V, Fd = fts.shape
         fts2 = ops.zero_rows_(fts.reshape(R * V, Fd).clone(), ix["mrc_fts_rows"]).view(R, V, Fd)
         o = self.bert(batch, "nav", fc, ix, img_fts=fts2)

@@ -101,7 +101,14 @@ def _gmap(path, cands):
     return vpids, step_ids, vmask
 
 
-def make_samples(task, B, L=80, T_max=5, G_max=20, seed=1234, with_labels=None, obj_dim=0, max_objects=6):
+def make_store(n_panos=512, seed=77, dtype=torch.bfloat16):
+    """A synthetic panorama feature database [n_panos, 36, 768] (unit-scale like CLIP ViT-B/16 features), rounded to
+    `dtype` so host-side gathers and the device store agree bit for bit."""
+    g = torch.Generator().manual_seed(seed)
+    return torch.randn(n_panos, N_VIEWS, IMG_DIM, generator=g).to(dtype)
+
+
+def make_samples(task, B, L=80, T_max=5, G_max=20, seed=1234, with_labels=None, obj_dim=0, max_objects=6, store=None):
     """task 'og' (object grounding, data/tasks.py:455-501): every panorama additionally carries 0..max_objects object
     tokens after its 36 views (token order [cand_views, noncand_views, objs], data/dataset.py:447,494-508)."""
     rs = np.random.RandomState(seed)
@@ -124,7 +131,21 @@ def make_samples(task, B, L=80, T_max=5, G_max=20, seed=1234, with_labels=None, 
             out["txt_labels"] = torch.LongTensor(labs)
         else:
             out["txt_ids"] = torch.LongTensor(toks)
-        out["traj_view_img_fts"] = [torch.from_numpy(rs.randn(N_VIEWS, IMG_DIM).astype(np.float32)) for _ in range(T)]
+        if store is None:
+            out["traj_view_img_fts"] = [torch.from_numpy(rs.randn(N_VIEWS, IMG_DIM).astype(np.float32))
+                                        for _ in range(T)]
+        else:
+            # featurizer.py: every step names a panorama of the store and the order of its views -- the candidate
+            # views first (in candidate order), then the remaining views ascending (dataset.py:742-756)
+            vps = rs.randint(0, store.shape[0], size=T)
+            perms = []
+            for t in range(T):
+                cv = rs.choice(N_VIEWS, size=len(cands[t]), replace=False)
+                rest = np.setdiff1d(np.arange(N_VIEWS), cv)
+                perms.append(np.concatenate([cv, rest]).astype(np.int32))
+            out["traj_vp_index"] = [int(v) for v in vps]
+            out["traj_view_perm"] = [torch.from_numpy(p_) for p_ in perms]
+            out["traj_view_img_fts"] = [store[int(v)][torch.from_numpy(p_).long()].float() for v, p_ in zip(vps, perms)]
         loc, nav = [], []
         n_objs = [int(rs.randint(0, max_objects + 1)) for _ in range(T)] if task == "og" else [0] * T
         if task == "og" and b == full_idx:
@@ -227,6 +248,9 @@ def collate(samples):
         batch["traj_reverie_obj_names"] = pad_tensors(sum(batch["traj_reverie_obj_names"], []))
         batch["obj_labels"] = torch.LongTensor(batch["obj_labels"])
     batch["traj_view_img_fts"] = pad_tensors(sum(batch["traj_view_img_fts"], []))
+    if "traj_vp_index" in batch:  # compact view keys (featurizer.py); not part of the reference schema
+        batch["traj_vp_index"] = torch.LongTensor(sum(batch["traj_vp_index"], []))
+        batch["traj_view_perm"] = torch.stack(sum(batch["traj_view_perm"], []), 0)
     batch["traj_loc_fts"] = pad_tensors(sum(batch["traj_loc_fts"], []))
     batch["traj_nav_types"] = _pad_1d(sum(batch["traj_nav_types"], []), 0)
     batch["traj_reverie_loc_fts"] = None
@@ -252,8 +276,8 @@ def collate(samples):
     return batch
 
 
-def make_batch(task, B, L=80, T_max=5, G_max=20, seed=1234, obj_dim=0, max_objects=6):
-    return collate(make_samples(task, B, L, T_max, G_max, seed, obj_dim=obj_dim, max_objects=max_objects))
+def make_batch(task, B, L=80, T_max=5, G_max=20, seed=1234, obj_dim=0, max_objects=6, store=None):
+    return collate(make_samples(task, B, L, T_max, G_max, seed, obj_dim=obj_dim, max_objects=max_objects, store=store))
 
 
 def batch_to(batch, device, non_blocking=False):
