@@ -74,6 +74,11 @@ int magic_attn_bwd(const void* q, const void* k, const void* v, long q_ld, long 
                    int Lk, const int* key_lens, const float* dists, const float* sprel_w, const float* sprel_b,
                    float scale, int dtype, float drop_p, unsigned salt, const unsigned long long* seed_ptr,
                    cudaStream_t st);
+/* Call-site state for the attention launches that follow (forward and backward): key `key_index` of every sequence is
+ * never attended (probability exactly 0, zero dK / dV), on top of the key-length mask; -1 switches it off.  The
+ * navigation graph's [MEM] slot sits INSIDE the valid prefix but is not a key (map_nav_src/r2r/agent.py:228,
+ * `batch_gmap_masks[:,1] = False`). */
+int magic_attn_set_key_skip(int key_index);
 /* One half of the bf16 tensor-core attention backward (run the halves on two streams): part 1 = query-major kernel
  * (delta, dQ, d sprel), part 2 = key-major kernel (dK, dV) with delta = dO . O from the forward output `out`.  Without a
  * KD-map gradient only.  Returns MAGIC_ERR_UNSUPPORTED (nothing launched) when not covered: use magic_attn_bwd then. */

@@ -539,3 +539,41 @@ def test_adamw_matches_reference_update_order():
         assert torch.equal(shadow, p.to(torch.bfloat16))
     close(m, rm, 5e-6, "adamw m")
     close(v, rv, 5e-6, "adamw v")
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 3e-5), (torch.bfloat16, 2e-2)])
+@pytest.mark.parametrize("cfg", [dict(B=3, H=2, L=20, sprel=True), dict(B=2, H=12, L=37, sprel=True),
+                                 dict(B=2, H=2, L=80, sprel=False)])
+def test_attention_key_skip(dtype, tol, cfg):
+    """`key_skip` (the navigation graph's [MEM] slot, agent.py:228): one key inside the valid prefix is never
+    attended -- probability exactly 0, no gradient into its K / V rows -- forward and backward, both kernel families."""
+    torch.manual_seed(21)
+    B, H, L = cfg["B"], cfg["H"], cfg["L"]
+    hd = H * 64
+    lens = torch.randint(max(3, L // 2), L + 1, (B,), device=DEV)
+    dists = torch.rand(B, L, L, device=DEV) * 30 if cfg["sprel"] else None
+    sw = torch.tensor([[-0.05]], device=DEV, requires_grad=True) if dists is not None else None
+    sb = torch.tensor([0.1], device=DEV, requires_grad=True) if dists is not None else None
+    qkv = torch.randn(B * L, 3 * hd, device=DEV).to(dtype).requires_grad_()
+    o, pbar = ops.attention(qkv, None, 0, hd, 2 * hd, B, H, L, L, lens.int(), dists, sw, sb, need_pbar=True, salt=77,
+                            key_skip=1)
+    ref_in = qkv.detach().float().requires_grad_()
+    q, k, v = [ref_in[:, i * hd:(i + 1) * hd].reshape(B, L, hd) for i in range(3)]
+    qh, kh, vh = [t.view(B, L, H, 64).transpose(1, 2) for t in (q, k, v)]
+    s = qh @ kh.transpose(-1, -2) / 8.0
+    if dists is not None:
+        s = s + (dists * sw.detach() + sb.detach())[:, None]
+    m = torch.arange(L, device=DEV)[None] < lens[:, None]
+    m[:, 1] = False
+    s = s.masked_fill(~m[:, None, None, :], float("-inf"))
+    p = torch.softmax(s, -1)
+    oref = (p @ vh).transpose(1, 2).reshape(B, L, hd)
+    close(o.view(B, L, hd), oref, tol, "key_skip out")
+    close(pbar, p.mean(1), max(tol, 1e-5), "key_skip pbar")
+    assert float(pbar[:, :, 1].abs().max()) == 0.0
+    go = torch.randn_like(oref)
+    (o.view(B, L, hd).float() * go.to(dtype).float()).sum().backward()
+    (oref * go.to(dtype).float()).sum().backward()
+    close(qkv.grad, ref_in.grad, tol * 4, "key_skip dqkv")
+    g3 = qkv.grad.float().view(B, L, 3 * hd)
+    assert float(g3[:, 1, hd:].abs().max()) == 0.0  # the skipped key's K and V rows get exactly zero gradient

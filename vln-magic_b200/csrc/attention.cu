@@ -135,7 +135,7 @@ __global__ void __launch_bounds__(NW * 32) attn_fwd_kernel(AttnParams P) {
     for (int jj = 0; jj < MAXJ; jj++) {
       const int j = jj * 32 + lane;
       s0[jj] = s1[jj] = -INFINITY;
-      if (jj * 32 < P.Lk && j < klen) {
+      if (jj * 32 < P.Lk && j < klen && j != P.key_skip) {
         float a0, a1;
         dot2_row(q0, q1, Ks + (size_t)j * DP, a0, a1);
         a0 *= P.scale;
@@ -249,7 +249,7 @@ __global__ void __launch_bounds__(NW * 32) attn_bwd_q_kernel(AttnParams P) {
     for (int jj = 0; jj < MAXJ; jj++) {
       const int j = jj * 32 + lane;
       pa[jj] = pc[jj] = ga[jj] = gc[jj] = 0.f;
-      if (jj * 32 < P.Lk && j < klen) {
+      if (jj * 32 < P.Lk && j < klen && j != P.key_skip) {
         float a0, a1, e0, e1;
         dot2_row(q0, q1, Ks + (size_t)j * DP, a0, a1);
         dot2_row(g0, g1, Vs + (size_t)j * DP, e0, e1);
@@ -287,7 +287,7 @@ __global__ void __launch_bounds__(NW * 32) attn_bwd_q_kernel(AttnParams P) {
         const float ds0 = pa[jj] * (ga[jj] - dl0), ds1 = pc[jj] * (gc[jj] - dl1);
         d0[j] = ds0;
         d1[j] = ds1;
-        if (P.dists && j < klen) {
+        if (P.dists && j < klen && j != P.key_skip) {
           acc_dw = fmaf(ds0, P.dists[((size_t)b * P.Lq + ia) * P.Lk + j], acc_dw);
           acc_db += ds0;
           if (act1) {
@@ -336,7 +336,7 @@ __global__ void __launch_bounds__(NW * 32) attn_bwd_kv_kernel(AttnParams P) {
   const int j0 = row0 + w * RPW;
   const bool act0 = j0 < P.Lk, act1 = j0 + 1 < P.Lk;
   const int ja = min(j0, P.Lk - 1), jb = min(j0 + 1, P.Lk - 1);
-  const bool m0 = ja < klen, m1 = jb < klen;   // unmasked keys
+  const bool m0 = ja < klen && ja != P.key_skip, m1 = jb < klen && jb != P.key_skip;  // unmasked keys
   float* k0 = ks + (w * RPW + 0) * D;
   float* k1 = ks + (w * RPW + 1) * D;
   float* v0 = vs + (w * RPW + 0) * D;
@@ -361,7 +361,7 @@ __global__ void __launch_bounds__(NW * 32) attn_bwd_kv_kernel(AttnParams P) {
     T* dk1 = (T*)P.dk + kb * P.dk_ld + hd * D;
     T* dv0 = (T*)P.dv + ka * P.dv_ld + hd * D;
     T* dv1 = (T*)P.dv + kb * P.dv_ld + hd * D;
-    if (!m0) {  // both keys masked (ja < jb): no gradient
+    if (!m0 && !m1) {  // both keys masked: no gradient
       const float2 z = make_float2(0.f, 0.f);
       store2(dk0, lane, z);
       store2(dv0, lane, z);
@@ -392,7 +392,7 @@ __global__ void __launch_bounds__(NW * 32) attn_bwd_kv_kernel(AttnParams P) {
             a0 += sw * P.dists[((size_t)b * P.Lq + i) * P.Lk + ja] + sb;
             a1 += sw * P.dists[((size_t)b * P.Lq + i) * P.Lk + jb] + sb;
           }
-          const float pa = __expf(a0 - ls[i]), pc = m1 ? __expf(a1 - ls[i]) : 0.f;
+          const float pa = m0 ? __expf(a0 - ls[i]) : 0.f, pc = m1 ? __expf(a1 - ls[i]) : 0.f;
           const size_t di = ((((size_t)b * P.H + hd) * P.Lq) + i) * P.Lk;
           const float sc0 = dr.scale(di + ja), sc1 = dr.scale(di + jb);
           g0 *= sc0;
@@ -438,6 +438,9 @@ int set_smem(K kernel, size_t bytes, const char* name) {
   return MAGIC_OK;
 }
 
+// call-site state (like magic_gemm_set_sm_budget): key index masked in the launches that follow, -1 = none
+int g_key_skip = -1;
+
 AttnParams make_params(const void* q, const void* k, const void* v, long q_ld, long k_ld, long v_ld, int B, int H,
                        int Lq, int Lk, const int* key_lens, const float* dists, const float* sprel_w,
                        const float* sprel_b, float scale, float drop_p, unsigned salt,
@@ -449,12 +452,18 @@ AttnParams make_params(const void* q, const void* k, const void* v, long q_ld, l
   P.B = B; P.H = H; P.Lq = Lq; P.Lk = Lk;
   P.key_lens = key_lens; P.dists = dists; P.sprel_w = sprel_w; P.sprel_b = sprel_b;
   P.scale = scale; P.drop_p = drop_p; P.salt = salt; P.seed_ptr = seed_ptr;
+  P.key_skip = g_key_skip;
   return P;
 }
 
 }  // namespace
 
 extern "C" {
+
+int magic_attn_set_key_skip(int key_index) {
+  g_key_skip = key_index < 0 ? -1 : key_index;
+  return MAGIC_OK;
+}
 
 int magic_attn_fwd(const void* q, const void* k, const void* v, long q_ld, long k_ld, long v_ld, void* out,
                    float* lse, float* pbar, long pbar_bs, long pbar_rs, int B, int H, int Lq, int Lk,

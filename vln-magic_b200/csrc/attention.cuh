@@ -11,6 +11,7 @@ struct AttnParams {
   float* pbar;                  // optional head-mean probs
   long pbar_bs, pbar_rs;        // batch / row strides (elements)
   const int* key_lens;          // [B] or null
+  int key_skip;                 // one key index that is never attended (the [MEM] slot of the navigation graph), -1 = none
   const float* dists;           // [B, Lq, Lk] or null
   const float *sprel_w, *sprel_b;
   int B, H, Lq, Lk;

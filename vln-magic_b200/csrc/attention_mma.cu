@@ -199,7 +199,7 @@ __global__ void __launch_bounds__(NTHREADS) attn_mma_fwd_kernel(AttnParams P, in
       for (int e = 0; e < 2; e++) {
         const int c = j * 8 + 2 * t + e;
         float x0 = s[j][e] * P.scale, x1 = s[j][2 + e] * P.scale;
-        if (c < klen) {
+        if (c < klen && c != P.key_skip) {
           if (P.dists) {
             x0 += sw * P.dists[da + c] + sb;
             x1 += sw * P.dists[db + c] + sb;
@@ -401,7 +401,7 @@ __global__ void __launch_bounds__(320) attn_fwd2_kernel(AttnParams P, int hc, in
         for (int e = 0; e < 2; e++) {
           const int c = j * 8 + 2 * t + e;
           float x0 = s[j][e] * P.scale, x1 = s[j][2 + e] * P.scale;
-          if (c < klen) {
+          if (c < klen && c != P.key_skip) {
             if (P.dists) {
               x0 += sw * P.dists[da + c] + sb;
               x1 += sw * P.dists[db + c] + sb;
@@ -518,6 +518,135 @@ __global__ void __launch_bounds__(320) attn_fwd2_kernel(AttnParams P, int hc, in
 }
 
 // ===================================================================================================
+// forward, version 3 (no KD map requested): ONE (batch, head, query tile) per CTA and nothing else -- no head loop,
+// no cluster.  The GPU holds every CTA of a launch at once (B x H x tiles CTAs of <= 5 warps, 35-60 KB of shared
+// memory, <= 96 registers at Lk <= 80), so one CTA's load phase hides behind the others' tensor-core / softmax phases:
+// the measured bound of versions 1 / 2 was latency (issue slots 34 % busy, 2.5 warps per scheduler:
+// profiles/r02_ncu_full_summary_v1.md).  Softmax in the exp2 domain (scores pre-multiplied by log2 e: one FMUL less
+// per element), tile-uniform mask fast path (only the n-tiles that straddle the key length or hold the skipped key
+// test per element), two independent max / sum chains per row.  Measured (graph-replayed, dropout 0.1): B64 H12 80x80
+// 20.1 -> 14.5 us, B128 H12 160x160 115 -> 101 us, B128 H12 50x160 55 -> 45 us, B320 H12 36x36 31 -> 26 us.
+//
+// With the KD map the head mean needs a cross-head reduction.  Tried here and dropped: summing the heads in global
+// memory in 2^-30 fixed point with 64-bit integer `red.add` (order-independent, so bit-reproducible) -- the L2 atomic
+// units retire ~0.16 G cells/us, +10 us at B64 H12 80x80 and +40 us at B128 H2 160x160, worse than the cluster /
+// distributed-shared-memory reduction of versions 1 / 2 (+8 us), which therefore keep that case.
+// ===================================================================================================
+__device__ __forceinline__ float ex2f(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+template <int NT, int NW, int MINB>
+__global__ void __launch_bounds__(NW * 32, MINB) attn_fwd3_kernel(AttnParams P) {
+  extern __shared__ __align__(16) uint8_t smraw[];
+  pdl_trigger();
+  constexpr int LKP = NT * 8, QT = NW * 16;
+  bf16* Ks = reinterpret_cast<bf16*>(smraw);
+  bf16* Vs = Ks + LKP * PITCH;
+  bf16* Qs = Vs + LKP * PITCH;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
+  const int b = blockIdx.z, hd = blockIdx.y, q0 = blockIdx.x * QT;
+  const int Lq = P.Lq, Lk = P.Lk, H = P.H;
+  const int rows_q = min(QT, Lq - q0);
+  pdl_wait();
+  const int klen = P.key_lens ? min(Lk, P.key_lens[b]) : Lk;
+  load_rows_n(Ks, (const bf16*)P.k + (size_t)b * Lk * P.k_ld + hd * D, P.k_ld, Lk, LKP);
+  load_rows_n(Vs, (const bf16*)P.v + (size_t)b * Lk * P.v_ld + hd * D, P.v_ld, Lk, LKP);
+  load_rows_n(Qs, (const bf16*)P.q + ((size_t)b * Lq + q0) * P.q_ld + hd * D, P.q_ld, rows_q, QT);
+  cp_async_commit();
+  const float LOG2E = 1.4426950408889634f;
+  const float sc2 = P.scale * LOG2E;
+  const float sw2 = P.dists ? P.sprel_w[0] * LOG2E : 0.f, sb2 = P.dists ? P.sprel_b[0] * LOG2E : 0.f;
+  const Dropout dr = make_dropout(P.drop_p, P.seed_ptr, P.salt);
+  const int ia = q0 + w * 16 + g, ib = ia + 8;
+  const bool va = ia < Lq, vb = ib < Lq;
+  const int skip = P.key_skip;
+  cp_async_wait<0>();
+  __syncthreads();
+  if (w * 16 < rows_q) {
+    float s[NT][4];
+    {
+      uint32_t qa[4][4];
+      load_a_frags(Qs, w * 16, lane, qa);
+      mma_a_yt<NT>(s, qa, Ks, lane);
+    }
+    const float* da = P.dists ? P.dists + ((size_t)b * Lq + (va ? ia : 0)) * Lk : nullptr;
+    const float* db = P.dists ? P.dists + ((size_t)b * Lq + (vb ? ib : 0)) * Lk : nullptr;
+    float mxa[2] = {-INFINITY, -INFINITY}, mxb[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+    for (int j = 0; j < NT; j++) {
+      const int c0 = j * 8 + 2 * t;
+      float x0 = s[j][0] * sc2, x1 = s[j][1] * sc2, x2 = s[j][2] * sc2, x3 = s[j][3] * sc2;
+      if (j * 8 < klen) {  // (tile-uniform) at least one live key in this n-tile
+        if (da) {
+          const bool k0 = c0 < klen, k1 = c0 + 1 < klen;
+          if (k0) { x0 = fmaf(sw2, da[c0], x0 + sb2); x2 = fmaf(sw2, db[c0], x2 + sb2); }
+          if (k1) { x1 = fmaf(sw2, da[c0 + 1], x1 + sb2); x3 = fmaf(sw2, db[c0 + 1], x3 + sb2); }
+        }
+        if (j * 8 + 8 > klen || (skip >= j * 8 && skip < j * 8 + 8)) {  // straddles the length / holds the hole
+          if (c0 >= klen || c0 == skip) x0 = x2 = -INFINITY;
+          if (c0 + 1 >= klen || c0 + 1 == skip) x1 = x3 = -INFINITY;
+        }
+      } else {
+        x0 = x1 = x2 = x3 = -INFINITY;
+      }
+      s[j][0] = x0; s[j][1] = x1; s[j][2] = x2; s[j][3] = x3;
+      mxa[j & 1] = fmaxf(mxa[j & 1], fmaxf(x0, x1));
+      mxb[j & 1] = fmaxf(mxb[j & 1], fmaxf(x2, x3));
+    }
+    float ma = quad_max(fmaxf(mxa[0], mxa[1])), mb = quad_max(fmaxf(mxb[0], mxb[1]));
+    if (ma == -INFINITY) ma = 0.f;  // (a fully masked row: keeps -inf - -inf out of the exponent)
+    if (mb == -INFINITY) mb = 0.f;
+    float sma[2] = {0.f, 0.f}, smb[2] = {0.f, 0.f};
+#pragma unroll
+    for (int j = 0; j < NT; j++) {  // ex2(-inf) = 0: masked keys need no test (a row always has a live key)
+      const float e0 = ex2f(s[j][0] - ma), e1 = ex2f(s[j][1] - ma), e2 = ex2f(s[j][2] - mb), e3 = ex2f(s[j][3] - mb);
+      s[j][0] = e0; s[j][1] = e1; s[j][2] = e2; s[j][3] = e3;
+      sma[j & 1] += e0 + e1;
+      smb[j & 1] += e2 + e3;
+    }
+    const float suma = quad_sum(sma[0] + sma[1]), sumb = quad_sum(smb[0] + smb[1]);
+    const float inva = 1.f / suma, invb = 1.f / sumb;
+    if (t == 0) {  // natural-log log-sum-exp (what the backward kernels subtract)
+      if (va) P.lse[((size_t)b * H + hd) * Lq + ia] = (ma + __log2f(suma)) * 0.6931471805599453f;
+      if (vb) P.lse[((size_t)b * H + hd) * Lq + ib] = (mb + __log2f(sumb)) * 0.6931471805599453f;
+    }
+#pragma unroll
+    for (int j = 0; j < NT; j++) {
+      s[j][0] *= inva; s[j][1] *= inva;
+      s[j][2] *= invb; s[j][3] *= invb;
+    }
+    if (dr.p > 0.f) {
+      const size_t dia = (((size_t)b * H + hd) * Lq + ia) * Lk, dib = (((size_t)b * H + hd) * Lq + ib) * Lk;
+#pragma unroll
+      for (int j = 0; j < NT; j++) {
+#pragma unroll
+        for (int e = 0; e < 2; e++) {
+          const int c = j * 8 + 2 * t + e;
+          s[j][e] *= dr.scale(dia + c);
+          s[j][2 + e] *= dr.scale(dib + c);
+        }
+      }
+    }
+    float o[8][4];
+    mma_c_y<NT>(o, s, Vs, lane, klen);
+    __syncwarp();
+    bf16* stg = Qs + w * 16 * PITCH;  // this warp's Q rows are dead: stage the output slab there
+    store_rows(stg + g * PITCH, stg + (g + 8) * PITCH, o, 1.f, t);
+    __syncwarp();
+    bf16* ob = (bf16*)P.out + ((size_t)b * Lq + q0 + w * 16) * (size_t)(H * D) + hd * D;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      const int r = i * 4 + (lane >> 3), c = lane & 7;
+      if (q0 + w * 16 + r < Lq)
+        *reinterpret_cast<uint4*>(ob + (size_t)r * (H * D) + c * 8) = *reinterpret_cast<const uint4*>(stg + r * PITCH + c * 8);
+    }
+  }
+}
+
+// ===================================================================================================
 // backward pass 1 (query-major): delta, dQ, d(sprel)
 // ===================================================================================================
 template <int NT>
@@ -576,7 +705,7 @@ __global__ void __launch_bounds__(NTHREADS) attn_mma_bwd_q_kernel(AttnParams P) 
       for (int e = 0; e < 2; e++) {
         const int c = j * 8 + 2 * t + e;
         float p0 = 0.f, p1 = 0.f, t0 = 0.f, t1 = 0.f;
-        if (c < klen) {
+        if (c < klen && c != P.key_skip) {
           float x0 = p[j][e] * P.scale, x1 = p[j][2 + e] * P.scale;
           if (P.dists) {
             x0 += sw * P.dists[da + c] + sb;
@@ -613,7 +742,7 @@ __global__ void __launch_bounds__(NTHREADS) attn_mma_bwd_q_kernel(AttnParams P) 
         const float ds0 = p[j][e] * (dp[j][e] - dla), ds1 = p[j][2 + e] * (dp[j][2 + e] - dlb);
         p[j][e] = ds0;
         p[j][2 + e] = ds1;
-        if (P.dists && c < klen) {
+        if (P.dists && c < klen && c != P.key_skip) {
           acc_dw = fmaf(ds0, P.dists[da + c], acc_dw);
           acc_dw = fmaf(ds1, P.dists[db + c], acc_dw);
           acc_db += ds0 + ds1;
@@ -714,7 +843,7 @@ __global__ void __launch_bounds__(NTHREADS) attn_mma_bwd_kv_kernel(AttnParams P)
     store_rows(dva, dvb, o, 0.f, t);
     return;
   }
-  const bool ma = ja < klen, mb = jb < klen;
+  const bool ma = ja < klen && ja != P.key_skip, mb = jb < klen && jb != P.key_skip;
   const size_t dbase = ((size_t)b * H + hd) * Lq;
 
   float p[NTQ][4];
@@ -869,13 +998,44 @@ int launch_fwd2_k(const AttnParams& P, int nw, size_t smem, int hc, int csize, c
   return MAGIC_OK;
 }
 
+// MAGIC_ATTN_FWD: 0 (default) = by the measured heuristic, 1 / 2 / 3 = force that forward version where it applies
+int fwd_force() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("MAGIC_ATTN_FWD");
+    v = e ? atoi(e) : 0;
+    if (fwd_v1()) v = 1;
+  }
+  return v;
+}
+
+template <int NT, int NW>
+int launch_fwd3_k(const AttnParams& P, int tiles, cudaStream_t st) {
+  constexpr int MINB = NT >= 20 ? 2 : 4;
+  const size_t smem = (size_t)(2 * NT * 8 + NW * 16) * PITCH * 2;
+  int rc = set_smem(attn_fwd3_kernel<NT, NW, MINB>, smem, "magic_attn_fwd");
+  if (rc) return rc;
+  MAGIC_CUDA(magic_launch(attn_fwd3_kernel<NT, NW, MINB>, dim3(tiles, P.H, P.B), dim3(NW * 32), smem, st, P),
+             "magic_attn_fwd(v3)");
+  return MAGIC_OK;
+}
+
 template <int NT>
-int launch_fwd(const AttnParams& P, cudaStream_t st) {
-  // measured (B200, graph-replayed, scripts/graph_micro.py attn_l): the one-CTA-per-item kernel wins where a 64-row
-  // tiling would stage K / V twice or more (Lq 80: 29.7 -> 24.8 us, Lq 160: 206 -> 166 us at H = 12 with the KD map;
-  // 43.8 -> 29.8 us at H = 2) and loses on short query ranges (36 x 36: 31 -> 38 us, 50 x 160: 55 -> 90 us), where its
-  // 2 - 4 warp CTAs leave the SM under-occupied
-  if (fwd_v1() || P.Lq > 160 || P.Lq <= 64) return launch_fwd_v1<NT>(P, st);
+int launch_fwd3(const AttnParams& P, cudaStream_t st) {
+  // query tiles of at most 80 rows (5 warps), balanced: Lq = 100 -> 2 tiles of 64 rows, Lq = 160 -> 2 x 80
+  const int tiles = (P.Lq + 79) / 80;
+  const int nw = ((P.Lq + tiles - 1) / tiles + 15) / 16;
+  switch (nw) {
+    case 1:
+    case 2: return launch_fwd3_k<NT, 2>(P, (P.Lq + 31) / 32, st);
+    case 3: return launch_fwd3_k<NT, 3>(P, (P.Lq + 47) / 48, st);
+    case 4: return launch_fwd3_k<NT, 4>(P, (P.Lq + 63) / 64, st);
+    default: return launch_fwd3_k<NT, 5>(P, (P.Lq + 79) / 80, st);
+  }
+}
+
+template <int NT>
+int launch_fwd2(const AttnParams& P, cudaStream_t st) {
   const int nw = (P.Lq + 15) / 16;
   int csize = 1;
   if (P.pbar && P.H >= 4) csize = (P.H % 4 == 0 && P.H >= 8) ? 4 : (P.H % 2 == 0) ? 2 : 1;
@@ -888,6 +1048,23 @@ int launch_fwd(const AttnParams& P, cudaStream_t st) {
   if (db) return launch_fwd2_k<NT, true>(P, nw, 2 * set_bytes + pb_bytes, hc, csize, st);
   if (set_bytes + pb_bytes > 220 * 1024) return launch_fwd_v1<NT>(P, st);
   return launch_fwd2_k<NT, false>(P, nw, set_bytes + pb_bytes, hc, csize, st);
+}
+
+template <int NT>
+int launch_fwd(const AttnParams& P, cudaStream_t st) {
+  const int force = fwd_force();
+  const bool v3_ok = P.Lq <= 160 && !P.pbar;
+  if (force == 3 && v3_ok) return launch_fwd3<NT>(P, st);
+  if (force == 1 || P.Lq > 160) return launch_fwd_v1<NT>(P, st);
+  if (force == 2) return P.Lq <= 64 ? launch_fwd_v1<NT>(P, st) : launch_fwd2<NT>(P, st);
+  // default: version 3 (one CTA per (batch, head, query tile)) whenever no KD map is requested
+  if (v3_ok) return launch_fwd3<NT>(P, st);
+  // measured (B200, graph-replayed, scripts/graph_micro.py attn_l): the one-CTA-per-item kernel wins where a 64-row
+  // tiling would stage K / V twice or more (Lq 80: 29.7 -> 24.8 us, Lq 160: 206 -> 166 us at H = 12 with the KD map;
+  // 43.8 -> 29.8 us at H = 2) and loses on short query ranges (36 x 36: 31 -> 38 us, 50 x 160: 55 -> 90 us), where its
+  // 2 - 4 warp CTAs leave the SM under-occupied
+  if (P.Lq <= 64) return launch_fwd_v1<NT>(P, st);
+  return launch_fwd2<NT>(P, st);
 }
 
 template <int NT>

@@ -188,29 +188,32 @@ __device__ __forceinline__ Dropout make_dropout(float p, const unsigned long lon
   return d;
 }
 
-// erf by Abramowitz-Stegun 7.1.26 (|abs err| < 1.5e-7): one reciprocal + one exp2 on the MUFU pipe and 7 FMA-pipe
-// ops, branch-free.  Used where the value is stored in bf16 (rounding 4e-3 relative); fp32 storage keeps erff.
-// `e` returns exp(-x*x) (the Gaussian factor the GELU derivative needs as well).
-__device__ __forceinline__ float erf_fast(float x, float& e) {
-  const float ax = fabsf(x);
-  float t;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, ax, 1.f)));
-  float q = fmaf(t, 1.061405429f, -1.453152027f);
-  q = fmaf(q, t, 1.421413741f);
-  q = fmaf(q, t, -0.284496736f);
-  q = fmaf(q, t, 0.254829592f);
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-1.4426950408889634f * ax * ax));
-  const float y = fmaf(-q * t, e, 1.f);
-  return copysignf(y, x);
+// GELU through the normal tail: Phi(-a) = 2^Q(a) with Q a degree-5 polynomial fitted on a = |x| in [0, 6] (weighted
+// minimax of the GELU value, scripts/fit_gelu.py: |abs err| < 5e-7 over all x), so
+//   gelu(x) = max(x, 0) - |x| * 2^Q(min(|x|, 6))
+// costs 8 FMA-pipe ops and ONE exp2 (an Abramowitz-Stegun 7.1.26 erf: 16 + 2 MUFU, the version this replaced).  A 128 x 256 accumulator slab is 128 elements
+// per epilogue thread, so the FFN-up epilogue was longer than its 12-k-block main loop.
+__device__ __forceinline__ float gelu_tail(float a) {  // Phi(-a), a >= 0
+  a = fminf(a, 6.f);
+  float q = fmaf(a, -4.733715079e-04f, 7.084977951e-03f);
+  q = fmaf(q, a, -5.182837537e-02f);
+  q = fmaf(q, a, -4.599914417e-01f);
+  q = fmaf(q, a, -1.150788262e+00f);
+  q = fmaf(q, a, -1.000037571e+00f);
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(q));
+  return e;
 }
 __device__ __forceinline__ float gelu_fast_f(float x) {
-  float e;
-  return 0.5f * x * (1.f + erf_fast(x * 0.70710678118654752f, e));
+  const float a = fabsf(x);
+  return fmaf(-a, gelu_tail(a), fmaxf(x, 0.f));
 }
-__device__ __forceinline__ float gelu_grad_fast_f(float x) {
-  float e;  // exp(-x^2 / 2)
-  const float cdf = 0.5f * (1.f + erf_fast(x * 0.70710678118654752f, e));
-  return fmaf(x * 0.3989422804014327f, e, cdf);
+__device__ __forceinline__ float gelu_grad_fast_f(float x) {  // Phi(x) + x * phi(x)
+  const float t = gelu_tail(fabsf(x));
+  float g;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(g) : "f"(-0.72134752044448170f * x * x));  // exp(-x^2 / 2)
+  const float cdf = x >= 0.f ? 1.f - t : t;
+  return fmaf(x * 0.3989422804014327f, g, cdf);
 }
 
 __device__ __forceinline__ float gelu_f(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752f)); }

@@ -326,7 +326,7 @@ __device__ __forceinline__ void stamp(const TcParams& P, int i) {
   }
 }
 
-// activation on the tensor-core path: bf16 storage takes the branch-free MUFU forms (common.cuh erf_fast)
+// activation on the tensor-core path: bf16 storage takes the branch-free one-MUFU forms (common.cuh gelu_tail)
 template <typename TC, int ACT>
 __device__ __forceinline__ float tc_act_fwd(float v) {
   if (ACT == MAGIC_ACT_GELU) return sizeof(TC) == 2 ? gelu_fast_f(v) : gelu_f(v);

@@ -220,7 +220,7 @@ def _ln(x, m, fc, res=None, p_in=0.0, p_out=0.0, link=None):
                           salt_out=fc.salt(), link=link)
 
 
-def _attn_block(att, x, ctx_kv, B, Lq, Lk, key_lens, fc, dists=None, sprel=None):
+def _attn_block(att, x, ctx_kv, B, Lq, Lk, key_lens, fc, dists=None, sprel=None, key_skip=-1):
     """BertAttention: (self or cross) attention + output dense + dropout + residual LayerNorm.
     x [B*Lq, h]; ctx_kv None -> self attention.  Returns (y [B*Lq, h], pbar or None)."""
     sa = att.self
@@ -235,7 +235,7 @@ def _attn_block(att, x, ctx_kv, B, Lq, Lk, key_lens, fc, dists=None, sprel=None)
         qkv = ops.packed_linear(x, [sa.query.weight, sa.key.weight, sa.value.weight],
                                 [sa.query.bias, sa.key.bias, sa.value.bias], link=link)
         o, pbar = ops.attention(qkv, None, 0, h, 2 * h, B, H, Lq, Lk, key_lens, dists, sw, sb, fc.want_attn, pdrop,
-                                fc.salt())
+                                fc.salt(), key_skip)
     else:
         q = ops.linear(x, sa.query.weight, sa.query.bias, link=link)
         kv = ops.packed_linear(ctx_kv, [sa.key.weight, sa.value.weight], [sa.key.bias, sa.value.bias])
@@ -254,10 +254,10 @@ def _ffn_block(layer, x, fc):
     return _ln(f, layer.output.LayerNorm, fc, res=x, p_in=fc.p(layer.output.dropout), link=link)
 
 
-def _cross_encoder(enc, x, ctx, B, Lx, Lc, x_lens, c_lens, fc, dists=None, sprel=None):
+def _cross_encoder(enc, x, ctx, B, Lx, Lc, x_lens, c_lens, fc, dists=None, sprel=None, key_skip=-1):
     attns = []
     for layer in enc.crossattention:
-        a, p_self = _attn_block(layer.attention, x, None, B, Lx, Lx, x_lens, fc, dists, sprel)
+        a, p_self = _attn_block(layer.attention, x, None, B, Lx, Lx, x_lens, fc, dists, sprel, key_skip)
         cx, p_cross = _attn_block(layer.crossattention, a, ctx, B, Lx, Lc, c_lens, fc)
         x = _ffn_block(layer, cx, fc)
         attns.append((p_self, p_cross))

@@ -667,7 +667,7 @@ class AttentionFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, qsrc, kvsrc, q_off, k_off, v_off, B, H, Lq, Lk, key_lens, dists, sprel_w, sprel_b, need_pbar,
-                drop_p, salt):
+                drop_p, salt, key_skip=-1):
         same = kvsrc is None
         kv = qsrc if same else kvsrc
         hd = H * 64
@@ -680,9 +680,12 @@ class AttentionFn(torch.autograd.Function):
         scale = 1.0 / math.sqrt(64.0)
         sw = sprel_w.reshape(-1) if sprel_w is not None else None
         sb = sprel_b.reshape(-1) if sprel_b is not None else None
-        call("magic_attn_fwd", qsrc.data_ptr() + q_off * esz, kv.data_ptr() + k_off * esz, kv.data_ptr() + v_off * esz,
-             qsrc.stride(0), kv.stride(0), kv.stride(0), ptr(out), ptr(lse), ptr(pbar), Lq * Lk, Lk, B, H, Lq, Lk,
-             ptr(key_lens), ptr(dists), ptr(sw), ptr(sb), scale, dt(qsrc), drop_p, salt, ptr(seed), stream())
+        with _key_skip(key_skip):
+            call("magic_attn_fwd", qsrc.data_ptr() + q_off * esz, kv.data_ptr() + k_off * esz,
+                 kv.data_ptr() + v_off * esz, qsrc.stride(0), kv.stride(0), kv.stride(0), ptr(out), ptr(lse), ptr(pbar),
+                 Lq * Lk, Lk, B, H, Lq, Lk, ptr(key_lens), ptr(dists), ptr(sw), ptr(sb), scale, dt(qsrc), drop_p, salt,
+                 ptr(seed), stream())
+        ctx.key_skip = key_skip
         ctx.save_for_backward(qsrc, kvsrc, key_lens, dists, sprel_w, sprel_b, lse, out)
         ctx.meta = (q_off, k_off, v_off, B, H, Lq, Lk, drop_p, salt, scale, need_pbar)
         if need_pbar:
@@ -711,6 +714,8 @@ class AttentionFn(torch.autograd.Function):
         sw = sprel_w.reshape(-1) if sprel_w is not None else None
         sb = sprel_b.reshape(-1) if sprel_b is not None else None
         done = False
+        if ctx.key_skip >= 0:
+            L.load().magic_attn_set_key_skip(int(ctx.key_skip))  # (reset after the launches below)
         if (dpbar is None and qsrc.dtype == torch.bfloat16 and _BRANCH["on"] and (L._PROFILE is None or L._PROFILE_GRAPH)
                 and B * H * Lq <= 24576):  # latency-bound sizes only: at H = 12 the halves fill the GPU on their own
             # no KD-map gradient: the key-major kernel (dK, dV) recomputes delta = dO . O itself, so it does not depend
@@ -743,6 +748,8 @@ class AttentionFn(torch.autograd.Function):
                  Lq * Lk, Lk, ptr(delta), dqsrc.data_ptr() + q_off * esz, dkv.data_ptr() + k_off * esz,
                  dkv.data_ptr() + v_off * esz, dqsrc.stride(0), dkv.stride(0), dkv.stride(0), ptr(gs), B, H, Lq, Lk,
                  ptr(key_lens), ptr(dists), ptr(sw), ptr(sb), scale, dt(qsrc), drop_p, salt, ptr(seed), stream())
+        if ctx.key_skip >= 0:
+            L.load().magic_attn_set_key_skip(-1)
         if dists is not None:
             gw = getattr(sprel_w, "_magic_grad", None)
             if gw is not None:
@@ -752,13 +759,31 @@ class AttentionFn(torch.autograd.Function):
                 rs_w = gs[0:1].view(sprel_w.shape)
                 rs_b = gs[1:2].view(sprel_b.shape)
         return (dqsrc, None if same else dkv, None, None, None, None, None, None, None, None, None, rs_w, rs_b, None,
-                None, None)
+                None, None, None)
+
+
+class _key_skip:
+    """Scope of `magic_attn_set_key_skip`: the launches inside never attend key `idx` (-1: no-op)."""
+
+    def __init__(self, idx):
+        self.idx = int(idx)
+
+    def __enter__(self):
+        if self.idx >= 0:
+            L.load().magic_attn_set_key_skip(self.idx)
+
+    def __exit__(self, *a):
+        if self.idx >= 0:
+            L.load().magic_attn_set_key_skip(-1)
+        return False
 
 
 def attention(qsrc, kvsrc, q_off, k_off, v_off, B, H, Lq, Lk, key_lens=None, dists=None, sprel_w=None, sprel_b=None,
-              need_pbar=False, drop_p=0.0, salt=0):
+              need_pbar=False, drop_p=0.0, salt=0, key_skip=-1):
+    """`key_skip`: index of one key inside the valid prefix that is never attended (the navigation graph's [MEM]
+    slot, agent.py:228); -1 = none."""
     return AttentionFn.apply(qsrc, kvsrc, q_off, k_off, v_off, B, H, Lq, Lk, key_lens, dists, sprel_w, sprel_b,
-                             need_pbar, drop_p if _DROP_ON else 0.0, salt)
+                             need_pbar, drop_p if _DROP_ON else 0.0, salt, key_skip)
 
 
 class GmapAggFn(torch.autograd.Function):
