@@ -251,6 +251,49 @@ int magic_gather_views(const void* store, int store_dt, long long n_store, const
 int magic_gather_pair_dists(const float* dist, long long N, const long long* node_vp, float* out, int B, int G,
                             cudaStream_t st);
 
+/* ---- GPU batch featuriser (graph half): builds, on the device, every tensor of a pretraining batch that derives from
+ * the navigation graph -- what pretrain_src/data/dataset.py builds per sample in DataLoader workers (get_cur_angle
+ * :433-443, get_traj_pano_fts :733-772, get_gmap_inputs :513-549, get_gmap_pos_fts :553-575, get_vp_pos_fts :577-586,
+ * get_act_labels :622-640), what data/tasks.py:110-166 collates, and the integer tables the model's viewpoint-id string
+ * loops reduce to (gmap source CSR + reverse, SAP masks, local -> global scatter).  Integer outputs are bit-exact
+ * against those loops; float features agree to 1-2 ulp.  All pointers are device memory; `status` receives the largest
+ * error code seen (0 = ok, 1 = more than 256 distinct viewpoints in a sample, 2 = graph larger than G, 3 = two candidates
+ * share a view, 4 / 5 = entry capacities E_s / E_cap / S_cap too small). */
+typedef struct MagicFeatArgs {
+  /* world (resident): N viewpoints, at most C candidates each */
+  const double* pos;       /* [N, 3] (fp64, like the connectivity files) */
+  const float* dist;       /* [N, N] shortest distances */
+  const int* hops;         /* [N, N] len(shortest path) - 1 */
+  const int* cand_vp;      /* [N, C] candidate viewpoint rows in scanvp_cands dict order */
+  const int* cand_view;    /* [N, C] view index of the candidate (v[0]) */
+  const float* cand_ang;   /* [N, C, 2] heading / elevation offsets (v[2], v[3]) */
+  const int* n_cand;       /* [N] */
+  const float* view_ang;   /* [36, 2] all_point_rel_angles[12] */
+  /* batch (per sample) */
+  const int* path;          /* [B, Tmax] viewpoint rows */
+  const int* path_len;      /* [B] */
+  const float* start_heading; /* [B] */
+  const int* next_vp;       /* [B] ground-truth next viewpoint, -1 = stop, -2 = unknown; NULL: no labels */
+  const int* row0;          /* [B] first panorama row of the sample (exclusive prefix sum of path_len) */
+  /* outputs: panoramas [R_cap rows] */
+  long long* traj_vp_index; int* traj_view_perm; float* traj_loc_fts; long long* traj_nav_types;
+  long long* traj_vp_view_lens;
+  /* outputs: graph / local branch / labels */
+  long long* gmap_node_vp; long long* gmap_step_ids; unsigned char* gmap_visited_masks; long long* gmap_lens;
+  float* gmap_pos_fts; float* gmap_pair_dists; float* vp_pos_fts; long long* global_act_labels;
+  long long* local_act_labels;
+  /* outputs: index tables (graph_index.build_index + pad_batch layout) */
+  int* node_ptr; int* entries; int* src_ids; int* src_ptr; int* src_nodes; float* src_w; int* n_src;
+  unsigned char* g_valid; unsigned char* l_valid; int* node2cand; unsigned char* bw_mask; long long* vp_gather;
+  int* key_lens_gmap; int* key_lens_vp; long long* last_rows;
+  /* scratch: per-sample slabs */
+  int* slab_entries; int* slab_nodes; int* slab_rank; int* slab_ptr; int* slab_total; int* slab_nvis;
+  int* status;
+  int N, C, B, Tmax, G, Vp, R, R_cap, E_s, E_cap, S_cap, correct_heading;
+} MagicFeatArgs;
+int magic_featurize_graph(const MagicFeatArgs* args, cudaStream_t st);
+int magic_feat_args_size(void); /* sizeof(MagicFeatArgs): lets a binding check its mirror of the struct */
+
 /* ---- optimizer (pretrain_src/optim/adamw.py:53-112, clip grad_norm r2r_magic_pretrain.json:22) ----- */
 /* out[0] (+)= sum g^2, deterministic (two-stage, no floating-point atomics: data-parallel replicas with identical
  * gradients compute the identical clip coefficient).  `out` must hold 1 + MAGIC_SUMSQ_SCRATCH floats: out[1..] is the
