@@ -376,6 +376,118 @@ def run_torch_gpu(args):
                       kind="oracle port, stock torch ops on cuda" + (", torch.compile" if args.compile else ", eager")))
 
 
+def nav_latency(dtype=torch.bfloat16, steps=12):
+    """Fine-tune / inference path (the "MAGIC-S real-time" claim): device time of one navigation
+    decision -- panorama mode + collators + navigation mode of nav.VLNBert (MAGIC-S, h = 128) over online GraphMaps on
+    synthetic worlds, batch 1 and 8, 80-token instructions, graphs growing to ~20 nodes -- through the public
+    `vln_bert(mode, batch)` call, host collation and H2D of the step's inputs included."""
+    import numpy as np
+    from magic_b200 import nav, nav_synth
+    from magic_b200.config import make_config
+    out = {}
+    for B in (1, 8):
+        cfg = make_config(128, hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0, pretrain_tasks=("sap",))
+        torch.manual_seed(0)
+        model = nav.VLNBert(cfg).to("cuda").eval().set_compute_dtype(dtype)
+        model.want_attn = False
+        rng = np.random.RandomState(5)
+        worlds = [nav_synth.NavWorld(n=40, seed=60 + b) for b in range(B)]
+        cur = [int(rng.randint(0, 40)) for _ in range(B)]
+        instr = [nav_synth.make_instr(rng, 80) for _ in range(B)]
+        obs = [w.observe(c, instr=i) for w, c, i in zip(worlds, cur, instr)]
+        gmaps = [nav.GraphMap(ob["viewpoint"]) for ob in obs]
+        for gm, ob in zip(gmaps, obs):
+            gm.update_graph(ob)
+        with torch.no_grad():
+            lang = nav.language_inputs(obs, "cuda")
+            txt, _ = model("language", lang)
+            last, times = None, []
+            for t in range(steps + 3):
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                for gm, ob in zip(gmaps, obs):
+                    gm.node_step_ids[ob["viewpoint"]] = t + 1
+                pin = nav.panorama_inputs(obs, "cuda")
+                pe, pm, pf, _ = model("panorama", pin)
+                for i, (gm, ob) in enumerate(zip(gmaps, obs)):
+                    gm.update_node_embed(ob["viewpoint"], pf[i], rewrite=True)
+                    for j, c in enumerate(pin["cand_vpids"][i]):
+                        if not gm.graph.visited(c):
+                            gm.update_node_embed(c, pe[i, j])
+                nin = nav.nav_gmap_inputs(obs, gmaps, last)
+                nin.update(nav.nav_vp_inputs_mem(obs, gmaps, pe, pin["cand_vpids"], pin["view_lens"], pin["nav_types"], last))
+                nin.update(txt_embeds=txt, txt_masks=lang["txt_masks"], txt_lens=lang["txt_lens"])
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                o = model("navigation", nin)
+                e1.record()
+                act = o["fused_logits"].argmax(1).tolist()  # device -> host read of the decision
+                torch.cuda.synchronize()
+                if t >= 3:
+                    times.append(((time.perf_counter() - t0) * 1e3, e0.elapsed_time(e1)))
+                last = o["cls_embeds"]
+                nxt = []
+                for i, (w, ob) in enumerate(zip(worlds, obs)):
+                    vp = nin["gmap_vpids"][i][act[i]]
+                    nb = np.nonzero(w.adj[w.index(ob["viewpoint"])])[0]
+                    j = w.index(vp) if vp is not None else int(nb[t % len(nb)])
+                    nxt.append(w.observe(j, heading=0.3 * t, instr=ob["instr_encoding"]))
+                obs = nxt
+                for gm, ob in zip(gmaps, obs):
+                    gm.update_graph(ob)
+        wall = sorted(x[0] for x in times)[len(times) // 2]
+        dev = sorted(x[1] for x in times)[len(times) // 2]
+        out[f"batch{B}"] = dict(ms_per_decision_end_to_end=round(wall, 3), ms_navigation_mode_device=round(dev, 3),
+                                decisions_per_s=round(B * 1e3 / wall, 1), graph_nodes=int(nin["gmap_masks"].shape[1]))
+    out["what"] = ("nav.VLNBert MAGIC-S bf16: panorama mode + GraphMap update + collators + navigation mode + argmax read-back "
+                   "per decision (median of %d), host python included" % steps)
+    return out
+
+
+def featurizer_rate(B=64, Tmax=5, calls=20):
+    """GPU batch featuriser, graph half: device time of one magic_featurize_graph call (the graph-
+    derived tensors and index tables of a B-sample batch) vs the host loops it replaces (graph_index.build_index on the
+    collated batch; the reference's per-sample dataset.py code is slower still)."""
+    import numpy as np
+    from magic_b200 import nav_synth, synth
+    from magic_b200.featurizer import GraphFeaturizer, GraphWorld
+    from magic_b200.graph_index import build_index
+    w = nav_synth.NavWorld(n=256, seed=9)
+    world = GraphWorld(*nav_synth.world_tables(w), device="cuda")
+    rng = np.random.RandomState(3)
+    paths = []
+    for b in range(B):
+        p = [int(rng.randint(0, w.n))]
+        for _ in range(int(rng.randint(1, Tmax))):
+            nb = np.nonzero(w.adj[p[-1]])[0][:8]
+            p.append(int(nb[rng.randint(len(nb))]))
+        paths.append(p)
+    feat = GraphFeaturizer(world, B, Tmax=Tmax, G=64)
+    heads = [0.1 * b for b in range(B)]
+    nxt = [-1] * B
+    feat(paths, heads, nxt)
+    feat.check()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e0.record()
+    for _ in range(calls):
+        feat(paths, heads, nxt)
+    e1.record()
+    torch.cuda.synchronize()
+    wall = (time.perf_counter() - t0) * 1e3 / calls
+    dev = e0.elapsed_time(e1) / calls
+    hb = synth.make_batch("sap", B, seed=1, T_max=Tmax)
+    t0 = time.perf_counter()
+    for _ in range(3):
+        build_index(hb)
+    host = (time.perf_counter() - t0) * 1e3 / 3
+    return dict(batch=B, ms_per_batch_device=round(dev, 3), ms_per_batch_wall=round(wall, 3),
+                host_build_index_ms=round(host, 3), h2d_bytes_per_batch=int(B * (Tmax + 4) * 4),
+                what="magic_featurize_graph (2 kernels) on a 256-viewpoint synthetic world vs graph_index.build_index "
+                     "(python loops over the collated id strings) for the same batch size")
+
+
 def workload_config(name, w, world, dropout, cuda_graphs=True, pool_n=None, in_bytes=None):
     B = w["B"]
     cfg = dict(workload=name, hidden=w["hidden"], layers=f"{w['n_l']}/{w['n_p']}/{w['n_x']}",
@@ -724,6 +836,13 @@ def run_ours(args):
             except Exception as e:
                 line["gpu_baseline"] = dict(error=repr(e)[:300])
             torch.cuda.empty_cache()
+        if world == 1 and not args.no_extras:
+            for key, fn in (("nav_inference", nav_latency), ("featurizer", featurizer_rate)):
+                try:
+                    line[key] = fn()
+                except Exception as e:
+                    line[key] = dict(error=repr(e)[:300])
+                torch.cuda.empty_cache()
         if world == 1 and not args.no_cpu:
             v, n, tstep = cpu_step_rate(w, args.cpu_seconds, args.dropout)
             line["cpu_baseline"] = dict(
@@ -790,6 +909,7 @@ def main():
     ap.add_argument("--side-stream", type=int, default=1)
     ap.add_argument("--branch-streams", type=int, default=1)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the nav-inference / featuriser side measurements")
     ap.add_argument("--timed-only", action="store_true",
                     help="profiling aid: run warm-up + the timed region only (no e2e / roofline / CPU passes, no JSON)")
     args = ap.parse_args()

@@ -57,3 +57,28 @@ class NavWorld:
 def make_instr(rng, L):
     n = int(rng.randint(max(4, L // 2), L + 1))
     return [0] + rng.randint(3, 50000, n - 2).tolist() + [2]
+
+
+def world_tables(world, max_hops_inf=10 ** 6):
+    """(pos, dist, hops, cands, view_ang) of a NavWorld in the layout featurizer.GraphWorld takes: all-pairs shortest
+    distances / hop counts by Floyd-Warshall, candidate tables in `observe()`'s neighbour order."""
+    n = world.n
+    d = np.full((n, n), np.inf)
+    hops = np.full((n, n), max_hops_inf, dtype=np.int64)
+    np.fill_diagonal(d, 0.0)
+    np.fill_diagonal(hops, 0)
+    e = np.linalg.norm(world.pos[:, None] - world.pos[None], axis=-1)
+    d[world.adj] = e[world.adj]
+    hops[world.adj] = 1
+    for k in range(n):
+        via = d[:, k, None] + d[None, k, :]
+        better = via < d
+        d[better] = via[better]
+        hv = hops[:, k, None] + hops[None, k, :]
+        hops[better] = np.broadcast_to(hv, (n, n))[better]
+    cands = []
+    for i in range(n):
+        nbrs = np.nonzero(world.adj[i])[0][:8]
+        points = np.random.RandomState(1000 + i).permutation(36)[:len(nbrs)]
+        cands.append([(int(j), int(p), 0.0, 0.0) for j, p in zip(nbrs, points)])
+    return world.pos.astype(np.float64), d.astype(np.float32), hops.astype(np.int32), cands, view_angles()
