@@ -377,70 +377,79 @@ def run_torch_gpu(args):
 
 
 def nav_latency(dtype=torch.bfloat16, steps=12):
-    """Fine-tune / inference path (the "MAGIC-S real-time" claim): device time of one navigation
-    decision -- panorama mode + collators + navigation mode of nav.VLNBert (MAGIC-S, h = 128) over online GraphMaps on
-    synthetic worlds, batch 1 and 8, 80-token instructions, graphs growing to ~20 nodes -- through the public
-    `vln_bert(mode, batch)` call, host collation and H2D of the step's inputs included."""
+    """Fine-tune / inference path (the "MAGIC-S real-time" claim): one navigation decision -- panorama
+    mode + GraphMap update + collators + navigation mode + read-back of the action -- of nav.VLNBert (MAGIC-S, h = 128)
+    over online GraphMaps on synthetic worlds, batch 1 and 8, 80-token instructions, graphs growing to ~35 nodes.
+    Eager (`vln_bert(mode, batch)`, the reference's call) and graph-replayed (nav.NavStepper); host python included in
+    the end-to-end figure, CUDA events around the navigation mode for the device figure."""
     import numpy as np
     from magic_b200 import nav, nav_synth
     from magic_b200.config import make_config
+
+    def rollout(model, stepper, B, replay):
+        rng = np.random.RandomState(5)
+        worlds = [nav_synth.NavWorld(n=40, seed=60 + b) for b in range(B)]
+        obs = [w.observe(int(rng.randint(0, 40)), instr=nav_synth.make_instr(rng, 80)) for w in worlds]
+        gmaps = [nav.GraphMap(ob["viewpoint"]) for ob in obs]
+        for gm, ob in zip(gmaps, obs):
+            gm.update_graph(ob)
+        lang = nav.language_inputs(obs, "cuda")
+        txt, _ = model("language", lang)
+        last, times, nodes = None, [], 0
+        for t in range(steps + 3):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for gm, ob in zip(gmaps, obs):
+                gm.node_step_ids[ob["viewpoint"]] = t + 1
+            pin = nav.panorama_inputs(obs, "cuda")
+            pe, pm, pf, _ = stepper.panorama(pin) if replay else model("panorama", pin)
+            for i, (gm, ob) in enumerate(zip(gmaps, obs)):
+                gm.update_node_embed(ob["viewpoint"], pf[i], rewrite=True)
+                for j, c in enumerate(pin["cand_vpids"][i]):
+                    if not gm.graph.visited(c):
+                        gm.update_node_embed(c, pe[i, j])
+            nin = nav.nav_gmap_inputs(obs, gmaps, last)
+            nin.update(nav.nav_vp_inputs_mem(obs, gmaps, pe, pin["cand_vpids"], pin["view_lens"], pin["nav_types"], last))
+            nin.update(txt_embeds=txt, txt_masks=lang["txt_masks"], txt_lens=lang["txt_lens"])
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            o = stepper.navigation(nin) if replay else model("navigation", nin)
+            e1.record()
+            act = o["fused_logits"].argmax(1).tolist()  # device -> host read of the decision
+            torch.cuda.synchronize()
+            if t >= 3:
+                times.append(((time.perf_counter() - t0) * 1e3, e0.elapsed_time(e1)))
+            last = o["cls_embeds"].clone()
+            nodes = int(nin["gmap_masks"].shape[1])
+            nxt = []
+            for i, (w, ob) in enumerate(zip(worlds, obs)):
+                vp = nin["gmap_vpids"][i][act[i]]
+                nb = np.nonzero(w.adj[w.index(ob["viewpoint"])])[0]
+                j = w.index(vp) if vp is not None else int(nb[t % len(nb)])
+                nxt.append(w.observe(j, heading=0.3 * t, instr=ob["instr_encoding"]))
+            obs = nxt
+            for gm, ob in zip(gmaps, obs):
+                gm.update_graph(ob)
+        wall = sorted(x[0] for x in times)[len(times) // 2]
+        dev = sorted(x[1] for x in times)[len(times) // 2]
+        return wall, dev, nodes
+
     out = {}
     for B in (1, 8):
         cfg = make_config(128, hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0, pretrain_tasks=("sap",))
         torch.manual_seed(0)
         model = nav.VLNBert(cfg).to("cuda").eval().set_compute_dtype(dtype)
         model.want_attn = False
-        rng = np.random.RandomState(5)
-        worlds = [nav_synth.NavWorld(n=40, seed=60 + b) for b in range(B)]
-        cur = [int(rng.randint(0, 40)) for _ in range(B)]
-        instr = [nav_synth.make_instr(rng, 80) for _ in range(B)]
-        obs = [w.observe(c, instr=i) for w, c, i in zip(worlds, cur, instr)]
-        gmaps = [nav.GraphMap(ob["viewpoint"]) for ob in obs]
-        for gm, ob in zip(gmaps, obs):
-            gm.update_graph(ob)
+        stepper = nav.NavStepper(model, B, G=64, Lt=80)
         with torch.no_grad():
-            lang = nav.language_inputs(obs, "cuda")
-            txt, _ = model("language", lang)
-            last, times = None, []
-            for t in range(steps + 3):
-                torch.cuda.synchronize()
-                t0 = time.perf_counter()
-                for gm, ob in zip(gmaps, obs):
-                    gm.node_step_ids[ob["viewpoint"]] = t + 1
-                pin = nav.panorama_inputs(obs, "cuda")
-                pe, pm, pf, _ = model("panorama", pin)
-                for i, (gm, ob) in enumerate(zip(gmaps, obs)):
-                    gm.update_node_embed(ob["viewpoint"], pf[i], rewrite=True)
-                    for j, c in enumerate(pin["cand_vpids"][i]):
-                        if not gm.graph.visited(c):
-                            gm.update_node_embed(c, pe[i, j])
-                nin = nav.nav_gmap_inputs(obs, gmaps, last)
-                nin.update(nav.nav_vp_inputs_mem(obs, gmaps, pe, pin["cand_vpids"], pin["view_lens"], pin["nav_types"], last))
-                nin.update(txt_embeds=txt, txt_masks=lang["txt_masks"], txt_lens=lang["txt_lens"])
-                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                e0.record()
-                o = model("navigation", nin)
-                e1.record()
-                act = o["fused_logits"].argmax(1).tolist()  # device -> host read of the decision
-                torch.cuda.synchronize()
-                if t >= 3:
-                    times.append(((time.perf_counter() - t0) * 1e3, e0.elapsed_time(e1)))
-                last = o["cls_embeds"]
-                nxt = []
-                for i, (w, ob) in enumerate(zip(worlds, obs)):
-                    vp = nin["gmap_vpids"][i][act[i]]
-                    nb = np.nonzero(w.adj[w.index(ob["viewpoint"])])[0]
-                    j = w.index(vp) if vp is not None else int(nb[t % len(nb)])
-                    nxt.append(w.observe(j, heading=0.3 * t, instr=ob["instr_encoding"]))
-                obs = nxt
-                for gm, ob in zip(gmaps, obs):
-                    gm.update_graph(ob)
-        wall = sorted(x[0] for x in times)[len(times) // 2]
-        dev = sorted(x[1] for x in times)[len(times) // 2]
-        out[f"batch{B}"] = dict(ms_per_decision_end_to_end=round(wall, 3), ms_navigation_mode_device=round(dev, 3),
-                                decisions_per_s=round(B * 1e3 / wall, 1), graph_nodes=int(nin["gmap_masks"].shape[1]))
+            ew, ed, nodes = rollout(model, stepper, B, False)
+            gw, gd, _ = rollout(model, stepper, B, True)
+        out[f"batch{B}"] = dict(eager=dict(ms_per_decision_end_to_end=round(ew, 3), ms_navigation_mode_device=round(ed, 3)),
+                                graph_replay=dict(ms_per_decision_end_to_end=round(gw, 3),
+                                                  ms_navigation_mode_device=round(gd, 3)),
+                                decisions_per_s=round(B * 1e3 / gw, 1), graph_nodes=nodes)
     out["what"] = ("nav.VLNBert MAGIC-S bf16: panorama mode + GraphMap update + collators + navigation mode + argmax read-back "
-                   "per decision (median of %d), host python included" % steps)
+                   "per decision (median of %d), host python included in the end-to-end figure" % steps)
     return out
 
 

@@ -17,7 +17,10 @@ reference code, and followed literally here:
                                          pinned against the reference file by tests/golden/kd_loss_*.pt)
   * MAKD aggregation                  -- map_nav_src/r2r/agent.py:546-719 (compute_kd_losses),
                                          :866-869 (MKRW), :1013-1020 (MKTD), :1110-1123 (mix)
-Everything else is tagged [DECISION] where it is made.
+  * block arithmetic                  -- tests/test_oracle_blocks_pinned.py: BertLayer / BertAttention (self, cross) /
+                                         BertEmbeddings vs `transformers`, PanoLayer vs torch.nn.TransformerEncoderLayer
+                                         (same state-dict keys, same activations)
+Everything else (how the blocks are wired) is tagged [DECISION] where it is made.
 """
 import math
 from types import SimpleNamespace

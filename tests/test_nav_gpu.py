@@ -135,3 +135,66 @@ def test_checkpoint_from_pretraining_loads():
     assert torch.equal(a, b)
     with pytest.raises(NotImplementedError):
         wrapped("nope", lang)
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-5), (torch.bfloat16, 1e-2)])
+def test_graph_replayed_decision_step_equals_eager(dtype, tol):
+    """nav.NavStepper (panorama + navigation modes as CUDA graphs over capacity-padded buffers) == the eager modes, for
+    graphs that grow from step to step."""
+    B = 4
+    _, prod = build(128)
+    prod.set_compute_dtype(dtype)
+    stepper = nav.NavStepper(prod, B, G=48, Lt=48)
+    rng = np.random.RandomState(11)
+    worlds = [nav_synth.NavWorld(n=22, seed=70 + b) for b in range(B)]
+    obs = [w.observe(int(rng.randint(0, 22)), instr=nav_synth.make_instr(rng, 40)) for w in worlds]
+    gmaps = [nav.GraphMap(ob["viewpoint"]) for ob in obs]
+    for gm, ob in zip(gmaps, obs):
+        gm.update_graph(ob)
+    lang = nav.language_inputs(obs, DEV)
+    with torch.no_grad():
+        txt, _ = prod("language", lang)
+    last = None
+    for t in range(4):
+        for gm, ob in zip(gmaps, obs):
+            gm.node_step_ids[ob["viewpoint"]] = t + 1
+        pin = nav.panorama_inputs(obs, DEV)
+        with torch.no_grad():
+            pe, pm, pf, pa = prod("panorama", pin)
+        pe2, pm2, pf2, pa2 = stepper.panorama(pin)
+        assert torch.equal(pm, pm2) and rel(pe2, pe) < tol and rel(pf2, pf) < tol and rel(pa2, pa) < tol
+        for i, (gm, ob) in enumerate(zip(gmaps, obs)):
+            gm.update_node_embed(ob["viewpoint"], pf[i], rewrite=True)
+            for j, c in enumerate(pin["cand_vpids"][i]):
+                if not gm.graph.visited(c):
+                    gm.update_node_embed(c, pe[i, j])
+        nin = nav.nav_gmap_inputs(obs, gmaps, last)
+        nin.update(nav.nav_vp_inputs_mem(obs, gmaps, pe, pin["cand_vpids"], pin["view_lens"], pin["nav_types"], last))
+        nin.update(txt_embeds=txt, txt_masks=lang["txt_masks"], txt_lens=lang["txt_lens"])
+        with torch.no_grad():
+            a = prod("navigation", nin)
+        b = stepper.navigation(nin)
+        for k in ("global_logits", "local_logits", "fused_logits"):
+            assert torch.equal(torch.isinf(a[k]), torch.isinf(b[k])), (t, k)
+            fin = ~torch.isinf(a[k])
+            assert rel(b[k][fin], a[k][fin]) < tol, (t, k)
+        assert torch.equal(a["fused_logits"].argmax(1), b["fused_logits"].argmax(1)) or dtype == torch.bfloat16
+        valid = nin["gmap_masks"].clone()
+        valid[:, 1] = True
+        mm = valid[..., None].expand_as(a["gmap_embeds"])
+        assert rel(b["gmap_embeds"].float()[mm], a["gmap_embeds"].float()[mm]) < tol
+        assert rel(b["vp_embeds"], a["vp_embeds"]) < tol and rel(b["cls_embeds"], a["cls_embeds"]) < tol
+        m4 = valid[:, None, :, None].expand_as(a["gmap_attns"])
+        assert a["gmap_attns"].shape == b["gmap_attns"].shape and rel(b["gmap_attns"][m4], a["gmap_attns"][m4]) < tol
+        assert rel(b["vp_attns"], a["vp_attns"]) < tol
+        last = a["cls_embeds"].clone()
+        act = a["fused_logits"].argmax(1).tolist()
+        nxt = []
+        for i, (w, ob) in enumerate(zip(worlds, obs)):
+            vp = nin["gmap_vpids"][i][act[i]]
+            nb = np.nonzero(w.adj[w.index(ob["viewpoint"])])[0]
+            j = w.index(vp) if vp is not None else int(nb[t % len(nb)])
+            nxt.append(w.observe(j, heading=0.4 * (t + 1), instr=ob["instr_encoding"]))
+        obs = nxt
+        for gm, ob in zip(gmaps, obs):
+            gm.update_graph(ob)

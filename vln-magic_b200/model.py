@@ -220,7 +220,7 @@ def _ln(x, m, fc, res=None, p_in=0.0, p_out=0.0, link=None):
                           salt_out=fc.salt(), link=link)
 
 
-def _attn_block(att, x, ctx_kv, B, Lq, Lk, key_lens, fc, dists=None, sprel=None, key_skip=-1):
+def _attn_block(att, x, ctx_kv, B, Lq, Lk, key_lens, fc, dists=None, sprel=None, key_skip=-1, want_map=True):
     """BertAttention: (self or cross) attention + output dense + dropout + residual LayerNorm.
     x [B*Lq, h]; ctx_kv None -> self attention.  Returns (y [B*Lq, h], pbar or None)."""
     sa = att.self
@@ -234,13 +234,13 @@ def _attn_block(att, x, ctx_kv, B, Lq, Lk, key_lens, fc, dists=None, sprel=None,
     if ctx_kv is None:
         qkv = ops.packed_linear(x, [sa.query.weight, sa.key.weight, sa.value.weight],
                                 [sa.query.bias, sa.key.bias, sa.value.bias], link=link)
-        o, pbar = ops.attention(qkv, None, 0, h, 2 * h, B, H, Lq, Lk, key_lens, dists, sw, sb, fc.want_attn, pdrop,
-                                fc.salt(), key_skip)
+        o, pbar = ops.attention(qkv, None, 0, h, 2 * h, B, H, Lq, Lk, key_lens, dists, sw, sb,
+                                fc.want_attn and want_map, pdrop, fc.salt(), key_skip)
     else:
         q = ops.linear(x, sa.query.weight, sa.query.bias, link=link)
         kv = ops.packed_linear(ctx_kv, [sa.key.weight, sa.value.weight], [sa.key.bias, sa.value.bias])
-        o, pbar = ops.attention(q, kv, 0, 0, h, B, H, Lq, Lk, key_lens, None, None, None, fc.want_attn, pdrop,
-                                fc.salt())
+        o, pbar = ops.attention(q, kv, 0, 0, h, B, H, Lq, Lk, key_lens, None, None, None, fc.want_attn and want_map,
+                                pdrop, fc.salt())
     so = att.output
     d = ops.linear(o, so.dense.weight, so.dense.bias)
     y = _ln(d, so.LayerNorm, fc, res=x, p_in=fc.p(so.dropout), link=link)
@@ -254,11 +254,14 @@ def _ffn_block(layer, x, fc):
     return _ln(f, layer.output.LayerNorm, fc, res=x, p_in=fc.p(layer.output.dropout), link=link)
 
 
-def _cross_encoder(enc, x, ctx, B, Lx, Lc, x_lens, c_lens, fc, dists=None, sprel=None, key_skip=-1):
+def _cross_encoder(enc, x, ctx, B, Lx, Lc, x_lens, c_lens, fc, dists=None, sprel=None, key_skip=-1, map_depth=None):
+    """`map_depth`: KD attention maps are only produced for the first `map_depth` layers (None = all): MAKD compares
+    the maps of teacher and student on their common depth (agent.py:560,654,671), deeper maps are never read."""
     attns = []
-    for layer in enc.crossattention:
-        a, p_self = _attn_block(layer.attention, x, None, B, Lx, Lx, x_lens, fc, dists, sprel, key_skip)
-        cx, p_cross = _attn_block(layer.crossattention, a, ctx, B, Lx, Lc, c_lens, fc)
+    for li, layer in enumerate(enc.crossattention):
+        wm = map_depth is None or li < map_depth
+        a, p_self = _attn_block(layer.attention, x, None, B, Lx, Lx, x_lens, fc, dists, sprel, key_skip, want_map=wm)
+        cx, p_cross = _attn_block(layer.crossattention, a, ctx, B, Lx, Lc, c_lens, fc, want_map=wm)
         x = _ffn_block(layer, cx, fc)
         attns.append((p_self, p_cross))
     return x, attns
@@ -270,6 +273,9 @@ class GlocalTextPathCMT(nn.Module):
     # activation's gradient is complete, i.e. every layer above it has issued its weight gradients, so the gradient
     # arena range of those layers can be exchanged while the layers below still back-propagate.
     stage_cb = None
+    # (text layers, cross-modal layers) whose KD attention maps are needed; None = all.  MAKD compares the maps of the two
+    # models on their common depth only (agent.py:560), so the deeper model skips the rest (train_step sets this)
+    kd_attn_depth = None
 
     def _mark(self, t, stage, key):
         cb = self.stage_cb
@@ -309,7 +315,8 @@ class GlocalTextPathCMT(nn.Module):
         for li, layer in enumerate(self.lang_encoder.layer):
             if li == mid and li > 0:
                 self._mark(x, 1, "txt_mid")  # gradient complete <=> text layers mid.. have finished backward
-            a, p = _attn_block(layer.attention, x, None, B, Lt, Lt, ix["key_lens_txt"], fc)
+            a, p = _attn_block(layer.attention, x, None, B, Lt, Lt, ix["key_lens_txt"], fc,
+                               want_map=self.kd_attn_depth is None or li < self.kd_attn_depth[0])
             x = _ffn_block(layer, a, fc)
             attns.append(p)
         if not _cfg(self.config, "update_lang_bert", True):
@@ -423,17 +430,21 @@ class GlocalTextPathCMT(nn.Module):
         # gradients of their three inputs are complete
         for t_, k_ in ((txt, "txt"), (g_in, "g_in"), (v_in, "v_in")):
             self._mark(t_, 0, k_)
+        xd = None if self.kd_attn_depth is None else self.kd_attn_depth[1]
         if mode == "nav":
             dists = batch["gmap_pair_dists"] if ge.sprel_linear is not None else None
             (v, v_attn), (g, g_attn) = ops.run_branches(
-                lambda: _cross_encoder(le.encoder, v_in, txt, B, Vp, Lt, ix["key_lens_vp"], ix["key_lens_txt"], fc),
+                lambda: _cross_encoder(le.encoder, v_in, txt, B, Vp, Lt, ix["key_lens_vp"], ix["key_lens_txt"], fc,
+                                       map_depth=xd),
                 lambda: _cross_encoder(ge.encoder, g_in, txt, B, G, Lt, ix["key_lens_gmap"], ix["key_lens_txt"], fc,
-                                       dists, ge.sprel_linear))
+                                       dists, ge.sprel_linear, map_depth=xd))
             g, v = g.view(B, G, h), v.view(B, Vp, h)
         else:
             (v, v_attn), (g, g_attn) = ops.run_branches(
-                lambda: _cross_encoder(le.encoder, txt, v_in, B, Lt, Vp, ix["key_lens_txt"], ix["key_lens_vp"], fc),
-                lambda: _cross_encoder(ge.encoder, txt, g_in, B, Lt, G, ix["key_lens_txt"], ix["key_lens_gmap"], fc))
+                lambda: _cross_encoder(le.encoder, txt, v_in, B, Lt, Vp, ix["key_lens_txt"], ix["key_lens_vp"], fc,
+                                       map_depth=xd),
+                lambda: _cross_encoder(ge.encoder, txt, g_in, B, Lt, G, ix["key_lens_txt"], ix["key_lens_gmap"], fc,
+                                       map_depth=xd))
             g, v = g.view(B, Lt, h), v.view(B, Lt, h)
         return dict(txt_embeds=txt.view(B, Lt, h), txt_attn_list=txt_attns, pano_embeds=pano,
                     pano_fused_embeds=fused, img_attn_list=img_attns, gmap_embeds=g, gmap_attn_list=g_attn,
@@ -442,6 +453,7 @@ class GlocalTextPathCMT(nn.Module):
 
 def stack_attns(lst):
     """KD attention maps in the oracle's 4-D layout: [B, n_layers, Lq, Lk] ([self | cross] for x-layers)."""
+    lst = [a for a in lst if (a[0] if isinstance(a, tuple) else a) is not None]  # (maps beyond kd_attn_depth)
     if not lst:
         return None
     if isinstance(lst[0], tuple):
@@ -520,6 +532,11 @@ class GlocalTextPathCMTPreTraining(nn.Module):
             model.load_info = dict(loaded=sorted(loaded), missing=sorted(set(own) - set(loaded)),
                                    unexpected=sorted(set(k for k in state_dict) - set(loaded)))
         return model
+
+    def set_kd_attn_depth(self, n_text=None, n_cross=None):
+        """Only the first `n_text` text layers / `n_cross` cross-modal layers produce KD attention maps (None: all)."""
+        self.bert.kd_attn_depth = None if n_text is None else (int(n_text), int(n_cross if n_cross is not None else n_text))
+        return self
 
     def set_compute_dtype(self, dtype):
         if dtype not in (torch.float32, torch.bfloat16):

@@ -45,6 +45,14 @@ class PretrainStepper:
             for p in teacher.parameters():
                 p.requires_grad_(False)
         self.opt = FusedAdamW(self.arena, lr=lr, betas=betas, weight_decay=weight_decay, max_grad_norm=max_grad_norm)
+        if teacher is not None:
+            # MAKD reads the attention maps of both models on their common depth only (agent.py:560,654,671; makd.py):
+            # the deeper model does not produce the maps nobody compares
+            cs, ct = student.config, teacher.config
+            n_txt = min(cs.num_l_layers, ct.num_l_layers)
+            n_x = min(cs.num_x_layers, ct.num_x_layers, n_txt)
+            student.set_kd_attn_depth(n_txt, n_x)
+            teacher.set_kd_attn_depth(n_txt, n_x)
         self.use_graphs = use_graphs
         ops.enable_side_stream(side_stream)
         ops.enable_branch_streams(branch_streams)
