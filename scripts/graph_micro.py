@@ -140,6 +140,8 @@ if which in ("all", "gemm_s"):
     gemm_cases([(5120, 128, 128), (5120, 384, 128), (5120, 512, 128), (5120, 128, 512), (8064, 128, 768), (1280, 128, 128)])
 if which in ("all", "gemm_l"):
     gemm_cases([(5120, 768, 768), (5120, 2304, 768), (5120, 3072, 768), (5120, 768, 3072)])
+if which == "gemm_m":  # MAGIC-L / ICoD shapes (B = 32: 2560 text rows, 1184 local rows, 640 graph rows)
+    gemm_cases([(2560, 768, 768), (2560, 2304, 768), (2560, 3072, 768), (2560, 768, 3072), (1184, 768, 768), (640, 768, 768)])
 if which in ("all", "attn"):
     attn_cases([(64, 2, 80, 80, False), (224, 2, 36, 36, False), (64, 2, 20, 20, True), (64, 2, 20, 80, False),
                 (64, 2, 37, 80, False), (64, 2, 80, 37, False), (64, 12, 80, 80, False)])

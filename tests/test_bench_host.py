@@ -33,7 +33,9 @@ def test_graph_profile_summary_three_rooflines_and_shapes():
     assert abs(top["frac"] - top["achieved"] / 1403.5) < 1e-9
     assert abs(top["avg_launch_us"] - gemm_ms * 1e3 / 12) < 1e-6
     kinds = {r["kernel"]: r for r in roofs}
-    assert set(kinds) == {"magic_gemm", "magic_attn"} and kinds["magic_attn"]["bound"] == "hbm"
+    big = "magic_gemm (launches >= 1 GFLOP: h=768 encoder GEMMs)"   # the family is also reported split by launch size
+    assert set(kinds) == {"magic_gemm", big, "magic_attn"} and kinds["magic_attn"]["bound"] == "hbm"
+    assert abs(kinds[big]["achieved"] - top["achieved"]) / top["achieved"] < 1e-9   # (every launch here is 6 GFLOP)
     assert kinds["magic_attn"]["peak"] == 6546.2
     assert {(d["op"], d["M"], d["N"], d["K"]) for d in shapes} == {("gemm", 5120, 768, 768), ("gemm_wgrad", 768, 768, 5120)}
     assert abs(note["sum_kernel_ms"] - (gemm_ms + 10 * 0.008 / 2)) < 1e-4 and note["profiled_step_ms"] == 0.2
