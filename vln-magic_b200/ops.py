@@ -157,7 +157,7 @@ def _side_stream(*sinks):
     if not _SIDE["on"] or any(getattr(p, "_magic_grad", None) is None for p in sinks if p is not None):
         return None
     if _SIDE["stream"] is None:
-        _SIDE["stream"] = torch.cuda.Stream()
+        _SIDE["stream"] = torch.cuda.Stream(priority=getattr(torch.cuda.current_stream(), "priority", 0))
     _SIDE["stream"].wait_stream(torch.cuda.current_stream())
     _SIDE["used"] = True
     return _SIDE["stream"]
@@ -201,7 +201,7 @@ def _attn_stream(main):
     """A second stream per launching stream for the key-major half of the attention backward."""
     k = main.cuda_stream
     if k not in _ATTN_STREAMS:
-        _ATTN_STREAMS[k] = torch.cuda.Stream()
+        _ATTN_STREAMS[k] = torch.cuda.Stream(priority=getattr(main, "priority", 0))
     return _ATTN_STREAMS[k]
 
 
@@ -218,7 +218,9 @@ def run_branches(side_fn, main_fn):
     pool = _BRANCH.setdefault("pool", {})
     side = pool.get(main.cuda_stream)
     if side is None:
-        side = pool[main.cuda_stream] = torch.cuda.Stream()
+        # (a branch inherits the priority of the stream it forks from: the training graph is captured on a high-
+        # priority stream, the frozen teacher's on a normal one -- train_step.PretrainStepper)
+        side = pool[main.cuda_stream] = torch.cuda.Stream(priority=getattr(main, "priority", 0))
     side.wait_stream(main)
     with torch.cuda.stream(side):
         a = side_fn()

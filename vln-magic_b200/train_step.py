@@ -311,7 +311,9 @@ class PretrainStepper:
             torch.cuda.current_stream().wait_stream(s)
             g = torch.cuda.CUDAGraph()
             n0 = _lib.COUNTERS["launches"]
-            with torch.cuda.graph(g):
+            import os as _os
+            tp = _os.environ.get("MAGIC_TEACHER_PRIO", "0") == "1"
+            with (torch.cuda.graph(g, stream=torch.cuda.Stream(priority=-1)) if tp else torch.cuda.graph(g)):
                 t_out = makd.teacher_forward(self.teacher, static, task)
         finally:
             lib.magic_gemm_set_sm_budget(0)
@@ -368,8 +370,15 @@ class PretrainStepper:
             g = torch.cuda.CUDAGraph()
             n0 = _lib.COUNTERS["launches"]
             _lib.load().magic_set_pdl(int(self.pdl[0]))
+            # kernel nodes inherit the priority of the stream they are captured on: the training graph (a latency-bound
+            # chain of small kernels) is captured at high priority, the frozen teacher's throughput-bound graph at the
+            # default one, so a student CTA never queues behind the teacher's pending CTAs when the two graphs run
+            # side by side (MAGIC_STUDENT_PRIO=0 switches this off)
+            import os as _os
+            hp = self.pipeline_teacher and _os.environ.get("MAGIC_STUDENT_PRIO", "0") == "1"
+            cap_stream = torch.cuda.Stream(priority=-1) if hp else None
             try:
-                with torch.cuda.graph(g):
+                with (torch.cuda.graph(g, stream=cap_stream) if cap_stream is not None else torch.cuda.graph(g)):
                     out = self._device_step(task, static, rw, finish=self.world == 1, mode="capture", t_out=t_out)
             finally:
                 _lib.load().magic_set_pdl(-1)
