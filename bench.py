@@ -534,7 +534,7 @@ class Runner:
             torch.manual_seed(0)
             teacher = magic_b200.GlocalTextPathCMTPreTraining(cfg_t).to(dev).set_compute_dtype(dtype)
             teacher = teacher.train() if w.get("co_update") else teacher.eval()
-        self.stepper = PretrainStepper(student, teacher, use_graphs=bool(args.graphs),
+        self.stepper = PretrainStepper(student, teacher, use_graphs=bool(args.graphs), tasks=("mlm", "sap"),
                                        co_update=bool(w.get("co_update")), side_stream=bool(args.side_stream),
                                        branch_streams=bool(args.branch_streams), overlap=bool(args.overlap),
                                        pipeline_teacher=bool(args.pipeline), teacher_sm_budget=args.teacher_sms,

@@ -301,6 +301,14 @@ int magic_feat_args_size(void); /* sizeof(MagicFeatArgs): lets a binding check i
 int magic_sumsq(const float* g, long long n, float* out, int zero_first, cudaStream_t st);
 int magic_adamw(float* p, const float* g, float* m, float* v, void* bf16_shadow, long long n, const float* hyper,
                 float weight_decay, const float* sumsq, cudaStream_t st);
+/* The same update when not every parameter took part in the step: adamw.py:66-67 skips parameters whose grad is None
+ * and :86 counts steps per parameter.  [0, n) is cut into nseg <= MAGIC_ADAMW_MAX_SEGS segments [bounds[s], bounds[s+1]);
+ * codes[s] < 0 leaves the segment untouched, codes[s] >= 0 selects the hyper slot (hyper + 8 * code) whose step size
+ * carries that segment's own step count.  bounds (nseg + 1 ints) / codes (nseg ints) are device memory. */
+#define MAGIC_ADAMW_MAX_SEGS 512
+int magic_adamw_seg(float* p, const float* g, float* m, float* v, void* bf16_shadow, long long n, const float* hyper,
+                    float weight_decay, const float* sumsq, const int* bounds, const int* codes, int nseg,
+                    cudaStream_t st);
 int magic_scale(float* x, long long n, float s, cudaStream_t st);
 
 #ifdef __cplusplus

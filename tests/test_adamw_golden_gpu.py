@@ -69,3 +69,47 @@ def test_shadow_follows_load_state_dict():
     assert model.out.weight.data_ptr() == arena.flat_p.data_ptr() + \
         [o for n, p, o, k in arena.entries if n == "out.weight"][0] * 4
     assert float(model.out.weight._magic_lowp.float().abs().max()) == 0.0
+
+
+class TwoHeads(nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.trunk = nn.Linear(24, 40)
+        self.LayerNorm = nn.LayerNorm(40)
+        self.head_a = nn.Linear(40, 5)
+        self.head_b = nn.Linear(40, 7)
+        self.never = nn.Linear(8, 8)
+
+
+@pytest.mark.parametrize("lowp", [False, True])
+def test_task_inactive_parameters_follow_the_reference(lowp):
+    """Multi-task loop: the other task's head has `grad is None` in the reference -- skipped entirely, with its own
+    step count (adamw.py:66-67, :86).  FusedAdamW.configure_tasks + magic_adamw_seg reproduce that on the flat arena
+    (fixture: tests/golden/gen_adamw_tasks_golden.py, the reference's own optimizer files)."""
+    gold = torch.load(os.path.join(os.path.dirname(GOLD), "adamw_tasks_ref.pt"))
+    model = TwoHeads().cuda()
+    model.load_state_dict(gold["init"])
+    opts = SimpleNamespace(**gold["opts"])
+    opt = MO.build_optimizer(model, opts, lowp=lowp)
+    inactive = lambda task, name: name.startswith("never.") or name.startswith("head_b." if task == "a" else "head_a.")
+    opt.configure_tasks(["a", "b"], inactive)
+    assert len(opt.slots) == 3 and opt.slots[0] == frozenset("ab")
+    params = dict(model.named_parameters())
+    for rec in gold["steps"]:
+        opt.zero_grad()
+        for n, g in rec["grads"].items():
+            params[n]._magic_grad.copy_(g)
+        opt.step(MO.get_lr_sched(rec["step"], opts), task=rec["task"])
+        assert abs(opt.grad_norm() - rec["grad_norm"]) <= 1e-5 * rec["grad_norm"]
+        for n, ref in rec["params"].items():
+            got = params[n].detach().cpu()
+            err = ((got - ref).norm() / ref.norm()).item()
+            assert err < 1e-6, (rec["step"], rec["task"], n, err)
+        for n in ("never.weight", "never.bias"):   # untouched by every task: bit-identical to the initial values
+            assert torch.equal(params[n].detach().cpu(), gold["init"][n])
+        if lowp:
+            for n, p in params.items():
+                assert torch.equal(p._magic_lowp, p.detach().to(torch.bfloat16)), n
+    # without the task tables every element would have been decayed: the fixture tells the two apart
+    a_w = gold["steps"][1]["params"]["head_a.weight"]
+    assert torch.equal(a_w, gold["steps"][0]["params"]["head_a.weight"])   # step 2 is task b: head_a untouched

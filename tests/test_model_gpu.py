@@ -337,3 +337,30 @@ def test_unknown_task_raises_like_reference():
     b = get_batch("sap", B=2, seed=5)
     with pytest.raises(ValueError):
         prod(b, "itm", True)
+
+
+@pytest.mark.parametrize("task,kd", [("mlm", False), ("sap", False), ("mrc", False), ("cfp", False), ("mlm", True),
+                                     ("sap", True)])
+def test_inactive_in_task_matches_the_gradient_flow(task, kd):
+    """model.inactive_in_task (which parameters the optimizer must leave alone in a step of `task`, like the
+    reference's `p.grad is None` skip) against the real backward: flagged parameters get an exactly-zero gradient,
+    every other parameter gets a non-zero one."""
+    from magic_b200.model import inactive_in_task
+    tasks = ("mlm", "sap", "mrc", "cfp")
+    oracle, prod = build_pair(128, ht=256 if kd else None, pretrain_tasks=tasks)
+    prod.train()
+    b = get_batch(task)
+    if kd:
+        t_oracle, teacher = build_pair(256, role="teacher", seed=3, pretrain_tasks=tasks)
+        mix = makd.distill_step_loss(prod, teacher.eval(), b, task, [1.0] * 5)[0]
+        mix[0].backward()
+    else:
+        prod(b, task, True)["loss"].float().sum().backward()
+    analytic_zero = ("key.bias", "sprel_linear.bias")   # softmax is shift invariant: these gradients vanish analytically
+    for n, p in prod.named_parameters():
+        g = p.grad
+        zero = g is None or float(g.abs().max()) == 0.0
+        if inactive_in_task(task, n, kd=kd):
+            assert zero, (task, kd, n, "flagged inactive but has a gradient")
+        elif zero:
+            assert n.endswith(analytic_zero) or "in_proj_bias" in n, (task, kd, n, "active but zero gradient")

@@ -67,3 +67,21 @@ def test_meta_loader_is_seeded_and_cycles():
     assert mlm[:4] == [1, 2, 1, 2][:len(mlm[:4])]          # a task's loader restarts when exhausted
     only = [t for t, _ in MetaLoader(loaders, [1, 0, 0], seed=1, num_steps=10)]
     assert set(only) == {"mlm"}
+
+
+def test_inactive_in_task_rules():
+    """model.inactive_in_task: which parameters a step of a task leaves without gradient (the optimizer skips them like
+    the reference's `p.grad is None`); the GPU test checks the same rule against the real backward."""
+    from magic_b200.model import inactive_in_task as ina
+    assert not ina("mlm", "mlm_head.predictions.transform.dense.weight") and ina("sap", "mlm_head.predictions.bias")
+    assert not ina("sap", "global_sap_head.net.0.weight") and ina("mlm", "sap_fuse_linear.net.3.bias")
+    assert ina("mlm", "bert.global_encoder.sprel_linear.weight") and not ina("sap", "bert.global_encoder.sprel_linear.weight")
+    assert ina("mrc", "bert.global_encoder.encoder.crossattention.0.attention.self.query.weight")
+    assert not ina("mrc", "bert.local_encoder.encoder.crossattention.0.attention.self.query.weight")
+    for t in ("mlm", "sap", "mrc", "cfp"):
+        assert not ina(t, "bert.lang_encoder.layer.0.attention.self.query.weight")
+        assert not ina(t, "bert.embeddings.word_embeddings.weight")
+        assert ina(t, "bert.txt_emb_w.weight", kd=False)            # KD projections only train under a teacher
+    assert not ina("mlm", "bert.vp_txt_w.weight", kd=True) and ina("sap", "bert.vp_txt_w.weight", kd=True)
+    assert not ina("sap", "bert.global_cross_w.weight", kd=True) and ina("mlm", "bert.local_cross_w.bias", kd=True)
+    assert not ina("sap", "bert.kdl_img_w.weight", kd=True) and not ina("mlm", "bert.kdl_txt_weight", kd=True)

@@ -63,6 +63,51 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// Same update for an arena whose parameters are not all active in this step (pretrain_src/optim/adamw.py:66-67 skips
+// parameters with `p.grad is None`, and :86 keeps a per-parameter state['step']): the arena range [0, n) is cut into
+// `nseg` segments [bounds[s], bounds[s+1]) with a code each -- code < 0: the segment is left untouched (no moment decay,
+// no weight decay, no step); code >= 0: the segment uses hyper slot `code` (hyper + 8 * code: its own bias-corrected
+// step size, i.e. its own step count).  The task heads and KD projections of the task that did not run this step are
+// such inactive segments.  bounds / codes live in device memory (one table per task: graph-replayable).
+__global__ void __launch_bounds__(256)
+    adamw_seg_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                     __nv_bfloat16* __restrict__ shadow, long long n, const float* __restrict__ hyper, float weight_decay,
+                     const float* __restrict__ sumsq, const int* __restrict__ bounds, const int* __restrict__ codes,
+                     int nseg) {
+  __shared__ int s_b[MAGIC_ADAMW_MAX_SEGS + 1];
+  __shared__ int s_c[MAGIC_ADAMW_MAX_SEGS];
+  for (int i = threadIdx.x; i <= nseg; i += blockDim.x) s_b[i] = bounds[i];
+  for (int i = threadIdx.x; i < nseg; i += blockDim.x) s_c[i] = codes[i];
+  __syncthreads();
+  const float maxn = hyper[5];
+  float clip = 1.f;
+  if (sumsq != nullptr && maxn > 0.f) {
+    const float c = maxn / (sqrtf(sumsq[0]) + 1e-6f);
+    clip = c < 1.f ? c : 1.f;
+  }
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    int lo = 0, hi = nseg - 1;  // last segment whose lower bound is <= i
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if ((long long)s_b[mid] <= i) lo = mid; else hi = mid - 1;
+    }
+    const int code = s_c[lo];
+    if (code < 0) continue;
+    const float* h = hyper + 8 * code;
+    const float lr = h[0], step = h[1], b1 = h[2], b2 = h[3], eps = h[4];
+    const float gi = g[i] * clip;
+    const float mi = m[i] * b1 + (1.f - b1) * gi;
+    const float vi = v[i] * b2 + (1.f - b2) * gi * gi;
+    const float denom = sqrtf(vi) + eps;
+    float pi = p[i] + (-step) * (mi / denom);
+    if (weight_decay > 0.f) pi = pi + (-lr * weight_decay) * pi;
+    m[i] = mi;
+    v[i] = vi;
+    p[i] = pi;
+    if (shadow) shadow[i] = __float2bfloat16_rn(pi);
+  }
+}
+
 __global__ void scale_kernel(float* __restrict__ x, long long n, float s) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
     x[i] *= s;
@@ -112,6 +157,22 @@ int magic_adamw(float* p, const float* g, float* m, float* v, void* bf16_shadow,
   if (blocks > cap) blocks = cap;
   adamw_kernel<<<(int)blocks, 256, 0, st>>>(p, g, m, v, (__nv_bfloat16*)bf16_shadow, n, hyper, weight_decay, sumsq);
   MAGIC_CHECK_LAUNCH("magic_adamw");
+  return MAGIC_OK;
+}
+
+int magic_adamw_seg(float* p, const float* g, float* m, float* v, void* bf16_shadow, long long n, const float* hyper,
+                    float weight_decay, const float* sumsq, const int* bounds, const int* codes, int nseg,
+                    cudaStream_t st) {
+  if (n <= 0) return MAGIC_OK;
+  MAGIC_CHECK_ARG(nseg >= 1 && nseg <= MAGIC_ADAMW_MAX_SEGS && bounds && codes, "magic_adamw_seg: bad segment table (%d)",
+                  nseg);
+  MAGIC_CHECK_ARG(n < (1LL << 31), "magic_adamw_seg: n too large for 32-bit segment bounds");
+  long long blocks = (n + 255) / 256;
+  const long long cap = 16LL * magic_num_sms();
+  if (blocks > cap) blocks = cap;
+  adamw_seg_kernel<<<(int)blocks, 256, 0, st>>>(p, g, m, v, (__nv_bfloat16*)bf16_shadow, n, hyper, weight_decay, sumsq,
+                                                bounds, codes, nseg);
+  MAGIC_CHECK_LAUNCH("magic_adamw_seg");
   return MAGIC_OK;
 }
 

@@ -451,6 +451,38 @@ class GlocalTextPathCMT(nn.Module):
                     vp_embeds=v, vp_attn_list=v_attn, pano_row_scale=ix.get("pano_row_scale"))
 
 
+_TASK_HEADS = {"mlm": ("mlm_head.",), "sap": ("global_sap_head.", "local_sap_head.", "sap_fuse_linear."),
+               "mrc": ("image_classifier.",), "og": ("og_head.",),
+               "cfp": ("cfp_gmap_proj.", "cfp_vp_proj.", "cfp_txt_proj.")}
+_ALL_HEADS = tuple(p for ps in _TASK_HEADS.values() for p in ps)
+_KD_COMMON = ("bert.txt_emb_w.", "bert.kdl_img_w.", "bert.kdl_avg_img_w.")
+_KD_MLM = ("bert.vp_txt_w.", "bert.gmap_txt_w.")
+_KD_NAV = ("bert.global_cross_w.", "bert.local_cross_w.")
+
+
+def inactive_in_task(task, name, kd=False):
+    """True when parameter `name` of GlocalTextPathCMTPreTraining receives NO gradient in a step of `task` (read off
+    the forward functions above): the heads of the other tasks, `sprel_linear` in the MLM branch (text queries attend
+    the graph without the distance bias), and the KD projections the step's MAKD losses do not use (all of them
+    without a teacher).  The reference optimizer skips exactly these (`p.grad is None`, optim/adamw.py:66-67)."""
+    t = task[:3] if task[:3] in _TASK_HEADS else task
+    if name.startswith(_ALL_HEADS):
+        return not name.startswith(_TASK_HEADS.get(t, ()))
+    if name.startswith("bert.global_encoder."):
+        if t in ("mrc", "og"):  # these heads read the LOCAL branch only: the global branch gets no gradient
+            return True
+        return t == "mlm" and name.startswith("bert.global_encoder.sprel_linear.")
+    if name.startswith(_KD_COMMON) or name.startswith("bert.kdl_") and name.endswith("_weight"):
+        return not (kd and t in ("mlm", "sap"))
+    if name.startswith(_KD_MLM):
+        return not (kd and t == "mlm")
+    if name.startswith(_KD_NAV):
+        return not (kd and t == "sap")
+    if name.startswith("bert.img_embeddings.obj_"):
+        return t != "og"
+    return False
+
+
 def stack_attns(lst):
     """KD attention maps in the oracle's 4-D layout: [B, n_layers, Lq, Lk] ([self | cross] for x-layers)."""
     lst = [a for a in lst if (a[0] if isinstance(a, tuple) else a) is not None]  # (maps beyond kd_attn_depth)

@@ -38,36 +38,103 @@ class FusedAdamW:
         self.sumsq = torch.zeros(1 + SUMSQ_SCRATCH, dtype=torch.float32, device=dev)  # [0] = sum g^2, rest = scratch
         self.step_count = 0
         self.param_groups = [dict(lr=lr)]  # so `for g in optimizer.param_groups: g['lr'] = ...` keeps working
+        # task activity (configure_tasks): parameters a task never touches are skipped in that task's steps and
+        # count their own steps, like the reference (adamw.py:66-67 `if p.grad is None: continue`, :86 state['step'])
+        self.slots = None          # [frozenset(tasks)] per hyper slot; slot 0 = every task
+        self.slot_steps = None
+        self.task_tables = {}      # task -> ((bounds, codes, nseg) for the decay group, same for the no-decay group)
 
-    def set_hyper(self, lr=None):
+    MAX_SLOTS = 16
+
+    def configure_tasks(self, tasks, inactive):
+        """`tasks`: the tasks the loop alternates between; `inactive(task, param_name) -> bool`: True when that
+        parameter receives NO gradient in a step of that task (model.inactive_in_task).  Afterwards pass the task to
+        set_hyper / apply / step."""
+        tasks = list(tasks)
+        a = self.arena
+        owners = [frozenset(t for t in tasks if not inactive(t, n)) for n, _, _, _ in a.entries]
+        slots = [frozenset(tasks)] + sorted({o for o in owners if o and o != frozenset(tasks)}, key=sorted)
+        if len(slots) > self.MAX_SLOTS:
+            raise ValueError("too many distinct task-activity sets")
+        slot_of = {o: i for i, o in enumerate(slots)}
+        self.slots, self.slot_steps = slots, [0] * len(slots)
+        self.hyper = torch.zeros(8 * self.MAX_SLOTS, dtype=torch.float32, device=a.device)
+        self.hyper_ring = PinnedRing(8 * self.MAX_SLOTS)
+        self.task_tables = {}
+        for t in tasks:
+            groups = []
+            for g_lo, g_hi in ((0, a.n_decay), (a.n_decay, a.total)):
+                bounds, codes = [0], []
+                for (n, _, o, k), own in zip(a.entries, owners):
+                    if not (g_lo <= o < g_hi):
+                        continue
+                    code = slot_of[own] if t in own else -1
+                    if codes and codes[-1] == code:
+                        continue           # same code as the running segment: it simply extends
+                    if codes:
+                        bounds.append(o - g_lo)
+                    codes.append(code)
+                bounds.append(g_hi - g_lo)
+                if not codes:
+                    codes = [0]
+                if len(codes) > 512:
+                    raise ValueError("too many activity segments in the arena")
+                dev = a.device
+                groups.append((torch.tensor(bounds, dtype=torch.int32, device=dev),
+                               torch.tensor(codes, dtype=torch.int32, device=dev), len(codes), codes == [0]))
+            self.task_tables[t] = tuple(groups)
+        return self
+
+    def set_hyper(self, lr=None, task=None):
         """Host -> device copy of the per-step scalars (call OUTSIDE a captured graph)."""
         self.step_count += 1
         lr = self.param_groups[0]["lr"] if lr is None else lr
         b1, b2 = self.betas
-        bc1, bc2 = 1.0 - b1 ** self.step_count, 1.0 - b2 ** self.step_count
-        self.hyper_ring.upload([lr, lr * math.sqrt(bc2) / bc1, b1, b2, self.eps,
-                                (self.max_grad_norm if self.max_grad_norm else 0.0), 0.0, 0.0], self.hyper)
 
-    def apply(self):
-        """Device work of one step (graph-capturable): grad-norm, AdamW on both groups, bf16 shadow."""
+        def row(t):
+            bc1, bc2 = 1.0 - b1 ** t, 1.0 - b2 ** t
+            return [lr, lr * math.sqrt(bc2) / bc1, b1, b2, self.eps, (self.max_grad_norm if self.max_grad_norm else 0.0),
+                    0.0, 0.0]
+
+        if self.slots is None or task is None or task not in self.task_tables:
+            if self.slots is not None:  # configured, but this step is not attributed to a task: everything steps
+                self.slot_steps = [c + 1 for c in self.slot_steps]
+                vals = sum((row(max(c, 1)) for c in self.slot_steps), [])
+                vals[:8] = row(self.step_count)
+                self.hyper_ring.upload(vals + [0.0] * (8 * self.MAX_SLOTS - len(vals)), self.hyper)
+                return
+            self.hyper_ring.upload(row(self.step_count), self.hyper)
+            return
+        for i, own in enumerate(self.slots):
+            if task in own:
+                self.slot_steps[i] += 1
+        vals = sum((row(max(c, 1)) for c in self.slot_steps), [])
+        self.hyper_ring.upload(vals + [0.0] * (8 * self.MAX_SLOTS - len(vals)), self.hyper)
+
+    def apply(self, task=None):
+        """Device work of one step (graph-capturable): grad-norm, AdamW on both groups, bf16 shadow.  With
+        configure_tasks() and a task, only the parameters that task touches are updated."""
         a = self.arena
         st = stream()
         call("magic_sumsq", ptr(a.flat_g), a.total, ptr(self.sumsq), 1, st)
         shadow = a.flat_lowp
         nd = a.n_decay
-        if nd > 0:
-            call("magic_adamw", ptr(a.flat_p), ptr(a.flat_g), ptr(self.m), ptr(self.v), ptr(shadow), nd,
-                 ptr(self.hyper), self.weight_decay, ptr(self.sumsq), st)
-        rest = a.total - nd
-        if rest > 0:
-            o4, o2 = nd * 4, nd * 2
-            call("magic_adamw", a.flat_p.data_ptr() + o4, a.flat_g.data_ptr() + o4, self.m.data_ptr() + o4,
-                 self.v.data_ptr() + o4, (shadow.data_ptr() + o2) if shadow is not None else None, rest,
-                 ptr(self.hyper), 0.0, ptr(self.sumsq), st)
+        tabs = self.task_tables.get(task) if task is not None else None
+        for gi, (lo, n, wd) in enumerate(((0, nd, self.weight_decay), (nd, a.total - nd, 0.0))):
+            if n <= 0:
+                continue
+            sh = (shadow.data_ptr() + lo * 2) if shadow is not None else None
+            args = (a.flat_p.data_ptr() + lo * 4, a.flat_g.data_ptr() + lo * 4, self.m.data_ptr() + lo * 4,
+                    self.v.data_ptr() + lo * 4, sh, n, ptr(self.hyper), wd, ptr(self.sumsq))
+            if tabs is None or tabs[gi][3]:  # no table, or one segment on slot 0: the plain kernel
+                call("magic_adamw", *args, st)
+            else:
+                bounds, codes, nseg, _ = tabs[gi]
+                call("magic_adamw_seg", *args, ptr(bounds), ptr(codes), nseg, st)
 
-    def step(self, lr=None):
-        self.set_hyper(lr)
-        self.apply()
+    def step(self, lr=None, task=None):
+        self.set_hyper(lr, task)
+        self.apply(task)
 
     def zero_grad(self):
         self.arena.zero_grad()
@@ -76,7 +143,8 @@ class FusedAdamW:
         """{step, exp_avg, exp_avg_sq} on the CPU, flat in arena order, plus the layout that makes them meaningful
         (ModelSaver dumps this next to the weights, utils/save.py:41-45)."""
         return dict(step=self.step_count, exp_avg=self.m.detach().cpu().clone(), exp_avg_sq=self.v.detach().cpu().clone(),
-                    layout=[(n, o, k) for n, _, o, k in self.arena.entries], lr=self.param_groups[0]["lr"])
+                    layout=[(n, o, k) for n, _, o, k in self.arena.entries], lr=self.param_groups[0]["lr"],
+                    slot_steps=list(self.slot_steps) if self.slot_steps is not None else None)
 
     def load_state_dict(self, sd):
         if [(n, o, k) for n, _, o, k in self.arena.entries] != [tuple(x) for x in sd["layout"]]:
@@ -85,6 +153,8 @@ class FusedAdamW:
         self.m.copy_(sd["exp_avg"])
         self.v.copy_(sd["exp_avg_sq"])
         self.param_groups[0]["lr"] = sd.get("lr", self.lr)
+        if self.slot_steps is not None and sd.get("slot_steps") is not None and len(sd["slot_steps"]) == len(self.slot_steps):
+            self.slot_steps = [int(x) for x in sd["slot_steps"]]
 
     def grad_norm(self):
         return float(self.sumsq[0].sqrt())

@@ -26,7 +26,7 @@ class PretrainStepper:
     def __init__(self, student, teacher=None, kdl=None, lr=5e-5, betas=(0.9, 0.98), weight_decay=0.01,
                  max_grad_norm=5.0, use_graphs=False, rw_generator=None, side_stream=True,
                  branch_streams=True, co_update=False, t_lr=None, max_graphs=16, overlap=True,
-                 pipeline_teacher=True, teacher_sm_budget=0, pdl=None):
+                 pipeline_teacher=True, teacher_sm_budget=0, pdl=None, tasks=None):
         """co_update=True is ICoD (`--train_kdl_teacher`, agent_base.py:260-279): the teacher is trained too, from
         the s2t losses, with its own arena / AdamW state / clip, and both models step once per batch."""
         self.student, self.teacher = student, teacher
@@ -45,6 +45,16 @@ class PretrainStepper:
             for p in teacher.parameters():
                 p.requires_grad_(False)
         self.opt = FusedAdamW(self.arena, lr=lr, betas=betas, weight_decay=weight_decay, max_grad_norm=max_grad_norm)
+        # task activity: with `tasks` (the tasks the loop alternates between) the optimizer leaves the parameters a
+        # step's task never touches alone -- heads of the other tasks, unused KD projections -- and counts their steps
+        # separately, as the reference AdamW does for parameters whose grad is None (optim/adamw.py:66-67, :86)
+        self.tasks = tuple(tasks) if tasks else None
+        if self.tasks:
+            from .model import inactive_in_task
+            kd = teacher is not None
+            self.opt.configure_tasks(self.tasks, lambda t, n: inactive_in_task(t, n, kd=kd))
+            if self.t_opt is not None:
+                self.t_opt.configure_tasks(self.tasks, lambda t, n: inactive_in_task(t, n, kd=False))
         if teacher is not None:
             # MAKD reads the attention maps of both models on their common depth only (agent.py:560,654,671; makd.py):
             # the deeper model does not produce the maps nobody compares
@@ -137,17 +147,17 @@ class PretrainStepper:
         return f"NCCL all-reduce(AVG) of the flat fp32 gradient arena, {n} buckets, issued after backward"
 
     # -- the device side of one step -------------------------------------------------------------
-    def _finish(self, fired=None):
+    def _finish(self, fired=None, task=None):
         """Gradient exchange + optimizer (kept outside the captured graph when world > 1)."""
         if self.overlap:
             # what backward did not already exchange; the teacher's exchange (ICoD) runs under the student's optimizer
             for i, sy in enumerate(self.syncs):
                 sy.issue_rest(sy.fired if fired is None else fired[i])
             self.syncs[0].wait()
-            self.opt.apply()
+            self.opt.apply(task)
             if self.co_update:
                 self.syncs[1].wait()
-                self.t_opt.apply()
+                self.t_opt.apply(task)
             return
         # both exchanges are issued up front: the teacher's all-reduce (ICoD) runs under the student's optimizer
         if self.allreduce is not None:
@@ -156,11 +166,11 @@ class PretrainStepper:
             self.t_allreduce.start()
         if self.allreduce is not None:
             self.allreduce.finish()
-        self.opt.apply()
+        self.opt.apply(task)
         if self.co_update:  # agent_base.py:271-274: clip + step the student, then clip + step the teacher
             if self.t_allreduce is not None:
                 self.t_allreduce.finish()
-            self.t_opt.apply()
+            self.t_opt.apply(task)
 
     def _device_step(self, task, batch, rw, finish=True, mode="eager", t_out=None):
         for sy in self.syncs:
@@ -179,7 +189,7 @@ class PretrainStepper:
             for sy in self.syncs:
                 sy.join_marker()
             if finish:
-                self._finish()
+                self._finish(task=task)
             return torch.cat([mix, mix_t]).detach()
         if self.teacher is not None and t_out is not None:  # teacher outputs computed by the teacher's own graph
             mix, res, s_out = makd.student_distill_loss(self.student, t_out, batch, task, rw, self.kdl)
@@ -195,7 +205,7 @@ class PretrainStepper:
         for sy in self.syncs:
             sy.join_marker()
         if finish:
-            self._finish()
+            self._finish(task=task)
         # values only: a tensor with a grad_fn would keep this step's autograd graph alive, and with it the per-
         # parameter AccumulateGrad nodes bound to the streams of THIS step -- a later capture whose ops run on other
         # streams would then be invalidated by the engine's sync with those (uncaptured) streams
@@ -262,9 +272,9 @@ class PretrainStepper:
                                        ring=self._rw_ring)
             else:
                 rw = makd.mkrw_weights(self.kdl["rw_temp"], generator=self.rw_generator)
-        self.opt.set_hyper(lr)
+        self.opt.set_hyper(lr, task)
         if self.co_update:
-            self.t_opt.set_hyper(None)
+            self.t_opt.set_hyper(None, task)
         ops.bump_seed(self.device)
         for a in (self.arena, self.t_arena):  # parameters written through torch since the last step (resume, EMA)
             if a is not None:
@@ -360,7 +370,7 @@ class PretrainStepper:
                     self._device_step(task, static, rw, finish=self.world == 1, mode=None, t_out=t_out)
                     if self.world > 1:
                         for _, o in pairs:
-                            o.apply()
+                            o.apply(task)
                 for (a, o), (p0, m0, v0) in zip(pairs, snap):
                     a.flat_p.copy_(p0)
                     o.m.copy_(m0)
@@ -408,5 +418,5 @@ class PretrainStepper:
             # the exchange of every stage that completed inside the graph starts at its in-graph event
             for sy, (fired, events) in zip(self.syncs, marks):
                 sy.after_replay(self.comm_stream, fired, events)
-            self._finish([f for f, _ in marks] if self.overlap else None)
+            self._finish([f for f, _ in marks] if self.overlap else None, task=task)
         return out
