@@ -85,26 +85,26 @@ __global__ void __launch_bounds__(256)
     const float c = maxn / (sqrtf(sumsq[0]) + 1e-6f);
     clip = c < 1.f ? c : 1.f;
   }
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    int lo = 0, hi = nseg - 1;  // last segment whose lower bound is <= i
-    while (lo < hi) {
-      const int mid = (lo + hi + 1) >> 1;
-      if ((long long)s_b[mid] <= i) lo = mid; else hi = mid - 1;
-    }
-    const int code = s_c[lo];
+  // segment by segment (a handful of them: heads and projections are contiguous in module order), grid-strided inside
+  for (int sg = 0; sg < nseg; sg++) {
+    const int code = s_c[sg];
     if (code < 0) continue;
     const float* h = hyper + 8 * code;
     const float lr = h[0], step = h[1], b1 = h[2], b2 = h[3], eps = h[4];
-    const float gi = g[i] * clip;
-    const float mi = m[i] * b1 + (1.f - b1) * gi;
-    const float vi = v[i] * b2 + (1.f - b2) * gi * gi;
-    const float denom = sqrtf(vi) + eps;
-    float pi = p[i] + (-step) * (mi / denom);
-    if (weight_decay > 0.f) pi = pi + (-lr * weight_decay) * pi;
-    m[i] = mi;
-    v[i] = vi;
-    p[i] = pi;
-    if (shadow) shadow[i] = __float2bfloat16_rn(pi);
+    const long long end = min((long long)s_b[sg + 1], n);
+    for (long long i = (long long)s_b[sg] + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < end;
+         i += (long long)gridDim.x * blockDim.x) {
+      const float gi = g[i] * clip;
+      const float mi = m[i] * b1 + (1.f - b1) * gi;
+      const float vi = v[i] * b2 + (1.f - b2) * gi * gi;
+      const float denom = sqrtf(vi) + eps;
+      float pi = p[i] + (-step) * (mi / denom);
+      if (weight_decay > 0.f) pi = pi + (-lr * weight_decay) * pi;
+      m[i] = mi;
+      v[i] = vi;
+      p[i] = pi;
+      if (shadow) shadow[i] = __float2bfloat16_rn(pi);
+    }
   }
 }
 

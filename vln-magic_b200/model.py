@@ -478,6 +478,8 @@ def inactive_in_task(task, name, kd=False):
         return not (kd and t == "mlm")
     if name.startswith(_KD_NAV):
         return not (kd and t == "sap")
+    if name.startswith("bert.img_embeddings.adaptive_pano_attn."):
+        return t in ("mrc", "og")  # the fused panorama embedding only feeds the global branch's visited nodes
     if name.startswith("bert.img_embeddings.obj_"):
         return t != "og"
     return False
