@@ -39,17 +39,17 @@ def run(overlap, graphs, steps=4):
         teacher = magic_b200.GlocalTextPathCMTPreTraining(cfg_t).to(dev).set_compute_dtype(torch.bfloat16)
         teacher = teacher.train() if w.get("co_update") else teacher.eval()
     st = PretrainStepper(student, teacher, use_graphs=graphs, co_update=bool(w.get("co_update")), overlap=overlap,
-                         rw_generator=torch.Generator().manual_seed(5))
+                         rw_generator=torch.Generator().manual_seed(5), tasks=("mlm", "sap"))
     ops.set_seed(dev, 999)
     orig, bad = st.opt.apply, []
 
-    def apply():  # the exchange has been waited for: compare the gradient arenas across the ranks
+    def apply(task=None):  # the exchange has been waited for: compare the gradient arenas across the ranks
         for a in (st.arena, st.t_arena if st.co_update else None):
             if a is not None:
                 other = a.flat_g.clone()
                 dist.broadcast(other, 0)
                 bad.append(float((other - a.flat_g).abs().max()))
-        orig()
+        orig(task)
 
     if not graphs:  # (graph mode: the warm-up steps before a capture run without the exchange)
         st.opt.apply = apply

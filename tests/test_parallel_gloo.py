@@ -59,7 +59,8 @@ dist.all_gather(before, arena.flat_g.clone())
 sy = parallel.StageSync(arena, 2, bucket_bytes=64 * 4)
 st0 = [entries[i][2] for i in (4, 6, 7, 8)]
 assert [lo for lo, hi in sy.stages[0]] == [entries[4][2], entries[6][2]] and sy.stages[1] == [(entries[2][2], entries[3][2])]
-cover = sorted(sy.stages[0] + sy.stages[1] + sy.rest)
+cover = sorted([r for st in sy.stages for r in st] + sy.rest)
+assert parallel.text_stage_cuts(9) == [6, 3] and parallel.text_stage_cuts(6) == [4, 2] and parallel.text_stage_cuts(1) == []
 assert cover[0][0] == 0 and cover[-1][1] == off and all(a[1] == b[0] for a, b in zip(cover[:-1], cover[1:]))
 sy.begin("eager")
 sy.expect(0, "txt"); sy.expect(0, "g_in"); sy.expect(1, "txt_mid")

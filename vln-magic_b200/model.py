@@ -311,10 +311,11 @@ class GlocalTextPathCMT(nn.Module):
                          e.LayerNorm.bias, e.LayerNorm.eps, fc.dtype, fc.p(e.dropout), fc.salt())
         x = x.view(B * Lt, -1)
         attns = []
-        mid = len(self.lang_encoder.layer) // 2
+        from .parallel import text_stage_cuts
+        cuts = text_stage_cuts(len(self.lang_encoder.layer)) if self.stage_cb is not None else []
         for li, layer in enumerate(self.lang_encoder.layer):
-            if li == mid and li > 0:
-                self._mark(x, 1, "txt_mid")  # gradient complete <=> text layers mid.. have finished backward
+            if li in cuts:  # gradient complete <=> text layers li.. have finished backward (stage 1 + position in cuts)
+                self._mark(x, 1 + cuts.index(li), f"txt_{li}")
             a, p = _attn_block(layer.attention, x, None, B, Lt, Lt, ix["key_lens_txt"], fc,
                                want_map=self.kd_attn_depth is None or li < self.kd_attn_depth[0])
             x = _ffn_block(layer, a, fc)
@@ -361,6 +362,9 @@ class GlocalTextPathCMT(nn.Module):
         attns = []
         H = h // 64
         if ie.pano_encoder is not None:
+            if self.stage_cb is not None:  # gradient complete <=> the panorama encoder has finished backward (last stage)
+                from .parallel import text_stage_cuts
+                self._mark(x, 2 + len(text_stage_cuts(len(self.lang_encoder.layer))) - 0, "pano_in")
             for layer in ie.pano_encoder.layers:
                 n1 = _ln(x, layer.norm1, fc)
                 mha = layer.self_attn

@@ -81,22 +81,51 @@ STAGE0_PREFIXES = ("bert.local_encoder.encoder.", "bert.global_encoder.encoder."
                    "local_sap_head.", "sap_fuse_linear.", "image_classifier.", "cfp_", "og_head.")
 
 
+def text_stage_cuts(n_text_layers):
+    """Text-layer indices at which the model marks a backward stage, top first: the gradient of the activation ENTERING
+    layer c is complete when layers c.. have finished backward.  9 layers -> [6, 3]; 6 -> [4, 2]; 2 -> [1]."""
+    if n_text_layers < 2:
+        return []
+    step = max(1, -(-n_text_layers // 3))
+    cuts, c = [], n_text_layers - step
+    while c > 0:
+        cuts.append(c)
+        c -= step
+    return cuts
+
+
+PANO_PREFIXES = ("bert.img_embeddings.pano_encoder.", "bert.img_embeddings.adaptive_pano_attn.")
+
+
 def stage_ranges(arena, n_text_layers):
-    """-> ([ranges of stage 0, ranges of stage 1], rest ranges) as (lo, hi) element offsets of the gradient arena.
+    """-> ([ranges of stage 0, 1, ...], rest ranges) as (lo, hi) element offsets of the gradient arena.
 
     Stage 0 = every weight-decay-group parameter of the cross-modal encoders, the KD projections and the task heads:
     complete when the gradients of the cross encoders' inputs (text output, gmap input, vp input) are complete.
-    Stage 1 = the upper half of the text encoder: complete when the gradient of the activation entering text layer
-    n/2 is complete.  (The position / step embedding weights of the two cross encoders produce gmap / vp INPUTS, so
-    their gradients arrive after the stage-0 point: they stay in the rest, with the biases and LayerNorm parameters
-    of the no-decay group, the embeddings, the lower text layers and the panorama encoder.)"""
-    mid = n_text_layers // 2
-    upper = tuple(f"bert.lang_encoder.layer.{i}." for i in range(mid, n_text_layers)) if mid > 0 else ()
-    stages = [[], []]
+    Stages 1.. = groups of text layers from the top (text_stage_cuts): complete when the gradient of the activation
+    entering the group's first layer is complete.  Last stage = the panorama encoder: complete when the gradient of its
+    input is.  (The position / step embedding weights of the two cross encoders produce gmap / vp INPUTS, so their
+    gradients arrive after the stage-0 point: they stay in the rest, with the biases and LayerNorm parameters of the
+    no-decay group, the embeddings, the lowest text layers and the image embeddings.)"""
+    cuts = text_stage_cuts(n_text_layers)
+    groups, hi_l = [], n_text_layers
+    for c in cuts:
+        groups.append(tuple(f"bert.lang_encoder.layer.{i}." for i in range(c, hi_l)))
+        hi_l = c
+    stages = [[] for _ in range(2 + len(groups))]
     for n, p, o, k in arena.entries:
         if o >= arena.n_decay:
             continue
-        st = 0 if n.startswith(STAGE0_PREFIXES) else (1 if upper and n.startswith(upper) else None)
+        st = None
+        if n.startswith(STAGE0_PREFIXES):
+            st = 0
+        elif n.startswith(PANO_PREFIXES):
+            st = 1 + len(groups)
+        else:
+            for gi, pre in enumerate(groups):
+                if n.startswith(pre):
+                    st = 1 + gi
+                    break
         if st is None:
             continue
         hi = o + (k + 7) // 8 * 8  # the arena pads every entry to 8 elements
@@ -132,8 +161,8 @@ class StageSync:
         self.stages, self.rest = stage_ranges(arena, n_text_layers)
         self.bucket = max(1, bucket_bytes // 4)
         self.mode = None
-        self.pending = [set(), set()]
-        self.expected = [False, False]
+        self.pending = [set() for _ in self.stages]
+        self.expected = [False] * len(self.stages)
         self.fired = []          # stages completed during the current backward, in order
         self.events = {}         # capture mode: stage -> GraphEvent
         self.handles = []
@@ -142,13 +171,13 @@ class StageSync:
 
     # -- called by the model ------------------------------------------------------------------------------
     def expect(self, stage, key):
-        if self.mode is None:
+        if self.mode is None or stage >= len(self.stages):
             return
         self.pending[stage].add(key)
         self.expected[stage] = True
 
     def fire(self, stage, key):
-        if self.mode is None:
+        if self.mode is None or stage >= len(self.stages):
             return
         self.pending[stage].discard(key)
         if self.expected[stage] and not self.pending[stage] and stage not in self.fired:
@@ -160,8 +189,8 @@ class StageSync:
         self.mode = mode
         # the step's (capture) origin stream; None on the CPU (gloo tests of the bucket plan)
         self.main = torch.cuda.current_stream() if (mode is not None and torch.cuda.is_available()) else None
-        self.pending = [set(), set()]
-        self.expected = [False, False]
+        self.pending = [set() for _ in self.stages]
+        self.expected = [False] * len(self.stages)
         self.fired = []
         if mode == "capture":
             self.events = {}
@@ -227,7 +256,7 @@ class StageSync:
     def issue_rest(self, fired):
         """Everything that was not exchanged during backward (call when backward has been issued completely)."""
         ranges = list(self.rest)
-        for st in (0, 1):
+        for st in range(len(self.stages)):
             if st not in fired:
                 ranges += self.stages[st]
         self._issue(sorted(ranges))

@@ -141,7 +141,7 @@ class PretrainStepper:
             mb = sum((hi - lo) * 4 for sy in self.syncs for st in sy.stages for lo, hi in st) / 1e6
             tot = sum(sy.arena.total * 4 for sy in self.syncs) / 1e6
             return (f"NCCL all-reduce(AVG) of the flat fp32 gradient arena in 64 MB buckets; {mb:.0f} of {tot:.0f} MB "
-                    "(cross-modal encoders + heads, upper text layers) start DURING backward from in-graph event "
+                    "(cross-modal encoders + heads, text layer groups from the top, panorama encoder) start DURING backward from in-graph event "
                     "nodes, the rest when backward has been issued")
         n = len(self.allreduce.bounds) + (len(self.t_allreduce.bounds) if self.t_allreduce is not None else 0)
         return f"NCCL all-reduce(AVG) of the flat fp32 gradient arena, {n} buckets, issued after backward"
