@@ -193,3 +193,29 @@ def test_nav_index_tables():
                 got[b, n] += l[b, c] if c >= 0 else bw
     assert torch.equal(torch.isinf(got), torch.isinf(want))
     assert torch.allclose(got[~torch.isinf(got)], want[~torch.isinf(want)])
+
+
+def test_world_tables_and_graphworld_on_cpu():
+    """nav_synth.world_tables (Floyd-Warshall distances / hop counts) against networkx, and featurizer.GraphWorld's table
+    layout (built on the CPU here; the kernels that read it are covered by tests/test_featurize_graph_gpu.py)."""
+    import networkx as nx
+    from magic_b200.featurizer import GraphWorld
+    w = nav_synth.NavWorld(n=30, seed=4)
+    pos, dist, hops, cands, view_ang = nav_synth.world_tables(w)
+    G = nx.Graph()
+    for i in range(w.n):
+        for j in np.nonzero(w.adj[i])[0]:
+            G.add_edge(i, int(j), weight=float(np.linalg.norm(w.pos[i] - w.pos[j])))
+    d = dict(nx.all_pairs_dijkstra_path_length(G))
+    for i in range(w.n):
+        for j in range(w.n):
+            assert dist[i, j] == pytest.approx(d[i][j], rel=1e-5, abs=1e-6)
+            assert dist[i, j] == 0 or hops[i, j] >= 1
+    assert np.array_equal(hops, hops.T) and view_ang.shape == (36, 2)
+    world = GraphWorld(pos, dist, hops, cands, view_ang, device="cpu")
+    assert world.N == 30 and world.C == max(len(c) for c in cands) == world.max_cands
+    for i, lst in enumerate(cands):
+        assert int(world.n_cand[i]) == len(lst)
+        assert world.cand_vp[i, :len(lst)].tolist() == [c[0] for c in lst] and (world.cand_vp[i, len(lst):] == -1).all()
+        assert world.cand_view[i, :len(lst)].tolist() == [c[1] for c in lst]
+    assert world.pos.dtype == torch.float64 and world.dist.dtype == torch.float32 and world.hops.dtype == torch.int32
