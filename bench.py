@@ -212,12 +212,11 @@ def family_cost(name, a):
             by += n * (esz(sg.s_dt) + esz(sg.t_dt)) + (n * esz(sg.s_dt) if name.endswith("bwd") else 0)
         return 0.0, by
     if name in ("magic_makd_kl_fwd", "magic_makd_kl_bwd"):
-        R, C = a[2], a[3] if name.endswith("fwd") else a[4]
         if name.endswith("bwd"):
             R, C, dtc = a[3], a[4], a[-2]
-            return 0.0, R * C * esz(dtc) * 3
-        dtc = a[-2]
-        return 0.0, R * C * esz(dtc) * 2 * 2   # two passes over student + teacher rows
+            return 0.0, R * C * esz(dtc) * 3   # reads student + teacher rows, writes dS
+        R, C, dtc = a[2], a[3], a[11]
+        return 0.0, R * C * esz(dtc) * 2       # single pass: every student / teacher logit is read once
     if name in ("magic_ce_fwd", "magic_ce_bwd"):
         R, C, dtc = (a[4], a[5], a[8]) if name.endswith("fwd") else (a[5], a[6], a[9])
         return 0.0, R * C * esz(dtc) * (1 if name.endswith("fwd") else 2)
