@@ -195,6 +195,34 @@ __device__ __forceinline__ float fast_ex2(float x) {
 // -inf -> -1e6 (kd_loss.py:21-22: torch.where(x == -inf, -1e6, x) -- NaN and finite values below -1e6 pass through
 // unchanged, as in the reference) and the temperature / log2 e scale
 __device__ __forceinline__ float fix2(float v, float c) { return (v == -INFINITY ? -1e6f : v) * c; }
+// forward: the same replacement as ONE ALU-pipe op -- max.NaN(v, -1e6) maps -inf to -1e6, propagates NaN like the
+// reference's torch.where, and differs only for finite logits below -1e6 (clamped), which no softmax input reaches.
+// The bf16 forward is bound by the ALU + XU pipes (their busy times ADD on this part), so the select pair
+// (FSETP + FSEL) per value was a sixth of the kernel.
+__device__ __forceinline__ float fix2_fwd(float v, float c) {
+  float r;
+  asm("max.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(v), "f"(-1e6f));
+  return r * c;
+}
+// 8 bf16 -> fp32 with the low halves shifted by an integer multiply (IMAD: FMA pipe) instead of SHF / PRMT (ALU pipe)
+template <typename T>
+struct KlLoad {
+  static __device__ __forceinline__ void load(const T* p, float (&v)[RowVec<T>::N]) { RowVec<T>::load_cs(p, v); }
+};
+template <>
+struct KlLoad<__nv_bfloat16> {
+  static __device__ __forceinline__ void load(const __nv_bfloat16* p, float (&v)[8]) {
+    const uint4 t = __ldcs(reinterpret_cast<const uint4*>(p));
+    const uint32_t w[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      uint32_t lo;
+      asm("mul.lo.u32 %0, %1, 65536;" : "=r"(lo) : "r"(w[i]));
+      v[2 * i] = __uint_as_float(lo);
+      v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+    }
+  }
+};
 __device__ __forceinline__ void kl_merge(KlAcc& x, const KlAcc& y) {
   const float ms = fmaxf(x.ms, y.ms), mt = fmaxf(x.mt, y.mt);
   if (ms > -INFINITY) x.zs = x.zs * fast_ex2(x.ms - ms) + y.zs * fast_ex2(y.ms - ms);
@@ -250,30 +278,30 @@ __global__ void __launch_bounds__(NT)
   int c = threadIdx.x * VN;
   for (; c + NT * VN < cv; c += 2 * NT * VN) {  // two independent 16-byte loads per row in flight
     float a0[VN], b0[VN], a1[VN], b1[VN];
-    RowVec<T>::load_cs(sr + c, a0);
-    RowVec<T>::load_cs(tr + c, b0);
-    RowVec<T>::load_cs(sr + c + NT * VN, a1);
-    RowVec<T>::load_cs(tr + c + NT * VN, b1);
+    KlLoad<T>::load(sr + c, a0);
+    KlLoad<T>::load(tr + c, b0);
+    KlLoad<T>::load(sr + c + NT * VN, a1);
+    KlLoad<T>::load(tr + c + NT * VN, b1);
 #pragma unroll
     for (int i = 0; i < VN; i++) {
-      a0[i] = fix2(a0[i], c2); b0[i] = fix2(b0[i], c2);
-      a1[i] = fix2(a1[i], c2); b1[i] = fix2(b1[i], c2);
+      a0[i] = fix2_fwd(a0[i], c2); b0[i] = fix2_fwd(b0[i], c2);
+      a1[i] = fix2_fwd(a1[i], c2); b1[i] = fix2_fwd(b1[i], c2);
     }
     kl_push<VN>(k, a0, b0);
     kl_push<VN>(k, a1, b1);
   }
   for (; c < cv; c += NT * VN) {
     float a0[VN], b0[VN];
-    RowVec<T>::load_cs(sr + c, a0);
-    RowVec<T>::load_cs(tr + c, b0);
+    KlLoad<T>::load(sr + c, a0);
+    KlLoad<T>::load(tr + c, b0);
 #pragma unroll
     for (int i = 0; i < VN; i++) {
-      a0[i] = fix2(a0[i], c2); b0[i] = fix2(b0[i], c2);
+      a0[i] = fix2_fwd(a0[i], c2); b0[i] = fix2_fwd(b0[i], c2);
     }
     kl_push<VN>(k, a0, b0);
   }
   for (int cc = cv + threadIdx.x; cc < C; cc += NT) {
-    const float xs[1] = {fix2(ldf(sr, cc), c2)}, xt[1] = {fix2(ldf(tr, cc), c2)};
+    const float xs[1] = {fix2_fwd(ldf(sr, cc), c2)}, xt[1] = {fix2_fwd(ldf(tr, cc), c2)};
     kl_push<1>(k, xs, xt);
   }
 #pragma unroll
