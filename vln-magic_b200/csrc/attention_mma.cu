@@ -315,6 +315,11 @@ __global__ void __launch_bounds__(NTHREADS) attn_mma_fwd_kernel(AttnParams P, in
 // tensor cores.  Each warp stages its 16 output rows in the shared rows its Q slab came from (dead once the A
 // fragments are in registers) and writes them with 16-byte row-contiguous stores.
 // ===================================================================================================
+__device__ __forceinline__ float ex2f(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() {
@@ -361,7 +366,10 @@ __global__ void __launch_bounds__(320) attn_fwd2_kernel(AttnParams P, int hc, in
     cp_async_commit();
   };
   const bool wact = w * 16 < Lq;
-  const float sw = P.dists ? P.sprel_w[0] : 0.f, sb = P.dists ? P.sprel_b[0] : 0.f;
+  const float LOG2E = 1.4426950408889634f;
+  const float sc2 = P.scale * LOG2E;  // exp2-domain softmax, as in version 3 below
+  const float sw2 = P.dists ? P.sprel_w[0] * LOG2E : 0.f, sb2 = P.dists ? P.sprel_b[0] * LOG2E : 0.f;
+  const int skip = P.key_skip;
   const Dropout dr = make_dropout(P.drop_p, P.seed_ptr, P.salt);
   const float invH = 1.f / (float)H;
   const int ia = w * 16 + g, ib = ia + 8;
@@ -393,53 +401,50 @@ __global__ void __launch_bounds__(320) attn_fwd2_kernel(AttnParams P, int hc, in
         load_a_frags(Qs, w * 16, lane, qa);
         mma_a_yt<NT>(s, qa, Ks, lane);
       }
-      const size_t da = ((size_t)b * Lq + (va ? ia : 0)) * Lk, db = ((size_t)b * Lq + (vb ? ib : 0)) * Lk;
-      float mxa = -INFINITY, mxb = -INFINITY;
+      const float* da = P.dists ? P.dists + ((size_t)b * Lq + (va ? ia : 0)) * Lk : nullptr;
+      const float* db = P.dists ? P.dists + ((size_t)b * Lq + (vb ? ib : 0)) * Lk : nullptr;
+      float mxa[2] = {-INFINITY, -INFINITY}, mxb[2] = {-INFINITY, -INFINITY};
 #pragma unroll
       for (int j = 0; j < NT; j++) {
-#pragma unroll
-        for (int e = 0; e < 2; e++) {
-          const int c = j * 8 + 2 * t + e;
-          float x0 = s[j][e] * P.scale, x1 = s[j][2 + e] * P.scale;
-          if (c < klen && c != P.key_skip) {
-            if (P.dists) {
-              x0 += sw * P.dists[da + c] + sb;
-              x1 += sw * P.dists[db + c] + sb;
-            }
-          } else {
-            x0 = x1 = -INFINITY;
+        const int c0 = j * 8 + 2 * t;
+        float x0 = s[j][0] * sc2, x1 = s[j][1] * sc2, x2 = s[j][2] * sc2, x3 = s[j][3] * sc2;
+        if (j * 8 < klen) {  // (tile-uniform) at least one live key in this n-tile
+          if (da) {
+            const bool k0 = c0 < klen, k1 = c0 + 1 < klen;
+            if (k0) { x0 = fmaf(sw2, da[c0], x0 + sb2); x2 = fmaf(sw2, db[c0], x2 + sb2); }
+            if (k1) { x1 = fmaf(sw2, da[c0 + 1], x1 + sb2); x3 = fmaf(sw2, db[c0 + 1], x3 + sb2); }
           }
-          s[j][e] = x0;
-          s[j][2 + e] = x1;
-          mxa = fmaxf(mxa, x0);
-          mxb = fmaxf(mxb, x1);
+          if (j * 8 + 8 > klen || (skip >= j * 8 && skip < j * 8 + 8)) {  // straddles the length / holds the hole
+            if (c0 >= klen || c0 == skip) x0 = x2 = -INFINITY;
+            if (c0 + 1 >= klen || c0 + 1 == skip) x1 = x3 = -INFINITY;
+          }
+        } else {
+          x0 = x1 = x2 = x3 = -INFINITY;
         }
+        s[j][0] = x0; s[j][1] = x1; s[j][2] = x2; s[j][3] = x3;
+        mxa[j & 1] = fmaxf(mxa[j & 1], fmaxf(x0, x1));
+        mxb[j & 1] = fmaxf(mxb[j & 1], fmaxf(x2, x3));
       }
-      mxa = quad_max(mxa);
-      mxb = quad_max(mxb);
-      float suma = 0.f, sumb = 0.f;
+      float ma = quad_max(fmaxf(mxa[0], mxa[1])), mb = quad_max(fmaxf(mxb[0], mxb[1]));
+      if (ma == -INFINITY) ma = 0.f;  // (a fully masked row: keeps -inf - -inf out of the exponent)
+      if (mb == -INFINITY) mb = 0.f;
+      float sma[2] = {0.f, 0.f}, smb[2] = {0.f, 0.f};
 #pragma unroll
-      for (int j = 0; j < NT; j++) {
-#pragma unroll
-        for (int e = 0; e < 2; e++) {
-          const float e0 = (s[j][e] == -INFINITY) ? 0.f : __expf(s[j][e] - mxa);
-          const float e1 = (s[j][2 + e] == -INFINITY) ? 0.f : __expf(s[j][2 + e] - mxb);
-          s[j][e] = e0;
-          s[j][2 + e] = e1;
-          suma += e0;
-          sumb += e1;
-        }
+      for (int j = 0; j < NT; j++) {  // ex2(-inf) = 0: masked keys need no test (a row always has a live key)
+        const float e0 = ex2f(s[j][0] - ma), e1 = ex2f(s[j][1] - ma), e2 = ex2f(s[j][2] - mb), e3 = ex2f(s[j][3] - mb);
+        s[j][0] = e0; s[j][1] = e1; s[j][2] = e2; s[j][3] = e3;
+        sma[j & 1] += e0 + e1;
+        smb[j & 1] += e2 + e3;
       }
-      suma = quad_sum(suma);
-      sumb = quad_sum(sumb);
+      const float suma = quad_sum(sma[0] + sma[1]), sumb = quad_sum(smb[0] + smb[1]);
       const float inva = 1.f / suma, invb = 1.f / sumb;
-      if (t == 0) {
-        if (va) P.lse[((size_t)b * H + hd) * Lq + ia] = mxa + __logf(suma);
-        if (vb) P.lse[((size_t)b * H + hd) * Lq + ib] = mxb + __logf(sumb);
+      if (t == 0) {  // natural-log log-sum-exp (what the backward kernels subtract)
+        if (va) P.lse[((size_t)b * H + hd) * Lq + ia] = (ma + __log2f(suma)) * 0.6931471805599453f;
+        if (vb) P.lse[((size_t)b * H + hd) * Lq + ib] = (mb + __log2f(sumb)) * 0.6931471805599453f;
       }
 #pragma unroll
       for (int j = 0; j < NT; j++) {
-        s[j][0] *= inva; s[j][1] *= inva;  // normalised probabilities: exactly 0 for masked / padded keys
+        s[j][0] *= inva; s[j][1] *= inva;
         s[j][2] *= invb; s[j][3] *= invb;
       }
       if (kd) {
@@ -532,11 +537,6 @@ __global__ void __launch_bounds__(320) attn_fwd2_kernel(AttnParams P, int hc, in
 // units retire ~0.16 G cells/us, +10 us at B64 H12 80x80 and +40 us at B128 H2 160x160, worse than the cluster /
 // distributed-shared-memory reduction of versions 1 / 2 (+8 us), which therefore keep that case.
 // ===================================================================================================
-__device__ __forceinline__ float ex2f(float x) {
-  float y;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
 
 template <int NT, int NW, int MINB>
 __global__ void __launch_bounds__(NW * 32, MINB) attn_fwd3_kernel(AttnParams P) {
