@@ -491,7 +491,7 @@ def featurizer_rate(B=64, Tmax=5, calls=20):
         build_index(hb)
     host = (time.perf_counter() - t0) * 1e3 / 3
     return dict(batch=B, ms_per_batch_device=round(dev, 3), ms_per_batch_wall=round(wall, 3),
-                host_build_index_ms=round(host, 3), h2d_bytes_per_batch=int(B * (Tmax + 4) * 4),
+                host_build_index_ms=round(host, 3), h2d_bytes_per_batch=int(B * (Tmax + 5) * 4),
                 what="magic_featurize_graph (2 kernels) on a 256-viewpoint synthetic world vs graph_index.build_index "
                      "(python loops over the collated id strings) for the same batch size")
 

@@ -274,6 +274,8 @@ typedef struct MagicFeatArgs {
   const int* path_len;      /* [B] */
   const float* start_heading; /* [B] */
   const int* next_vp;       /* [B] ground-truth next viewpoint, -1 = stop, -2 = unknown; NULL: no labels */
+  const int* prev_vp;       /* [B] viewpoint the agent came from (the heading's source, dataset.py:433-443); -1 or NULL:
+                               path[len - 2].  Differs when the loader cut a long path to 20 viewpoints + the end one */
   const int* row0;          /* [B] first panorama row of the sample (exclusive prefix sum of path_len) */
   /* outputs: panoramas [R_cap rows] */
   long long* traj_vp_index; int* traj_view_perm; float* traj_loc_fts; long long* traj_nav_types;

@@ -1,3 +1,2 @@
 #!/bin/bash
-OUT=gpurun_out
-timeout 900 python -m pytest tests/test_featurize_graph_gpu.py tests/test_featurizer_gpu.py -m gpu -q --timeout 600 -p no:cacheprovider > $OUT/s_pytest.log 2>&1; echo "pytest rc=$?"; tail -40 $OUT/s_pytest.log | cut -c1-250
+timeout 600 python -m pytest tests/test_featurize_graph_gpu.py tests/test_featurizer_gpu.py -m gpu -q --timeout 600 -p no:cacheprovider > gpurun_out/s_pytest.log 2>&1; tail -3 gpurun_out/s_pytest.log; grep -n "^E " gpurun_out/s_pytest.log | head -6 | cut -c1-300

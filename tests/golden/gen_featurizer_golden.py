@@ -96,11 +96,11 @@ def sample_paths(rng, graphs, n, t_max):
     return items
 
 
-def main():
+def main(tag="", n_per=18, n_items=12, t_max=9, seed=2024):
     mods = ref_modules()
     ds, tasks, common = mods["dataset"], mods["tasks"], mods["common"]
-    rng = np.random.RandomState(2024)
-    graphs, cands = make_world(rng)
+    rng = np.random.RandomState(seed)
+    graphs, cands = make_world(rng, n_per=n_per)
     sd = {s: dict(nx.all_pairs_dijkstra_path_length(G)) for s, G in graphs.items()}
     sp = {s: dict(nx.all_pairs_dijkstra_path(G)) for s, G in graphs.items()}
     feats = {}
@@ -119,7 +119,7 @@ def main():
                 feats[key] = np.random.RandomState(abs(hash(key)) % (2 ** 31)).randn(36, 16 + 8).astype(np.float32)
             return feats[key]
         db.get_scanvp_feature = get_feat
-        db.data = sample_paths(rng, graphs, 12, 9)
+        db.data = sample_paths(rng, graphs, n_items, t_max)
         sap = tasks.SapDataset.__new__(tasks.SapDataset)
         sap.nav_db = db
         sap.end_vp_pos_ratio = 0.2
@@ -127,29 +127,44 @@ def main():
         ends = []
         orig = db.get_input
 
+        rec = {}
+        orig_angle, orig_labels = db.get_cur_angle, db.get_act_labels
+
+        def spy_angle(scan, path, start_heading):   # the path BEFORE the TRAIN_MAX_STEP truncation (dataset.py:660-665)
+            rec["prev"] = path[-2] if len(path) > 1 else None
+            return orig_angle(scan, path, start_heading)
+
+        def spy_labels(end_vp, end_idx, item, gmap_vpids, traj_cand_vpids):
+            rec["end_idx"] = end_idx
+            return orig_labels(end_vp, end_idx, item, gmap_vpids, traj_cand_vpids)
+        db.get_cur_angle, db.get_act_labels = spy_angle, spy_labels
+
         def spy(idx, end_vp_type, **kw):
             out = orig(idx, end_vp_type, **kw)
-            ends.append((idx, len(out["traj_vpids"])))
+            ends.append((idx, rec["end_idx"], rec["prev"]))
             return out
         db.get_input = spy
         samples = [sap[i] for i in range(len(db.data))]
         batch = tasks.sap_collate([dict(s) for s in samples])
         # what the device featuriser receives: the truncated path (as taken by get_input) and the next gt viewpoint
-        paths, nxt = [], []
-        for (idx, n_steps), s in zip(ends, samples):
+        paths, nxt, prevs = [], [], []
+        for (idx, end_idx, prev), s in zip(ends, samples):
             item = db.data[idx]
             paths.append(list(s["traj_vpids"]))
             full = item["path"]
             # R2R get_act_labels (dataset.py:622-640) decides "stop" by VALUE: a prefix that ends on the final viewpoint
             # (the path revisits it) is labelled stop as well
-            nxt.append(None if s["traj_vpids"][-1] == full[-1] else full[n_steps])
+            nxt.append(None if s["traj_vpids"][-1] == full[-1] else full[end_idx + 1])
+            # the heading comes from the TRUE predecessor of the end viewpoint; a path longer than TRAIN_MAX_STEP is cut
+            # to its first 20 viewpoints + the end viewpoint afterwards, so traj_vpids[-2] is not it
+            prevs.append(prev)
         from magic_b200.graph_index import build_index
         index = build_index(batch)
         keep = {k: v for k, v in batch.items() if torch.is_tensor(v) and k != "traj_view_img_fts"}
         keep.update(traj_step_lens=batch["traj_step_lens"], gmap_vpids=batch["gmap_vpids"],
                     traj_cand_vpids=batch["traj_cand_vpids"], traj_vpids=batch["traj_vpids"])
-        cases[name] = dict(batch=keep, index={k: v for k, v in index.items()}, paths=paths, next_vp=nxt,
-                           scans=[db.data[i]["scan"] for i, _ in ends], headings=[db.data[i]["heading"] for i, _ in ends],
+        cases[name] = dict(batch=keep, index={k: v for k, v in index.items()}, paths=paths, next_vp=nxt, prev_vp=prevs,
+                           scans=[db.data[e[0]]["scan"] for e in ends], headings=[db.data[e[0]]["heading"] for e in ends],
                            correct_heading=correct)
     world = dict(
         nodes={s: list(G.nodes) for s, G in graphs.items()},
@@ -157,10 +172,13 @@ def main():
         dist=sd, paths_len={s: {a: {b: len(p) for b, p in d.items()} for a, d in sp[s].items()} for s in sp},
         cands=cands, view_ang=common.get_view_rel_angles(baseViewId=12) if False else
         [common.get_view_rel_angles(baseViewId=i) for i in range(36)][12])
-    out = os.path.join(ROOT, "tests", "golden", "featurizer_graph.pt")
+    out = os.path.join(ROOT, "tests", "golden", f"featurizer_graph{tag}.pt")
     torch.save(dict(world=world, cases=cases, numpy=np.__version__), out)
     print("wrote", out, os.path.getsize(out), "bytes;", {k: len(v["paths"]) for k, v in cases.items()})
 
 
 if __name__ == "__main__":
     main()
+    # long-horizon case (RxR-like): 40-viewpoint scans, paths of up to 21 viewpoints (TRAIN_MAX_STEP = 20 + the end
+    # viewpoint, dataset.py:663-665), graphs of 40+ nodes, many revisits
+    main(tag="_long", n_per=40, n_items=16, t_max=22, seed=77)

@@ -14,21 +14,25 @@ from magic_b200.featurizer import GraphFeaturizer, GraphWorld, attach_text  # no
 from magic_b200.graph_index import INDEX_KEY  # noqa: E402
 
 DEV = "cuda"
-GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "featurizer_graph.pt")
+GOLD_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+# "" = 18-viewpoint scans, paths of up to 9 steps; "_long" = 40-viewpoint scans, paths of up to 21 viewpoints (the
+# loader's TRAIN_MAX_STEP + 1), graphs of 30 nodes, many revisits
+FIXTURES = ["", "_long"]
 
 
-def load():
-    g = torch.load(GOLD, weights_only=False)
+def load(tag=""):
+    g = torch.load(os.path.join(GOLD_DIR, f"featurizer_graph{tag}.pt"), weights_only=False)
     w = g["world"]
     positions = {s: {v: w["pos"][s][v] for v in w["nodes"][s]} for s in w["nodes"]}
     world, rows = GraphWorld.from_tables(positions, w["dist"], w["paths_len"], w["cands"], w["view_ang"], DEV)
     return g, world, rows
 
 
+@pytest.mark.parametrize("tag", FIXTURES)
 @pytest.mark.parametrize("case", ["plain", "correct_heading"])
 @pytest.mark.parametrize("slack", [0, 3])
-def test_featuriser_matches_reference_loader(case, slack):
-    g, world, rows = load()
+def test_featuriser_matches_reference_loader(case, slack, tag):
+    g, world, rows = load(tag)
     c = g["cases"][case]
     ref, rix = c["batch"], c["index"]
     B = len(c["paths"])
@@ -39,8 +43,9 @@ def test_featuriser_matches_reference_loader(case, slack):
                            E_cap=n_ent + 5 * slack, S_cap=n_ent + 7 * slack, correct_heading=c["correct_heading"])
     paths = [[rows[f"{s}_{v}"] for v in p] for s, p in zip(c["scans"], c["paths"])]
     nxt = [-1 if v is None else rows[f"{s}_{v}"] for s, v in zip(c["scans"], c["next_vp"])]
+    prev = [None if v is None else rows[f"{s}_{v}"] for s, v in zip(c["scans"], c["prev_vp"])]
     for rep in range(2):  # the second call reuses every buffer
-        out = feat(paths, c["headings"], nxt)
+        out = feat(paths, c["headings"], nxt, prev)
         feat.check()
     ix = out[INDEX_KEY]
     G0 = ref["gmap_step_ids"].shape[1]

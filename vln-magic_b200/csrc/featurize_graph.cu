@@ -136,8 +136,9 @@ __global__ void __launch_bounds__(FT) featurize_sample_kernel(const MagicFeatArg
   // ---- current heading / elevation (get_cur_angle) ---------------------------------------------------
   const int cur = path[T - 1];
   double cur_h = (double)A.start_heading[b], cur_e = 0.0;
-  if (T >= 2) {
-    const int prev = path[T - 2];
+  const int prev_given = A.prev_vp != nullptr ? A.prev_vp[b] : -1;
+  if (T >= 2 || prev_given >= 0) {
+    const int prev = prev_given >= 0 ? prev_given : path[T - 2];
     int view = 0;
     for (int j = 0; j < A.n_cand[prev]; j++)
       if (A.cand_vp[(size_t)prev * C + j] == cur) view = A.cand_view[(size_t)prev * C + j];  // dict: the last key wins

@@ -86,7 +86,7 @@ from .graph_index import INDEX_KEY  # noqa: E402
 
 class MagicFeatArgs(ctypes.Structure):
     """Mirror of `MagicFeatArgs` in include/magic_b200.h (field order matters)."""
-    _PTRS = ("pos dist hops cand_vp cand_view cand_ang n_cand view_ang path path_len start_heading next_vp row0 "
+    _PTRS = ("pos dist hops cand_vp cand_view cand_ang n_cand view_ang path path_len start_heading next_vp prev_vp row0 "
              "traj_vp_index traj_view_perm traj_loc_fts traj_nav_types traj_vp_view_lens gmap_node_vp gmap_step_ids "
              "gmap_visited_masks gmap_lens gmap_pos_fts gmap_pair_dists vp_pos_fts global_act_labels local_act_labels "
              "node_ptr entries src_ids src_ptr src_nodes src_w n_src g_valid l_valid node2cand bw_mask vp_gather "
@@ -191,17 +191,20 @@ class GraphFeaturizer:
                          slab_total=z(B, torch.int32), slab_nvis=z(B, torch.int32))
         self.status = z(1, torch.int32)
         self.inp = dict(path=z((B, Tmax), torch.int32), path_len=z(B, torch.int32), start_heading=z(B, torch.float32),
-                        next_vp=z(B, torch.int32), row0=z(B, torch.int32))
+                        next_vp=z(B, torch.int32), prev_vp=z(B, torch.int32), row0=z(B, torch.int32))
         from .ops import PinnedRing
-        self.ring = PinnedRing(B * (Tmax + 4), dtype=torch.int32, n=4)
-        self.wire = z((B, Tmax + 4), torch.int32)
+        self.ring = PinnedRing(B * (Tmax + 5), dtype=torch.int32, n=4)
+        self.wire = z((B, Tmax + 5), torch.int32)
         self.correct_heading = int(bool(correct_heading))
         self.stop_rows_g = torch.arange(B, dtype=torch.int64, device=dev) * G
         self.stop_rows_v = torch.arange(B, dtype=torch.int64, device=dev) * Vp
 
-    def __call__(self, paths, start_headings, next_vps=None):
+    def __call__(self, paths, start_headings, next_vps=None, prev_vps=None):
         """paths: B lists of viewpoint rows (len <= Tmax); next_vps: ground-truth next row per sample, -1 = stop
-        (None: no labels).  -> batch dict (device tensors, views of the featuriser's buffers)."""
+        (None: no labels); prev_vps: the viewpoint each agent came from, when it is not paths[b][-2] (the reference loader
+        cuts a path longer than TRAIN_MAX_STEP to its first 20 viewpoints + the end one AFTER reading the heading off the
+        true predecessor, dataset.py:658-665); None / -1: paths[b][-2].
+        -> batch dict (device tensors, views of the featuriser's buffers)."""
         B, Tmax, w = self.B, self.Tmax, self.world
         if len(paths) != B:
             raise ValueError(f"expected {B} paths")
@@ -212,20 +215,22 @@ class GraphFeaturizer:
         if R > self.R_cap:
             raise ValueError(f"panorama capacity {self.R_cap} < {R}")
         # the ~B*(Tmax+4) integers a batch costs on the wire: one pinned staging buffer, one H2D copy
-        h = torch.zeros(B, Tmax + 4, dtype=torch.int32)
+        h = torch.zeros(B, Tmax + 5, dtype=torch.int32)
         row0 = 0
         for b, p in enumerate(paths):
             h[b, :lens[b]] = torch.as_tensor(p, dtype=torch.int32)
             h[b, Tmax] = lens[b]
             h[b, Tmax + 1] = row0
             h[b, Tmax + 2] = (-2 if next_vps is None else int(next_vps[b]))
+            h[b, Tmax + 4] = (-1 if prev_vps is None or prev_vps[b] is None else int(prev_vps[b]))
             row0 += lens[b]
         h[:, Tmax + 3] = torch.as_tensor(np.asarray(start_headings, dtype=np.float32)).view(torch.int32)
-        d = self.ring.upload(h, self.wire.view(-1)).view(B, Tmax + 4)
+        d = self.ring.upload(h, self.wire.view(-1)).view(B, Tmax + 5)
         self.inp["path"].copy_(d[:, :Tmax])
         self.inp["path_len"].copy_(d[:, Tmax])
         self.inp["row0"].copy_(d[:, Tmax + 1])
         self.inp["next_vp"].copy_(d[:, Tmax + 2])
+        self.inp["prev_vp"].copy_(d[:, Tmax + 4])
         self.inp["start_heading"].copy_(d[:, Tmax + 3].contiguous().view(torch.float32))
         a = MagicFeatArgs()
         for k in ("pos", "dist", "hops", "cand_vp", "cand_view", "cand_ang", "n_cand", "view_ang"):
