@@ -85,3 +85,37 @@ def test_inactive_in_task_rules():
     assert not ina("mlm", "bert.vp_txt_w.weight", kd=True) and ina("sap", "bert.vp_txt_w.weight", kd=True)
     assert not ina("sap", "bert.global_cross_w.weight", kd=True) and ina("mlm", "bert.local_cross_w.bias", kd=True)
     assert not ina("sap", "bert.kdl_img_w.weight", kd=True) and not ina("mlm", "bert.kdl_txt_weight", kd=True)
+
+
+def test_task_tables_of_the_task_aware_adamw():
+    """optim.task_tables: per-task segment tables of magic_adamw_seg from an arena layout (pure host logic)."""
+    from magic_b200.model import inactive_in_task
+    from magic_b200.optim import task_tables
+    names = ["bert.embeddings.word_embeddings.weight", "bert.lang_encoder.layer.0.attention.self.query.weight",
+             "bert.global_encoder.sprel_linear.weight", "bert.txt_emb_w.weight", "bert.vp_txt_w.weight",
+             "bert.global_cross_w.weight", "mlm_head.predictions.transform.dense.weight", "global_sap_head.net.0.weight",
+             # no-decay group
+             "bert.lang_encoder.layer.0.attention.self.query.bias", "mlm_head.predictions.bias", "global_sap_head.net.0.bias"]
+    entries, off = [], 0
+    for i, n in enumerate(names):
+        k = 10 + 3 * i
+        entries.append((n, off, k))
+        off += (k + 7) // 8 * 8
+        if i == 7:
+            n_decay = off
+    slots, tabs = task_tables(entries, n_decay, off, ["mlm", "sap"], lambda t, n: inactive_in_task(t, n, kd=True))
+    assert slots == [frozenset({"mlm", "sap"}), frozenset({"mlm"}), frozenset({"sap"})]
+    o = {n: e[1] for n, e in zip(names, entries)}
+    (b_m, c_m), (b_m2, c_m2) = tabs["mlm"]
+    # decay group in an MLM step: trunk (slot 0) | sprel_linear (untouched) | txt_emb_w (0) | vp_txt_w (mlm-only slot 1) |
+    # global_cross_w (untouched) | mlm head (slot 1) | sap head (untouched)
+    assert c_m == [0, -1, 0, 1, -1, 1, -1]
+    assert b_m == [0, o[names[2]], o[names[3]], o[names[4]], o[names[5]], o[names[6]], o[names[7]], n_decay]
+    assert c_m2 == [0, 1, -1] and b_m2 == [0, o[names[9]] - n_decay, o[names[10]] - n_decay, off - n_decay]
+    (b_s, c_s), (_, c_s2) = tabs["sap"]
+    # SAP step: trunk | sprel_linear (sap-only: slot 2) | txt_emb_w | vp_txt_w (untouched) | global_cross_w (2) | mlm head | sap head
+    assert c_s == [0, 2, 0, -1, 2, -1, 2] and c_s2 == [0, -1, 2]
+    assert b_s[0] == 0 and b_s[-1] == n_decay and b_s == sorted(b_s)
+    # one task only: every parameter it touches is slot 0, the rest is skipped
+    slots1, tabs1 = task_tables(entries, n_decay, off, ["sap"], lambda t, n: inactive_in_task(t, n, kd=False))
+    assert slots1 == [frozenset({"sap"})] and set(tabs1["sap"][0][1]) == {0, -1}

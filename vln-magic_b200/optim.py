@@ -25,6 +25,42 @@ def get_lr_sched(global_step, opts):
     return lr if lr > 0 else 1e-8
 
 
+def task_tables(entries, n_decay, total, tasks, inactive, max_slots=16, max_segs=512):
+    """Segment tables of the task-aware AdamW (magic_adamw_seg) from the arena layout: `entries` = [(name, offset,
+    numel)] in arena order.  -> (slots, {task: [(bounds, codes) for the decay group, (bounds, codes) for the no-decay
+    group]}): `slots[i]` = the set of tasks that step hyper slot i (slot 0 = every task); per task and group the sorted
+    segment bounds (relative to the group's start, first 0, last the group's size) and one code per segment: the hyper
+    slot of the parameters in it, or -1 when the task leaves them untouched.  Host-only, exact integer logic."""
+    all_t = frozenset(tasks)
+    owners = [frozenset(t for t in tasks if not inactive(t, n)) for n, _, _ in entries]
+    slots = [all_t] + sorted({o for o in owners if o and o != all_t}, key=sorted)
+    if len(slots) > max_slots:
+        raise ValueError("too many distinct task-activity sets")
+    slot_of = {o: i for i, o in enumerate(slots)}
+    tables = {}
+    for t in tasks:
+        groups = []
+        for g_lo, g_hi in ((0, n_decay), (n_decay, total)):
+            bounds, codes = [0], []
+            for (n, o, k), own in zip(entries, owners):
+                if not (g_lo <= o < g_hi):
+                    continue
+                code = slot_of[own] if t in own else -1
+                if codes and codes[-1] == code:
+                    continue           # same code as the running segment: it simply extends
+                if codes:
+                    bounds.append(o - g_lo)
+                codes.append(code)
+            bounds.append(g_hi - g_lo)
+            if not codes:
+                codes = [0]
+            if len(codes) > max_segs:
+                raise ValueError("too many activity segments in the arena")
+            groups.append((bounds, codes))
+        tables[t] = groups
+    return slots, tables
+
+
 class FusedAdamW:
     def __init__(self, arena: ParamArena, lr=5e-5, betas=(0.9, 0.98), eps=1e-6, weight_decay=0.01, max_grad_norm=5.0):
         self.arena = arena
@@ -50,39 +86,16 @@ class FusedAdamW:
         """`tasks`: the tasks the loop alternates between; `inactive(task, param_name) -> bool`: True when that
         parameter receives NO gradient in a step of that task (model.inactive_in_task).  Afterwards pass the task to
         set_hyper / apply / step."""
-        tasks = list(tasks)
         a = self.arena
-        owners = [frozenset(t for t in tasks if not inactive(t, n)) for n, _, _, _ in a.entries]
-        slots = [frozenset(tasks)] + sorted({o for o in owners if o and o != frozenset(tasks)}, key=sorted)
-        if len(slots) > self.MAX_SLOTS:
-            raise ValueError("too many distinct task-activity sets")
-        slot_of = {o: i for i, o in enumerate(slots)}
+        slots, tables = task_tables([(n, o, k) for n, _, o, k in a.entries], a.n_decay, a.total, list(tasks), inactive,
+                                    self.MAX_SLOTS)
         self.slots, self.slot_steps = slots, [0] * len(slots)
         self.hyper = torch.zeros(8 * self.MAX_SLOTS, dtype=torch.float32, device=a.device)
         self.hyper_ring = PinnedRing(8 * self.MAX_SLOTS)
-        self.task_tables = {}
-        for t in tasks:
-            groups = []
-            for g_lo, g_hi in ((0, a.n_decay), (a.n_decay, a.total)):
-                bounds, codes = [0], []
-                for (n, _, o, k), own in zip(a.entries, owners):
-                    if not (g_lo <= o < g_hi):
-                        continue
-                    code = slot_of[own] if t in own else -1
-                    if codes and codes[-1] == code:
-                        continue           # same code as the running segment: it simply extends
-                    if codes:
-                        bounds.append(o - g_lo)
-                    codes.append(code)
-                bounds.append(g_hi - g_lo)
-                if not codes:
-                    codes = [0]
-                if len(codes) > 512:
-                    raise ValueError("too many activity segments in the arena")
-                dev = a.device
-                groups.append((torch.tensor(bounds, dtype=torch.int32, device=dev),
-                               torch.tensor(codes, dtype=torch.int32, device=dev), len(codes), codes == [0]))
-            self.task_tables[t] = tuple(groups)
+        dev = a.device
+        self.task_tables = {t: tuple((torch.tensor(bounds, dtype=torch.int32, device=dev),
+                                      torch.tensor(codes, dtype=torch.int32, device=dev), len(codes), codes == [0])
+                                     for bounds, codes in groups) for t, groups in tables.items()}
         return self
 
     def set_hyper(self, lr=None, task=None):
