@@ -702,19 +702,21 @@ def mktd_weights(t_sample_loss, decay=0.7, preprocess="exp"):
     return KD.exponential_decay(t_sample_loss.detach(), decay_rate=decay)
 
 
-def ability_weights(student, k, rw):
-    """-> (5 multipliers, divisor of the two image embedding losses): agent.py:583-593, 616-625, 675-693, 710-717."""
+def ability_weights(student, k, rw, weight_owner=None):
+    """-> (5 multipliers, divisor of the two image embedding losses): agent.py:583-593, 616-625, 675-693, 710-717.
+    `weight_owner`: the model whose learned kdl_*_weight parameters scale the losses -- `s_model` of agent.py:553,557,
+    i.e. the LEARNER: the small model for role t2s (default), the large model for role s2t."""
     if not k.get("kdl_adaptive_ability_weight", True):
         return [1.0] * 5, 2.0
     kind = k.get("kdl_adaptive_ability_weight_type", "RW")
     if kind == "learned_weight":
-        b = student.bert
+        b = (weight_owner if weight_owner is not None else student).bert
         return [F.softplus(getattr(b, n)).squeeze(0) for n in ("kdl_txt_weight", "kdl_img_weight", "kdl_global_weight",
                                                                "kdl_local_weight", "kdl_predict_weight")], 2.0
     return rw, 1.0
 
 
-def makd_losses(student, s_out, t_out, task, rw, t_w, kdl=None, role="t2s"):
+def makd_losses(student, s_out, t_out, task, rw, t_w, kdl=None, role="t2s", weight_owner=None):
     """agent.py:546-719 with the pretrain reductions of optim/kd_loss.py.  `student` is always the SMALL model: it
     owns the up-projections (txt_emb_w, kdl_img_w, kdl_avg_img_w, global_cross_w, local_cross_w).
       role 't2s' (agent.py:550-552): learner = small model; prediction = proj(s_out), target = t_out.detach().
@@ -722,12 +724,19 @@ def makd_losses(student, s_out, t_out, task, rw, t_w, kdl=None, role="t2s"):
         (large model's outputs, small model's outputs) exactly like agent.py:1022; prediction = s_out as is,
         target = proj(t_out).detach() (agent.py:571,605-606,647,665); `t_w` are then the SMALL model's MKTD
         weights (agent.py:1009-1011 stored under the same 'sample_weights' key).
+    Reductions: `kd_loss_type` None (default) = the pretraining file's `mean` semantics (silent fallback on a weight /
+    batch mismatch); 'mean' / 'sum' = the fine-tune file's (map_nav_src/utils/kd_loss.py; agent.py:554 for role t2s,
+    always 'mean' for role s2t, :557).  PINNED: tests/test_makd_agent_pinned.py runs this function against
+    tests/golden/makd_agent_ref.pt, which the reference's own compute_kd_losses SOURCE produced.
     Returns dict of the 10 named scalars (agent.py:824-835 names)."""
     k = dict(KDL_DEFAULT)
     if kdl:
         k.update(kdl)
     bert = student.bert
-    rw, img_div = ability_weights(student, k, rw)
+    rw, img_div = ability_weights(student, k, rw, weight_owner)
+    lt = k.get("kd_loss_type")
+    if role == "s2t" and lt is not None:
+        lt = "mean"
     T = k["kd_temperature"]
     emb = "emb" in k["kdl_task_types"]
     att = "attn" in k["kdl_task_types"]
@@ -744,28 +753,33 @@ def makd_losses(student, s_out, t_out, task, rw, t_w, kdl=None, role="t2s"):
         return s_out[key], proj(t_out[key]).detach()
 
     def e(proj, key, ri):
-        return KD.mse_loss(*pair(proj, key), t_w) * rw[ri] if emb else z
+        return KD.mse_loss(*pair(proj, key), t_w, loss_type=lt) * rw[ri] if emb else z
+
+    def a(key, n, ri):
+        sa, ta = (s_out[key], t_out[key]) if n is None else (s_out[key][:, :n], t_out[key][:, :n])
+        return KD.mse_loss(sa, ta.detach(), t_w, loss_type=lt) * rw[ri] if att else z
 
     if "txt" in k["kdl_tasks"]:
         L["txt_emb_loss"] = e(bert.txt_emb_w, "txt_embeds", 0)
-        L["txt_attn_loss"] = KD.mse_loss(s_out["txt_attns"][:, :min_len], t_out["txt_attns"][:, :min_len].detach(), t_w) * rw[0] if att else z
+        L["txt_attn_loss"] = a("txt_attns", min_len, 0)
     if "img" in k["kdl_tasks"]:
         # agent.py:620-622: under RW the two image emb losses are NOT halved; :618-619, :624-625 otherwise halved
         L["img_emb_loss"] = e(bert.kdl_img_w, "pano_embeds", 1) / img_div
         L["avg_img_emb_loss"] = e(bert.kdl_avg_img_w, "pano_fused_embeds", 1) / img_div
-        L["img_attn_loss"] = KD.mse_loss(s_out["img_attns"], t_out["img_attns"].detach(), t_w) * rw[1] if att else z  # agent.py:628 unsliced
+        L["img_attn_loss"] = a("img_attns", None, 1)  # agent.py:628 unsliced
     gw, lw = (bert.gmap_txt_w, bert.vp_txt_w) if task.startswith("mlm") else (bert.global_cross_w, bert.local_cross_w)
     if "global" in k["kdl_tasks"]:
         L["global_emb_loss"] = e(gw, "gmap_embeds", 2)
-        L["global_attn_loss"] = KD.mse_loss(s_out["gmap_attns"][:, :nx], t_out["gmap_attns"][:, :nx].detach(), t_w) * rw[2] if att else z
+        L["global_attn_loss"] = a("gmap_attns", nx, 2)
     if "local" in k["kdl_tasks"]:
         L["local_emb_loss"] = e(lw, "vp_embeds", 3)
-        L["local_attn_loss"] = KD.mse_loss(s_out["vp_attns"][:, :nx], t_out["vp_attns"][:, :nx].detach(), t_w) * rw[3] if att else z
+        L["local_attn_loss"] = a("vp_attns", nx, 3)
     if "predict" in k["kdl_tasks"]:
         w = t_w
         if w is not None and task.startswith("mlm"):
             w = t_w[s_out["row_sample"]]  # [DECISION] per-row weights for the [n_masked, vocab] logits
-        L["predict_loss"] = KD.kd_loss(s_out["logits"], t_out["logits"].detach(), temperature=T, t_sample_weights=w) * rw[4]
+        L["predict_loss"] = KD.kd_loss(s_out["logits"], t_out["logits"].detach(), temperature=T, t_sample_weights=w,
+                                       loss_type=lt) * rw[4]
     return L
 
 
@@ -806,7 +820,10 @@ def icod_step_loss(student, teacher, batch, task, rw, t_rw, kdl=None):
     t_w = mktd_weights(t_out["sample_loss"], k["t_sample_preprocess_exp_decay"], pre) if k["teacher_sample_hard_mining"] else None
     s_w = mktd_weights(s_out["sample_loss"], k["t_sample_preprocess_exp_decay"], pre) if k["teacher_sample_hard_mining"] else None
     Ls = makd_losses(student, s_out, t_out, task, rw, t_w, k, role="t2s")
-    Lt = makd_losses(student, t_out, s_out, task, t_rw, s_w, k, role="s2t")
+    # agent.py:553,557: in role s2t the learned ability weights are the LARGE model's own kdl_*_weight parameters;
+    # [DECISION] a large model built without them (pretraining teacher configs carry no kdl block) uses the small one's
+    owner = teacher if hasattr(teacher.bert, "kdl_txt_weight") else None
+    Lt = makd_losses(student, t_out, s_out, task, t_rw, s_w, k, role="s2t", weight_owner=owner)
     total_s = k["kd_alpha"] * sum(Ls.values()) + (1 - k["kd_alpha"]) * s_out["loss"].mean()
     total_t = k["t_kd_alpha"] * sum(Lt.values()) + (1 - k["t_kd_alpha"]) * t_out["loss"].mean()  # agent.py:1145
     return total_s, total_t, Ls, Lt, s_out, t_out

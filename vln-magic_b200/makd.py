@@ -64,8 +64,12 @@ def _sample_weights(out, k):
     return mktd_weights(out["sample_loss"], k["t_sample_preprocess_exp_decay"], k.get("t_sample_preprocess", "exp"))
 
 
-def _w_for(x, w):
-    return w if (w is not None and x.shape[0] == w.shape[0]) else None
+def _w_for(x, w, strict=False):
+    if w is None or x.shape[0] == w.shape[0]:
+        return w
+    if strict:  # map_nav_src/utils/kd_loss.py:16-17
+        raise ValueError("Shape mismatch between sample weights and inputs")
+    return None  # pretrain_src/optim/kd_loss.py:15-16: silently unweighted
 
 
 class _Softplus5(torch.autograd.Function):
@@ -85,8 +89,10 @@ class _Softplus5(torch.autograd.Function):
         return tuple(g[i:i + 1] for i in range(p.numel()))
 
 
-def ability_weights(student, k, rw):
+def ability_weights(student, k, rw, weight_owner=None):
     """-> (host multipliers [5], device multipliers [5] or None, divisor of the two image embedding losses).
+    `weight_owner`: the model whose learned kdl_*_weight parameters are used -- the LEARNER (`s_model`, agent.py:553,
+    557): the small model in role t2s (default), the large model in role s2t.
     agent.py:583-593, 616-625, 675-693, 710-717: 'RW' / 'grad' multiply by softmax_weights[a] (image embedding losses
     NOT halved); 'learned_weight' multiplies by softplus(s_model.kdl_<a>_weight) and halves the two image embedding
     losses; without kdl_adaptive_ability_weight every weight is 1 and the two image embedding losses are halved."""
@@ -101,15 +107,16 @@ def ability_weights(student, k, rw):
             return [1.0] * 5, rw.float().contiguous(), 1.0
         return [float(x) for x in rw], None, 1.0
     if kind == "learned_weight":
-        ps = [getattr(student.bert, n, None) for n in LEARNED_WEIGHTS]
+        owner = weight_owner if weight_owner is not None else student
+        ps = [getattr(owner.bert, n, None) for n in LEARNED_WEIGHTS]
         if any(p is None for p in ps):
-            raise ValueError("kdl_adaptive_ability_weight_type='learned_weight' needs the student's kdl_*_weight "
-                             "parameters (build the student with that kdl config)")
+            raise ValueError("kdl_adaptive_ability_weight_type='learned_weight' needs the learner's kdl_*_weight "
+                             "parameters (build the model with that kdl config)")
         return [1.0] * 5, _Softplus5.apply(*[p.reshape(1) for p in ps]), 2.0
     raise ValueError("kdl_adaptive_ability_weight_type must be RW, grad or learned_weight")
 
 
-def compute_kd_losses(student, s_out, t_out, task, rw, t_w, kdl=None, role="t2s"):
+def compute_kd_losses(student, s_out, t_out, task, rw, t_w, kdl=None, role="t2s", weight_owner=None):
     """-> (named dict of per-ability scalars as a [10] tensor view, mse_total scalar, kl scalar or None).
     `rw`: the 5 MKRW ability weights, either python floats (baked into the kernel arguments) or a DEVICE tensor
     [5] (read by the kernels at run time, so a captured CUDA graph follows the per-step draw).
@@ -119,9 +126,19 @@ def compute_kd_losses(student, s_out, t_out, task, rw, t_w, kdl=None, role="t2s"
     does; prediction = s_out, target = proj(t_out).detach() (agent.py:571,605-606,647,665) and `t_w` are the small
     model's MKTD weights.
     Batches padded by graph_index.pad_batch carry `pano_row_scale` / `row_scale` (model outputs): padded panoramas
-    and padded masked-token rows get weight 0 and the means are taken over the real rows."""
+    and padded masked-token rows get weight 0 and the means are taken over the real rows.
+    Reductions (`kdl['kd_loss_type']`): None (default) = the pretraining file's `mean` with its silent fallback on a
+    weight / batch mismatch (pretrain_src/optim/kd_loss.py); 'mean' / 'sum' = the fine-tune file's, which raises on
+    the mismatch (map_nav_src/utils/kd_loss.py; agent.py:554 for role t2s, always 'mean' for role s2t, :557).
+    Pinned against the reference's own compute_kd_losses source: tests/test_makd_agent_pinned.py."""
     k = kdl_config(kdl)
-    aw, aw_dev, img_div = ability_weights(student, k, rw)
+    aw, aw_dev, img_div = ability_weights(student, k, rw, weight_owner)
+    lt = k.get("kd_loss_type")
+    if lt not in (None, "mean", "sum"):
+        raise ValueError("Unsupported loss_type. Choose 'sum' or 'mean'.")
+    if role == "s2t" and lt is not None:
+        lt = "mean"
+    total = lt == "sum"
 
     def sdev(i):
         return aw_dev.detach()[i:i + 1] if aw_dev is not None else None
@@ -133,7 +150,7 @@ def compute_kd_losses(student, s_out, t_out, task, rw, t_w, kdl=None, role="t2s"
     pano_scale = s_out.get("pano_row_scale")
 
     def row_w(x, pano):
-        w = _w_for(x, t_w)
+        w = _w_for(x, t_w, strict=lt is not None)
         if pano and pano_scale is not None and pano_scale.shape[0] == x.shape[0]:
             return ops.row_weights(w, None, pano_scale, x.shape[0])
         return w
@@ -147,7 +164,7 @@ def compute_kd_losses(student, s_out, t_out, task, rw, t_w, kdl=None, role="t2s"
         else:
             with torch.no_grad():
                 ps, t = s, ops.linear(t.detach(), proj.weight, proj.bias)
-        pairs.append((ps, t, row_w(ps, pano), aw[ri] / (ps.numel() * div), sdev(ri)))
+        pairs.append((ps, t, row_w(ps, pano), aw[ri] / ((1 if total else ps.numel()) * div), sdev(ri)))
         owner.append(name)
         ability.append(ri)
 
@@ -160,7 +177,7 @@ def compute_kd_losses(student, s_out, t_out, task, rw, t_w, kdl=None, role="t2s"
                 items += [(sl[0], tl[0]), (sl[1], tl[1])]
             else:
                 items.append((sl, tl))
-        numel = sum(a.numel() for a, _ in items)
+        numel = 1 if total else sum(a.numel() for a, _ in items)
         w = row_w(items[0][0], pano) if items else None
         for a, b in items:
             pairs.append((a, b.detach(), w, aw[ri] / numel, sdev(ri)))
@@ -201,7 +218,7 @@ def compute_kd_losses(student, s_out, t_out, task, rw, t_w, kdl=None, role="t2s"
             if t_w is not None or rs is not None:
                 w = ops.row_weights(t_w, s_out["row_sample"] if t_w is not None else None, rs, R)
         T = float(k["kd_temperature"])
-        scale = (T * T / R if t_w is not None else T * T / (R * C)) * aw[4]
+        scale = (T * T if total else T * T / R if t_w is not None else T * T / (R * C)) * aw[4]
         kl = ops.makd_kl(s_log, t_log, T, w, scale, sdev(4), aw_dev)
     return dict(per_seg=per_seg, owner=owner, mse_total=mse_total, kl=kl)
 
@@ -265,7 +282,10 @@ def icod_step_loss(student, teacher, batch, task, rw, t_rw, kdl=None):
     s_out = student(batch, task, True, output_kd=True)
     t_w, s_w = _sample_weights(t_out, k), _sample_weights(s_out, k)
     res_s = compute_kd_losses(student, s_out, t_out, task, rw, t_w, k, role="t2s")
-    res_t = compute_kd_losses(student, t_out, s_out, task, t_rw, s_w, k, role="s2t")
+    # agent.py:553,557: in role s2t the learned ability weights are the LARGE model's own kdl_*_weight parameters; a
+    # large model built without them (pretraining teacher configs carry no kdl block) uses the small model's
+    owner = teacher if getattr(teacher.bert, LEARNED_WEIGHTS[0], None) is not None else None
+    res_t = compute_kd_losses(student, t_out, s_out, task, t_rw, s_w, k, role="s2t", weight_owner=owner)
     mix_s = ops.loss_mix(res_s["mse_total"], res_s["kl"], s_out["loss"], k["kd_alpha"], s_out.get("loss_inv_n"))
     mix_t = ops.loss_mix(res_t["mse_total"], res_t["kl"], t_out["loss"], k["t_kd_alpha"], t_out.get("loss_inv_n"))
     return mix_s, mix_t, res_s, res_t, s_out, t_out
