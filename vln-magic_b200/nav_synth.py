@@ -8,7 +8,8 @@ import numpy as np
 
 
 def view_angles():
-    """Heading / elevation of the 36 discretised views (12 headings x 3 elevations), map_nav_src/utils/data.py:184-196."""
+    """Heading / elevation of the 36 discretised views (12 headings x 3 elevations) = `get_view_rel_angles(12)` of
+    map_nav_src/utils/data.py:184-200, the table the agent reads (agent.py:1409,1416)."""
     ang = np.zeros((36, 2), dtype=np.float32)
     for i in range(36):
         ang[i] = ((i % 12) * math.radians(30), (i // 12 - 1) * math.radians(30))

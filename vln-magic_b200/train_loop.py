@@ -211,23 +211,37 @@ def validate(model, val_dataloaders, setname="", max_metrix=None, tem=None, log=
 class MetaLoader:
     """data/loader.py:18-75: samples the next task from `mix_ratio` and yields (task, batch).  The reference
     broadcasts the rank-0 draw every step; here every rank derives the same seeded schedule (parallel.task_schedule),
-    so no collective is needed.  `loaders`: {task: iterable of host batches (graph_index.prepare_batch output)}."""
+    so no collective is needed.  `loaders`: {task: iterable of host batches (graph_index.prepare_batch output)} or,
+    like the reference (:29-33), {task: (iterable, ratio, pre_epoch)} with `pre_epoch(epoch_id)` called before a
+    task's loader restarts (the sampler's `set_epoch`, :66-71).  The task is re-drawn every `accum_steps` steps
+    (:55-56).  tests/test_host_pinned_live.py replays the schedule through the reference's own class."""
 
-    def __init__(self, loaders, mix_ratio=None, seed=0, num_steps=1 << 20):
+    def __init__(self, loaders, mix_ratio=None, seed=0, num_steps=1 << 20, accum_steps=1):
         self.tasks = list(loaders.keys())
-        self.iters = {t: iter(l) for t, l in loaders.items()}
-        self.loaders = loaders
-        ratios = [1] * len(self.tasks) if mix_ratio is None else list(mix_ratio)
-        self.schedule = task_schedule(seed, num_steps, self.tasks, ratios)
+        self.loaders, self.pre_epoch, ratios = {}, {}, []
+        for t, l in loaders.items():
+            l, r, p = l if isinstance(l, tuple) else (l, 1, None)
+            self.loaders[t], self.pre_epoch[t] = l, p
+            ratios.append(r)
+        self.iters = {t: iter(l) for t, l in self.loaders.items()}
+        if mix_ratio is not None:
+            ratios = list(mix_ratio)
+        self.accum_steps = max(int(accum_steps), 1)
+        self.num_steps = num_steps
+        self.schedule = task_schedule(seed, (num_steps + self.accum_steps - 1) // self.accum_steps, self.tasks, ratios)
         self.step = 0
+        self.epoch_id = 0
 
     def __iter__(self):
-        while self.step < len(self.schedule):
-            task = self.schedule[self.step]
+        while self.step < self.num_steps:
+            task = self.schedule[self.step // self.accum_steps]
             self.step += 1
             try:
                 batch = next(self.iters[task])
             except StopIteration:  # a new epoch of that task
+                self.epoch_id += 1
+                if self.pre_epoch[task] is not None:
+                    self.pre_epoch[task](self.epoch_id)
                 self.iters[task] = iter(self.loaders[task])
                 batch = next(self.iters[task])
             yield task, batch
