@@ -146,3 +146,36 @@ def test_language_inputs_match_the_reference_collator(monkeypatch):
     assert torch.equal(got["txt_ids"], want["txt_ids"]) and got["txt_ids"].dtype == want["txt_ids"].dtype
     assert torch.equal(got["txt_masks"], want["txt_masks"])
     assert got["txt_lens"].tolist() == [len(o["instr_encoding"]) for o in obs]
+
+
+def _agent_snippet(first, last):
+    """Lines of the reference rollout (inline code, not a function) from the one containing `first` to the one
+    containing `last`, dedented."""
+    lines = open(f"{REF}/map_nav_src/r2r/agent.py").read().splitlines()
+    i = next(k for k, ln in enumerate(lines) if first in ln)
+    j = next(k for k in range(i, len(lines)) if last in lines[k])
+    return textwrap.dedent("\n".join(lines[i:j + 1]))
+
+
+@needs_ref
+def test_ability_weight_draws_match_the_reference_rollout(monkeypatch):
+    """MKRW (agent.py:866-869) and the 'grad' flavour (agent.py:857-860), executed from the rollout's own lines."""
+    import torch.nn.functional as F
+    from magic_b200 import makd
+    monkeypatch.setattr(torch.Tensor, "cuda", lambda self, *a, **k: self)
+    me = types.SimpleNamespace(args=types.SimpleNamespace(rw_temp=4.0))
+    # MKRW: the reference draws torch.randn(5) from the global CPU generator, so does mkrw_weights without a generator
+    code = _agent_snippet("loss_weights = torch.randn(5)", "s_softmax_weights = F.softmax(loss_weights")
+    for seed in (0, 7):
+        ns = dict(torch=torch, F=F, self=me)
+        torch.manual_seed(seed)
+        exec(code, ns)
+        torch.manual_seed(seed)
+        ours = makd.mkrw_weights(rw_temp=4.0)
+        assert np.allclose(ours, ns["s_softmax_weights"].tolist(), rtol=1e-6) and abs(sum(ours) - 5) < 1e-5
+    # 'grad': softmax(-grads / temp) * 5 in the key order [txt, img, local, global, action]
+    code = _agent_snippet("key_order = ['txt', 'img', 'local', 'global', 'action']", "s_softmax_weights = F.softmax(current_iter_grads")
+    grads = {"txt": 0.8, "img": 2.5, "local": 0.1, "global": 1.7, "action": 0.4}
+    ns = dict(torch=torch, F=F, self=me, current_iter_grads=dict(grads))
+    exec(code, ns)
+    assert np.allclose(makd.grad_weights(grads, rw_temp=4.0), ns["s_softmax_weights"].tolist(), rtol=1e-6)
