@@ -338,7 +338,9 @@ class GlocalTextPathCMT(nn.Module):
         h = self.config.hidden_size
         x_in = fts.reshape(R * V, Fd)
         if x_in.dtype != fc.dtype:
-            x_in = x_in.to(fc.dtype)  # TODO(fuse): fp32 -> bf16 cast of the CLIP features into the GEMM loader
+            # materialised fp32 features (the reference collate's layout) in bf16 mode: one cast kernel.  The feature
+            # store (featurizer.FeatureStore, `view_features` above) gathers straight into the compute dtype instead
+            x_in = x_in.to(fc.dtype)
         z = ops.linear(x_in, ie.img_linear.weight, ie.img_linear.bias)
         a = _ln(z, ie.img_layer_norm, fc)
         view_lens = batch["traj_vp_view_lens"]
