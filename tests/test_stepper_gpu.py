@@ -22,23 +22,24 @@ def rel(a, b):
     return ((a - b).norm() / (b.norm() + 1e-20)).item()
 
 
-def models(teacher, dtype=torch.float32):
+def models(teacher, dtype=torch.float32, tasks=("mlm", "sap")):
     cfg_s = make_config(128, role="student", teacher_hidden_size=256 if teacher else None, hidden_dropout_prob=0.0,
-                        attention_probs_dropout_prob=0.0)
+                        attention_probs_dropout_prob=0.0, pretrain_tasks=tasks)
     torch.manual_seed(1)
     s = magic_b200.GlocalTextPathCMTPreTraining(cfg_s).to(DEV).train().set_compute_dtype(dtype)
     t = None
     if teacher:
-        cfg_t = make_config(256, role="teacher", hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0)
+        cfg_t = make_config(256, role="teacher", hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0,
+                            pretrain_tasks=tasks)
         torch.manual_seed(0)
         t = magic_b200.GlocalTextPathCMTPreTraining(cfg_t).to(DEV).eval().set_compute_dtype(dtype)
     return s, t
 
 
-def host_pool(n=3, B=4):
+def host_pool(n=3, B=4, tasks=("mlm", "sap")):
     pools = {}
-    for task in ("mlm", "sap"):
-        bs = [prepare_batch(synth.make_batch(task, B, seed=50 + i + (0 if task == "mlm" else 100))) for i in range(n)]
+    for ti, task in enumerate(tasks):
+        bs = [prepare_batch(synth.make_batch(task, B, seed=50 + i + 100 * ti)) for i in range(n)]
         K = magic_b200.INDEX_KEY
         rcap = (max(b["traj_view_img_fts"].shape[0] for b in bs) + 7) // 8 * 8
         mcap = (max(b[K]["mlm_rows"].numel() for b in bs) + 63) // 64 * 64 if task == "mlm" else None
@@ -51,12 +52,13 @@ def host_pool(n=3, B=4):
 def run(teacher, n_steps=4, prefetch=False, lookahead=False, order=None, **kw):
     """`lookahead`: announce the next batch to step() (frozen-teacher pipelining: its teacher forward runs under the
     current step's backward).  `order`: task sequence (default MLM / SAP alternating)."""
-    s, t = models(teacher)
+    order = order or ["mlm" if i % 2 == 0 else "sap" for i in range(n_steps)]
+    tasks = tuple(t_ for t_ in ("mlm", "sap", "cfp") if t_ in order or t_ != "cfp")
+    s, t = models(teacher, tasks=tasks)
     g = torch.Generator().manual_seed(7)
     st = PretrainStepper(s, t, lr=1e-3, rw_generator=g, **kw)
-    pools = host_pool()
-    order = order or ["mlm" if i % 2 == 0 else "sap" for i in range(n_steps)]
-    seen = {"mlm": 0, "sap": 0}
+    pools = host_pool(tasks=tasks)
+    seen = {t_: 0 for t_ in tasks}
 
     def stage(task):
         hb = pools[task][seen[task] % len(pools[task])]
@@ -79,6 +81,7 @@ def run(teacher, n_steps=4, prefetch=False, lookahead=False, order=None, **kw):
         else:
             losses.append(st.step(task, b).clone())
     torch.cuda.synchronize()
+    run.last_stepper = st
     return torch.stack(losses).cpu(), st.arena.flat_p.clone().cpu()
 
 
@@ -153,3 +156,21 @@ def test_icod_co_update_steps_both_models_and_graph_replay_matches_eager():
         res[graphs] = (outs, st.arena.flat_p.clone().cpu(), st.t_arena.flat_p.clone().cpu())
     for a, b in zip(res[True], res[False]):
         assert rel(a, b) < 2e-5
+
+
+def test_tasks_without_makd_take_the_supervised_step_beside_a_teacher():
+    """The reference's own task list is [mlm, sap, cfp] with distillation on (config/r2r_magic_pretrain.json:49-53,
+    :62-64).  MAKD is defined for the MLM and SAP steps; a cfp step of the same run is the plain
+    supervised step -- KD term exactly 0, no teacher forward -- and graph replay + teacher pipelining across such a
+    step reproduce the eager order.  `tasks=` switches the task-aware AdamW on, as the loop does."""
+    order = ["cfp", "mlm", "cfp", "sap", "mlm", "cfp"]
+    tasks = ("mlm", "sap", "cfp")
+    base_l, base_p = run(True, order=order, use_graphs=False, side_stream=False, branch_streams=False, tasks=tasks)
+    assert torch.isfinite(base_l).all()
+    is_cfp = torch.tensor([t == "cfp" for t in order])
+    assert (base_l[is_cfp, 2] == 0).all() and (base_l[~is_cfp, 2] > 0).all()
+    assert torch.allclose(base_l[is_cfp, 0], base_l[is_cfp, 1], rtol=1e-6)  # total == supervised mean
+    assert run.last_stepper.last_named_losses() is None            # the last step (cfp) carried no KD terms
+    l, p = run(True, order=order, use_graphs=True, side_stream=True, branch_streams=True, lookahead=True, tasks=tasks)
+    assert rel(l, base_l) < 2e-5, (l, base_l)
+    assert rel(p, base_p) < 2e-5

@@ -118,6 +118,15 @@ class PretrainStepper:
         self._next = None
         self._last_res = None
 
+    KD_TASKS = ("mlm", "sap")
+
+    def kd_task(self, task):
+        """MAKD is defined for MLM and SAP steps (the `predict` ability needs the task's logits, the
+        MKTD weights the teacher's per-sample task loss; model.inactive_in_task encodes the same rule for the
+        optimizer).  The other tasks of a run that has a teacher -- `cfp` in the reference's own task list
+        (config/r2r_magic_pretrain.json:49-53), `mrc`, `og` -- take the plain supervised step."""
+        return self.teacher is not None and task[:3] in self.KD_TASKS
+
     @staticmethod
     def _detach_res(res):
         """Values only: holding the loss tensors themselves would keep the step's autograd graph (and its
@@ -176,10 +185,17 @@ class PretrainStepper:
         for sy in self.syncs:
             sy.begin(mode)
         self.arena.zero_grad()
+        kd = self.kd_task(task)
         if self.co_update:
             self.t_arena.zero_grad()
-            # agent.py:869-871: under RW the teacher's ability weights ARE the student's draw of this step
-            mix, mix_t, res, _, _, _ = makd.icod_step_loss(self.student, self.teacher, batch, task, rw, rw, self.kdl)
+            if kd:
+                # agent.py:869-871: under RW the teacher's ability weights ARE the student's draw of this step
+                mix, mix_t, res, _, _, _ = makd.icod_step_loss(self.student, self.teacher, batch, task, rw, rw,
+                                                               self.kdl)
+            else:  # a task MAKD is not defined for: each model takes its own supervised step
+                res = None
+                mix, mix_t = (ops.loss_mix(None, None, o["loss"], 0.0, o.get("loss_inv_n"))
+                              for o in (self.student(batch, task, True), self.teacher(batch, task, True)))
             self._last_res = self._detach_res(res)
             # the reference calls loss.backward(retain_graph=True) then t_loss.backward() (agent_base.py:260-268);
             # every cross-model target is detached, so the two graphs are disjoint and one pass over their sum
@@ -191,11 +207,11 @@ class PretrainStepper:
             if finish:
                 self._finish(task=task)
             return torch.cat([mix, mix_t]).detach()
-        if self.teacher is not None and t_out is not None:  # teacher outputs computed by the teacher's own graph
+        if kd and t_out is not None:  # teacher outputs computed by the teacher's own graph
             mix, res, s_out = makd.student_distill_loss(self.student, t_out, batch, task, rw, self.kdl)
-        elif self.teacher is not None:
+        elif kd:
             mix, res, s_out, t_out = makd.distill_step_loss(self.student, self.teacher, batch, task, rw, self.kdl)
-        else:
+        else:  # no teacher, or a task MAKD is not defined for (kd_task): the supervised step
             res = None
             s_out = self.student(batch, task, True)
             mix = ops.loss_mix(None, None, s_out["loss"], 0.0, s_out.get("loss_inv_n"))
@@ -353,7 +369,7 @@ class PretrainStepper:
             dev = self.device
             t_ent = None
             self._t_inflight = None
-            if self.pipeline_teacher:
+            if self.pipeline_teacher and self.kd_task(task):
                 t_ent = self._capture_teacher(task, batch)
                 t_ent["g"].replay()  # valid teacher outputs for the student's warm-up runs and capture
             t_out = t_ent["t_out"] if t_ent is not None else None
@@ -407,13 +423,15 @@ class PretrainStepper:
         _lib.COUNTERS["launches"] += n_launch  # kernels replayed inside the graph
         if t_ent is not None:
             t_ent["done"].record(cur)
-            if self._next is not None:  # the next batch's teacher forward starts now, under this step's backward
-                t2, b2, ready2 = self._next
-                sig2 = self._signature(t2, b2)
-                e2 = self.graphs.get(sig2)
-                if e2 is not None and e2[5] is not None:
-                    self._launch_teacher(e2[5], b2, ready=ready2)
-                    self._t_inflight = (sig2, id(b2))
+        if self._next is not None and self.pipeline_teacher:
+            # the next batch's teacher forward starts now, under this step's backward (also when this step itself had
+            # no teacher: a cfp step between two distillation steps)
+            t2, b2, ready2 = self._next
+            sig2 = self._signature(t2, b2)
+            e2 = self.graphs.get(sig2)
+            if e2 is not None and e2[5] is not None:
+                self._launch_teacher(e2[5], b2, ready=ready2)
+                self._t_inflight = (sig2, id(b2))
         if self.world > 1:
             # the exchange of every stage that completed inside the graph starts at its in-graph event
             for sy, (fired, events) in zip(self.syncs, marks):
