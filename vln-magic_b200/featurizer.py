@@ -12,7 +12,7 @@ The view ORDER stays the reference's: candidate views first (in candidate order)
 ascending view index (dataset.py:742-756): it is computed on the host with the rest of the (tiny) geometry."""
 import torch
 
-from ._lib import BF16, F32, call, dt, ptr, stream
+from ._lib import call, dt, ptr, stream
 
 VIEW_KEYS = ("traj_vp_index", "traj_view_perm")
 

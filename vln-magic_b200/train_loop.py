@@ -19,7 +19,7 @@ from collections import defaultdict
 import torch
 import torch.distributed as dist
 
-from . import makd, ops
+from . import ops
 from .optim import get_lr_sched
 from .parallel import task_schedule
 
