@@ -16,7 +16,10 @@ reference code, and followed literally here:
   * KD loss arithmetic                -- pretrain_src/optim/kd_loss.py:5-54 (restated in kd_loss_oracle.py,
                                          pinned against the reference file by tests/golden/kd_loss_*.pt)
   * MAKD aggregation                  -- map_nav_src/r2r/agent.py:546-719 (compute_kd_losses),
-                                         :866-869 (MKRW), :1013-1020 (MKTD), :1110-1123 (mix)
+                                         :866-869 (MKRW), :1013-1020 (MKTD), :1110-1123 (mix); `makd_losses` is PINNED:
+                                         tests/test_makd_agent_pinned.py checks it against tests/golden/makd_agent_ref.pt,
+                                         produced by executing the reference function's own source (both roles, all
+                                         ability-weight branches, weighted / unweighted, mean / sum)
   * block arithmetic                  -- tests/test_oracle_blocks_pinned.py: BertLayer / BertAttention (self, cross) /
                                          BertEmbeddings vs `transformers`, PanoLayer vs torch.nn.TransformerEncoderLayer
                                          (same state-dict keys, same activations)
