@@ -148,3 +148,53 @@ def test_cuda_makd_matches_the_reference_agent(rec):
         owner_p, owner_o = (small, small_o) if case["role"] == "t2s" else (large, large_o)
         for n in G.LEARNED:
             assert rel(getattr(owner_p.bert, n).grad, getattr(owner_o.bert, n).grad) < 2e-3, n
+
+
+@pytest.mark.skipif(not os.path.exists(G.REF_AGENT), reason="reference tree not mounted")
+def test_reference_function_runs_on_our_models():
+    """Drop-in level 1 of INTEGRATION.md 1b: the reference agent's own `compute_kd_losses` source, unmodified, on a
+    pair of OUR models wrapped like the agent wraps them (`self.vln_bert.vln_bert`): the KD heads and learned weights
+    it reaches for (`s_model.txt_emb_w`, `s_model.kdl_txt_weight`, agent.py:552-568, 585) resolve on our model, and
+    the result equals the oracle composition on the same tensors (CPU: the heads are plain nn.Linear modules)."""
+    import magic_b200
+    from magic_b200.config import make_config
+    kd = G.load(G.REF_KD, "ref_kd_fin_dropin")
+    fn = G.reference_method(kd)
+    kdl = dict(kdl_adaptive_ability_weight=True, kdl_adaptive_ability_weight_type="learned_weight")
+    cfg_s = make_config(128, role="student", teacher_hidden_size=256, pretrain_tasks=("sap",), kdl=kdl)
+    cfg_t = make_config(256, role="teacher", pretrain_tasks=("sap",))
+    torch.manual_seed(0)
+    small = magic_b200.GlocalTextPathCMTPreTraining(cfg_s)
+    large = magic_b200.GlocalTextPathCMTPreTraining(cfg_t)
+    assert small.txt_emb_w is small.bert.txt_emb_w and small.kdl_txt_weight is small.bert.kdl_txt_weight
+    with pytest.raises(AttributeError):
+        small.no_such_head
+    with pytest.raises(AttributeError):
+        large.txt_emb_w                      # the large model owns no up-projections
+    g = torch.Generator().manual_seed(5)
+    B, L, V, Gn, VP = 3, 9, 6, 5, 7
+
+    def outs(h, n_l):
+        def r(*s):
+            return torch.randn(*s, generator=g)
+        return dict(txt_embeds=r(B, L, h), txt_attns=torch.softmax(r(B, n_l, L, L), -1), pano_embeds=r(B, V, h),
+                    pano_fused_embeds=r(B, h), img_attns=torch.softmax(r(B, 2, V, V), -1),
+                    nav_outs=dict(gmap_embeds=r(B, Gn, h), gmap_attns=torch.softmax(r(B, 3, Gn, Gn + L), -1),
+                                  vp_embeds=r(B, VP, h), vp_attns=torch.softmax(r(B, 3, VP, VP + L), -1)),
+                    nav_logits=r(B, Gn) * 2, sample_weights=torch.rand(B, generator=g))
+
+    s_out, t_out = outs(128, 6), outs(256, 6)
+    args = types.SimpleNamespace(
+        kd_loss_type="mean", kd_ability_types=["txt", "img", "local", "global", "action"], train_kdl_noFeat=False,
+        train_kdl_noAttn=False, train_kdl_noLogit=False, kdl_temperature=2.0, kdl_adaptive_ability_weight=True,
+        kdl_adaptive_ability_weight_type="learned_weight", kdl_logit_loss="kd", ignoreid=-100, kdl_dkd_alpha=1.0,
+        kdl_dkd_beta=1.0)
+    agent = types.SimpleNamespace(args=args, vln_bert=types.SimpleNamespace(vln_bert=small),
+                                  teacher_vln_bert=types.SimpleNamespace(vln_bert=large),
+                                  kdl_feat_loss=kd.mse_loss, kdl_attn_loss=kd.mse_loss, kdl_logit_loss=kd.kd_loss)
+    with torch.no_grad():
+        ref = fn(agent, 0, s_out, t_out, {n: 0. for n in G.NAMES}, torch.zeros(B, dtype=torch.long), role="t2s")
+        mine = O.makd_losses(small, flat(s_out), flat(t_out), "sap", None, t_out["sample_weights"],
+                             dict(kdl, kd_loss_type="mean", kd_temperature=2.0), role="t2s")
+    for k in G.NAMES:
+        assert abs(float(ref[k]) - float(mine[k])) <= 1e-5 * abs(float(ref[k])) + 1e-8, k

@@ -539,6 +539,17 @@ class GlocalTextPathCMTPreTraining(nn.Module):
         self.feature_store = None  # featurizer.FeatureStore.attach(model)
         self.apply(self._init_weights)
 
+    def __getattr__(self, name):
+        """The fine-tune agent reaches the KD heads and the learned ability weights directly on the model it wraps
+        (`s_model = self.vln_bert.vln_bert; s_model.txt_emb_w(...)`, `s_model.kdl_txt_weight`: agent.py:552-568,585);
+        here they live on `.bert` with the encoders, so those names -- and only those -- resolve through it."""
+        try:
+            return super().__getattr__(name)
+        except AttributeError:
+            if name in KD_HEADS or name in KD_LEARNED_WEIGHTS:
+                return getattr(super().__getattr__("bert"), name)
+            raise
+
     # -- construction ------------------------------------------------------------------------------
     def _init_weights(self, m):
         r = self.config.initializer_range
