@@ -219,3 +219,35 @@ def test_world_tables_and_graphworld_on_cpu():
         assert world.cand_vp[i, :len(lst)].tolist() == [c[0] for c in lst] and (world.cand_vp[i, len(lst):] == -1).all()
         assert world.cand_view[i, :len(lst)].tolist() == [c[1] for c in lst]
     assert world.pos.dtype == torch.float64 and world.dist.dtype == torch.float32 and world.hops.dtype == torch.int32
+
+
+def test_checkpoint_layouts_the_wrapper_accepts():
+    """nav.remap_agent_keys / VLNBert.load_state_dict: our own layout, a DDP-prefixed one, the reference's fine-tune
+    layout ([INFERRED]: no `.bert` level under `vln_bert`, agent_base.py:328-330) and a bare pretraining checkpoint
+    (train_r2r_magic.py:189-208 key tree) all load into the same parameters; unknown keys are still reported."""
+    import copy
+    from magic_b200.config import make_config
+    cfg = make_config(128, role="student", teacher_hidden_size=256, pretrain_tasks=("sap",))
+    torch.manual_seed(3)
+    src = nav.VLNBert(copy.copy(cfg))
+    own = src.state_dict()
+    assert any(k.startswith("vln_bert.bert.txt_emb_w.") for k in own) and "vln_bert.global_sap_head.net.0.weight" in own
+    layouts = {
+        "own": dict(own),
+        "ddp": {"module." + k: v for k, v in own.items()},
+        "reference_finetune": {k.replace("vln_bert.bert.", "vln_bert.", 1): v for k, v in own.items()},
+        "pretraining": {k[len("vln_bert."):]: v for k, v in own.items()},
+    }
+    assert "vln_bert.txt_emb_w.weight" in layouts["reference_finetune"] and "bert.txt_emb_w.weight" in layouts["pretraining"]
+    for name, sd in layouts.items():
+        torch.manual_seed(4)
+        dst = nav.VLNBert(copy.copy(cfg))
+        res = dst.load_state_dict(sd)  # strict
+        assert not res.missing_keys and not res.unexpected_keys, name
+        for k, v in dst.state_dict().items():
+            assert torch.equal(v, own[k]), (name, k)
+    dst = nav.VLNBert(copy.copy(cfg))
+    res = dst.load_state_dict(dict(own, **{"vln_bert.not_a_module.weight": torch.zeros(1)}), strict=False)
+    assert res.unexpected_keys == ["vln_bert.not_a_module.weight"]
+    with pytest.raises(RuntimeError):
+        dst.load_state_dict({k: v for k, v in own.items() if "global_sap_head" not in k})  # strict: missing keys raise

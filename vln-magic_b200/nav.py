@@ -363,6 +363,32 @@ def nav_index(nav_inputs, n_special=2):
 
 # ---------------------------------------------------------------------------------------------------
 # model
+def remap_agent_keys(state_dict, own_keys):
+    """Checkpoint keys of the other layouts this model meets -> ours (`vln_bert.bert.<encoders, KD heads>`,
+    `vln_bert.<task heads>`).  A key that already matches stays; otherwise
+      * a DDP `module.` prefix is dropped (agent_base.py:336-339);
+      * `vln_bert.X` becomes `vln_bert.bert.X` -- [INFERRED] the layout of the reference's fine-tune checkpoints: its
+        agent reaches the KD heads and learned weights directly on the wrapped model (`vln_bert.vln_bert.txt_emb_w`,
+        agent.py:552-568; `k.split('.')[1] in ['txt_emb_w', ...]`, agent_base.py:328-330), i.e. without a `.bert` level;
+      * a pretraining key (`bert.X`, `global_sap_head.X`; train_r2r_magic.py:189-208) gains the `vln_bert.` prefix.
+    Keys that match nothing are passed through for `load_state_dict` to report."""
+    own = set(own_keys)
+    out = {}
+    for k, v in state_dict.items():
+        if k not in own:
+            k2 = k[7:] if k.startswith("module.") else k
+            if k2 in own:
+                k = k2
+            elif k2.startswith("vln_bert.") and "vln_bert.bert." + k2[9:] in own:
+                k = "vln_bert.bert." + k2[9:]
+            elif "vln_bert." + k2 in own:
+                k = "vln_bert." + k2
+            elif "vln_bert.bert." + k2 in own:
+                k = "vln_bert.bert." + k2
+        out[k] = v
+    return out
+
+
 # ---------------------------------------------------------------------------------------------------
 class VLNBert(nn.Module):
     """`VLNBert(config, role)`; `forward(mode, batch)` with mode in {'language', 'panorama', 'navigation'}
@@ -391,6 +417,11 @@ class VLNBert(nn.Module):
     def set_compute_dtype(self, dtype):
         self.vln_bert.set_compute_dtype(dtype)
         return self
+
+    def load_state_dict(self, state_dict, strict=True, **kw):
+        """Also accepts the agent-level layouts `remap_agent_keys` lists (DDP prefix, the reference's fine-tune layout,
+        a bare pretraining checkpoint)."""
+        return super().load_state_dict(remap_agent_keys(state_dict, self.state_dict().keys()), strict=strict, **kw)
 
     def _fc(self):
         m = self.vln_bert
