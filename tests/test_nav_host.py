@@ -251,3 +251,37 @@ def test_checkpoint_layouts_the_wrapper_accepts():
     assert res.unexpected_keys == ["vln_bert.not_a_module.weight"]
     with pytest.raises(RuntimeError):
         dst.load_state_dict({k: v for k, v in own.items() if "global_sap_head" not in k})  # strict: missing keys raise
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/map_nav_src/r2r/parser.py"), reason="reference tree not mounted")
+def test_agent_args_build_both_roles(monkeypatch):
+    """`VLNBert(self.args, role=...)` exactly as the agent calls it (agent.py:36-38), with the namespace the reference's
+    own parser produces for the flags of scripts/run_r2r_kdl_valid.sh (MAGIC-B student 384 <- teacher 768)."""
+    import sys
+    import warnings
+    src = open("/root/reference/map_nav_src/r2r/parser.py").read()
+    ns = {}
+    exec(src, ns)
+    ns["postprocess_args"] = lambda a: a  # the path bookkeeping creates directories; the model flags are untouched by it
+    flags = ("--mode valid --tokenizer roberta --enc_full_graph --graph_sprels --fusion dynamic --num_l_layers 6 "
+             "--num_x_layers 3 --num_pano_layers 2 --angle_feat_size 4 --dropout 0.1 --adaptive_pano_fusion --train_kdl "
+             "--kdl_temperature 2 --teacher_hidden_size 768 --teacher_num_l_layers 6 --teacher_num_pano_layers 2 "
+             "--teacher_num_x_layers 3 --teacher_mlp_ratio 4 --student_num_l_layers 6 --student_num_x_layers 3 "
+             "--student_num_pano_layers 2 --student_hidden_size 384 --student_mlp_ratio 4 --kdl_adaptive_ability_weight "
+             "--kdl_adaptive_ability_weight_type RW --rw_temp 4 --do_back_txt").split()
+    monkeypatch.setattr(sys, "argv", ["main_nav.py"] + flags)
+    args = ns["parse_args"]()
+    args.image_feat_size = 768  # set by postprocess_args (parser.py:218)
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        student = nav.VLNBert(args, role="student")
+        teacher = nav.VLNBert(args, role="teacher")
+    assert any("causal-intervention" in str(x.message) for x in w)  # --do_back_txt is outside this path: said, not silent
+    cs, ct = student.config, teacher.config
+    assert (cs.hidden_size, cs.num_attention_heads, cs.intermediate_size) == (384, 6, 1536)
+    assert (ct.hidden_size, ct.num_attention_heads, ct.intermediate_size) == (768, 12, 3072)
+    assert (cs.num_l_layers, cs.num_x_layers, cs.num_pano_layers) == (6, 3, 2) and cs.vocab_size == 50265
+    assert cs.role == "student" and ct.role == "teacher" and student.want_attn and teacher.want_attn
+    # the student owns the up-projections to the teacher's width; the teacher has none (agent.py:550-568)
+    assert student.vln_bert.txt_emb_w.weight.shape == (768, 384) and not hasattr(teacher.vln_bert, "txt_emb_w")
+    assert student.vln_bert.bert.embeddings.word_embeddings.weight.shape == (50265, 384)

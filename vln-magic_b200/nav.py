@@ -363,6 +363,48 @@ def nav_index(nav_inputs, n_special=2):
 
 # ---------------------------------------------------------------------------------------------------
 # model
+_TOKENIZER_VOCAB = {"bert": (30522, 2, 512), "roberta": (50265, 1, 514), "xlm": (250002, 1, 514)}
+
+
+def config_from_agent_args(args, role="student"):
+    """The model config of one role from the fine-tune agent's argparse namespace, the object the agent hands to
+    `VLNBert(self.args, role=...)` (agent.py:36-38; flags: r2r/parser.py:56-66, 118, 173-193, scripts/run_r2r_kdl_valid.sh).
+    `<role>_hidden_size / _num_l_layers / _num_pano_layers / _num_x_layers / _mlp_ratio` give the sizes the way
+    train_r2r_magic.py:141-160 derives them for pretraining (intermediate = hidden * mlp_ratio, heads = hidden / 64);
+    `train_kdl` switches the KD outputs on and gives the student its up-projections to `teacher_hidden_size`.
+    [INFERRED] (models/model.py is absent upstream): dropout = `--dropout` for hidden and attention probabilities;
+    vocabulary / type / position sizes follow `--tokenizer`; R2R / RxR carry no object tokens (obj_feat_size 0).
+    The causal-intervention dictionaries (`do_back_*`, `do_front_*`) are outside this path and ignored."""
+    from .config import make_config
+    pre = "teacher" if role == "teacher" else "student"
+
+    def g(name, default=None):
+        return getattr(args, f"{pre}_{name}", getattr(args, name, default))
+
+    kd = bool(getattr(args, "train_kdl", False))
+    vocab, types, positions = _TOKENIZER_VOCAB[getattr(args, "tokenizer", "roberta")]
+    if any(getattr(args, k, False) for k in ("do_back_img", "do_back_txt", "do_front_img", "do_front_his", "do_front_txt")):
+        import warnings
+        warnings.warn("magic_b200.nav.VLNBert: the causal-intervention inputs (do_back_* / do_front_*) are not part of "
+                      "this path and are ignored")
+    kdl = None
+    if kd and pre == "student":
+        kdl = dict(kdl_adaptive_ability_weight=bool(getattr(args, "kdl_adaptive_ability_weight", False)),
+                   kdl_adaptive_ability_weight_type=getattr(args, "kdl_adaptive_ability_weight_type", "RW"))
+    over = dict(kdl=kdl) if kdl is not None else {}
+    p = float(getattr(args, "dropout", 0.1))
+    return make_config(
+        int(g("hidden_size")), int(g("num_l_layers", 6)), int(g("num_x_layers", 3)), int(g("num_pano_layers", 2)),
+        mlp_ratio=g("mlp_ratio", 4), role=pre, teacher_hidden_size=int(args.teacher_hidden_size) if kd and pre == "student" else None,
+        pretrain_tasks=("sap",), hidden_dropout_prob=p, attention_probs_dropout_prob=p,
+        image_feat_size=int(getattr(args, "image_feat_size", 768)), angle_feat_size=int(getattr(args, "angle_feat_size", 4)),
+        obj_feat_size=0, graph_sprels=bool(getattr(args, "graph_sprels", True)),
+        glocal_fuse=getattr(args, "fusion", "dynamic") == "dynamic",
+        adaptive_pano_fusion=bool(getattr(args, "adaptive_pano_fusion", True)),
+        cfp_temperature=float(getattr(args, "cfp_temperature", 1.0)), vocab_size=vocab, type_vocab_size=types,
+        max_position_embeddings=positions, kd=kd, **over)
+
+
 def remap_agent_keys(state_dict, own_keys):
     """Checkpoint keys of the other layouts this model meets -> ours (`vln_bert.bert.<encoders, KD heads>`,
     `vln_bert.<task heads>`).  A key that already matches stays; otherwise
@@ -397,6 +439,8 @@ class VLNBert(nn.Module):
 
     def __init__(self, config, role="student"):
         super().__init__()
+        if not hasattr(config, "hidden_size") and hasattr(config, "student_hidden_size"):
+            config = config_from_agent_args(config, role)  # the agent's `VLNBert(self.args, role=...)`, agent.py:36-38
         if not hasattr(config, "pretrain_tasks"):
             config.pretrain_tasks = ("sap",)
         config.role = role
