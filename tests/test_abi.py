@@ -45,3 +45,25 @@ def test_ops_refuse_cpu_tensors():
     m = magic_b200.GlocalTextPathCMTPreTraining(make_config(128))
     with pytest.raises(Exception):
         m(synth.make_batch("sap", 2), "sap", True)   # no CPU fallback exists
+
+
+def test_header_compiles_as_c_and_links_from_a_c_program(tmp_path):
+    """The boundary is usable from plain C (what a cgo / JNI / FFI binding sees): include/magic_b200.h compiles with
+    `gcc -std=c99 -pedantic -Wall -Werror`, and a C program links against the shared library and calls the entry
+    points that need no device (version, last error, the GEMM capability query) without a GPU."""
+    lib_path = _ensure_built()
+    c = tmp_path / "abi.c"
+    c.write_text(
+        '#include <stdio.h>\n#include <string.h>\n#include "magic_b200.h"\n'
+        "int main(void) {\n"
+        "  int v = magic_version();\n"
+        "  const char* e = magic_last_error();\n"
+        '  printf("%d %d %d\\n", v, e != NULL, magic_gemm_tc_supported(5120, 768, 768));\n'
+        "  return v >= 100 ? 0 : 1;\n"
+        "}\n")
+    exe = tmp_path / "abi"
+    libdir = os.path.dirname(lib_path)
+    subprocess.run(["gcc", "-std=c99", "-pedantic", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), str(c), "-o",
+                    str(exe), "-L", libdir, "-lmagic_b200", f"-Wl,-rpath,{libdir}"], check=True, capture_output=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()
+    assert int(out[0]) >= 100 and out[1] == "1" and out[2] in ("0", "1")
