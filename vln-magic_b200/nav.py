@@ -415,7 +415,9 @@ def remap_agent_keys(state_dict, own_keys):
       * a pretraining key (`bert.X`, `global_sap_head.X`; train_r2r_magic.py:189-208) gains the `vln_bert.` prefix.
     Keys that match nothing are passed through for `load_state_dict` to report."""
     own = set(own_keys)
-    out = {}
+    out = type(state_dict)() if isinstance(state_dict, dict) else {}
+    if hasattr(state_dict, "_metadata"):
+        out._metadata = state_dict._metadata  # torch's per-module version records travel with the OrderedDict
     for k, v in state_dict.items():
         if k not in own:
             k2 = k[7:] if k.startswith("module.") else k
