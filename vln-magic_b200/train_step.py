@@ -29,6 +29,11 @@ class PretrainStepper:
                  pipeline_teacher=True, teacher_sm_budget=0, pdl=None, tasks=None):
         """co_update=True is ICoD (`--train_kdl_teacher`, agent_base.py:260-279): the teacher is trained too, from
         the s2t losses, with its own arena / AdamW state / clip, and both models step once per batch."""
+        # a model the caller already wrapped like the reference does (wrap_model, utils/misc.py:57-71) is unwrapped: the
+        # stepper exchanges the flat gradient arena itself and never calls forward through the DDP reducer
+        DDP = torch.nn.parallel.DistributedDataParallel
+        student = student.module if isinstance(student, DDP) else student
+        teacher = teacher.module if isinstance(teacher, DDP) else teacher
         self.student, self.teacher = student, teacher
         self.kdl = makd.kdl_config(kdl)
         self.co_update = bool(co_update and teacher is not None)
