@@ -179,3 +179,26 @@ def test_ability_weight_draws_match_the_reference_rollout(monkeypatch):
     ns = dict(torch=torch, F=F, self=me, current_iter_grads=dict(grads))
     exec(code, ns)
     assert np.allclose(makd.grad_weights(grads, rw_temp=4.0), ns["s_softmax_weights"].tolist(), rtol=1e-6)
+
+
+@needs_ref
+def test_prepared_batches_travel_through_the_reference_prefetch_loader():
+    """A collate batch with our index tables attached (graph_index.prepare_batch, done in the loader worker) survives
+    the reference's own `move_to_cuda` / `PrefetchLoader` (data/loader.py:76-124) unchanged: tensors moved, the nested
+    table dict, python lists of viewpoint ids and None entries kept."""
+    from magic_b200 import synth
+    from magic_b200.graph_index import prepare_batch
+    ref = _load(f"{REF}/pretrain_src/data/loader.py", "ref_loader2")
+    batches = [prepare_batch(synth.make_batch(t, 3, seed=5 + i)) for i, t in enumerate(("mlm", "sap"))]
+    out = list(ref.PrefetchLoader(batches, torch.device("cpu")))
+    assert len(out) == 2
+    K = magic_b200.INDEX_KEY
+    for a, b in zip(batches, out):
+        assert set(a) == set(b) and isinstance(b[K], dict) and set(a[K]) == set(b[K])
+        for k, v in a.items():
+            if torch.is_tensor(v):
+                assert torch.equal(v, b[k]), k
+            elif k != K:
+                assert v == b[k], k
+        for k, v in a[K].items():
+            assert torch.equal(v, b[K][k]) if torch.is_tensor(v) else v == b[K][k], k
