@@ -99,3 +99,25 @@ def test_mlm_row_order_and_padding():
     assert abs(float(ix["mlm_inv_n"]) - 1.0 / n) < 1e-9
     sp = ix["src_ptr"]
     assert sp.numel() == ix["src_ids"].numel() + 1 and int(sp[-1]) == int(sp[-4])    # padded sources are empty
+
+
+def _collate_with_index(samples):
+    return prepare_batch(synth.collate(samples))
+
+
+def test_index_tables_are_built_in_loader_workers():
+    """the collate function attaches the index tables in the DataLoader worker, so the training
+    process never walks the viewpoint-id strings.  A torch DataLoader with worker processes returns batches whose
+    tables equal the ones built in the main process."""
+    import torch.utils.data as tud
+    samples = synth.make_samples("sap", 12, seed=21)
+    want = [_collate_with_index([dict(s) for s in samples[i:i + 4]]) for i in range(0, 12, 4)]
+    got = list(tud.DataLoader([dict(s) for s in samples], batch_size=4, shuffle=False, num_workers=2,
+                              collate_fn=_collate_with_index))
+    assert len(got) == 3
+    K = magic_b200.INDEX_KEY
+    for a, b in zip(want, got):
+        assert set(a[K]) == set(b[K])
+        for k, v in a[K].items():
+            assert torch.equal(v, b[K][k]) if torch.is_tensor(v) else v == b[K][k], k
+        assert torch.equal(a["gmap_pair_dists"], b["gmap_pair_dists"]) and a["gmap_vpids"] == b["gmap_vpids"]
