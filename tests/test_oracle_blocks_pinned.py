@@ -130,3 +130,27 @@ def test_embeddings_match_transformers_bert_embeddings():
         want = hf(input_ids=ids, token_type_ids=torch.zeros_like(ids), position_ids=torch.arange(23)[None])
         got = mine(ids)
     assert torch.allclose(got, want, rtol=1e-5, atol=1e-6)
+
+
+def test_mlm_head_matches_transformers():
+    """`mlm_head.predictions.{transform.dense, transform.LayerNorm, decoder, bias}` (the key names of a DUET-lineage
+    pretraining checkpoint) = HF BertOnlyMLMHead: same state dict, same logits."""
+    tr = pytest.importorskip("transformers")
+    from transformers.models.bert.modeling_bert import BertOnlyMLMHead
+    c = _cfg()
+    hf_cfg = tr.BertConfig(hidden_size=c.hidden_size, vocab_size=997, hidden_act="gelu", layer_norm_eps=c.layer_norm_eps)
+    torch.manual_seed(2)
+    hf = BertOnlyMLMHead(hf_cfg).eval()
+    for p in hf.parameters():
+        p.data.normal_(0, 0.05)
+    hf.predictions.decoder.bias = hf.predictions.bias  # the tie a full HF model applies (`_tie_weights`)
+    c.vocab_size = 997
+    mine = O.BertOnlyMLMHead(c).eval()
+    sd = {k: v for k, v in hf.state_dict().items()}
+    missing, unexpected = mine.load_state_dict(sd, strict=False)
+    # HF ties `decoder.bias` to `predictions.bias` and lists the alias in its state dict; the head keeps the one tensor
+    assert not missing and unexpected == ["predictions.decoder.bias"], (missing, unexpected)
+    assert torch.equal(sd["predictions.decoder.bias"], sd["predictions.bias"])
+    x = torch.randn(11, c.hidden_size)
+    with torch.no_grad():
+        assert torch.allclose(mine(x), hf(x), rtol=1e-5, atol=1e-6)
