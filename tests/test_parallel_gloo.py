@@ -72,6 +72,9 @@ sy.fire(0, "g_in"); assert fired == [0]          # a stage starts once
 sy.issue_rest(sy.fired)                           # stage 1 never completed: its range travels with the rest
 sy.wait()
 assert torch.allclose(arena.flat_g, (before[0] + before[1]) / 2, atol=1e-6)
+# validation metrics are reduced like the reference does (train_r2r_magic.py:456-458: sum(all_gather(x)))
+from magic_b200.train_loop import all_gather
+assert all_gather(rank * 1.5 + 1) == [1.0, 2.5] and all_gather({"n": rank}) == [{"n": 0}, {"n": 1}]
 dist.barrier()
 sys.stdout.write("rank " + str(rank) + " ok\n")
 sys.stdout.flush()
